@@ -1,0 +1,99 @@
+"""Helpers shared by the CPU (oracle) and GPU (C-ABI) parity tests: load a golden
+fixture written by tests/golden/make_golden.py and compare a solver's outputs with it."""
+import glob
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import box_qp_oracle as orc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+INF = float("inf")
+
+
+def case_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(f).startswith("lu_layer"))
+
+
+class Case:
+    def __init__(self, name):
+        self.name = name
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+        self.z = z
+        self.dtype = getattr(torch, str(z["dtype"]))
+        self.control = json.loads(str(z["control"]))
+        self.has_A = bool(z["has_A"])
+        self.iter = int(z["iter"])
+        self.rho_is_tensor = bool(z["rho_is_tensor"])
+        self.full_inputs = "Q" in z.files
+
+    def t(self, key):
+        return torch.from_numpy(self.z[key]) if key in self.z.files else None
+
+    def inputs(self):
+        if self.full_inputs:
+            return (self.t("Q"), self.t("p"), self.t("A"), self.t("b"), self.t("lb"), self.t("ub"))
+        # large cases: regenerate from the seed in the file name and pin by checksum
+        parts = self.name.split("_")          # exp1_n500_b8_f64
+        n, B = int(parts[1][1:]), int(parts[2][1:])
+        seed = {"exp1_n500_b8_f64": 0, "exp1_n500_b8_f32": 0, "exp1_n250_b8_f64": 1, "exp1_n1000_b2_f64": 0}[self.name]
+        Q, p, A, b, lb, ub = orc.make_exp1_data(n, B, seed=seed, dtype=self.dtype)
+        chk = np.array([float(Q.double().sum()), float(p.double().sum()),
+                        float(lb.double().sum()), float(ub.double().sum())])
+        np.testing.assert_allclose(chk, self.z["input_checksum"], rtol=1e-9)
+        return Q, p, A, b, lb, ub
+
+    def control_dict(self):
+        return dict(self.control)
+
+
+def rel_err(a, b):
+    """max-norm relative error ||a-b||_inf / max(||b||_inf, tiny), the yardstick of
+    north_star ('within 1e-8 relative')."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = max(np.abs(b).max(), 1e-300) if b.size else 1.0
+    return float(np.abs(a - b).max() / den) if b.size else 0.0
+
+
+def compare(case: Case, sol: dict, grads, tol: dict, skip=()):
+    """sol: dict with x,z,u,lams,nus,rho,iter (torch CPU tensors / numbers);
+    grads: (dQ, dp, dA, db, dlb, dub).  tol maps key -> relative tolerance
+    ('default' applies to keys not listed)."""
+    z = case.z
+    errs = {}
+
+    def chk(key, val):
+        if key in skip or key not in z.files:
+            return
+        e = rel_err(val.detach().cpu().numpy() if torch.is_tensor(val) else val, z[key])
+        errs[key] = e
+        lim = tol.get(key, tol["default"])
+        assert e <= lim, f"{case.name}: {key} rel err {e:.3e} > {lim:.1e}"
+
+    for k in ("x", "z", "u", "lams", "nus"):
+        if sol.get(k) is not None:
+            chk(k, sol[k])
+    if "iter" not in skip:
+        assert abs(int(sol["iter"]) - case.iter) <= tol.get("iter", 0), \
+            f"{case.name}: iter {sol['iter']} vs reference {case.iter}"
+    if "rho" not in skip:
+        assert torch.is_tensor(sol["rho"]) == case.rho_is_tensor, f"{case.name}: rho type"
+        chk("rho", sol["rho"] if torch.is_tensor(sol["rho"]) else np.float64(sol["rho"]))
+    if grads is not None:
+        dQ, dp, dA, db, dlb, dub = grads
+        for k, v in (("dp", dp), ("dA", dA), ("db", db), ("dlb", dlb), ("dub", dub)):
+            if v is not None:
+                chk(k, v)
+        if dQ is not None:
+            if "dQ" in z.files:
+                chk("dQ", dQ)
+            else:
+                gen = torch.Generator().manual_seed(4321)
+                w = torch.randn(dQ.shape[0], dQ.shape[1], 2, generator=gen, dtype=case.dtype)
+                chk("dQ_probe", torch.matmul(dQ.cpu(), w))
+                chk("dQ_fro", torch.linalg.matrix_norm(dQ.cpu()))
+    return errs

@@ -1,0 +1,145 @@
+/*
+ * lqpb.h -- C ABI of the B200-native batched ADMM box-QP solver.
+ *
+ * This is the drop-in boundary underneath the reference's Python API.  The reference
+ * (ipo-lab/lqp_py) has no FFI of its own: its hot path is the pair of torch functions
+ *
+ *   torch_solve_box_qp      lqp_py/solve_box_qp_admm_torch.py:108-333   (forward ADMM solve)
+ *   torch_solve_box_qp_grad lqp_py/solve_box_qp_admm_torch.py:349-432   (fixed-point backward)
+ *   TorchLULayer            lqp_py/lu_layer.py:18-58                    (cached-factor LU solve)
+ *
+ * and every entry point below replaces one of them (see the comment on each).  All pointers
+ * are plain device pointers borrowed for the duration of the call (row-major, contiguous,
+ * exactly the torch layouts of the reference: Q (B,n,n), p (B,n,1), A (B,m,n), b (B,m,1),
+ * lb/ub (B,n,1)); `stream` is a cudaStream_t passed as void*; the workspace is allocated by the
+ * caller (torch) with the size the *_workspace_bytes function returns.  No global solver state:
+ * calls on different streams with different workspaces are independent.  Return value 0 = OK,
+ * otherwise an LQPB_E_* code; lqpb_last_error() gives a message for the calling thread.
+ *
+ * One function set per dtype: suffix _f32 (float) and _f64 (double).
+ */
+#ifndef LQPB_H
+#define LQPB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQPB_ABI_VERSION 1
+
+enum {
+  LQPB_OK = 0,
+  LQPB_E_ARG = 1,        /* bad argument (shape, null pointer, unsupported size) */
+  LQPB_E_WORKSPACE = 2,  /* workspace too small */
+  LQPB_E_CUDA = 3,       /* CUDA runtime error, see lqpb_last_error() */
+  LQPB_E_NOT_BLACKWELL = 4 /* device is not sm_100 */
+};
+
+/* status written to lqpb_info.status */
+enum { LQPB_STATUS_CONVERGED = 1, LQPB_STATUS_MAX_ITERS = 2 };
+
+/* Derived settings of solve_box_qp_admm_torch.py:134-154 (the keys the solver *reads*),
+ * flattened by the Python adapter (lqp_py_b200/solve_box_qp_admm_torch.py). */
+typedef struct lqpb_config {
+  int32_t max_iters;             /* :134 */
+  int32_t check_solved;          /* :139 derived: max(round(sqrt(n)/10)*10, 1) unless control['check_solved'] */
+  int32_t adaptive_rho;          /* :143 */
+  int32_t adaptive_rho_iter;     /* :145-147 already rounded to a multiple of check_solved */
+  int32_t adaptive_rho_max_iter; /* :148 ('adaptive_max_iter', default 1000) */
+  int32_t scale;                 /* :152 */
+  int32_t rho_auto;              /* 1 when control['rho'] is None (:200) */
+  int32_t beta_auto;             /* 1 when control['beta'] is None (:171) */
+  int32_t verbose;               /* :151 -- per-check residual log is returned in lqpb_info */
+  int32_t reserved;
+  double eps_abs;                /* :135-136 clamped to >= 1e-12 */
+  double eps_rel;                /* :137-138 */
+  double rho;                    /* user rho when rho_auto == 0 */
+  double rho_min, rho_max;       /* :141-142 */
+  double adaptive_rho_tol;       /* :144 */
+  double adaptive_rho_threshold; /* :149-150 (value after rounding to the default dtype) */
+  double beta;                   /* user beta when beta_auto == 0 */
+  double zero_clamp;             /* :229-230 (1e-16 rounded to the default dtype) */
+} lqpb_config;
+
+#define LQPB_LOG_CAP 64
+
+/* Host-side result record of a forward solve. */
+typedef struct lqpb_info {
+  int32_t iter;            /* value of the loop index at exit (:331 'iter') */
+  int32_t status;          /* LQPB_STATUS_* */
+  int32_t n_factor;        /* factorisations done (1 + adaptive-rho updates) */
+  int32_t any_lb, any_ub;  /* :129-130 evaluated on device over the whole batch */
+  int32_t n_log;           /* number of valid entries in the log (verbose) */
+  int32_t log_iter[LQPB_LOG_CAP];
+  double log_primal[LQPB_LOG_CAP]; /* max over batch of the primal residual at each check (:290) */
+  double log_dual[LQPB_LOG_CAP];
+} lqpb_info;
+
+/* Per-phase device times (ms) of the last call on this thread when profiling is on. */
+typedef struct lqpb_profile {
+  float scale_ms, factor_ms, iterate_ms, finalize_ms; /* forward */
+  float bwd_factor_ms, bwd_solve_ms, bwd_grad_ms;     /* backward */
+  int32_t iterate_launches, factor_launches;
+  int32_t kernel_launches; /* all kernels launched by the last forward/backward call */
+} lqpb_profile;
+
+int lqpb_abi_version(void);
+const char* lqpb_last_error(void);
+void lqpb_profile_enable(int on);
+void lqpb_profile_get(lqpb_profile* out); /* blocks on the recorded events */
+
+/* ---- forward: replaces torch_solve_box_qp (solve_box_qp_admm_torch.py:108-333) ------------
+ * A/b may be NULL with m == 0.  Outputs: x,z,u (B,n), lams (B,2n), nus (B,m) (ignored if m==0),
+ * rho_out (B) (rho per problem after the solve).  `info` is host memory.  The call enqueues all
+ * kernels on `stream` and synchronises the stream once per segment (a segment ends at
+ * convergence, at max_iters, or at an adaptive-rho update): never once per iteration. */
+size_t lqpb_forward_workspace_bytes_f32(int B, int n, int m);
+size_t lqpb_forward_workspace_bytes_f64(int B, int n, int m);
+int lqpb_forward_f32(const lqpb_config* cfg, int B, int n, int m, const float* Q, const float* p,
+                     const float* A, const float* b, const float* lb, const float* ub, float* x,
+                     float* z, float* u, float* lams, float* nus, float* rho_out, lqpb_info* info,
+                     void* workspace, size_t workspace_bytes, void* stream);
+int lqpb_forward_f64(const lqpb_config* cfg, int B, int n, int m, const double* Q, const double* p,
+                     const double* A, const double* b, const double* lb, const double* ub,
+                     double* x, double* z, double* u, double* lams, double* nus, double* rho_out,
+                     lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- backward: replaces torch_solve_box_qp_grad (solve_box_qp_admm_torch.py:349-432) ------
+ * rho_dev: per-problem rho (B) or NULL, in which case rho_scalar is used (:356-357, :379-382).
+ * Any of dQ (B,n,n), dp (B,n), dA (B,m,n), db (B,m), dlb (B,n), dub (B,n) may be NULL: that
+ * gradient is skipped (ctx.needs_input_grad).  Fully asynchronous on `stream`. */
+size_t lqpb_backward_workspace_bytes_f32(int B, int n, int m);
+size_t lqpb_backward_workspace_bytes_f64(int B, int n, int m);
+int lqpb_backward_f32(int B, int n, int m, const float* dl_dz, const float* x, const float* u,
+                      const float* lams, const float* nus, const float* Q, const float* A,
+                      const float* lb, const float* ub, const float* rho_dev, double rho_scalar,
+                      float* dQ, float* dp, float* dA, float* db, float* dlb, float* dub,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x, const double* u,
+                      const double* lams, const double* nus, const double* Q, const double* A,
+                      const double* lb, const double* ub, const double* rho_dev, double rho_scalar,
+                      double* dQ, double* dp, double* dA, double* db, double* dlb, double* dub,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- lu_layer: replaces TorchLU / TorchLULayer (lu_layer.py:5-58) -------------------------
+ * lu_factor: partial-pivoting LU of B general N x N matrices (torch.linalg.lu_factor, :10,:30);
+ *            LU (B,N,N) packed L\U, piv (B,N) 1-based row swaps like LAPACK getrf.
+ * lu_solve:  X = A^-1 RHS from cached factors (torch.linalg.lu_solve, :33,:52); RHS/X (B,N,nrhs);
+ *            `negate_rhs` solves with -RHS (:52).
+ * outer:     C (B,N,M) = a (B,N) b(B,M)^T, the dl_dA = dx x^T of :53. */
+int lqpb_lu_factor_f32(int B, int N, const float* A, float* LU, int32_t* piv, void* stream);
+int lqpb_lu_factor_f64(int B, int N, const double* A, double* LU, int32_t* piv, void* stream);
+int lqpb_lu_solve_f32(int B, int N, int nrhs, const float* LU, const int32_t* piv, const float* rhs,
+                      float* x, int negate_rhs, void* stream);
+int lqpb_lu_solve_f64(int B, int N, int nrhs, const double* LU, const int32_t* piv,
+                      const double* rhs, double* x, int negate_rhs, void* stream);
+int lqpb_outer_f32(int B, int N, int M, const float* a, const float* b, float* C, void* stream);
+int lqpb_outer_f64(int B, int N, int M, const double* a, const double* b, double* C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQPB_H */

@@ -1,0 +1,294 @@
+// C ABI (include/lqpb.h): argument validation, workspace carving, kernel orchestration, profiling.
+// Host code only; every kernel lives in scale.cu / factor.cu / iterate.cu / backward.cu / lu.cu.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "layout.cuh"
+
+namespace lqpb {
+template <typename T>
+cudaError_t launch_lu_factor(int B, int N, const T* A, T* LU, int32_t* piv, cudaStream_t st);
+template <typename T>
+cudaError_t launch_lu_solve(int B, int N, int nrhs, const T* LU, const int32_t* piv, const T* rhs, T* x, int negate,
+                            cudaStream_t st);
+template <typename T>
+cudaError_t launch_outer(int B, int N, int M, const T* a, const T* b, T* C, cudaStream_t st);
+}  // namespace lqpb
+
+using namespace lqpb;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local bool g_prof_on = false;
+
+constexpr int kMaxSeg = 16;
+struct ProfState {
+  bool have_events = false;
+  cudaEvent_t ev[8 + 2 * kMaxSeg + 2 * kMaxSeg];
+  // forward: 0 start, 1 after scale, [factor segs], [iterate segs], fin0, fin1 ; backward: 4..7
+  int n_fac = 0, n_it = 0;
+  bool fwd_valid = false, bwd_valid = false;
+  int launches = 0, it_launches = 0, fac_launches = 0;
+  cudaEvent_t fac0[kMaxSeg], fac1[kMaxSeg], it0[kMaxSeg], it1[kMaxSeg];
+};
+thread_local ProfState g_prof;
+
+void prof_init() {
+  if (g_prof.have_events) return;
+  for (auto& e : g_prof.ev) cudaEventCreate(&e);
+  for (int i = 0; i < kMaxSeg; ++i) {
+    cudaEventCreate(&g_prof.fac0[i]);
+    cudaEventCreate(&g_prof.fac1[i]);
+    cudaEventCreate(&g_prof.it0[i]);
+    cudaEventCreate(&g_prof.it1[i]);
+  }
+  g_prof.have_events = true;
+}
+
+int fail(int code, const char* what, cudaError_t ce = cudaSuccess) {
+  g_err = what;
+  if (ce != cudaSuccess) {
+    g_err += ": ";
+    g_err += cudaGetErrorString(ce);
+  }
+  return code;
+}
+
+#define CK(call, what)                                          \
+  do {                                                          \
+    cudaError_t ce__ = (call);                                  \
+    if (ce__ != cudaSuccess) return fail(LQPB_E_CUDA, what, ce__); \
+  } while (0)
+
+int check_device() {
+  static thread_local int ok_dev = -1;
+  int dev = 0;
+  cudaError_t ce = cudaGetDevice(&dev);
+  if (ce != cudaSuccess) return fail(LQPB_E_CUDA, "cudaGetDevice", ce);
+  if (dev == ok_dev) return LQPB_OK;
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) return fail(LQPB_E_NOT_BLACKWELL, "lqpb kernels are built for sm_100a (B200) only");
+  ok_dev = dev;
+  return LQPB_OK;
+}
+
+struct HostCtrl {
+  Ctrl* pinned = nullptr;
+  ~HostCtrl() {}
+};
+thread_local HostCtrl g_hctrl;
+
+template <typename T>
+int factor_forward(const FwdWs<T>& w, cudaStream_t st) {
+  CK(launch_gj_inverse<T>(w.B, w.n, w.np, w.Qs, w.ld, w.rho, T(0), nullptr, 0, w.W, w.Vg, w.Wg, w.K, w.ld, st),
+     "gj_inverse (forward)");
+  CK(launch_schur<T>(w, st), "schur");
+  g_prof.launches += (w.m > 0 ? 2 : 1);
+  g_prof.fac_launches += 1;
+  return LQPB_OK;
+}
+
+template <typename T>
+int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A, const T* b,
+                 const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, lqpb_info* info, void* ws,
+                 size_t ws_bytes, void* stream) {
+  if (!cfg || !Q || !p || !lb || !ub || !x || !z || !u || !lams || !rho_out || !info || !ws)
+    return fail(LQPB_E_ARG, "null pointer argument");
+  if (B <= 0 || n <= 0 || m < 0) return fail(LQPB_E_ARG, "bad dimensions");
+  if (m > 0 && (!A || !b || !nus)) return fail(LQPB_E_ARG, "A, b and nus are required when m > 0");
+  if (m > kMaxM) return fail(LQPB_E_ARG, "more than 64 equality rows are not supported");
+  if (cfg->max_iters < 1 || cfg->check_solved < 1 || cfg->adaptive_rho_iter < 1)
+    return fail(LQPB_E_ARG, "max_iters, check_solved and adaptive_rho_iter must be >= 1");
+  int rc = check_device();
+  if (rc) return rc;
+  FwdWs<T> w = carve_fwd<T>(ws, B, n, m);
+  if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
+  if ((size_t)m * w.ld > (size_t)w.np * w.np) return fail(LQPB_E_ARG, "m too large for n");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!g_hctrl.pinned) CK(cudaMallocHost(&g_hctrl.pinned, sizeof(Ctrl)), "cudaMallocHost");
+  Ctrl* hc = g_hctrl.pinned;
+
+  const bool prof = g_prof_on;
+  if (prof) prof_init();
+  g_prof.launches = g_prof.it_launches = g_prof.fac_launches = 0;
+  g_prof.n_fac = g_prof.n_it = 0;
+  g_prof.fwd_valid = false;
+
+  CK(cudaMemsetAsync(w.ctrl, 0, sizeof(Ctrl), st), "memset ctrl");
+  if (prof) cudaEventRecord(g_prof.ev[0], st);
+  CK(launch_scale<T>(*cfg, w, Q, p, A, b, lb, ub, st), "scale");
+  CK(launch_select_rho<T>(*cfg, w, st), "select_rho");
+  g_prof.launches += 2;
+  if (prof) cudaEventRecord(g_prof.ev[1], st);
+
+  int n_factor = 0, i0 = 0, skip = 0;
+  while (true) {
+    if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac0[g_prof.n_fac], st);
+    rc = factor_forward<T>(w, st);
+    if (rc) return rc;
+    if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac1[g_prof.n_fac++], st);
+    ++n_factor;
+    if (prof && g_prof.n_it < kMaxSeg) cudaEventRecord(g_prof.it0[g_prof.n_it], st);
+    CK(launch_iterate<T>(*cfg, w, i0, skip, nus, &g_prof.it_launches, st), "iterate");
+    if (prof && g_prof.n_it < kMaxSeg) cudaEventRecord(g_prof.it1[g_prof.n_it++], st);
+    if (prof) cudaEventRecord(g_prof.ev[2], st);
+    CK(launch_finalize<T>(w, x, z, u, lams, rho_out, st), "finalize");
+    if (prof) cudaEventRecord(g_prof.ev[3], st);
+    g_prof.launches += 2;
+    CK(cudaMemcpyAsync(hc, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st), "copy ctrl");
+    CK(cudaStreamSynchronize(st), "synchronize (segment end)");
+    if (hc->status == 3) {
+      i0 = hc->next_i;
+      skip = 1;
+      CK(cudaMemsetAsync(&w.ctrl->status, 0, sizeof(int), st), "reset status");
+      continue;
+    }
+    break;
+  }
+  if (hc->status != LQPB_STATUS_CONVERGED && hc->status != LQPB_STATUS_MAX_ITERS)
+    return fail(LQPB_E_CUDA, "iteration kernel ended without a status");
+  info->iter = hc->iter;
+  info->status = hc->status;
+  info->n_factor = n_factor;
+  info->any_lb = hc->any_lb;
+  info->any_ub = hc->any_ub;
+  info->n_log = cfg->verbose ? hc->n_log : 0;
+  if (cfg->verbose) {
+    memcpy(info->log_iter, hc->log_iter, sizeof(info->log_iter));
+    memcpy(info->log_primal, hc->log_primal, sizeof(info->log_primal));
+    memcpy(info->log_dual, hc->log_dual, sizeof(info->log_dual));
+  }
+  g_prof.fwd_valid = prof;
+  return LQPB_OK;
+}
+
+template <typename T>
+int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
+                  const T* Q, const T* A, const T* lb, const T* ub, const T* rho_dev, double rho_scalar, T* dQ,
+                  T* dp, T* dA, T* db, T* dlb, T* dub, void* ws, size_t ws_bytes, void* stream) {
+  if (!dl_dz || !x || !u || !lams || !Q || !lb || !ub || !ws) return fail(LQPB_E_ARG, "null pointer argument");
+  if (B <= 0 || n <= 0 || m < 0) return fail(LQPB_E_ARG, "bad dimensions");
+  if (m > 0 && (!A || !nus)) return fail(LQPB_E_ARG, "A and nus are required when m > 0");
+  if (m > kMaxM) return fail(LQPB_E_ARG, "more than 64 equality rows are not supported");
+  int rc = check_device();
+  if (rc) return rc;
+  BwdWs<T> w = carve_bwd<T>(ws, B, n, m);
+  if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
+  if ((size_t)(m + 1) * w.ld > (size_t)w.np * w.np) return fail(LQPB_E_ARG, "m too large for n");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool prof = g_prof_on;
+  if (prof) prof_init();
+  g_prof.bwd_valid = false;
+  g_prof.launches = 0;
+  if (prof) cudaEventRecord(g_prof.ev[4], st);
+  CK(launch_bwd_mask<T>(w, x, u, lb, ub, st), "bwd_mask");
+  CK(launch_gj_inverse<T>(B, n, w.np, Q, n, nullptr, T(1e-8), w.mask, w.ld, w.W, w.Vg, w.Wg, w.Minv, w.ld, st),
+     "gj_inverse (backward)");
+  if (prof) cudaEventRecord(g_prof.ev[5], st);
+  CK(launch_bwd_solve<T>(w, dl_dz, A, st), "bwd_solve");
+  if (prof) cudaEventRecord(g_prof.ev[6], st);
+  CK(launch_bwd_grads<T>(w, dl_dz, x, u, lams, nus, Q, A, rho_dev, rho_scalar, dQ, dp, dA, db, dlb, dub, st),
+     "bwd_grads");
+  if (prof) cudaEventRecord(g_prof.ev[7], st);
+  g_prof.launches = 4;
+  g_prof.bwd_valid = prof;
+  return LQPB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lqpb_abi_version(void) { return LQPB_ABI_VERSION; }
+const char* lqpb_last_error(void) { return g_err.c_str(); }
+void lqpb_profile_enable(int on) { g_prof_on = on != 0; }
+
+void lqpb_profile_get(lqpb_profile* out) {
+  if (!out) return;
+  memset(out, 0, sizeof(*out));
+  auto el = [](cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0.f;
+    cudaEventSynchronize(b);
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+  };
+  if (g_prof.fwd_valid) {
+    out->scale_ms = el(g_prof.ev[0], g_prof.ev[1]);
+    for (int i = 0; i < g_prof.n_fac; ++i) out->factor_ms += el(g_prof.fac0[i], g_prof.fac1[i]);
+    for (int i = 0; i < g_prof.n_it; ++i) out->iterate_ms += el(g_prof.it0[i], g_prof.it1[i]);
+    out->finalize_ms = el(g_prof.ev[2], g_prof.ev[3]);
+  }
+  if (g_prof.bwd_valid) {
+    out->bwd_factor_ms = el(g_prof.ev[4], g_prof.ev[5]);
+    out->bwd_solve_ms = el(g_prof.ev[5], g_prof.ev[6]);
+    out->bwd_grad_ms = el(g_prof.ev[6], g_prof.ev[7]);
+  }
+  out->iterate_launches = g_prof.it_launches;
+  out->factor_launches = g_prof.fac_launches;
+  out->kernel_launches = g_prof.launches;
+}
+
+size_t lqpb_forward_workspace_bytes_f32(int B, int n, int m) { return carve_fwd<float>(nullptr, B, n, m).bytes; }
+size_t lqpb_forward_workspace_bytes_f64(int B, int n, int m) { return carve_fwd<double>(nullptr, B, n, m).bytes; }
+size_t lqpb_backward_workspace_bytes_f32(int B, int n, int m) { return carve_bwd<float>(nullptr, B, n, m).bytes; }
+size_t lqpb_backward_workspace_bytes_f64(int B, int n, int m) { return carve_bwd<double>(nullptr, B, n, m).bytes; }
+
+int lqpb_forward_f32(const lqpb_config* cfg, int B, int n, int m, const float* Q, const float* p, const float* A,
+                     const float* b, const float* lb, const float* ub, float* x, float* z, float* u, float* lams,
+                     float* nus, float* rho_out, lqpb_info* info, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  return forward_impl<float>(cfg, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, workspace,
+                             workspace_bytes, stream);
+}
+int lqpb_forward_f64(const lqpb_config* cfg, int B, int n, int m, const double* Q, const double* p, const double* A,
+                     const double* b, const double* lb, const double* ub, double* x, double* z, double* u,
+                     double* lams, double* nus, double* rho_out, lqpb_info* info, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  return forward_impl<double>(cfg, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, workspace,
+                              workspace_bytes, stream);
+}
+
+int lqpb_backward_f32(int B, int n, int m, const float* dl_dz, const float* x, const float* u, const float* lams,
+                      const float* nus, const float* Q, const float* A, const float* lb, const float* ub,
+                      const float* rho_dev, double rho_scalar, float* dQ, float* dp, float* dA, float* db,
+                      float* dlb, float* dub, void* workspace, size_t workspace_bytes, void* stream) {
+  return backward_impl<float>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db, dlb,
+                              dub, workspace, workspace_bytes, stream);
+}
+int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x, const double* u, const double* lams,
+                      const double* nus, const double* Q, const double* A, const double* lb, const double* ub,
+                      const double* rho_dev, double rho_scalar, double* dQ, double* dp, double* dA, double* db,
+                      double* dlb, double* dub, void* workspace, size_t workspace_bytes, void* stream) {
+  return backward_impl<double>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db,
+                               dlb, dub, workspace, workspace_bytes, stream);
+}
+
+#define LU_ENTRY(SFX, T)                                                                                          \
+  int lqpb_lu_factor_##SFX(int B, int N, const T* A, T* LU, int32_t* piv, void* stream) {                          \
+    if (!A || !LU || !piv || B <= 0 || N <= 0) return fail(LQPB_E_ARG, "bad argument");                           \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    CK(launch_lu_factor<T>(B, N, A, LU, piv, (cudaStream_t)stream), "lu_factor");                                  \
+    return LQPB_OK;                                                                                                \
+  }                                                                                                                \
+  int lqpb_lu_solve_##SFX(int B, int N, int nrhs, const T* LU, const int32_t* piv, const T* rhs, T* x,            \
+                          int negate_rhs, void* stream) {                                                          \
+    if (!LU || !piv || !rhs || !x || B <= 0 || N <= 0 || nrhs <= 0) return fail(LQPB_E_ARG, "bad argument");       \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    CK(launch_lu_solve<T>(B, N, nrhs, LU, piv, rhs, x, negate_rhs, (cudaStream_t)stream), "lu_solve");             \
+    return LQPB_OK;                                                                                                \
+  }                                                                                                                \
+  int lqpb_outer_##SFX(int B, int N, int M, const T* a, const T* b, T* C, void* stream) {                          \
+    if (!a || !b || !C || B <= 0 || N <= 0 || M <= 0) return fail(LQPB_E_ARG, "bad argument");                    \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    CK(launch_outer<T>(B, N, M, a, b, C, (cudaStream_t)stream), "outer");                                          \
+    return LQPB_OK;                                                                                                \
+  }
+LU_ENTRY(f32, float)
+LU_ENTRY(f64, double)
+
+}  // extern "C"

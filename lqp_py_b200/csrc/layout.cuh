@@ -1,0 +1,142 @@
+// Workspace layout (HBM) of one forward / backward call and the kernel launch prototypes.
+// All matrices are row-major; `ld` is the padded row stride of the compact n x n matrices
+// (16-byte multiple so that rows are legal bulk-TMA sources), `np` the dimension padded to the
+// 32 x 32 tiles of the Gauss-Jordan inversion.
+#pragma once
+#include "common.cuh"
+#include "../../include/lqpb.h"
+
+namespace lqpb {
+
+constexpr int kTile = 32;      // Gauss-Jordan tile edge
+constexpr int kMacro = 64;     // macro tile edge of the trailing update (np is a multiple of it)
+constexpr int kMaxM = 64;      // max equality rows handled by the Schur-complement path
+
+template <typename T>
+struct FwdWs {
+  int B, n, m, ld, np;
+  T* Qs;        // B*n*ld   scaled Q~ = D Q D            (read at every check: Q~ x~)
+  T* K;         // B*n*ld   x-update operator K11 (symmetric)  -- streamed every iteration
+  T* W;         // B*np*np  Gauss-Jordan work matrix (lower triangle)
+  T* Vg;        // B*np*kTile   column panel before the sweep step
+  T* Wg;        // B*np*kTile   column panel after the sweep step
+  T *D, *pt, *lbt, *ubt, *c, *z, *u, *xs;   // B*ld each: scaling, p~, lb~, ub~, c = K12 b~, ADMM state, last x~
+  T *At, *Gt;   // B*m*ld   A~ and (H^-1 A~^T)^T
+  T* Sinv;      // B*m*m    inverse Schur complement
+  T *bt, *E;    // B*m
+  T *rho, *rho_cand, *pnorm, *ratio;   // B
+  T* chk;       // B*4  [primal, dual, tol_primal_rel, tol_dual_rel] of the last check
+  int* wants;   // B    do_rho_update of the last check
+  Ctrl* ctrl;
+  size_t bytes;
+};
+
+template <typename T>
+inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
+  FwdWs<T> w;
+  w.B = B; w.n = n; w.m = m;
+  w.ld = round_up(n, Vec<T>::N);
+  w.np = round_up(n, kMacro);
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t count, size_t elt) {
+    void* r = p ? p + off : nullptr;
+    off = round_up_sz(off + count * elt, 256);
+    return r;
+  };
+  const size_t Bn = (size_t)B;
+  w.ctrl = (Ctrl*)take(1, sizeof(Ctrl));
+  w.Qs = (T*)take(Bn * n * w.ld, sizeof(T));
+  w.K = (T*)take(Bn * n * w.ld, sizeof(T));
+  w.W = (T*)take(Bn * w.np * w.np, sizeof(T));
+  w.Vg = (T*)take(Bn * w.np * kTile, sizeof(T));
+  w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
+  T** vecs[] = {&w.D, &w.pt, &w.lbt, &w.ubt, &w.c, &w.z, &w.u, &w.xs};
+  for (auto v : vecs) *v = (T*)take(Bn * w.ld, sizeof(T));
+  const size_t mm = m > 0 ? m : 1;
+  w.At = (T*)take(Bn * mm * w.ld, sizeof(T));
+  w.Gt = (T*)take(Bn * mm * w.ld, sizeof(T));
+  w.Sinv = (T*)take(Bn * mm * mm, sizeof(T));
+  w.bt = (T*)take(Bn * mm, sizeof(T));
+  w.E = (T*)take(Bn * mm, sizeof(T));
+  w.rho = (T*)take(Bn, sizeof(T));
+  w.rho_cand = (T*)take(Bn, sizeof(T));
+  w.pnorm = (T*)take(Bn, sizeof(T));
+  w.ratio = (T*)take(Bn, sizeof(T));
+  w.chk = (T*)take(Bn * 4, sizeof(T));
+  w.wants = (int*)take(Bn, sizeof(int));
+  w.bytes = off;
+  return w;
+}
+
+template <typename T>
+struct BwdWs {
+  int B, n, m, ld, np;
+  T* Minv;      // B*n*ld   inverse of the masked system matrix (symmetric)
+  T* W;         // B*np*np
+  T *Vg, *Wg;   // B*np*kTile
+  T *mask, *dv; // B*ld
+  T* dnu;       // B*m
+  size_t bytes;
+};
+
+template <typename T>
+inline BwdWs<T> carve_bwd(void* base, int B, int n, int m) {
+  BwdWs<T> w;
+  w.B = B; w.n = n; w.m = m;
+  w.ld = round_up(n, Vec<T>::N);
+  w.np = round_up(n, kMacro);
+  char* p = static_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t count, size_t elt) {
+    void* r = p ? p + off : nullptr;
+    off = round_up_sz(off + count * elt, 256);
+    return r;
+  };
+  const size_t Bn = (size_t)B;
+  w.Minv = (T*)take(Bn * n * w.ld, sizeof(T));
+  w.W = (T*)take(Bn * w.np * w.np, sizeof(T));
+  w.Vg = (T*)take(Bn * w.np * kTile, sizeof(T));
+  w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
+  w.mask = (T*)take(Bn * w.ld, sizeof(T));
+  w.dv = (T*)take(Bn * w.ld, sizeof(T));
+  w.dnu = (T*)take(Bn * (m > 0 ? m : 1), sizeof(T));
+  w.bytes = off;
+  return w;
+}
+
+// ------------------------------------------------------------------ launchers (one per .cu)
+// scale.cu  -- K1: Ruiz-style equilibration, rho candidate, bound flags, state reset
+template <typename T>
+cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, const T* p, const T* A, const T* b,
+                         const T* lb, const T* ub, cudaStream_t st);
+
+// factor.cu -- K2: H = Q~ + rho I  ->  H^-1 by tiled symmetric Gauss-Jordan, Schur complement, K11, c
+// src: B matrices with row stride lds (lower triangle read); mask (B*ldm, 1 = keep, 0 = replace row/col by
+// identity) may be null; diag_shift (per problem, may be null) + diag_const are added on kept diagonal entries.
+template <typename T>
+cudaError_t launch_gj_inverse(int B, int n, int np, const T* src, int lds, const T* diag_shift, T diag_const,
+                              const T* mask, int ldm, T* W, T* Vg, T* Wg, T* dst, int ldd, cudaStream_t st);
+template <typename T>
+cudaError_t launch_select_rho(const lqpb_config& cfg, const FwdWs<T>& w, cudaStream_t st);
+template <typename T>
+cudaError_t launch_schur(const FwdWs<T>& w, cudaStream_t st);
+
+// iterate.cu -- K3 (+K4): persistent ADMM loop and finalisation
+template <typename T>
+cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
+                           int* launches, cudaStream_t st);
+template <typename T>
+cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho_out, cudaStream_t st);
+
+// backward.cu -- K5/K6
+template <typename T>
+cudaError_t launch_bwd_mask(const BwdWs<T>& w, const T* x, const T* u, const T* lb, const T* ub, cudaStream_t st);
+template <typename T>
+cudaError_t launch_bwd_solve(const BwdWs<T>& w, const T* dl_dz, const T* A, cudaStream_t st);
+template <typename T>
+cudaError_t launch_bwd_grads(const BwdWs<T>& w, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
+                             const T* Q, const T* A, const T* rho_dev, double rho_scalar, T* dQ, T* dp, T* dA, T* db,
+                             T* dlb, T* dub, cudaStream_t st);
+
+}  // namespace lqpb

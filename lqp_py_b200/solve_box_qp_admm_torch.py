@@ -1,0 +1,272 @@
+"""Batched, differentiable box-constrained QP layer (ADMM) -- B200-native drop-in.
+
+    x* = argmin_x 1/2 x^T Q x + p^T x   s.t.  A x = b,  lb <= x <= ub
+
+Same module / autograd surface as the reference file of the same name
+(``lqp_py/solve_box_qp_admm_torch.py``):
+
+* ``SolveBoxQP(control).forward(Q, p, A, b, lb, ub) -> x (B, n, 1)``            (:7-18)
+* ``SolveBoxQPLayer.apply(Q, p, A, b, lb, ub, control)``                        (:21-67)
+* ``torch_solve_box_qp(Q, p, A, b, lb, ub, control) -> dict(x,z,u,lams,nus,rho,iter)`` (:108-333)
+* ``torch_solve_box_qp_grad(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho) -> 7-tuple``     (:349-432)
+
+but none of the arithmetic happens in torch: the functions flatten the settings into a POD
+struct and call the hand-written sm_100a kernels through the C ABI of ``include/lqpb.h``
+(scaling + Gauss-Jordan operator setup, the persistent TMA-streamed ADMM kernel, the
+masked-inverse backward).  PyTorch only owns device memory and the CUDA stream.
+
+Tensors may live on the GPU (zero copy) or on the CPU like in the reference's experiments;
+CPU tensors are staged to the current CUDA device and the results are returned on the CPU.
+There is no CPU compute path: without a CUDA device (or without ``_lqpb.so``) the calls raise.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+from .utils import get_ncon
+
+_INF = float("inf")
+
+
+class SolveBoxQP(nn.Module):
+    """``nn.Module`` front end (reference :7-18)."""
+
+    def __init__(self, control):
+        super().__init__()
+        self.control = control
+
+    def forward(self, Q, p, A, b, lb, ub):
+        if self.control.get('unroll', False):
+            return torch_solve_box_qp(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub, control=self.control)
+        return SolveBoxQPLayer.apply(Q, p, A, b, lb, ub, self.control)
+
+
+class SolveBoxQPLayer(torch.autograd.Function):
+    """ADMM forward solve + implicit (fixed-point) backward (reference :21-67)."""
+
+    @staticmethod
+    def forward(ctx, Q, p, A, b, lb, ub, control):
+        out_device = p.device
+        sol = _solve_device(Q, p, A, b, lb, ub, control)
+        # reference :33-38 -- with no finite bound the caller's dict is switched to rho = 0
+        if not (sol["_any_lb"] or sol["_any_ub"]):
+            control['rho'] = 0
+        ctx.rho = sol["rho"]
+        ctx.backward_method = control.get('backward', 'fixed_point')
+        ctx.out_device = out_device
+        ctx.input_devices = tuple(None if t is None else t.device for t in (Q, p, A, b, lb, ub))
+        # saved tensors are the CUDA-resident copies: the backward never re-uploads Q
+        dv = sol["_dev"]
+        ctx.save_for_backward(sol["_x_dev"], sol["_u_dev"], sol["_lams_dev"], sol["_nus_dev"],
+                              dv["Q"], dv["A"], dv["lb"], dv["ub"])
+        return sol["x"]
+
+    @staticmethod
+    def backward(ctx, dl_dz):
+        x, u, lams, nus, Q, A, lb, ub = ctx.saved_tensors
+        if ctx.backward_method == 'kkt':
+            raise NotImplementedError(
+                "backward='kkt' (reference :435-584) is outside this build's hot path; use 'fixed_point'")
+        need = ctx.needs_input_grad[:6]
+        grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need)
+        out = []
+        for g, dev in zip(grads, ctx.input_devices):
+            out.append(None if g is None else _to_device_of(g, dev))
+        return (*out, None)
+
+
+# ------------------------------------------------------------------------------------------
+# functional API
+# ------------------------------------------------------------------------------------------
+def torch_solve_box_qp(Q, p, A, b, lb, ub, control):
+    """Forward solve (reference :108-333).  Returns the same dict
+    ``{"x","z","u","lams","nus","rho","iter"}``; ``rho`` is a ``(B,1,1)`` tensor when it was
+    selected automatically or adapted and the caller's scalar otherwise, ``iter`` a Python int."""
+    if control.get('unroll', False):
+        raise NotImplementedError(
+            "unroll=True (differentiating through the loop, reference :13-15, :264-265) is outside this build's "
+            "hot path; use the default implicit fixed-point backward")
+    sol = _solve_device(Q, p, A, b, lb, ub, control)
+    return {k: sol[k] for k in ("x", "z", "u", "lams", "nus", "rho", "iter")}
+
+
+def torch_solve_box_qp_grad(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho):
+    """Fixed-point backward (reference :349-432).  Returns ``(dQ, dp, dA, db, dlb, dub, None)``."""
+    devs = [t.device for t in (Q, x, A if A is not None else x, A if A is not None else x, lb, ub)]
+    dv = _stage(dict(dl_dz=dl_dz, x=x, u=u, lams=lams, nus=nus, Q=Q, A=A, lb=lb, ub=ub))
+    rho_d = rho.to(dv["x"].device) if torch.is_tensor(rho) else rho
+    grads = _grad_device(dv["dl_dz"], dv["x"], dv["u"], dv["lams"], dv["nus"], dv["Q"], dv["A"], dv["lb"], dv["ub"],
+                         rho_d, (True,) * 6)
+    out = [None if g is None else _to_device_of(g, d) for g, d in zip(grads, devs)]
+    return (*out, None)
+
+
+# ------------------------------------------------------------------------------------------
+# internals
+# ------------------------------------------------------------------------------------------
+def _cuda_device(ref):
+    if ref.is_cuda:
+        return ref.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("lqp_py_b200 runs on a CUDA device (B200, sm_100a) only; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stage(tensors):
+    """Move a dict of (optional) tensors to one CUDA device, contiguous, same dtype."""
+    ref = next(t for t in tensors.values() if t is not None)
+    dev = _cuda_device(next((t for t in tensors.values() if t is not None and t.is_cuda), ref))
+    out = {}
+    for k, t in tensors.items():
+        if t is None:
+            out[k] = None
+            continue
+        if t.dtype != ref.dtype:
+            raise TypeError(f"all tensors must share one dtype, got {ref.dtype} and {t.dtype} ({k})")
+        t = t.detach()
+        if t.device != dev:
+            t = t.to(dev, non_blocking=True)
+        out[k] = t.contiguous()
+    return out
+
+
+def _to_device_of(t, device):
+    if device is None or t.device == device:
+        return t
+    if device.type == "cpu":
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return host
+    return t.to(device)
+
+
+def _default_dtype_value(v):
+    """The reference builds some constants with ``torch.ones(1) * v`` in the *default* dtype
+    (:150, :230); reproduce the rounding."""
+    return float((torch.ones(1) * v).item())
+
+
+def _derive_config(control, n_x):
+    """Flatten the control dict exactly as the reference unpacks it (:134-154)."""
+    g = control.get
+    cfg = _abi.Config()
+    cfg.max_iters = int(g('max_iters', 10_000))
+    cfg.eps_abs = max(g('eps_abs', 1e-3), 1e-12)
+    cfg.eps_rel = max(g('eps_rel', 1e-3), 1e-12)
+    check = g('check_solved', max(round((n_x ** 0.5) / 10) * 10, 1))
+    cfg.check_solved = int(check)
+    rho = g('rho', None)
+    cfg.rho_auto = 1 if rho is None else 0
+    cfg.rho = 0.0 if rho is None else float(rho)
+    cfg.rho_min = g('rho_min', 1e-6)
+    cfg.rho_max = g('rho_max', 1e6)
+    cfg.adaptive_rho = 1 if g('adaptive_rho', False) else 0
+    cfg.adaptive_rho_tol = g('adaptive_rho_tol', 5)
+    it = g('adaptive_rho_iter', 100)
+    cfg.adaptive_rho_iter = int(max(round(it / check) * check, 1))
+    cfg.adaptive_rho_max_iter = int(g('adaptive_max_iter', 1000))
+    cfg.adaptive_rho_threshold = _default_dtype_value(g('adaptive_rho_threshold', 1e-5))
+    cfg.verbose = 1 if g('verbose', False) else 0
+    cfg.scale = 1 if g('scale', False) else 0
+    beta = g('beta')
+    cfg.beta_auto = 1 if beta is None else 0
+    cfg.beta = 0.0 if beta is None else float(beta)
+    cfg.zero_clamp = _default_dtype_value(1e-16)
+    if cfg.max_iters < 1:
+        raise ValueError("max_iters must be >= 1")
+    if cfg.check_solved < 1:
+        raise ValueError("check_solved must be >= 1")
+    return cfg
+
+
+def _solve_device(Q, p, A, b, lb, ub, control):
+    L = _abi.lib()
+    out_device = p.device
+    dv = _stage(dict(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub))
+    Qd, pd = dv["Q"], dv["p"]
+    dev, dt = pd.device, pd.dtype
+    sfx = _abi.suffix(dt)
+    B, n = Qd.shape[0], pd.shape[1]
+    m = get_ncon(dv["A"], dim=1)
+    cfg = _derive_config(control, n)
+    with torch.cuda.device(dev):
+        new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+        x, z, u = new(B, n, 1), new(B, n, 1), new(B, n, 1)
+        lams = new(B, 2 * n, 1)
+        nus = new(B, m, 1) if m > 0 else None
+        rho_t = new(B, 1, 1)
+        ws_bytes = getattr(L, f"lqpb_forward_workspace_bytes_{sfx}")(B, n, m)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        info = _abi.Info()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = getattr(L, f"lqpb_forward_{sfx}")(
+            C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
+            _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u), _abi.ptr(lams),
+            _abi.ptr(nus), _abi.ptr(rho_t), C.byref(info), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
+        _abi.check(rc, "lqpb_forward")
+    if cfg.verbose:
+        for k in range(info.n_log):          # same text as the reference prints (:289-294)
+            print(f'iteration = {info.log_iter[k]}')
+            print(f'|| primal_error|| = {info.log_primal[k]:.10f}')
+            print(f'|| dual_error|| = {info.log_dual[k]:.10f}')
+    any_ineq = bool(info.any_lb or info.any_ub)
+    user_rho = control.get('rho', None)
+    if not any_ineq:
+        rho = 0                                   # :157-158
+    elif user_rho is None or info.n_factor > 1:
+        rho = rho_t                               # :200-203 / :248-250
+    else:
+        rho = user_rho
+    host = lambda t: None if t is None else _to_device_of(t, out_device)
+    rho_out = host(rho) if torch.is_tensor(rho) else rho
+    return {"x": host(x), "z": host(z), "u": host(u), "lams": host(lams), "nus": host(nus), "rho": rho_out,
+            "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor),
+            "_any_lb": bool(info.any_lb), "_any_ub": bool(info.any_ub), "_dev": dv,
+            "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus,
+            "rho_dev": rho if torch.is_tensor(rho) else None}
+
+
+def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need):
+    """All tensor arguments already on one CUDA device (except dl_dz, which is staged here)."""
+    L = _abi.lib()
+    dev, dt = x.device, x.dtype
+    sfx = _abi.suffix(dt)
+    B, n = Q.shape[0], Q.shape[1]
+    m = get_ncon(A, dim=1)
+    g = dl_dz.detach()
+    if g.dtype != dt:
+        raise TypeError(f"dl_dz has dtype {g.dtype}, expected {dt}")
+    if g.device != dev:
+        g = g.to(dev, non_blocking=True)
+    g = g.contiguous()
+    if rho is None:
+        rho = 1.0                                  # :356-357
+    rho_dev = None
+    rho_scalar = 0.0
+    if torch.is_tensor(rho):
+        rho_dev = rho.detach().to(device=dev, dtype=dt).reshape(-1).contiguous()
+        if rho_dev.numel() == 1 and B > 1:
+            rho_dev = rho_dev.expand(B).contiguous()
+    else:
+        rho_scalar = float(rho)
+    nQ, np_, nA, nb, nlb, nub = need
+    with torch.cuda.device(dev):
+        new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+        dQ = new(B, n, n) if nQ else None
+        dp = new(B, n, 1) if np_ else None
+        dA = new(B, m, n) if (nA and m > 0) else None
+        db = new(B, m, 1) if (nb and m > 0) else None
+        dlb = new(B, n, 1) if nlb else None
+        dub = new(B, n, 1) if nub else None
+        ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{sfx}")(B, n, m)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = getattr(L, f"lqpb_backward_{sfx}")(
+            B, n, m, _abi.ptr(g), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A),
+            _abi.ptr(lb), _abi.ptr(ub), _abi.ptr(rho_dev), rho_scalar, _abi.ptr(dQ), _abi.ptr(dp), _abi.ptr(dA),
+            _abi.ptr(db), _abi.ptr(dlb), _abi.ptr(dub), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
+        _abi.check(rc, "lqpb_backward")
+    return dQ, dp, dA, db, dlb, dub

@@ -20,7 +20,7 @@ using namespace lqpb;
 namespace {
 
 thread_local std::string g_err;
-thread_local bool g_prof_on = false;
+bool g_prof_on = false;   // process-wide: autograd runs the backward on its own thread
 
 constexpr int kMaxSeg = 16;
 struct ProfState {
@@ -32,7 +32,7 @@ struct ProfState {
   int launches = 0, it_launches = 0, fac_launches = 0;
   cudaEvent_t fac0[kMaxSeg], fac1[kMaxSeg], it0[kMaxSeg], it1[kMaxSeg];
 };
-thread_local ProfState g_prof;
+ProfState g_prof;
 
 void prof_init() {
   if (g_prof.have_events) return;
@@ -82,10 +82,17 @@ thread_local HostCtrl g_hctrl;
 
 template <typename T>
 int factor_forward(const FwdWs<T>& w, cudaStream_t st) {
-  CK(launch_gj_inverse<T>(w.B, w.n, w.np, w.Qs, w.ld, w.rho, T(0), nullptr, 0, w.W, w.Vg, w.Wg, w.K, w.ld, st),
-     "gj_inverse (forward)");
-  CK(launch_schur<T>(w, st), "schur");
-  g_prof.launches += (w.m > 0 ? 2 : 1);
+  GjArgs<T> a{};
+  a.n = w.n; a.m = w.m; a.np = w.np;
+  a.src = w.Qs; a.lds = w.ld;
+  a.diag_shift = w.rho; a.diag_const = T(0);
+  a.mask = nullptr; a.ldm = 0;
+  a.Arows = w.At; a.lda = w.ld; a.a_diag = T(0);
+  a.W = w.W; a.Vg = w.Vg; a.Wg = w.Wg;
+  a.dst = w.K; a.ldd = w.ld; a.G21 = w.Gt; a.K22 = w.Sinv;
+  a.bt = w.bt; a.c_out = w.m > 0 ? w.c : nullptr;
+  CK(launch_gj_inverse<T>(w.B, a, st), "gj_inverse (forward)");
+  g_prof.launches += 1;
   g_prof.fac_launches += 1;
   return LQPB_OK;
 }
@@ -105,7 +112,6 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
   if (rc) return rc;
   FwdWs<T> w = carve_fwd<T>(ws, B, n, m);
   if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
-  if ((size_t)m * w.ld > (size_t)w.np * w.np) return fail(LQPB_E_ARG, "m too large for n");
   cudaStream_t st = (cudaStream_t)stream;
   if (!g_hctrl.pinned) CK(cudaMallocHost(&g_hctrl.pinned, sizeof(Ctrl)), "cudaMallocHost");
   Ctrl* hc = g_hctrl.pinned;
@@ -176,7 +182,6 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   if (rc) return rc;
   BwdWs<T> w = carve_bwd<T>(ws, B, n, m);
   if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
-  if ((size_t)(m + 1) * w.ld > (size_t)w.np * w.np) return fail(LQPB_E_ARG, "m too large for n");
   cudaStream_t st = (cudaStream_t)stream;
   const bool prof = g_prof_on;
   if (prof) prof_init();
@@ -184,10 +189,20 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   g_prof.launches = 0;
   if (prof) cudaEventRecord(g_prof.ev[4], st);
   CK(launch_bwd_mask<T>(w, x, u, lb, ub, st), "bwd_mask");
-  CK(launch_gj_inverse<T>(B, n, w.np, Q, n, nullptr, T(1e-8), w.mask, w.ld, w.W, w.Vg, w.Wg, w.Minv, w.ld, st),
-     "gj_inverse (backward)");
+  {
+    GjArgs<T> a{};
+    a.n = n; a.m = m; a.np = w.np;
+    a.src = Q; a.lds = n;
+    a.diag_shift = nullptr; a.diag_const = T(1e-8);      // :392 small regulariser on the whole diagonal
+    a.mask = w.mask; a.ldm = w.ld;
+    a.Arows = A; a.lda = n; a.a_diag = T(1e-8);
+    a.W = w.W; a.Vg = w.Vg; a.Wg = w.Wg;
+    a.dst = w.Minv; a.ldd = w.ld; a.G21 = w.G21; a.K22 = w.K22;
+    a.bt = nullptr; a.c_out = nullptr;
+    CK(launch_gj_inverse<T>(B, a, st), "gj_inverse (backward)");
+  }
   if (prof) cudaEventRecord(g_prof.ev[5], st);
-  CK(launch_bwd_solve<T>(w, dl_dz, A, st), "bwd_solve");
+  CK(launch_bwd_solve<T>(w, dl_dz, st), "bwd_solve");
   if (prof) cudaEventRecord(g_prof.ev[6], st);
   CK(launch_bwd_grads<T>(w, dl_dz, x, u, lams, nus, Q, A, rho_dev, rho_scalar, dQ, dp, dA, db, dlb, dub, st),
      "bwd_grads");

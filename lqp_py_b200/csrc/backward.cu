@@ -5,7 +5,7 @@
 //   :378-393  lhs = [[dpi*Q with diag += rho (1-dpi), dpi*A^T], [A, 0]] + 1e-8 I ; solve lhs d = [-dpi*dl_dz; 0]
 //             The masked rows decouple (their solution is exactly 0), so the system is solved on the
 //             free set F as the symmetric  [[Q_FF + 1e-8 I, A_F^T], [A_F, 1e-8 I]]  (SURVEY App. A.5):
-//             inverse of the masked matrix by factor.cu's Gauss-Jordan kernel, then a Schur step here.
+//             factor.cu inverts that masked KKT matrix (equality rows included), the solve is then two GEMVs.
 //   :396-427  dp = dv, dQ = 1/2 (dv x^T + x dv^T), dA = dnu x^T + nus dv^T, db = -dnu,
 //             dlam = (-dl_dz - Q dv - A^T dnu) / (rho u | 1), dlb = dlam lams[:n], dub = -dlam lams[n:]
 #include "layout.cuh"
@@ -35,120 +35,51 @@ cudaError_t launch_bwd_mask(const BwdWs<T>& w, const T* x, const T* u, const T* 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Solve on the free set with the explicit inverse Minv (symmetric):
-//   Y = Minv [g_F, A_F^T]          (1 + m right-hand sides, chunks of 8 share one pass over Minv)
-//   S' = A_F Y_A - 1e-8 I,  dnu = -S'^-1 A_F y_g,   dv = -(y_g + Y_A dnu)
-constexpr int kBwdThreads = 512;
-constexpr int kBwdChunk = 8;
+// With the inverse of the masked KKT matrix at hand ([[K11, K21^T], [K21, K22]], factor.cu) the adjoint
+// solve is a pair of matrix-vector products with the masked upstream gradient g_F = dpi * dl_dz:
+//   dv = -K11 g_F,   dnu = -K21 g_F.
+// grid = (row chunks, B); one warp per row, 128-byte coalesced row reads.
+constexpr int kBwdThreads = 256;
+constexpr int kBwdRows = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(kBwdThreads)
-bwd_solve_kernel(BwdWs<T> w, const T* __restrict__ dl_dz, const T* __restrict__ A, T* Yall) {
+bwd_solve_kernel(BwdWs<T> w, const T* __restrict__ dl_dz) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = w.n, m = w.m, ld = w.ld;
-  T* R = reinterpret_cast<T*>(smem_raw);    // [kBwdChunk][ld] masked right-hand sides
-  T* S = R + kBwdChunk * ld;                // [m][m+1]
-  T* rs = S + m * (m + 1);                  // [m] rhs of the Schur system, then dnu
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  T* gF = reinterpret_cast<T*>(smem_raw);    // [n]
+  const int b = blockIdx.y, r0 = blockIdx.x * kBwdRows;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const T* Mi = w.Minv + (size_t)b * n * ld;
   const T* mk = w.mask + (size_t)b * ld;
-  T* Y = Yall + (size_t)b * (m + 1) * ld;
-  const T* Ab = A ? A + (size_t)b * m * n : nullptr;
-
-  for (int q0 = 0; q0 < 1 + m; q0 += kBwdChunk) {
-    const int qc = min(kBwdChunk, 1 + m - q0);
-    __syncthreads();
-    for (int e = tid; e < qc * ld; e += kBwdThreads) {
-      const int qq = q0 + e / ld, j = e % ld;
-      T v = T(0);
-      if (j < n) v = mk[j] * (qq == 0 ? dl_dz[(size_t)b * n + j] : Ab[(size_t)(qq - 1) * n + j]);
-      R[e] = v;
-    }
-    __syncthreads();
-    for (int i = tid; i < ld; i += kBwdThreads) {
-      T acc[kBwdChunk];
-#pragma unroll
-      for (int k = 0; k < kBwdChunk; ++k) acc[k] = T(0);
-      if (i < n) {
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-          const T kv = Mi[(size_t)j * ld + i];
-#pragma unroll
-          for (int k = 0; k < kBwdChunk; ++k)
-            if (k < qc) acc[k] += kv * R[k * ld + j];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kBwdChunk; ++k)
-        if (k < qc) Y[(size_t)(q0 + k) * ld + i] = acc[k];
-    }
-  }
+  for (int j = tid; j < n; j += kBwdThreads) gF[j] = mk[j] * dl_dz[(size_t)b * n + j];
   __syncthreads();
-  T* dv = w.dv + (size_t)b * ld;
-  if (m > 0) {
-    // S' and its right-hand side (warp per entry; column m of the loop is the rhs)
-    for (int e = wid; e < m * (m + 1); e += kBwdThreads / 32) {
-      const int l = e / (m + 1), l2 = e % (m + 1);
-      T acc = T(0);
-      const T* yrow = Y + (size_t)(l2 == m ? 0 : 1 + l2) * ld;
-      for (int i = lane; i < n; i += 32) acc += mk[i] * Ab[(size_t)l * n + i] * yrow[i];
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        if (l2 == m) rs[l] = -acc;
-        else S[l * (m + 1) + l2] = acc - (l == l2 ? T(1e-8) : T(0));
-      }
-    }
-    __syncthreads();
-    // S <- -(S^-1) by the sweep, then dnu = S^-1 rs
-    for (int s = 0; s < m; ++s) {
-      const T piv = T(1) / S[s * (m + 1) + s];
-      __syncthreads();
-      T nv[(kMaxM * kMaxM + kBwdThreads - 1) / kBwdThreads];
-      int q = 0;
-      for (int e = tid; e < m * m; e += kBwdThreads, ++q) {
-        const int r = e / m, c = e % m;
-        const T ars = S[r * (m + 1) + s], asc = S[s * (m + 1) + c], arc = S[r * (m + 1) + c];
-        T v;
-        if (r == s && c == s) v = -piv;
-        else if (r == s) v = asc * piv;
-        else if (c == s) v = ars * piv;
-        else v = arc - ars * asc * piv;
-        nv[q] = v;
-      }
-      __syncthreads();
-      q = 0;
-      for (int e = tid; e < m * m; e += kBwdThreads, ++q) S[(e / m) * (m + 1) + e % m] = nv[q];
-      __syncthreads();
-    }
-    T dn = T(0);
-    if (tid < m) {
-      for (int l = 0; l < m; ++l) dn -= S[tid * (m + 1) + l] * rs[l];
-    }
-    __syncthreads();
-    if (tid < m) {
-      rs[tid] = dn;
-      w.dnu[(size_t)b * m + tid] = dn;
-    }
-    __syncthreads();
+  const int r1 = min(r0 + kBwdRows, n);
+  for (int i = r0 + wid; i < r1; i += kBwdThreads / 32) {
+    const T* row = Mi + (size_t)i * ld;
+    T acc = T(0);
+    for (int j = lane; j < n; j += 32) acc += row[j] * gF[j];
+    acc = warp_sum(acc);
+    if (lane == 0) w.dv[(size_t)b * ld + i] = -acc;
   }
-  for (int i = tid; i < ld; i += kBwdThreads) {
-    T a = T(0);
-    if (i < n) {
-      a = Y[i];
-      for (int l = 0; l < m; ++l) a += Y[(size_t)(1 + l) * ld + i] * rs[l];
-      a = -a;
+  if (blockIdx.x == 0 && m > 0) {
+    const T* G = w.G21 + (size_t)b * m * ld;
+    for (int l = wid; l < m; l += kBwdThreads / 32) {
+      T acc = T(0);
+      for (int j = lane; j < n; j += 32) acc += G[(size_t)l * ld + j] * gF[j];
+      acc = warp_sum(acc);
+      if (lane == 0) w.dnu[(size_t)b * m + l] = -acc;
     }
-    dv[i] = a;
   }
 }
 
 template <typename T>
-cudaError_t launch_bwd_solve(const BwdWs<T>& w, const T* dl_dz, const T* A, cudaStream_t st) {
-  const size_t smem = (size_t)(kBwdChunk * w.ld + w.m * (w.m + 1) + w.m + 8) * sizeof(T);
+cudaError_t launch_bwd_solve(const BwdWs<T>& w, const T* dl_dz, cudaStream_t st) {
+  const size_t smem = (size_t)w.n * sizeof(T);
   cudaError_t e = cudaFuncSetAttribute(bwd_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  // Y scratch ((m+1) x ld per problem) lives in the Gauss-Jordan work matrix, free after the inversion
-  bwd_solve_kernel<T><<<w.B, kBwdThreads, smem, st>>>(w, dl_dz, A, w.W);
+  dim3 grid((w.n + kBwdRows - 1) / kBwdRows, w.B);
+  bwd_solve_kernel<T><<<grid, kBwdThreads, smem, st>>>(w, dl_dz);
   return cudaGetLastError();
 }
 
@@ -241,7 +172,7 @@ cudaError_t launch_bwd_grads(const BwdWs<T>& w, const T* dl_dz, const T* x, cons
 
 #define INST(T)                                                                                                       \
   template cudaError_t launch_bwd_mask<T>(const BwdWs<T>&, const T*, const T*, const T*, const T*, cudaStream_t);    \
-  template cudaError_t launch_bwd_solve<T>(const BwdWs<T>&, const T*, const T*, cudaStream_t);                       \
+  template cudaError_t launch_bwd_solve<T>(const BwdWs<T>&, const T*, cudaStream_t);                       \
   template cudaError_t launch_bwd_grads<T>(const BwdWs<T>&, const T*, const T*, const T*, const T*, const T*,        \
                                            const T*, const T*, const T*, double, T*, T*, T*, T*, T*, T*, cudaStream_t);
 INST(float)

@@ -1,15 +1,17 @@
-// K2 -- batched dense inversion of the SPD matrix H = Q~ + rho I (forward) or of the masked
-// adjoint matrix (backward) by a tiled, symmetric Gauss-Jordan ("sweep") elimination, plus the
-// Schur-complement step that folds the equality rows into the x-update operator.
+// K2 -- batched dense inversion of the symmetric quasi-definite KKT matrix
+//     M = [[H, A^T], [A, d I]],   H = Q~ + rho I (forward, d = 0)  or  masked Q + 1e-8 I (backward, d = 1e-8)
+// by a tiled, symmetric Gauss-Jordan ("sweep") elimination without pivoting: every H pivot is positive
+// and the equality rows are swept last, when their pivot block has become the negative-definite
+// -(A H^-1 A^T) + d I.
 //
-// This replaces the reference's batched LU of the KKT matrix
-//   torch.linalg.lu_factor(M), M = [[Q~ + rho I, A~^T], [A~, 0]]   solve_box_qp_admm_torch.py:206-215, :252-254
+// This replaces the reference's batched LU of the same matrix
+//   torch.linalg.lu_factor(M)        solve_box_qp_admm_torch.py:206-215, :252-254
 // and the fresh LU inside torch.linalg.solve of the backward (:393).  Instead of LU factors the
-// iteration kernel streams the explicit symmetric operator
-//   K11 = H^-1 - G S^-1 G^T,  G = H^-1 A~^T,  S = A~ G,   c = G S^-1 b~,   nu = S^-1 (G^T r - b~)
-// which is the top-left block of M^-1 (identical iterates to ~1e-15).
+// iteration kernel streams the explicit symmetric top-left block K11 of M^-1 = [[K11, K21^T], [K21, K22]]:
+//   x = K11 rhs + K21^T b~,   nu = K21 rhs + K22 b~        (identical iterates to ~1e-15)
+// The m equality rows live in the identity padding that the 64 x 64 tiling needs anyway, so they cost nothing.
 //
-// One CTA per problem.  The lower triangle lives in HBM/L2 (np x np, np = n padded to 64 with an
+// One CTA per problem.  The lower triangle lives in HBM/L2 (np x np, np = n + m padded to 64 with an
 // identity block); step k inverts the 32 x 32 pivot tile in shared memory, forms the column panels
 // V = A[:,k] and W = V * inv(A_kk) (stored k-major so the trailing update reads them as 16-byte
 // vectors), and applies the rank-32 update C -= W V^T to every 64 x 64 lower macro tile with
@@ -26,9 +28,7 @@ template <> struct GjCfg<float>  { static constexpr int NT = 1024; };
 template <> struct GjCfg<double> { static constexpr int NT = 512; };
 
 template <typename T, int NT>
-__global__ void __launch_bounds__(NT)
-gj_inverse_kernel(int n, int np, const T* __restrict__ src, int lds, const T* __restrict__ diag_shift, T diag_const,
-                  const T* __restrict__ mask, int ldm, T* Wall, T* Vall, T* Wgall, T* dst, int ldd) {
+__global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
   constexpr int NG = NT / kGroup;
   constexpr int VN = Vec<T>::N;
   using V4 = typename Vec<T>::type;
@@ -37,15 +37,19 @@ gj_inverse_kernel(int n, int np, const T* __restrict__ src, int lds, const T* __
   T(*Wt)[kTile][kMacro] = reinterpret_cast<T(*)[kTile][kMacro]>(gj_smem);   // [NG][32][64] k-major W panel tile
   T(*Vt)[kTile][kMacro] = Wt + NG;                                          // [NG][32][64] k-major V panel tile
 
+  const int n = a.n, m = a.m, np = a.np;
   const int b = blockIdx.x, tid = threadIdx.x;
-  T* Wb = Wall + (size_t)b * np * np;
-  T* Vb = Vall + (size_t)b * np * kTile;    // k-major: Vb[c * np + i]
-  T* Wg = Wgall + (size_t)b * np * kTile;
-  const T* srcb = src + (size_t)b * n * lds;
-  const T* maskb = mask ? mask + (size_t)b * ldm : nullptr;
-  const T shift = (diag_shift ? diag_shift[b] : T(0)) + diag_const;
+  T* Wb = a.W + (size_t)b * np * np;
+  T* Vb = a.Vg + (size_t)b * np * kTile;    // k-major: Vb[c * np + i]
+  T* Wg = a.Wg + (size_t)b * np * kTile;
+  const T* srcb = a.src + (size_t)b * n * a.lds;
+  const T* maskb = a.mask ? a.mask + (size_t)b * a.ldm : nullptr;
+  const T* Ab = (m > 0) ? a.Arows + (size_t)b * m * a.lda : nullptr;
+  const T shift = (a.diag_shift ? a.diag_shift[b] : T(0)) + a.diag_const;
 
-  // ---- prologue: lower triangle of the (masked, shifted, identity-padded) matrix
+  // ---- prologue: lower triangle of the KKT matrix [[H, A^T], [A, a_diag I]] embedded in the np x np
+  //      work matrix: H masked / shifted, the m equality rows right below it (inside the padding that
+  //      the tiling needs anyway), identity on the rest of the padding.
   for (int idx = tid; idx < np * np; idx += NT) {
     const int i = idx / np, j = idx - i * np;
     if (j > i) continue;
@@ -53,8 +57,15 @@ gj_inverse_kernel(int n, int np, const T* __restrict__ src, int lds, const T* __
     if (i < n) {   // j <= i < n
       const T fi = maskb ? maskb[i] : T(1), fj = maskb ? maskb[j] : T(1);
       const bool keep = (fi != T(0)) && (fj != T(0));
-      if (keep) v = srcb[(size_t)i * lds + j];
+      if (keep) v = srcb[(size_t)i * a.lds + j];
       if (i == j) v = keep ? v + shift : T(1);
+    } else if (i < n + m) {
+      if (j < n) {
+        v = Ab[(size_t)(i - n) * a.lda + j];
+        if (maskb) v *= maskb[j];
+      } else if (i == j) {
+        v = a.a_diag;
+      }
     } else if (i == j) {
       v = T(1);
     }
@@ -192,8 +203,20 @@ gj_inverse_kernel(int n, int np, const T* __restrict__ src, int lds, const T* __
     __syncthreads();
   }
 
-  // ---- epilogue: dst = -(Wb) mirrored to a full symmetric n x n matrix with row stride ldd
-  T* dstb = dst + (size_t)b * n * ldd;
+  // ---- epilogue: -(Wb) = KKT^-1 = [[K11, K21^T], [K21, K22]]; K11 is mirrored to a full symmetric n x n
+  //      matrix with row stride ldd, K21 (m x n) and K22 (m x m) go to their own buffers.
+  T* dstb = a.dst + (size_t)b * n * a.ldd;
+  T* g21 = (m > 0) ? a.G21 + (size_t)b * m * a.ldd : nullptr;
+  T* k22 = (m > 0) ? a.K22 + (size_t)b * m * m : nullptr;
+  const int ldd = a.ldd;
+  auto emit = [&](int gi, int gj, T val) {
+    if (gi < n) {
+      if (gj < n) dstb[(size_t)gi * ldd + gj] = val;
+    } else if (gi < n + m) {
+      if (gj < n) g21[(size_t)(gi - n) * ldd + gj] = val;
+      else if (gj < n + m) k22[(size_t)(gi - n) * m + (gj - n)] = val;
+    }
+  };
   T(*ts)[kTile + 1] = Ps;
   const int ntl = nt * (nt + 1) / 2;
   for (int t = 0; t < ntl; ++t) {
@@ -201,6 +224,7 @@ gj_inverse_kernel(int n, int np, const T* __restrict__ src, int lds, const T* __
     while ((I + 1) * (I + 2) / 2 <= t) ++I;
     while (I * (I + 1) / 2 > t) --I;
     const int J = t - I * (I + 1) / 2;
+    if (J * kTile >= n + m) continue;      // identity padding only
     __syncthreads();
     for (int e = tid; e < kTile * kTile; e += NT) {
       const int r = e / kTile, c = e % kTile;
@@ -213,29 +237,38 @@ gj_inverse_kernel(int n, int np, const T* __restrict__ src, int lds, const T* __
     __syncthreads();
     for (int e = tid; e < kTile * kTile; e += NT) {
       const int r = e / kTile, c = e % kTile;
-      int gi = I * kTile + r, gj = J * kTile + c;
-      if (gi < n && gj < n) dstb[(size_t)gi * ldd + gj] = ts[r][c];
-      if (I != J) {
-        gi = J * kTile + r; gj = I * kTile + c;   // transposed tile, coalesced along c
-        if (gi < n && gj < n) dstb[(size_t)gi * ldd + gj] = ts[c][r];
-      }
+      emit(I * kTile + r, J * kTile + c, ts[r][c]);
+      if (I != J) emit(J * kTile + r, I * kTile + c, ts[c][r]);   // transposed tile, coalesced along c
     }
   }
   // zero the row padding so that padded columns never contribute
-  for (int idx = tid; idx < n * (ldd - n); idx += NT) {
-    const int i = idx / (ldd - n), j = n + idx % (ldd - n);
-    dstb[(size_t)i * ldd + j] = T(0);
+  if (ldd > n) {
+    for (int idx = tid; idx < (n + m) * (ldd - n); idx += NT) {
+      const int i = idx / (ldd - n), j = n + idx % (ldd - n);
+      if (i < n) dstb[(size_t)i * ldd + j] = T(0);
+      else g21[(size_t)(i - n) * ldd + j] = T(0);
+    }
+  }
+  // c = K12 b~ = K21^T b~  (constant part of the x-update)
+  if (a.c_out) {
+    __syncthreads();
+    T* cb = a.c_out + (size_t)b * ldd;
+    for (int i = tid; i < ldd; i += NT) {
+      T acc = T(0);
+      if (i < n)
+        for (int l = 0; l < m; ++l) acc += g21[(size_t)l * ldd + i] * a.bt[(size_t)b * m + l];
+      cb[i] = acc;
+    }
   }
 }
 
 template <typename T>
-cudaError_t launch_gj_inverse(int B, int n, int np, const T* src, int lds, const T* diag_shift, T diag_const,
-                              const T* mask, int ldm, T* W, T* Vg, T* Wg, T* dst, int ldd, cudaStream_t st) {
+cudaError_t launch_gj_inverse(int B, const GjArgs<T>& a, cudaStream_t st) {
   constexpr int NT = GjCfg<T>::NT;
   const size_t smem = (size_t)2 * (NT / kGroup) * kTile * kMacro * sizeof(T);
   cudaError_t e = cudaFuncSetAttribute(gj_inverse_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  gj_inverse_kernel<T, NT><<<B, NT, smem, st>>>(n, np, src, lds, diag_shift, diag_const, mask, ldm, W, Vg, Wg, dst, ldd);
+  gj_inverse_kernel<T, NT><<<B, NT, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -258,133 +291,9 @@ cudaError_t launch_select_rho(const lqpb_config& cfg, const FwdWs<T>& w, cudaStr
   return cudaGetLastError();
 }
 
-// ---------------------------------------------------------------------------------------------
-// Schur complement of the equality rows (m >= 1): on entry K = H^-1 (symmetric, stride ld).
-//   G^T = A~ H^-1  (m x n),  S = A~ G,  K <- K - G S^-1 G^T,  c = G S^-1 b~
-constexpr int kSchurThreads = 512;
-constexpr int kSchurChunk = 8;
-
-template <typename T>
-__global__ void __launch_bounds__(kSchurThreads) schur_kernel(FwdWs<T> w, T* Ht_all) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* Ac = reinterpret_cast<T*>(smem_raw);        // [kSchurChunk][ld] chunk of A~ rows
-  T* S = Ac + kSchurChunk * w.ld;                // [m][m+1]
-  T* y = S + w.m * (w.m + 1);                    // [m]
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n = w.n, m = w.m, ld = w.ld;
-  T* Kb = w.K + (size_t)b * n * ld;
-  const T* At = w.At + (size_t)b * m * ld;
-  T* Gt = w.Gt + (size_t)b * m * ld;
-  T* Ht = Ht_all + (size_t)b * m * ld;
-  T* Sinv = w.Sinv + (size_t)b * m * m;
-
-  // G^T[l][i] = sum_j K[j][i] A~[l][j]  (K symmetric: column sweep over contiguous rows)
-  for (int l0 = 0; l0 < m; l0 += kSchurChunk) {
-    const int lc = min(kSchurChunk, m - l0);
-    __syncthreads();
-    for (int e = tid; e < lc * ld; e += kSchurThreads) Ac[e] = At[(size_t)l0 * ld + e];
-    __syncthreads();
-    for (int i = tid; i < ld; i += kSchurThreads) {
-      T acc[kSchurChunk];
-#pragma unroll
-      for (int q = 0; q < kSchurChunk; ++q) acc[q] = T(0);
-      if (i < n) {
-#pragma unroll 4
-        for (int j = 0; j < n; ++j) {
-          const T kv = Kb[(size_t)j * ld + i];
-#pragma unroll
-          for (int q = 0; q < kSchurChunk; ++q)
-            if (q < lc) acc[q] += kv * Ac[q * ld + j];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < kSchurChunk; ++q)
-        if (q < lc) Gt[(size_t)(l0 + q) * ld + i] = acc[q];
-    }
-  }
-  __syncthreads();
-  // S = A~ G  (warp per entry)
-  for (int e = wid; e < m * m; e += kSchurThreads / 32) {
-    const int l = e / m, l2 = e % m;
-    T acc = T(0);
-    for (int i = lane; i < n; i += 32) acc += At[(size_t)l * ld + i] * Gt[(size_t)l2 * ld + i];
-    acc = warp_sum(acc);
-    if (lane == 0) S[l * (m + 1) + l2] = acc;
-  }
-  __syncthreads();
-  // S <- -(S^-1) by the symmetric sweep (S is SPD), then Sinv = -S
-  for (int s = 0; s < m; ++s) {
-    const T piv = T(1) / S[s * (m + 1) + s];
-    __syncthreads();
-    T nv[(kMaxM * kMaxM + kSchurThreads - 1) / kSchurThreads];
-    int q = 0;
-    for (int e = tid; e < m * m; e += kSchurThreads, ++q) {
-      const int r = e / m, c = e % m;
-      const T ars = S[r * (m + 1) + s], asc = S[s * (m + 1) + c], arc = S[r * (m + 1) + c];
-      T v;
-      if (r == s && c == s) v = -piv;
-      else if (r == s) v = asc * piv;
-      else if (c == s) v = ars * piv;
-      else v = arc - ars * asc * piv;
-      nv[q] = v;
-    }
-    __syncthreads();
-    q = 0;
-    for (int e = tid; e < m * m; e += kSchurThreads, ++q) S[(e / m) * (m + 1) + e % m] = nv[q];
-    __syncthreads();
-  }
-  for (int e = tid; e < m * m; e += kSchurThreads) {
-    const T v = -S[(e / m) * (m + 1) + e % m];
-    S[(e / m) * (m + 1) + e % m] = v;
-    Sinv[e] = v;
-  }
-  __syncthreads();
-  // y = Sinv b~ ;  c = G y ;  H^T = Sinv G^T
-  if (tid < m) {
-    T acc = T(0);
-    for (int l = 0; l < m; ++l) acc += S[tid * (m + 1) + l] * w.bt[(size_t)b * m + l];
-    y[tid] = acc;
-  }
-  __syncthreads();
-  for (int i = tid; i < ld; i += kSchurThreads) {
-    T acc = T(0);
-    if (i < n)
-      for (int l = 0; l < m; ++l) acc += Gt[(size_t)l * ld + i] * y[l];
-    w.c[(size_t)b * ld + i] = acc;
-    for (int l = 0; l < m; ++l) {
-      T h = T(0);
-      if (i < n)
-        for (int l2 = 0; l2 < m; ++l2) h += S[l * (m + 1) + l2] * Gt[(size_t)l2 * ld + i];
-      Ht[(size_t)l * ld + i] = h;
-    }
-  }
-  __syncthreads();
-  // K <- K - G H  (K_ij -= sum_l G^T[l][i] H^T[l][j])
-  for (int idx = tid; idx < n * ld; idx += kSchurThreads) {
-    const int i = idx / ld, j = idx - i * ld;
-    if (j >= n) continue;
-    T acc = T(0);
-    for (int l = 0; l < m; ++l) acc += Gt[(size_t)l * ld + i] * Ht[(size_t)l * ld + j];
-    Kb[idx] -= acc;
-  }
-}
-
-template <typename T>
-cudaError_t launch_schur(const FwdWs<T>& w, cudaStream_t st) {
-  if (w.m <= 0) return cudaSuccess;
-  const size_t smem = (size_t)(kSchurChunk * w.ld + w.m * (w.m + 1) + w.m + 8) * sizeof(T);
-  cudaError_t e = cudaFuncSetAttribute(schur_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  // H^T scratch: the Gauss-Jordan work matrix is free at this point (np*np >= m*ld for m <= kMaxM <= np)
-  schur_kernel<T><<<w.B, kSchurThreads, smem, st>>>(w, w.W);
-  return cudaGetLastError();
-}
-
-#define INST(T)                                                                                                    \
-  template cudaError_t launch_gj_inverse<T>(int, int, int, const T*, int, const T*, T, const T*, int, T*, T*, T*, T*, \
-                                            int, cudaStream_t);                                                    \
-  template cudaError_t launch_select_rho<T>(const lqpb_config&, const FwdWs<T>&, cudaStream_t);                    \
-  template cudaError_t launch_schur<T>(const FwdWs<T>&, cudaStream_t);
+#define INST(T)                                                                                \
+  template cudaError_t launch_gj_inverse<T>(int, const GjArgs<T>&, cudaStream_t);              \
+  template cudaError_t launch_select_rho<T>(const lqpb_config&, const FwdWs<T>&, cudaStream_t);
 INST(float)
 INST(double)
 #undef INST

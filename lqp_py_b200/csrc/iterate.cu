@@ -27,19 +27,45 @@ namespace lqpb {
 constexpr int kIterConsumers = 512;
 constexpr int kIterThreads = kIterConsumers + 32;   // + one producer warp
 constexpr int kConsBar = 1;                         // named barrier of the consumer threads
-constexpr int kMaxChunks = 4;                       // 16-byte column chunks per consumer thread
+constexpr int kMaxChunks = 4;                       // max 16-byte column chunks per consumer thread
 
 struct IterGeom {
   int tpr;          // threads per panel row (each owns `cpt` 16-byte chunks of columns)
-  int ng;           // row groups
-  int cpt;          // chunks per thread
-  int rows;         // rows per panel (stage)
+  int ng;           // row groups; group g owns the `rpg` contiguous panel rows [g*rpg, (g+1)*rpg)
+  int cpt;          // chunks per thread (template parameter of the kernel)
+  int rpg;          // rows per group and panel (1..8, dispatched to unrolled code)
+  int rows;         // rows per panel (stage) = ng * rpg; every panel is full: the last one is shifted
+                    // up to end at row n and the rows it shares with its predecessor are masked out
   int panels;       // panels per matrix
   int stages;       // ring depth
   int stage_elems;  // elements per stage
 };
 
-template <typename T>
+// One panel of the column sweep: acc[c][:] += sum_rr K[g*rpg + rr][cols_c] * v[g*rpg + rr].
+template <typename T, int CPT, int RPG>
+__device__ __forceinline__ void sweep_panel(const T* __restrict__ P, const T* __restrict__ vp, int skip, int row_base,
+                                            int ld, int col0, int col_stride, T (&acc)[CPT][Vec<T>::N]) {
+  constexpr int VN = Vec<T>::N;
+  using V4 = typename Vec<T>::type;
+  T vr[RPG];
+#pragma unroll
+  for (int rr = 0; rr < RPG; ++rr) vr[rr] = (row_base + rr >= skip) ? vp[row_base + rr] : T(0);
+#pragma unroll
+  for (int rr = 0; rr < RPG; ++rr) {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int col = col0 + c * col_stride;
+      if (CPT == 1 || col < ld) {
+        const V4 kv = *reinterpret_cast<const V4*>(P + (size_t)(row_base + rr) * ld + col);
+        const T* kp = reinterpret_cast<const T*>(&kv);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc[c][e] += kp[e] * vr[rr];
+      }
+    }
+  }
+}
+
+template <typename T, int CPT>
 __global__ void __launch_bounds__(kIterThreads, 1)
 iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, IterGeom geo) {
   constexpr int VN = Vec<T>::N;
@@ -80,10 +106,13 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
 
   // consumer thread geometry
   const int g = tid / geo.tpr, t = tid % geo.tpr;
-  const bool gemv_active = !is_producer && g < geo.ng;
+  const bool gemv_active = !is_producer && g < geo.ng && t * VN < ld;
   const int nwc = kIterConsumers >> 5;
+  const int R = geo.rows;
+  const int last_start = n - R;      // first row of the (shifted) last panel
 
-  uint32_t q = 0;           // panel sequence number (same schedule in producer and consumers)
+  int stage = 0;            // ring position and phase: same schedule in producer and consumers
+  uint32_t phase = 0;
   bool have_v = false;      // v already holds the rhs of this iteration (single-problem CTAs)
   int i = i0;
   int status = 0;
@@ -119,14 +148,13 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
           const int b = blockIdx.x + k * gridDim.x;
           for (int pass = 0; pass < (is_check ? 2 : 1); ++pass) {
             const T* src = (pass == 0 ? w.K : w.Qs) + (size_t)b * n * ld;
-            for (int pn = 0; pn < geo.panels; ++pn, ++q) {
-              const int s = q % geo.stages;
-              const uint32_t ph = (q / geo.stages) & 1u;
-              mbar_wait(&empty[s], ph ^ 1u);
-              const int rows = min(geo.rows, n - pn * geo.rows);
-              const uint32_t bytes = (uint32_t)(rows * ld * sizeof(T));
-              mbar_arrive_expect_tx(&full[s], bytes);
-              tma_load_1d(ring + (size_t)s * geo.stage_elems, src + (size_t)pn * geo.rows * ld, bytes, &full[s]);
+            const uint32_t bytes = (uint32_t)(R * ld * sizeof(T));
+            for (int pn = 0; pn < geo.panels; ++pn) {
+              mbar_wait(&empty[stage], phase ^ 1u);
+              const int start = min(pn * R, last_start);
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              tma_load_1d(ring + (size_t)stage * geo.stage_elems, src + (size_t)start * ld, bytes, &full[stage]);
+              if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
             }
           }
         }
@@ -145,49 +173,48 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
           bar_sync(kConsBar, kIterConsumers);
         }
         // ---- x~ = K11 v : column sweep over the streamed row panels
-        T acc[kMaxChunks][VN];
+        T acc[CPT][VN];
 #pragma unroll
-        for (int c = 0; c < kMaxChunks; ++c)
+        for (int c = 0; c < CPT; ++c)
 #pragma unroll
           for (int e = 0; e < VN; ++e) acc[c][e] = T(0);
-        for (int pn = 0; pn < geo.panels; ++pn, ++q) {
-          const int s = q % geo.stages;
-          const uint32_t ph = (q / geo.stages) & 1u;
-          mbar_wait(&full[s], ph);
-          if (gemv_active) {
-            const int rows = min(geo.rows, n - pn * geo.rows);
-            const T* P = ring + (size_t)s * geo.stage_elems;
-            const T* vp = v + pn * geo.rows;
-#pragma unroll 4
-            for (int r = g; r < rows; r += geo.ng) {
-              const T vr = vp[r];
-#pragma unroll
-              for (int c = 0; c < kMaxChunks; ++c) {
-                const int col = (t + c * geo.tpr) * VN;
-                if (c < geo.cpt && col < ld) {
-                  const V4 kv = *reinterpret_cast<const V4*>(P + (size_t)r * ld + col);
-                  const T* kp = reinterpret_cast<const T*>(&kv);
-#pragma unroll
-                  for (int e = 0; e < VN; ++e) acc[c][e] += kp[e] * vr;
-                }
+        {
+          const int row_base = g * geo.rpg, col0 = t * VN, cstride = geo.tpr * VN;
+          for (int pn = 0; pn < geo.panels; ++pn) {
+            mbar_wait(&full[stage], phase);
+            if (gemv_active) {
+              const int start = min(pn * R, last_start);
+              const int skip = pn * R - start;          // rows already covered by the previous panel
+              const T* P = ring + (size_t)stage * geo.stage_elems;
+              const T* vp = v + start;
+              switch (geo.rpg) {
+                case 1: sweep_panel<T, CPT, 1>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
+                case 2: sweep_panel<T, CPT, 2>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
+                case 3: sweep_panel<T, CPT, 3>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
+                case 4: sweep_panel<T, CPT, 4>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
+                case 5: sweep_panel<T, CPT, 5>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
+                case 6: sweep_panel<T, CPT, 6>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
+                case 7: sweep_panel<T, CPT, 7>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
+                default: sweep_panel<T, CPT, 8>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
               }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);
         }
         if (gemv_active) {
 #pragma unroll
-          for (int c = 0; c < kMaxChunks; ++c) {
+          for (int c = 0; c < CPT; ++c) {
             const int col = (t + c * geo.tpr) * VN;
-            if (c < geo.cpt && col < ld) {
+            if (CPT == 1 || col < ld) {
 #pragma unroll
               for (int e = 0; e < VN; ++e) part[(size_t)g * ld + col + e] = acc[c][e];
             }
           }
         }
         bar_sync(kConsBar, kIterConsumers);
-        // ---- G^T rhs for nu (:327), from the rhs of THIS solve (before v is overwritten)
+        // ---- K21 rhs for nu (:327), from the rhs of THIS solve (before v is overwritten)
         if (maybe_final && m > 0) {
           const T* Gt = w.Gt + (size_t)b * m * ld;
           for (int l = wid; l < m; l += nwc) {
@@ -232,22 +259,21 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
           for (int e = n + tid; e < ld; e += kIterConsumers) xs[e] = T(0);
         have_v = (nprob == 1);
         bar_sync(kConsBar, kIterConsumers);
-        if (maybe_final && m > 0 && tid < m) {
-          const T* Sinv = w.Sinv + (size_t)b * m * m;
-          T a = T(0);
-          for (int l = 0; l < m; ++l) a += Sinv[tid * m + l] * (tdot[l] - w.bt[(size_t)b * m + l]);
+        if (maybe_final && m > 0 && tid < m) {     // nu = K21 rhs + K22 b~, unscaled by E (:327)
+          const T* K22 = w.Sinv + (size_t)b * m * m;
+          T a = tdot[tid];
+          for (int l = 0; l < m; ++l) a += K22[tid * m + l] * w.bt[(size_t)b * m + l];
           nus_out[(size_t)b * m + tid] = a * w.E[(size_t)b * m + tid];
         }
         if (is_check) {
           // ---- ||Q~ x~ / D||_inf (:299): row dots over the streamed Q~ panels, one warp per row
           T mx_q = T(0);
-          for (int pn = 0; pn < geo.panels; ++pn, ++q) {
-            const int s = q % geo.stages;
-            const uint32_t ph = (q / geo.stages) & 1u;
-            mbar_wait(&full[s], ph);
-            const int rows = min(geo.rows, n - pn * geo.rows);
-            const T* P = ring + (size_t)s * geo.stage_elems;
-            for (int r = wid; r < rows; r += nwc) {
+          for (int pn = 0; pn < geo.panels; ++pn) {
+            mbar_wait(&full[stage], phase);
+            const int start = min(pn * R, last_start);
+            const int skip = pn * R - start;
+            const T* P = ring + (size_t)stage * geo.stage_elems;
+            for (int r = skip + wid; r < R; r += nwc) {
               T d = T(0);
               for (int col = lane * VN; col < ld; col += 32 * VN) {
                 const V4 kv = *reinterpret_cast<const V4*>(P + (size_t)r * ld + col);
@@ -258,10 +284,11 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
                 for (int e = 0; e < VN; ++e) d += kp[e] * xp[e];
               }
               d = warp_sum(d);
-              mx_q = t_max(mx_q, t_abs(d / Ds[pn * geo.rows + r]));
+              mx_q = t_max(mx_q, t_abs(d / Ds[start + r]));
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
           }
           // ---- block reduction of the six maxima
           mx_p = warp_max(mx_p); mx_d = warp_max(mx_d); mx_x = warp_max(mx_x);
@@ -381,16 +408,25 @@ static IterGeom make_geom(const FwdWs<T>& w, size_t* smem_bytes, int max_smem) {
   if (tpr > kIterConsumers) tpr = kIterConsumers;
   g.tpr = tpr;
   g.cpt = (chunks + tpr - 1) / tpr;
-  g.ng = kIterConsumers / tpr;
-  if (g.ng > 16) g.ng = 16;
   const size_t row_bytes = (size_t)w.ld * sizeof(T);
-  int rows = (int)(32768 / row_bytes);
-  if (rows < 1) rows = 1;
-  if (rows > w.n) rows = w.n;
-  if (rows >= g.ng) rows = rows / g.ng * g.ng;
-  g.rows = rows;
-  g.panels = (w.n + rows - 1) / rows;
-  g.stage_elems = (int)(round_up_sz((size_t)rows * row_bytes, 128) / sizeof(T));
+  int target = (int)(40960 / row_bytes);          // ~40 KB stages
+  if (target < 1) target = 1;
+  if (target > w.n) target = w.n;
+  int ng = kIterConsumers / tpr;
+  if (ng > 16) ng = 16;
+  while (ng > target) ng >>= 1;                    // power of two <= target rows
+  if (ng < 1) ng = 1;
+  g.ng = ng;
+  int rpg = target / ng;
+  if (rpg > 8) rpg = 8;
+  if (rpg < 1) rpg = 1;
+  // prefer a panel height that divides n (no shifted last panel), searching a little below the target
+  for (int cand = rpg; cand >= 1 && cand >= rpg - 2; --cand)
+    if (w.n % (cand * ng) == 0) { rpg = cand; break; }
+  g.rpg = rpg;
+  g.rows = rpg * ng;
+  g.panels = (w.n + g.rows - 1) / g.rows;
+  g.stage_elems = (int)(round_up_sz((size_t)g.rows * row_bytes, 128) / sizeof(T));
   const size_t fixed = ((size_t)g.ng * w.ld + 3 * (size_t)w.ld + (w.m > 0 ? round_up(w.m, 4) : 4) + 6 * 16 + 4) * sizeof(T) +
                        2 * 16 * sizeof(uint64_t) + 256;
   const size_t stage_bytes = (size_t)g.stage_elems * sizeof(T);
@@ -399,6 +435,17 @@ static IterGeom make_geom(const FwdWs<T>& w, size_t* smem_bytes, int max_smem) {
   g.stages = stages;
   *smem_bytes = fixed + stages * stage_bytes;
   return g;
+}
+
+template <typename T, int CPT>
+static cudaError_t launch_iterate_cpt(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check,
+                                      T* nus_out, IterGeom geo, size_t smem, int grid, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(iterate_kernel<T, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lqpb_config c = cfg;
+  FwdWs<T> ww = w;
+  void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo};
+  return cudaLaunchCooperativeKernel((void*)iterate_kernel<T, CPT>, dim3(grid), dim3(kIterThreads), args, smem, st);
 }
 
 template <typename T>
@@ -412,15 +459,12 @@ cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, in
   size_t smem = 0;
   IterGeom geo = make_geom(w, &smem, max_smem - 1024);
   if (geo.stages < 2 || geo.cpt > kMaxChunks) return cudaErrorInvalidConfiguration;
-  e = cudaFuncSetAttribute(iterate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   const int grid = w.B < sms ? w.B : sms;   // one CTA per SM: all CTAs co-resident (needed by the grid barrier)
   e = cudaMemsetAsync(&w.ctrl->barrier, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  lqpb_config c = cfg;
-  FwdWs<T> ww = w;
-  void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo};
-  e = cudaLaunchCooperativeKernel((void*)iterate_kernel<T>, dim3(grid), dim3(kIterThreads), args, smem, st);
+  if (geo.cpt == 1) e = launch_iterate_cpt<T, 1>(cfg, w, i0, skip_rho_check, nus_out, geo, smem, grid, st);
+  else if (geo.cpt == 2) e = launch_iterate_cpt<T, 2>(cfg, w, i0, skip_rho_check, nus_out, geo, smem, grid, st);
+  else e = launch_iterate_cpt<T, 4>(cfg, w, i0, skip_rho_check, nus_out, geo, smem, grid, st);
   if (launches) ++*launches;
   return e;
 }

@@ -21,8 +21,8 @@ struct FwdWs {
   T* Vg;        // B*np*kTile   column panel before the sweep step
   T* Wg;        // B*np*kTile   column panel after the sweep step
   T *D, *pt, *lbt, *ubt, *c, *z, *u, *xs;   // B*ld each: scaling, p~, lb~, ub~, c = K12 b~, ADMM state, last x~
-  T *At, *Gt;   // B*m*ld   A~ and (H^-1 A~^T)^T
-  T* Sinv;      // B*m*m    inverse Schur complement
+  T *At, *Gt;   // B*m*ld   A~ and K21 (the (2,1) block of the KKT inverse)
+  T* Sinv;      // B*m*m    K22 (the (2,2) block of the KKT inverse = -(A~ H^-1 A~^T)^-1)
   T *bt, *E;    // B*m
   T *rho, *rho_cand, *pnorm, *ratio;   // B
   T* chk;       // B*4  [primal, dual, tol_primal_rel, tol_dual_rel] of the last check
@@ -36,7 +36,7 @@ inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
   FwdWs<T> w;
   w.B = B; w.n = n; w.m = m;
   w.ld = round_up(n, Vec<T>::N);
-  w.np = round_up(n, kMacro);
+  w.np = round_up(n + m, kMacro);
   char* p = static_cast<char*>(base);
   size_t off = 0;
   auto take = [&](size_t count, size_t elt) {
@@ -76,6 +76,8 @@ struct BwdWs {
   T* W;         // B*np*np
   T *Vg, *Wg;   // B*np*kTile
   T *mask, *dv; // B*ld
+  T* G21;       // B*m*ld   K21 of the masked KKT inverse
+  T* K22;       // B*m*m
   T* dnu;       // B*m
   size_t bytes;
 };
@@ -85,7 +87,7 @@ inline BwdWs<T> carve_bwd(void* base, int B, int n, int m) {
   BwdWs<T> w;
   w.B = B; w.n = n; w.m = m;
   w.ld = round_up(n, Vec<T>::N);
-  w.np = round_up(n, kMacro);
+  w.np = round_up(n + m, kMacro);
   char* p = static_cast<char*>(base);
   size_t off = 0;
   auto take = [&](size_t count, size_t elt) {
@@ -100,6 +102,8 @@ inline BwdWs<T> carve_bwd(void* base, int B, int n, int m) {
   w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
   w.mask = (T*)take(Bn * w.ld, sizeof(T));
   w.dv = (T*)take(Bn * w.ld, sizeof(T));
+  w.G21 = (T*)take(Bn * (m > 0 ? m : 1) * w.ld, sizeof(T));
+  w.K22 = (T*)take(Bn * (m > 0 ? m * m : 1), sizeof(T));
   w.dnu = (T*)take(Bn * (m > 0 ? m : 1), sizeof(T));
   w.bytes = off;
   return w;
@@ -111,16 +115,26 @@ template <typename T>
 cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, const T* p, const T* A, const T* b,
                          const T* lb, const T* ub, cudaStream_t st);
 
-// factor.cu -- K2: H = Q~ + rho I  ->  H^-1 by tiled symmetric Gauss-Jordan, Schur complement, K11, c
-// src: B matrices with row stride lds (lower triangle read); mask (B*ldm, 1 = keep, 0 = replace row/col by
-// identity) may be null; diag_shift (per problem, may be null) + diag_const are added on kept diagonal entries.
+// factor.cu -- K2: inverse of the KKT matrix [[H, A^T], [A, a_diag I]] by tiled symmetric Gauss-Jordan
 template <typename T>
-cudaError_t launch_gj_inverse(int B, int n, int np, const T* src, int lds, const T* diag_shift, T diag_const,
-                              const T* mask, int ldm, T* W, T* Vg, T* Wg, T* dst, int ldd, cudaStream_t st);
+struct GjArgs {
+  int n, m, np;
+  const T* src; int lds;          // B matrices, row stride lds, lower triangle read
+  const T* diag_shift;            // per problem, may be null
+  T diag_const;                   // added to the kept diagonal entries of H
+  const T* mask; int ldm;         // 1 = keep, 0 = replace row/col of H by identity (and zero that column of A); may be null
+  const T* Arows; int lda;        // B*m rows (row stride lda); unused when m == 0
+  T a_diag;                       // diagonal of the (2,2) block
+  T *W, *Vg, *Wg;                 // work: B*np*np, B*np*32, B*np*32
+  T* dst; int ldd;                // K11 (B*n*ldd, full symmetric)
+  T* G21;                         // K21 (B*m*ldd)
+  T* K22;                         // K22 (B*m*m)
+  const T* bt; T* c_out;          // optional: c = K21^T b~ (B*ldd)
+};
+template <typename T>
+cudaError_t launch_gj_inverse(int B, const GjArgs<T>& a, cudaStream_t st);
 template <typename T>
 cudaError_t launch_select_rho(const lqpb_config& cfg, const FwdWs<T>& w, cudaStream_t st);
-template <typename T>
-cudaError_t launch_schur(const FwdWs<T>& w, cudaStream_t st);
 
 // iterate.cu -- K3 (+K4): persistent ADMM loop and finalisation
 template <typename T>
@@ -133,7 +147,7 @@ cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho
 template <typename T>
 cudaError_t launch_bwd_mask(const BwdWs<T>& w, const T* x, const T* u, const T* lb, const T* ub, cudaStream_t st);
 template <typename T>
-cudaError_t launch_bwd_solve(const BwdWs<T>& w, const T* dl_dz, const T* A, cudaStream_t st);
+cudaError_t launch_bwd_solve(const BwdWs<T>& w, const T* dl_dz, cudaStream_t st);
 template <typename T>
 cudaError_t launch_bwd_grads(const BwdWs<T>& w, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
                              const T* Q, const T* A, const T* rho_dev, double rho_scalar, T* dQ, T* dp, T* dA, T* db,

@@ -31,6 +31,66 @@ __device__ __forceinline__ T torch_lerp(T a, T b, T w) {
   return w < T(0.5) ? a + w * (b - a) : b - (b - a) * (T(1) - w);
 }
 
+// Column max-abs of an n x n row-major matrix (row stride n) into smem cm[] (pre-zeroed), VW-wide loads.
+template <typename T, int VW>
+__device__ __forceinline__ void col_absmax(const T* __restrict__ Qb, int n, T* cm, int tid) {
+  const int chunks = n / VW;
+  const int tpc = chunks < kScaleThreads ? round_up(chunks, 32) : kScaleThreads;
+  const int ng = kScaleThreads / tpc;
+  const int g = tid / tpc, t = tid % tpc;
+  if (g >= ng) return;
+  for (int c = t; c < chunks; c += tpc) {
+    T mx[VW];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) mx[e] = T(0);
+#pragma unroll 8
+    for (int i = g; i < n; i += ng) {
+      alignas(16) T v[VW];
+      if (VW == 1) v[0] = Qb[(size_t)i * n + c];
+      else *reinterpret_cast<typename Vec<T>::type*>(v) =
+               *reinterpret_cast<const typename Vec<T>::type*>(Qb + (size_t)i * n + c * VW);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) mx[e] = t_max(mx[e], t_abs(v[e]));
+    }
+#pragma unroll
+    for (int e = 0; e < VW; ++e) smem_atomic_max_nonneg(&cm[c * VW + e], mx[e]);
+  }
+}
+
+// Q~ = (D_i Q_ij) D_j written with row stride ld (== n when VW > 1); returns this thread's share of ||Q~||_F^2.
+template <typename T, int VW>
+__device__ __forceinline__ double scale_rows(const T* __restrict__ Qb, T* __restrict__ Qsb, int n, int ld,
+                                             const T* Ds, bool do_scale, int tid) {
+  const int chunks = ld / VW;                     // VW == 1: includes the zero padding columns
+  const int tpc = chunks < kScaleThreads ? round_up(chunks, 32) : kScaleThreads;
+  const int ng = kScaleThreads / tpc;
+  const int g = tid / tpc, t = tid % tpc;
+  double fro = 0.0;
+  if (g >= ng) return fro;
+  for (int c = t; c < chunks; c += tpc) {
+    T dj[VW];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) dj[e] = Ds[c * VW + e];
+#pragma unroll 4
+    for (int i = g; i < n; i += ng) {
+      alignas(16) T v[VW];
+      if (VW == 1) v[0] = (c < n) ? Qb[(size_t)i * n + c] : T(0);
+      else *reinterpret_cast<typename Vec<T>::type*>(v) =
+               *reinterpret_cast<const typename Vec<T>::type*>(Qb + (size_t)i * n + c * VW);
+      const T di = Ds[i];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        if (do_scale) v[e] = (di * v[e]) * dj[e];
+        fro += (double)v[e] * (double)v[e];
+      }
+      if (VW == 1) Qsb[(size_t)i * ld + c] = v[0];
+      else *reinterpret_cast<typename Vec<T>::type*>(Qsb + (size_t)i * ld + c * VW) =
+               *reinterpret_cast<typename Vec<T>::type*>(v);
+    }
+  }
+  return fro;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kScaleThreads)
 scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __restrict__ p,
@@ -54,17 +114,9 @@ scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __re
   if (cfg.scale) {
     for (int j = tid; j < ld; j += kScaleThreads) Ds[j] = T(0);
     __syncthreads();
-    const int tpc = n < kScaleThreads ? round_up(n, 32) : kScaleThreads;
-    const int ng = kScaleThreads / tpc;
-    const int g = tid / tpc, t = tid % tpc;
-    if (g < ng) {
-      for (int j = t; j < n; j += tpc) {
-        T mx = T(0);
-#pragma unroll 8
-        for (int i = g; i < n; i += ng) mx = t_max(mx, t_abs(Qb[(size_t)i * n + j]));
-        smem_atomic_max_nonneg(&Ds[j], mx);
-      }
-    }
+    const bool vec_ok = (n % Vec<T>::N) == 0 && ((uintptr_t)Q % 16) == 0;
+    if (vec_ok) col_absmax<T, Vec<T>::N>(Qb, n, Ds, tid);
+    else col_absmax<T, 1>(Qb, n, Ds, tid);
     __syncthreads();
     // mean of the norms (:166), zero guard (:164-168), D = sqrt(1/norm) (:170)
     double part = 0.0;
@@ -122,19 +174,11 @@ scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __re
   }
 
   // ---- Q~ = (D_i Q_ij) D_j (:176), Frobenius norm (:201), written with the padded row stride
-  double fro = 0.0;
+  double fro;
   {
-    const int total = n * ld;
-    for (int idx = tid; idx < total; idx += kScaleThreads) {
-      const int i = idx / ld, j = idx - i * ld;
-      T v = T(0);
-      if (j < n) {
-        v = Qb[(size_t)i * n + j];
-        if (cfg.scale) v = (Ds[i] * v) * Ds[j];
-        fro += (double)v * (double)v;
-      }
-      Qsb[idx] = v;
-    }
+    const bool vec_ok = (n % Vec<T>::N) == 0 && ((uintptr_t)Q % 16) == 0;
+    if (vec_ok) fro = scale_rows<T, Vec<T>::N>(Qb, Qsb, n, ld, Ds, cfg.scale != 0, tid);
+    else fro = scale_rows<T, 1>(Qb, Qsb, n, ld, Ds, cfg.scale != 0, tid);
   }
   const double fro_tot = group_sum(fro, dscratch, tid, kScaleThreads, 0);
 

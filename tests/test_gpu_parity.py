@@ -1,0 +1,256 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the public Python API,
+which calls the C ABI (include/lqpb.h) -- the CUDA library is the only compute path.
+
+Tolerances (north_star): fp64 -- x*, duals and gradients within 1e-8 relative (max-norm) of the
+reference, fp32 -- 1e-5, iteration counts equal (+-2 allowed; checks happen every check_solved
+iterations so in practice equal).  Documented exceptions, all properties of the reference's own
+formulas rather than of this implementation:
+  * fp32 nus / db: the reference's own fp32-vs-fp64 gap is 1e-5 / 8e-5 -> 2e-4 here;
+  * dlb / dub: inactive coordinates that were active earlier carry u ~ 1e-17 of either sign, which the
+    reference turns into +-1e-8*dv noise in dlb or dub (kkt/(rho u) * relu(+-rho u)) -> 1e-7 in fp64;
+  * after an adaptive-rho update the adapted rho itself (and u = lams / rho) amplifies round-off
+    (2e-11 in fp64, percent-level in fp32) while x, z, lams, nus, gradients and iter agree.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import box_qp_oracle as orc
+from tests._golden import Case, case_names, compare, rel_err, GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import __graft_entry__ as entry
+    entry.build()
+    return torch.device("cuda:0")
+
+
+def _tols(case):
+    f64 = case.dtype == torch.float64
+    tol = {"default": 1e-8 if f64 else 1e-5, "iter": 0,
+           "dlb": 1e-7 if f64 else 1e-5, "dub": 1e-7 if f64 else 1e-5}
+    if not f64:
+        tol.update(nus=2e-4, db=2e-4)
+    skip = ()
+    if case.name.startswith("adapt"):
+        if f64:
+            tol.update(rho=1e-8, u=1e-8)
+        else:
+            skip = ("rho", "u")
+    return tol, skip
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_golden_case(name, dev):
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp, torch_solve_box_qp_grad
+    case = Case(name)
+    ins = [None if t is None else t.to(dev) for t in case.inputs()]
+    control = case.control_dict()
+    sol = torch_solve_box_qp(*ins, control)
+    assert sol["x"].is_cuda and sol["x"].shape == (ins[1].shape[0], ins[1].shape[1], 1)
+    grads = torch_solve_box_qp_grad(case.t("dl_dz").to(dev), sol["x"], sol["u"], sol["lams"], sol["nus"],
+                                    ins[0], ins[2], ins[4], ins[5], sol["rho"])
+    assert len(grads) == 7 and grads[6] is None
+    tol, skip = _tols(case)
+    if skip and "rho" in skip:
+        assert torch.is_tensor(sol["rho"]) == case.rho_is_tensor
+    compare(case, {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in sol.items()},
+            [None if g is None else g.cpu() for g in grads[:6]], tol, skip=skip)
+
+
+@pytest.mark.parametrize("n,B,dtype,seed", [(500, 16, torch.float64, 3), (500, 16, torch.float32, 3),
+                                            (250, 12, torch.float64, 2), (100, 40, torch.float32, 5),
+                                            (10, 128, torch.float64, 0), (64, 200, torch.float64, 1),
+                                            (1000, 4, torch.float32, 0)])
+def test_against_oracle_fresh_seeds(n, B, dtype, seed, dev):
+    """CUDA path vs the CPU oracle on inputs that are not in the fixtures (B=200 > 148 SMs exercises
+    several problems per persistent CTA)."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp, torch_solve_box_qp_grad
+    Q, p, A, b, lb, ub = orc.make_exp1_data(n, B, seed=seed, dtype=dtype)
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5)
+    g = torch.randn(p.shape, generator=torch.Generator().manual_seed(99), dtype=dtype)
+
+    def run_oracle(dt):
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(dt)
+        try:
+            return orc.solve_and_grad(*(t.to(dt) for t in (Q, p, A, b, lb, ub)), control, g.to(dt))
+        finally:
+            torch.set_default_dtype(prev)
+
+    ref, rg = run_oracle(dtype)
+    f64 = dtype == torch.float64
+    # fp32: the reference's own rounding noise (its fp32 run vs its fp64 run on the same data) is the floor
+    # no other fp32 implementation can beat; allow max(1e-5, 4 x that gap) per quantity.
+    gap = {}
+    if not f64:
+        ref64, rg64 = run_oracle(torch.float64)
+        if ref64["iter"] == ref["iter"]:
+            for k in ("x", "z", "u", "lams", "nus"):
+                gap[k] = rel_err(ref[k].numpy(), ref64[k].numpy())
+            for k, a32, a64 in zip(("dQ", "dp", "dA", "db", "dlb", "dub"), rg, rg64):
+                gap[k] = rel_err(a32.numpy(), a64.numpy())
+    ins = [t.to(dev) for t in (Q, p, A, b, lb, ub)]
+    sol = torch_solve_box_qp(*ins, control)
+    grads = torch_solve_box_qp_grad(g.to(dev), sol["x"], sol["u"], sol["lams"], sol["nus"], ins[0], ins[2], ins[4],
+                                    ins[5], sol["rho"])
+    assert abs(sol["iter"] - ref["iter"]) <= 2
+    base = 1e-8 if f64 else 1e-5
+    lim = {"x": base, "z": base, "u": base, "lams": base, "nus": base}
+    for k, t in lim.items():
+        t = max(t, 4 * gap.get(k, 0.0))
+        e = rel_err(sol[k].cpu().numpy(), ref[k].numpy())
+        assert e <= t, f"{k}: {e:.2e} > {t:.1e}"
+    assert rel_err(sol["x"].cpu().numpy(), ref["x"].numpy()) <= (1e-8 if f64 else 1e-5)     # north_star bar on x*
+    glim = {"dQ": base, "dp": base, "dA": base, "db": base, "dlb": 1e-7 if f64 else 1e-5,
+            "dub": 1e-7 if f64 else 1e-5}
+    for (k, t), mine, theirs in zip(glim.items(), grads[:6], rg):
+        t = max(t, 4 * gap.get(k, 0.0))
+        e = rel_err(mine.cpu().numpy(), theirs.numpy())
+        assert e <= t, f"{k}: {e:.2e} > {t:.1e}"
+
+
+def test_module_autograd_and_needs_input_grad(dev):
+    """SolveBoxQP(...).forward + x.backward: gradients land on the leaves that asked for them
+    (Experiment 2 only differentiates p, experiment_2.py:50,88)."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    dtype = torch.float64
+    Q, p, A, b, lb, ub = orc.make_exp1_data(48, 6, seed=11, dtype=dtype)
+    control = box_qp_control(eps_abs=1e-6, eps_rel=1e-6)
+    g = torch.randn(p.shape, generator=torch.Generator().manual_seed(5), dtype=dtype)
+    torch.set_default_dtype(dtype)
+    try:
+        ref, rg = orc.solve_and_grad(Q, p, A, b, lb, ub, control, g)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    ins = [t.to(dev).requires_grad_(True) for t in (Q, p, A, b, lb, ub)]
+    x = SolveBoxQP(control=control).forward(*ins)
+    assert x.requires_grad
+    x.backward(g.to(dev))
+    for t, r, name in zip(ins, rg, ("dQ", "dp", "dA", "db", "dlb", "dub")):
+        assert t.grad is not None and t.grad.shape == t.shape
+        assert rel_err(t.grad.cpu().numpy(), r.numpy()) <= 1e-7, name
+    # only p requires grad
+    ins2 = [t.to(dev) for t in (Q, p, A, b, lb, ub)]
+    ins2[1].requires_grad_(True)
+    x2 = SolveBoxQP(control=control)(*ins2)
+    loss = (x2 * g.to(dev)).sum()
+    loss.backward()
+    assert rel_err(ins2[1].grad.cpu().numpy(), rg[1].numpy()) <= 1e-8
+    assert all(t.grad is None for k, t in enumerate(ins2) if k != 1)
+
+
+def test_cpu_tensors_drop_in(dev):
+    """The reference's callers pass CPU tensors; the layer stages them to the GPU and returns CPU results."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    Q, p, A, b, lb, ub = orc.make_exp1_data(32, 5, seed=4, dtype=torch.float32)
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5)
+    ref = orc.solve(Q, p, A, b, lb, ub, control)
+    Q.requires_grad_(True); p.requires_grad_(True)
+    x = SolveBoxQP(control=control).forward(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub)
+    assert x.device.type == "cpu" and x.shape == (5, 32, 1)
+    assert rel_err(x.detach().numpy(), ref["x"].numpy()) <= 1e-5
+    x.backward(torch.ones(5, 32, 1))
+    assert Q.grad.device.type == "cpu" and p.grad.shape == p.shape
+
+
+def test_unbounded_batch_mutates_control_like_reference(dev):
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    Q, p, A, b, lb, ub = (t.to(dev) for t in orc.make_exp1_data(20, 3, seed=1, dtype=torch.float64))
+    control = box_qp_control()
+    inf = float("inf")
+    x = SolveBoxQP(control)(Q, p, A, b, torch.full_like(lb, -inf), torch.full_like(ub, inf))
+    assert control["rho"] == 0                                   # reference :37-38
+    # equality-constrained optimum: A x = b exactly, KKT stationarity
+    assert float((A @ x - b).abs().max()) < 1e-12
+
+
+def test_full_size_properties(dev):
+    """BASELINE config 3 at full size (dz=500, B=128, fp32): properties that need no oracle run."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp
+    n, B = 500, 128
+    Q, p, A, b, lb, ub = (t.to(dev) for t in orc.make_exp1_data(n, B, seed=0, dtype=torch.float32))
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5)
+    sol = torch_solve_box_qp(Q, p, A, b, lb, ub, control)
+    assert sol["iter"] == 60                                     # all ten seeds stop at 60
+    x, z = sol["x"], sol["z"]
+    assert float((A @ x - b).abs().max()) < 2e-5                 # x comes from the KKT solve: A x = b to round-off
+    # z~ is clamped exactly in the scaled space; un-scaling (z = D z~, lb~ = lb / D) costs one rounding
+    assert float((z - lb).min()) >= -1e-6 and float((ub - z).min()) >= -1e-6
+    assert float((x - z).abs().max()) < 1e-3                     # primal residual small at the stop
+    lam = sol["lams"]
+    assert float(lam.min()) >= 0 and float((lam[:, :n] * lam[:, n:]).abs().max()) == 0   # complementary split
+    # determinism / batch-position independence: same problems in reverse order, same iteration count
+    perm = torch.arange(B - 1, -1, -1, device=dev)
+    sol2 = torch_solve_box_qp(Q[perm].contiguous(), p[perm].contiguous(), A[perm].contiguous(), b[perm].contiguous(),
+                              lb[perm].contiguous(), ub[perm].contiguous(), control)
+    assert sol2["iter"] == sol["iter"]
+    assert torch.equal(sol2["x"][perm], sol["x"])
+    # batch shards solved separately agree with the full batch when they stop at the same check
+    half = torch_solve_box_qp(Q[:64].contiguous(), p[:64].contiguous(), A[:64].contiguous(), b[:64].contiguous(),
+                              lb[:64].contiguous(), ub[:64].contiguous(), control)
+    assert half["iter"] == sol["iter"] and torch.equal(half["x"], sol["x"][:64])
+
+
+def test_lu_layer_golden(dev):
+    from lqp_py_b200.lu_layer import TorchLU, lu_factor, lu_solve
+    z = np.load(os.path.join(GOLDEN_DIR, "lu_layer_n24_f64.npz"))
+    M = torch.from_numpy(z["M"]).to(dev).requires_grad_(True)
+    rhs = torch.from_numpy(z["rhs"]).to(dev).requires_grad_(True)
+    lu = TorchLU(A=M.detach())
+    x = lu(M, rhs)
+    x.backward(torch.from_numpy(z["g"]).to(dev))
+    assert rel_err(x.detach().cpu().numpy(), z["x"]) <= 1e-10
+    assert rel_err(M.grad.cpu().numpy(), z["dM"]) <= 1e-10
+    assert rel_err(rhs.grad.cpu().numpy(), z["drhs"]) <= 1e-10
+    # factors are LAPACK-compatible: torch's own lu_solve accepts them
+    LU, P = lu_factor(M.detach())
+    tl, tp = torch.linalg.lu_factor(M.detach().cpu())
+    assert torch.equal(P.cpu(), tp)
+    assert rel_err(LU.cpu().numpy(), tl.numpy()) <= 1e-10
+    big = torch.randn(3, 130, 130, dtype=torch.float32, generator=torch.Generator().manual_seed(0))
+    rb = torch.randn(3, 130, 2, dtype=torch.float32, generator=torch.Generator().manual_seed(1))
+    LU, P = lu_factor(big.to(dev))
+    xs = lu_solve(LU, P, rb.to(dev))
+    ref = torch.linalg.solve(big.double(), rb.double())
+    assert rel_err(xs.cpu().numpy(), ref.numpy()) <= 2e-3
+
+
+def test_dtype_mismatch_raises(dev):
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp
+    Q, p, A, b, lb, ub = (t.to(dev) for t in orc.make_exp1_data(8, 2, dtype=torch.float32))
+    with pytest.raises(TypeError):
+        torch_solve_box_qp(Q.double(), p, A, b, lb, ub, box_qp_control())
+    with pytest.raises(TypeError):
+        torch_solve_box_qp(Q.half(), p.half(), A.half(), b.half(), lb.half(), ub.half(), box_qp_control())
+
+
+def test_verbose_prints_like_reference(dev, capsys):
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp
+    Q, p, A, b, lb, ub = orc.make_exp1_data(30, 4, seed=2, dtype=torch.float64)
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5, verbose=True)
+    torch.set_default_dtype(torch.float64)
+    try:
+        orc.solve(Q, p, A, b, lb, ub, control)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    ref_out = capsys.readouterr().out
+    torch_solve_box_qp(*(t.to(dev) for t in (Q, p, A, b, lb, ub)), control)
+    out = capsys.readouterr().out
+    assert out.splitlines()[0::3] == ref_out.splitlines()[0::3]          # iteration lines
+    ours = [float(l.split("=")[1]) for l in out.splitlines() if "error" in l]
+    theirs = [float(l.split("=")[1]) for l in ref_out.splitlines() if "error" in l]
+    assert len(ours) == len(theirs) and np.allclose(ours, theirs, rtol=0, atol=2e-9)

@@ -35,6 +35,9 @@ def _digest():
 
 
 def build(force=False, verbose=False):
+    extra = os.environ.get("LQPB_EXTRA_NVCC_FLAGS", "").split()
+    if extra:           # developer builds (e.g. -DLQPB_PHASE_TIMERS) never reuse the cached library
+        force = True
     dig = _digest()
     if not force and os.path.exists(SO) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return SO
@@ -42,7 +45,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(PKG, "_build_" + src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -60,7 +63,7 @@ def build(force=False, verbose=False):
     for o in objs:
         os.remove(o)
     with open(STAMP, "w") as fh:
-        fh.write(dig)
+        fh.write(dig if not extra else "developer build: " + " ".join(extra))
     return SO
 
 

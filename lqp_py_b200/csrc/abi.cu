@@ -197,17 +197,17 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
     a.mask = w.mask; a.ldm = w.ld;
     a.Arows = A; a.lda = n; a.a_diag = T(1e-8);
     a.W = w.W; a.Vg = w.Vg; a.Wg = w.Wg;
-    a.dst = w.Minv; a.ldd = w.ld; a.G21 = w.G21; a.K22 = w.K22;
+    a.dst = nullptr; a.ldd = w.ld; a.G21 = nullptr; a.K22 = nullptr;
     a.bt = nullptr; a.c_out = nullptr;
-    CK(launch_gj_inverse<T>(B, a, st), "gj_inverse (backward)");
+    a.rhs_g = dl_dz; a.sol_x = w.dv; a.sol_nu = w.dnu;
+    CK(launch_ldl_solve<T>(B, a, st), "ldl_solve (backward)");
   }
   if (prof) cudaEventRecord(g_prof.ev[5], st);
-  CK(launch_bwd_solve<T>(w, dl_dz, st), "bwd_solve");
   if (prof) cudaEventRecord(g_prof.ev[6], st);
   CK(launch_bwd_grads<T>(w, dl_dz, x, u, lams, nus, Q, A, rho_dev, rho_scalar, dQ, dp, dA, db, dlb, dub, st),
      "bwd_grads");
   if (prof) cudaEventRecord(g_prof.ev[7], st);
-  g_prof.launches = 4;
+  g_prof.launches = 3;
   g_prof.bwd_valid = prof;
   return LQPB_OK;
 }

@@ -5,7 +5,8 @@
 //   :378-393  lhs = [[dpi*Q with diag += rho (1-dpi), dpi*A^T], [A, 0]] + 1e-8 I ; solve lhs d = [-dpi*dl_dz; 0]
 //             The masked rows decouple (their solution is exactly 0), so the system is solved on the
 //             free set F as the symmetric  [[Q_FF + 1e-8 I, A_F^T], [A_F, 1e-8 I]]  (SURVEY App. A.5):
-//             factor.cu inverts that masked KKT matrix (equality rows included), the solve is then two GEMVs.
+//             factor.cu solves that masked KKT system (equality rows included) by a tiled block LDL^T
+//             elimination with the right-hand side carried along (launch_ldl_solve): dv, dnu.
 //   :396-427  dp = dv, dQ = 1/2 (dv x^T + x dv^T), dA = dnu x^T + nus dv^T, db = -dnu,
 //             dlam = (-dl_dz - Q dv - A^T dnu) / (rho u | 1), dlb = dlam lams[:n], dub = -dlam lams[n:]
 #include "layout.cuh"
@@ -31,55 +32,6 @@ template <typename T>
 cudaError_t launch_bwd_mask(const BwdWs<T>& w, const T* x, const T* u, const T* lb, const T* ub, cudaStream_t st) {
   dim3 grid((w.ld + 127) / 128, w.B);
   bwd_mask_kernel<T><<<grid, 128, 0, st>>>(w, x, u, lb, ub);
-  return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------
-// With the inverse of the masked KKT matrix at hand ([[K11, K21^T], [K21, K22]], factor.cu) the adjoint
-// solve is a pair of matrix-vector products with the masked upstream gradient g_F = dpi * dl_dz:
-//   dv = -K11 g_F,   dnu = -K21 g_F.
-// grid = (row chunks, B); one warp per row, 128-byte coalesced row reads.
-constexpr int kBwdThreads = 256;
-constexpr int kBwdRows = 32;
-
-template <typename T>
-__global__ void __launch_bounds__(kBwdThreads)
-bwd_solve_kernel(BwdWs<T> w, const T* __restrict__ dl_dz) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n = w.n, m = w.m, ld = w.ld;
-  T* gF = reinterpret_cast<T*>(smem_raw);    // [n]
-  const int b = blockIdx.y, r0 = blockIdx.x * kBwdRows;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const T* Mi = w.Minv + (size_t)b * n * ld;
-  const T* mk = w.mask + (size_t)b * ld;
-  for (int j = tid; j < n; j += kBwdThreads) gF[j] = mk[j] * dl_dz[(size_t)b * n + j];
-  __syncthreads();
-  const int r1 = min(r0 + kBwdRows, n);
-  for (int i = r0 + wid; i < r1; i += kBwdThreads / 32) {
-    const T* row = Mi + (size_t)i * ld;
-    T acc = T(0);
-    for (int j = lane; j < n; j += 32) acc += row[j] * gF[j];
-    acc = warp_sum(acc);
-    if (lane == 0) w.dv[(size_t)b * ld + i] = -acc;
-  }
-  if (blockIdx.x == 0 && m > 0) {
-    const T* G = w.G21 + (size_t)b * m * ld;
-    for (int l = wid; l < m; l += kBwdThreads / 32) {
-      T acc = T(0);
-      for (int j = lane; j < n; j += 32) acc += G[(size_t)l * ld + j] * gF[j];
-      acc = warp_sum(acc);
-      if (lane == 0) w.dnu[(size_t)b * m + l] = -acc;
-    }
-  }
-}
-
-template <typename T>
-cudaError_t launch_bwd_solve(const BwdWs<T>& w, const T* dl_dz, cudaStream_t st) {
-  const size_t smem = (size_t)w.n * sizeof(T);
-  cudaError_t e = cudaFuncSetAttribute(bwd_solve_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  dim3 grid((w.n + kBwdRows - 1) / kBwdRows, w.B);
-  bwd_solve_kernel<T><<<grid, kBwdThreads, smem, st>>>(w, dl_dz);
   return cudaGetLastError();
 }
 
@@ -172,7 +124,6 @@ cudaError_t launch_bwd_grads(const BwdWs<T>& w, const T* dl_dz, const T* x, cons
 
 #define INST(T)                                                                                                       \
   template cudaError_t launch_bwd_mask<T>(const BwdWs<T>&, const T*, const T*, const T*, const T*, cudaStream_t);    \
-  template cudaError_t launch_bwd_solve<T>(const BwdWs<T>&, const T*, cudaStream_t);                       \
   template cudaError_t launch_bwd_grads<T>(const BwdWs<T>&, const T*, const T*, const T*, const T*, const T*,        \
                                            const T*, const T*, const T*, double, T*, T*, T*, T*, T*, T*, cudaStream_t);
 INST(float)

@@ -14,8 +14,8 @@
 // One CTA per problem.  The lower triangle lives in HBM/L2 (np x np, np = n + m padded to 64 with an
 // identity block); step k inverts the 32 x 32 pivot tile in shared memory, forms the column panels
 // V = A[:,k] and W = V * inv(A_kk) (stored k-major so the trailing update reads them as 16-byte
-// vectors), and applies the rank-32 update C -= W V^T to every 64 x 64 lower macro tile with
-// 4 x 4 register tiles.  After np/32 steps the buffer holds -(H^-1); the epilogue negates,
+// vectors), and applies the rank-32 update C -= W V^T to every 64 x 64 lower macro tile on the tensor
+// cores (3xTF32 mma.sync for fp32, DMMA for fp64).  After np/32 steps the buffer holds -(H^-1); the epilogue negates,
 // mirrors and compacts it into the row stride the iteration kernel streams.
 #include "layout.cuh"
 
@@ -23,109 +23,322 @@ namespace lqpb {
 
 constexpr int kGroup = 256;        // threads per macro-tile group (16 x 16 threads, 4 x 4 each)
 
+#ifdef LQPB_PHASE_TIMERS
+__device__ long long g_phase_cycles[16];
+#define PHASE_T0() long long t__ = clock64()
+#define PHASE_ADD(k) do { __syncthreads(); if (blockIdx.x == 0 && threadIdx.x == 0) { long long n__ = clock64(); \
+    g_phase_cycles[k] += n__ - t__; t__ = n__; } } while (0)
+#else
+#define PHASE_T0()
+#define PHASE_ADD(k)
+#endif
+
 template <typename T> struct GjCfg;
 template <> struct GjCfg<float>  { static constexpr int NT = 1024; };
 template <> struct GjCfg<double> { static constexpr int NT = 512; };
 
-template <typename T, int NT>
-__global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
-  constexpr int NG = NT / kGroup;
+// ---------------------------------------------------------------------------------------------
+// Rank-32 update of one 64 x 64 macro tile, C -= W V^T, by a group of 256 threads with the two 32 x 64
+// panel tiles staged k-major in shared memory ("staged" path: used when the panels of a whole step do
+// not fit in shared memory, i.e. fp64 and np > 512).
+//   fp64: DMMA (mma.sync m8n8k4, the only tensor-core path that takes fp64 operands), 8 warps as 2 x 4,
+//         each a 32 x 16 sub-tile; row stride 68 makes every fragment load bank-conflict free.
+//   fp32: 4 x 4 register tiles of FFMA.  (A 3xTF32 mma.sync variant was measured in round 1: not faster --
+//         the update is latency-, not FLOP-bound -- and 10x less accurate, so fp32 stays on the FP32 pipe.)
+template <typename T> struct TileCfg;
+template <> struct TileCfg<float>  { static constexpr int LDS = 64; static constexpr int ARRAYS = 2; };
+template <> struct TileCfg<double> { static constexpr int LDS = 68; static constexpr int ARRAYS = 2; };
+
+// per-group shared scratch: the staged panel tiles, or a 32 x 33 transpose tile in the epilogue
+template <typename T> struct GroupSmem {
+  static constexpr int staged = TileCfg<T>::ARRAYS * kTile * TileCfg<T>::LDS;
+  static constexpr int value = staged > kTile * (kTile + 1) ? staged : kTile * (kTile + 1);
+};
+
+__device__ __forceinline__ void mma_f64(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
+
+// float: smem = [W | V], each [32][64]
+__device__ __forceinline__ void tile_update(float* sm, const float* Wg, const float* Vb, float* Wb, int np, int i_base,
+                                            int j_base, int gt, int bar) {
+  constexpr int L = TileCfg<float>::LDS;
+  float* Wt = sm;
+  float* Vt = sm + kTile * L;
+  bar_sync(bar, kGroup);   // previous tile's reads are done
+  for (int e = gt; e < kTile * kMacro / 4; e += kGroup) {
+    const int kk = e / (kMacro / 4), cc = (e % (kMacro / 4)) * 4;
+    *reinterpret_cast<float4*>(Wt + kk * L + cc) = *reinterpret_cast<const float4*>(Wg + (size_t)kk * np + i_base + cc);
+    *reinterpret_cast<float4*>(Vt + kk * L + cc) = *reinterpret_cast<const float4*>(Vb + (size_t)kk * np + j_base + cc);
+  }
+  bar_sync(bar, kGroup);
+  const int ty = gt / 16, tx = gt % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll 8
+  for (int kk = 0; kk < kTile; ++kk) {
+    const float4 wa = *reinterpret_cast<const float4*>(Wt + kk * L + ty * 4);
+    const float4 vb = *reinterpret_cast<const float4*>(Vt + kk * L + tx * 4);
+    const float w[4] = {wa.x, wa.y, wa.z, wa.w}, v[4] = {vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] += w[a] * v[c];
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    float4* cp = reinterpret_cast<float4*>(Wb + (size_t)(i_base + ty * 4 + a) * np + j_base + tx * 4);
+    float4 cv = *cp;
+    cv.x -= acc[a][0]; cv.y -= acc[a][1]; cv.z -= acc[a][2]; cv.w -= acc[a][3];
+    *cp = cv;
+  }
+}
+
+// double: smem = [W | V], each [32][68] (W negated); DMMA m8n8k4
+__device__ __forceinline__ void tile_update(double* sm, const double* Wg, const double* Vb, double* Wb, int np,
+                                            int i_base, int j_base, int gt, int bar) {
+  constexpr int L = TileCfg<double>::LDS;
+  double* Ws = sm;
+  double* Vs = sm + kTile * L;
+  bar_sync(bar, kGroup);
+  for (int e = gt; e < kTile * kMacro / 2; e += kGroup) {
+    const int kk = e / (kMacro / 2), cc = (e % (kMacro / 2)) * 2;
+    double2 w2 = *reinterpret_cast<const double2*>(Wg + (size_t)kk * np + i_base + cc);
+    const double2 v2 = *reinterpret_cast<const double2*>(Vb + (size_t)kk * np + j_base + cc);
+    w2.x = -w2.x; w2.y = -w2.y;
+    *reinterpret_cast<double2*>(Ws + kk * L + cc) = w2;
+    *reinterpret_cast<double2*>(Vs + kk * L + cc) = v2;
+  }
+  bar_sync(bar, kGroup);
+  const int warp = gt >> 5, lane = gt & 31, gid = lane >> 2, tig = lane & 3;
+  const int wi = (warp >> 2) * 32, wj = (warp & 3) * 16;
+  double acc[4][2][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int nj = 0; nj < 2; ++nj) {
+      const double2 c = *reinterpret_cast<const double2*>(Wb + (size_t)(i_base + wi + mi * 8 + gid) * np + j_base + wj +
+                                                          nj * 8 + 2 * tig);
+      acc[mi][nj][0] = c.x; acc[mi][nj][1] = c.y;
+    }
+#pragma unroll
+  for (int k4 = 0; k4 < kTile; k4 += 4) {
+    double af[4], bf[2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) af[mi] = Ws[(k4 + tig) * L + wi + mi * 8 + gid];
+#pragma unroll
+    for (int nj = 0; nj < 2; ++nj) bf[nj] = Vs[(k4 + tig) * L + wj + nj * 8 + gid];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int nj = 0; nj < 2; ++nj) mma_f64(acc[mi][nj], af[mi], bf[nj]);
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int nj = 0; nj < 2; ++nj)
+      *reinterpret_cast<double2*>(Wb + (size_t)(i_base + wi + mi * 8 + gid) * np + j_base + wj + nj * 8 + 2 * tig) =
+          make_double2(acc[mi][nj][0], acc[mi][nj][1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resident-panel path: one warp updates a 16 x 32 sub-tile  C -= W V^T  from the k-major panels in shared
+// memory (row stride lp): lanes form a 4 x 8 grid with a 4 x 4 register tile each; the C loads are issued
+// first and stay in flight during the k loop.
+// (Measured in round 1 and rejected for fp32: mma.sync TF32 with the 3xTF32 split.  With zero-initialised
+//  accumulators it is as accurate as FFMA, but the legacy HMMA path on sm_100 runs at about FFMA rate, so
+//  three MMAs per product made the update 13% slower.  Only tcgen05 would pay off here -- see DESIGN.md.)
+template <typename T>
+__device__ __forceinline__ void subtile_update(const T* Wg, const T* Vb, int lp, T* Wb, int np, int i0, int j0,
+                                               int lane) {
   constexpr int VN = Vec<T>::N;
   using V4 = typename Vec<T>::type;
-  __shared__ T Ps[kTile][kTile + 1];
-  extern __shared__ __align__(16) unsigned char gj_smem[];
-  T(*Wt)[kTile][kMacro] = reinterpret_cast<T(*)[kTile][kMacro]>(gj_smem);   // [NG][32][64] k-major W panel tile
-  T(*Vt)[kTile][kMacro] = Wt + NG;                                          // [NG][32][64] k-major V panel tile
+  i0 += (lane >> 3) * 4;
+  j0 += (lane & 7) * 4;
+  T cr[4][4], acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int q = 0; q < 4; q += VN)
+      *reinterpret_cast<V4*>(&cr[r][q]) = *reinterpret_cast<const V4*>(Wb + (size_t)(i0 + r) * np + j0 + q);
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = T(0);
+#pragma unroll 8
+  for (int kk = 0; kk < kTile; ++kk) {
+    T wa[4], vb[4];
+#pragma unroll
+    for (int q = 0; q < 4; q += VN) {
+      *reinterpret_cast<V4*>(&wa[q]) = *reinterpret_cast<const V4*>(Wg + (size_t)kk * lp + i0 + q);
+      *reinterpret_cast<V4*>(&vb[q]) = *reinterpret_cast<const V4*>(Vb + (size_t)kk * lp + j0 + q);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] += wa[r] * vb[c];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cr[r][c] -= acc[r][c];
+#pragma unroll
+    for (int q = 0; q < 4; q += VN)
+      *reinterpret_cast<V4*>(Wb + (size_t)(i0 + r) * np + j0 + q) = *reinterpret_cast<V4*>(&cr[r][q]);
+  }
+}
 
+// Symmetric sweep of the 32 x 32 pivot tile by 4 warps (threads t = 0..127; thread = column t % 32, rows
+// t / 32 + 4 q), ping-pong between two shared tiles so that each of the 32 steps needs one 128-thread
+// named barrier.  The tile starts in P0 and, after an even number of steps, ends in P0 = -(A_kk)^-1.
+constexpr int kSweepBar = 8;        // named barrier id of the 4 sweep warps
+template <typename T>
+__device__ __forceinline__ void sweep_pivot_tile(T (*P0)[kTile + 1], T (*P1)[kTile + 1], int t) {
+  const int c = t & 31, w = t >> 5;
+  T(*src)[kTile + 1] = P0;
+  T(*dst)[kTile + 1] = P1;
+  for (int s = 0; s < kTile; ++s) {
+    const T piv = T(1) / src[s][s];
+    const T asc = src[s][c];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int r = w + 4 * q;
+      const T ars = src[r][s], arc = src[r][c];
+      T v;
+      if (r == s) v = (c == s) ? -piv : asc * piv;
+      else v = (c == s) ? ars * piv : arc - ars * asc * piv;
+      dst[r][c] = v;
+    }
+    bar_sync(kSweepBar, 128);
+    T(*tmp)[kTile + 1] = src; src = dst; dst = tmp;
+  }
+}
+
+// LDL = false: full symmetric sweep, the buffer ends as -(M^-1) and the epilogue extracts K11 / K21 / K22.
+// LDL = true : elimination restricted to the trailing sub-matrix (block LDL^T, one third of the flops),
+//              forward substitution of the embedded right-hand side on the fly, back substitution at the
+//              end: solves M d = [-dpi*dl_dz; 0] for the backward pass without forming the inverse.
+// RES = true : the two k-major column panels of a step (2 x 32 x np elements) stay resident in shared
+//              memory; the trailing update then needs no staging and no barriers: every warp walks its own
+//              16 x 32 sub-tiles (4 x 4 per lane), with the C loads in flight during the k loop.
+// RES = false: panels in HBM/L2 scratch (Vg/Wg), macro tiles staged per 256-thread group (tile_update).
+template <typename T, int NT, bool LDL, bool RES>
+__global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
+  constexpr int NG = NT / kGroup;
+  constexpr int NW = NT / 32;
+  constexpr int VN = Vec<T>::N;
+  using V4 = typename Vec<T>::type;
+  __shared__ T Pbuf[2][kTile][kTile + 1];     // pivot tiles: current step / look-ahead (and sweep ping-pong)
+  __shared__ int pool_next;                    // RES: dynamic warp-tile counter of the trailing update
+  extern __shared__ __align__(16) unsigned char gj_smem[];
+  constexpr int kGroupSmem = GroupSmem<T>::value;                           // elements of per-group scratch
   const int n = a.n, m = a.m, np = a.np;
-  const int b = blockIdx.x, tid = threadIdx.x;
+  T* tiles = reinterpret_cast<T*>(gj_smem);                                 // staged: [NG][kGroupSmem]; RES: V | W panels
+  const int lp = RES ? np + 8 : np;                                         // row stride of the k-major panels
+  const int scratch_elems = (RES && 2 * kTile * lp > NG * kGroupSmem) ? 2 * kTile * lp : NG * kGroupSmem;
+  T* ys = tiles + scratch_elems;                                            // [np] LDL: running rhs (forward subst.)
+  T* wv = ys + np;                                                          // [np] LDL: D^-1 L^-1 rhs, then the solution
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   T* Wb = a.W + (size_t)b * np * np;
-  T* Vb = a.Vg + (size_t)b * np * kTile;    // k-major: Vb[c * np + i]
-  T* Wg = a.Wg + (size_t)b * np * kTile;
+  T* Vb = RES ? tiles : a.Vg + (size_t)b * np * kTile;                      // k-major: Vb[c * lp + i]
+  T* Wg = RES ? tiles + kTile * lp : a.Wg + (size_t)b * np * kTile;
   const T* srcb = a.src + (size_t)b * n * a.lds;
   const T* maskb = a.mask ? a.mask + (size_t)b * a.ldm : nullptr;
   const T* Ab = (m > 0) ? a.Arows + (size_t)b * m * a.lda : nullptr;
   const T shift = (a.diag_shift ? a.diag_shift[b] : T(0)) + a.diag_const;
 
+  PHASE_T0();
   // ---- prologue: lower triangle of the KKT matrix [[H, A^T], [A, a_diag I]] embedded in the np x np
   //      work matrix: H masked / shifted, the m equality rows right below it (inside the padding that
-  //      the tiling needs anyway), identity on the rest of the padding.
-  for (int idx = tid; idx < np * np; idx += NT) {
-    const int i = idx / np, j = idx - i * np;
-    if (j > i) continue;
-    T v = T(0);
-    if (i < n) {   // j <= i < n
-      const T fi = maskb ? maskb[i] : T(1), fj = maskb ? maskb[j] : T(1);
-      const bool keep = (fi != T(0)) && (fj != T(0));
-      if (keep) v = srcb[(size_t)i * a.lds + j];
-      if (i == j) v = keep ? v + shift : T(1);
-    } else if (i < n + m) {
-      if (j < n) {
-        v = Ab[(size_t)(i - n) * a.lda + j];
-        if (maskb) v *= maskb[j];
-      } else if (i == j) {
-        v = a.a_diag;
+  //      the tiling needs anyway), identity on the rest of the padding.  One warp per row, coalesced.
+  for (int i = warp; i < np; i += NW) {
+    T* wrow = Wb + (size_t)i * np;
+    if (i < n) {
+      const T fi = maskb ? maskb[i] : T(1);
+      const T* srow = srcb + (size_t)i * a.lds;
+      for (int j = lane; j <= i; j += 32) {
+        const T fj = maskb ? maskb[j] : T(1);
+        const bool keep = (fi != T(0)) && (fj != T(0));
+        T v = keep ? srow[j] : T(0);
+        if (i == j) v = keep ? v + shift : T(1);
+        wrow[j] = v;
       }
-    } else if (i == j) {
-      v = T(1);
+    } else if (i < n + m) {
+      const T* arow = Ab + (size_t)(i - n) * a.lda;
+      for (int j = lane; j <= i; j += 32) {
+        T v = T(0);
+        if (j < n) v = maskb ? arow[j] * maskb[j] : arow[j];
+        else if (j == i) v = a.a_diag;
+        wrow[j] = v;
+      }
+    } else {
+      for (int j = lane; j <= i; j += 32) wrow[j] = (j == i) ? T(1) : T(0);
     }
-    Wb[idx] = v;
+  }
+  if (LDL) {
+    for (int i = tid; i < np; i += NT) {
+      ys[i] = (i < n) ? -(maskb[i] * a.rhs_g[(size_t)b * n + i]) : T(0);   // [-dpi*dl_dz; 0]  (:368-375)
+      wv[i] = T(0);
+    }
   }
   __syncthreads();
+  PHASE_ADD(0);
 
   const int nt = np / kTile;        // sweep steps
   const int nm = np / kMacro;       // macro tiles per side
   const int nmac = nm * (nm + 1) / 2;
   const int g = tid / kGroup, gt = tid % kGroup;
-  const int ty = gt / 16, tx = gt % 16;
 
   for (int k = 0; k < nt; ++k) {
     const int k0 = k * kTile;
-    // ---- A: pivot tile -> shared (mirrored), swept in place: Ps <- -(A_kk)^-1
-    for (int e = tid; e < kTile * kTile; e += NT) {
-      const int r = e / kTile, c = e % kTile;
-      Ps[r][c] = r >= c ? Wb[(size_t)(k0 + r) * np + k0 + c] : Wb[(size_t)(k0 + c) * np + k0 + r];
-    }
-    __syncthreads();
-    for (int s = 0; s < kTile; ++s) {
-      T nv[(kTile * kTile + NT - 1) / NT];
-      const T piv = T(1) / Ps[s][s];
-      int q = 0;
-      for (int e = tid; e < kTile * kTile; e += NT, ++q) {
+    // ---- A: the swept pivot tile Ps = -(A_kk)^-1.  RES: it was produced during the previous step's
+    //         trailing update (look-ahead), except for k = 0.  While warps 0-3 sweep, the other warps copy
+    //         the column panel V = A[:, k] k-major: rows below the pivot block are contiguous 128-byte
+    //         segments, rows above are stored transposed in block row k (LDL: rows above are finished,
+    //         their panel entries are zero).
+    T(*Ps)[kTile + 1] = Pbuf[k & 1];
+    T(*Pscratch)[kTile + 1] = Pbuf[(k & 1) ^ 1];
+    const bool need_sweep = !RES || k == 0;
+    if (need_sweep) {
+      for (int e = tid; e < kTile * kTile; e += NT) {
         const int r = e / kTile, c = e % kTile;
-        const T ars = Ps[r][s], asc = Ps[s][c], arc = Ps[r][c];
-        T v;
-        if (r == s && c == s) v = -piv;
-        else if (r == s) v = asc * piv;
-        else if (c == s) v = ars * piv;
-        else v = arc - ars * asc * piv;
-        nv[q] = v;
+        Ps[r][c] = r >= c ? Wb[(size_t)(k0 + r) * np + k0 + c] : Wb[(size_t)(k0 + c) * np + k0 + r];
       }
       __syncthreads();
-      q = 0;
-      for (int e = tid; e < kTile * kTile; e += NT, ++q) Ps[e / kTile][e % kTile] = nv[q];
-      __syncthreads();
     }
-    // ---- B: column panels V (before) and W = V * inv(A_kk) = -(V * Ps), k-major in HBM/L2.
-    // Pass 1 copies the panel (rows below the pivot block are contiguous, rows above are stored
-    // transposed); pass 2 re-reads it (L1/L2 hits, coalesced) in 4 chunks of 8 outputs to keep registers low.
-    for (int idx = tid; idx < np * (kTile / VN); idx += NT) {
-      const int i = idx / (kTile / VN), cv = (idx % (kTile / VN)) * VN;   // consecutive threads -> one 128B row segment
-      if (i >= k0 + kTile) {
-        const V4 t4 = *reinterpret_cast<const V4*>(Wb + (size_t)i * np + k0 + cv);
-        const T* tp = reinterpret_cast<const T*>(&t4);
+    if (need_sweep && tid < 128) {
+      sweep_pivot_tile<T>(Ps, Pscratch, tid);
+    } else {
+      const int first = need_sweep ? 128 : 0;
+      for (int i = tid - first; i < np; i += NT - first) {
+        if (i >= k0 + kTile) {
+          const V4* rowp = reinterpret_cast<const V4*>(Wb + (size_t)i * np + k0);
 #pragma unroll
-        for (int q = 0; q < VN; ++q) Vb[(size_t)(cv + q) * np + i] = tp[q];
-      } else if (i >= k0) {
+          for (int cv = 0; cv < kTile / VN; ++cv) {
+            const V4 t4 = rowp[cv];
+            const T* tp = reinterpret_cast<const T*>(&t4);
 #pragma unroll
-        for (int q = 0; q < VN; ++q) Vb[(size_t)(cv + q) * np + i] = T(0);
+            for (int q = 0; q < VN; ++q) Vb[(size_t)(cv * VN + q) * lp + i] = tp[q];
+          }
+        } else if (i >= k0) {
+#pragma unroll
+          for (int c = 0; c < kTile; ++c) Vb[(size_t)c * lp + i] = T(0);
+        } else {
+#pragma unroll 8
+          for (int c = 0; c < kTile; ++c) Vb[(size_t)c * lp + i] = LDL ? T(0) : Wb[(size_t)(k0 + c) * np + i];
+        }
       }
-    }
-    for (int idx = tid; idx < k0 * kTile; idx += NT) {
-      const int c = idx / k0, i = idx - c * k0;            // consecutive threads -> consecutive i
-      Vb[(size_t)c * np + i] = Wb[(size_t)(k0 + c) * np + i];
     }
     __syncthreads();
+    PHASE_ADD(1);
+    // ---- B: W = V * inv(A_kk) = -(V * Ps), k-major panel; the swept panel is also written straight back
+    //         into the matrix (the trailing update adds zero to block row / column k, so the order is safe).
     for (int idx = tid; idx < np * 4; idx += NT) {
       const int c0 = (idx / np) * 8, i = idx % np;         // consecutive threads -> consecutive i
       T acc[8];
@@ -133,78 +346,118 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
       for (int q = 0; q < 8; ++q) acc[q] = T(0);
 #pragma unroll 8
       for (int c = 0; c < kTile; ++c) {
-        const T vc = Vb[(size_t)c * np + i];
+        const T vc = Vb[(size_t)c * lp + i];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] -= vc * Ps[c][c0 + q];
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) Wg[(size_t)(c0 + q) * np + i] = acc[q];
-    }
-    __syncthreads();
-    // ---- C: rank-32 update of every lower 64 x 64 macro tile, one group of 256 threads per tile
-    for (int t = g; t < nmac; t += NG) {
-      int I = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
-      while ((I + 1) * (I + 2) / 2 <= t) ++I;
-      while (I * (I + 1) / 2 > t) --I;
-      const int J = t - I * (I + 1) / 2;
-      const int i_base = I * kMacro, j_base = J * kMacro;
-      bar_sync(1 + g, kGroup);   // previous tile's reads of Wt/Vt are done
-      for (int e = gt; e < kTile * kMacro / VN; e += kGroup) {
-        const int kk = e / (kMacro / VN), cc = (e % (kMacro / VN)) * VN;
-        *reinterpret_cast<V4*>(&Wt[g][kk][cc]) = *reinterpret_cast<const V4*>(Wg + (size_t)kk * np + i_base + cc);
-        *reinterpret_cast<V4*>(&Vt[g][kk][cc]) = *reinterpret_cast<const V4*>(Vb + (size_t)kk * np + j_base + cc);
+      for (int q = 0; q < 8; ++q) Wg[(size_t)(c0 + q) * lp + i] = acc[q];
+      if (i >= k0 + kTile) {                               // rows below: 32 contiguous bytes of row i
+#pragma unroll
+        for (int q = 0; q < 8; q += VN)
+          *reinterpret_cast<V4*>(Wb + (size_t)i * np + k0 + c0 + q) = *reinterpret_cast<V4*>(&acc[q]);
+      } else if (!LDL && i < k0) {                         // rows above: transposed, coalesced along i
+#pragma unroll
+        for (int q = 0; q < 8; ++q) Wb[(size_t)(k0 + c0 + q) * np + i] = acc[q];
       }
-      bar_sync(1 + g, kGroup);
-      T acc[4][4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][c] = T(0);
-#pragma unroll 8
-      for (int kk = 0; kk < kTile; ++kk) {
-        T wa[4], vb[4];
-#pragma unroll
-        for (int q = 0; q < 4; q += VN) {
-          *reinterpret_cast<V4*>(&wa[q]) = *reinterpret_cast<const V4*>(&Wt[g][kk][ty * 4 + q]);
-          *reinterpret_cast<V4*>(&vb[q]) = *reinterpret_cast<const V4*>(&Vt[g][kk][tx * 4 + q]);
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[a][c] += wa[a] * vb[c];
-      }
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        T* cp = Wb + (size_t)(i_base + ty * 4 + a) * np + j_base + tx * 4;
-#pragma unroll
-        for (int q = 0; q < 4; q += VN) {
-          V4 cv = *reinterpret_cast<V4*>(cp + q);
-          T* cvp = reinterpret_cast<T*>(&cv);
-#pragma unroll
-          for (int r = 0; r < VN; ++r) cvp[r] -= acc[a][q + r];
-          *reinterpret_cast<V4*>(cp + q) = cv;
-        }
-      }
-    }
-    __syncthreads();
-    // ---- D: write the swept column panel and pivot tile back
-    for (int idx = tid; idx < k0 * kTile; idx += NT) {          // rows above the pivot block: stored transposed
-      const int c = idx / k0, i = idx - c * k0;                   // consecutive threads -> consecutive i
-      Wb[(size_t)(k0 + c) * np + i] = Wg[(size_t)c * np + i];
-    }
-    for (int idx = tid; idx < (np - k0 - kTile) * kTile; idx += NT) {   // rows below: consecutive threads -> consecutive c
-      const int i = k0 + kTile + idx / kTile, c = idx % kTile;
-      Wb[(size_t)i * np + k0 + c] = Wg[(size_t)c * np + i];
     }
     for (int e = tid; e < kTile * kTile; e += NT) {
       const int r = e / kTile, c = e % kTile;
       if (r >= c) Wb[(size_t)(k0 + r) * np + k0 + c] = Ps[r][c];
     }
+    if (tid == 0) pool_next = 0;
     __syncthreads();
+    PHASE_ADD(2);
+    if (LDL) {
+      // forward substitution with this block column: z_k = ys[k0..], w_k = inv(A_kk) z_k, ys[i] -= L_ik z_k
+      if (tid < kTile) {
+        T acc = T(0);
+        for (int c = 0; c < kTile; ++c) acc -= Ps[tid][c] * ys[k0 + c];
+        wv[k0 + tid] = acc;
+      }
+      for (int i = k0 + kTile + tid; i < np; i += NT) {
+        T acc = T(0);
+#pragma unroll 8
+        for (int c = 0; c < kTile; ++c) acc += Wg[(size_t)c * lp + i] * ys[k0 + c];
+        ys[i] -= acc;
+      }
+    }
+    PHASE_ADD(3);
+    // ---- C: rank-32 update of the lower 64 x 64 macro tiles (LDL: trailing ones only)
+    const int I0 = LDL ? (k0 + kTile) / kMacro : 0;
+    const int nma = LDL ? (nm - I0) * (nm - I0 + 1) / 2 : nmac;
+    if (RES) {
+      // Look-ahead: warps 0-3 first update the macro tile that holds the NEXT pivot tile, read it back and
+      // sweep it into the other pivot buffer while the remaining warps work through the other sub-tiles;
+      // sub-tiles are handed out through a shared counter, so the four warps simply join in late.
+      const int k1 = k0 + kTile;
+      const int t_la = (k + 1 < nt) ? ((k1 / kMacro - I0) * (k1 / kMacro - I0 + 1) / 2 + (k1 / kMacro - I0)) : -1;
+      auto do_subtile = [&](int wt) {
+        const int t = wt >> 3, sub = wt & 7;
+        int I = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+        while ((I + 1) * (I + 2) / 2 <= t) ++I;
+        while (I * (I + 1) / 2 > t) --I;
+        const int J = t - I * (I + 1) / 2 + I0;
+        I += I0;
+        subtile_update(Wg, Vb, lp, Wb, np, I * kMacro + (sub >> 1) * 16, J * kMacro + (sub & 1) * 32, lane);
+      };
+      if (t_la >= 0 && warp < 4) {
+        do_subtile(t_la * 8 + warp);
+        do_subtile(t_la * 8 + 4 + warp);
+        bar_sync(kSweepBar, 128);
+        T(*Pn)[kTile + 1] = Pbuf[(k + 1) & 1];
+        for (int e = tid; e < kTile * kTile; e += 128) {
+          const int r = e / kTile, c = e % kTile;
+          Pn[r][c] = r >= c ? Wb[(size_t)(k1 + r) * np + k1 + c] : Wb[(size_t)(k1 + c) * np + k1 + r];
+        }
+        bar_sync(kSweepBar, 128);
+        sweep_pivot_tile<T>(Pn, Pbuf[k & 1], tid);
+      }
+      while (true) {
+        int wt = 0;
+        if (lane == 0) wt = atomicAdd(&pool_next, 1);
+        wt = __shfl_sync(0xffffffffu, wt, 0);
+        if (wt >= nma * 8) break;
+        if ((wt >> 3) == t_la) continue;
+        do_subtile(wt);
+      }
+    } else {
+      for (int t = g; t < nma; t += NG) {
+        int I = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
+        while ((I + 1) * (I + 2) / 2 <= t) ++I;
+        while (I * (I + 1) / 2 > t) --I;
+        const int J = t - I * (I + 1) / 2 + I0;
+        I += I0;
+        tile_update(tiles + g * kGroupSmem, Wg, Vb, Wb, np, I * kMacro, J * kMacro, gt, 1 + g);
+      }
+    }
+    __syncthreads();
+    PHASE_ADD(4);
   }
 
+  if (LDL) {
+    // ---- back substitution d_k = w_k - sum_{I>k} L_Ik^T d_I, bottom up; wv becomes the solution in place
+    T* red = reinterpret_cast<T*>(gj_smem);      // [NT/32][32] (the panel tiles are no longer needed)
+    for (int k = nt - 1; k >= 0; --k) {
+      const int k0 = k * kTile;
+      T acc = T(0);
+      for (int i = k0 + kTile + warp; i < np; i += NW) acc += Wb[(size_t)i * np + k0 + lane] * wv[i];
+      red[warp * 32 + lane] = acc;
+      __syncthreads();
+      if (tid < kTile) {
+        T tot = T(0);
+        for (int q = 0; q < NW; ++q) tot += red[q * 32 + tid];
+        wv[k0 + tid] -= tot;
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < a.ldd; i += NT) a.sol_x[(size_t)b * a.ldd + i] = i < n ? wv[i] : T(0);
+    for (int l = tid; l < m; l += NT) a.sol_nu[(size_t)b * m + l] = wv[n + l];
+    return;
+  }
   // ---- epilogue: -(Wb) = KKT^-1 = [[K11, K21^T], [K21, K22]]; K11 is mirrored to a full symmetric n x n
-  //      matrix with row stride ldd, K21 (m x n) and K22 (m x m) go to their own buffers.
+  //      matrix with row stride ldd, K21 (m x n) and K22 (m x m) go to their own buffers.  Each group of
+  //      256 threads transposes its own 32 x 32 tiles through shared memory.
   T* dstb = a.dst + (size_t)b * n * a.ldd;
   T* g21 = (m > 0) ? a.G21 + (size_t)b * m * a.ldd : nullptr;
   T* k22 = (m > 0) ? a.K22 + (size_t)b * m * m : nullptr;
@@ -217,28 +470,31 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
       else if (gj < n + m) k22[(size_t)(gi - n) * m + (gj - n)] = val;
     }
   };
-  T(*ts)[kTile + 1] = Ps;
+  T* ts = tiles + g * kGroupSmem;     // [32][33] per group
   const int ntl = nt * (nt + 1) / 2;
-  for (int t = 0; t < ntl; ++t) {
+  for (int t = g; t < ntl; t += NG) {
     int I = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
     while ((I + 1) * (I + 2) / 2 <= t) ++I;
     while (I * (I + 1) / 2 > t) --I;
     const int J = t - I * (I + 1) / 2;
-    if (J * kTile >= n + m) continue;      // identity padding only
-    __syncthreads();
-    for (int e = tid; e < kTile * kTile; e += NT) {
-      const int r = e / kTile, c = e % kTile;
-      const int gi = I * kTile + r, gj = J * kTile + c;
-      T v = T(0);
-      if (I != J || r >= c) v = Wb[(size_t)gi * np + gj];
-      else v = Wb[(size_t)gj * np + gi];   // diagonal tile: mirror inside the tile
-      ts[r][c] = -v;
+    bar_sync(1 + g, kGroup);
+    if (J * kTile < n + m) {
+      for (int e = gt; e < kTile * kTile; e += kGroup) {
+        const int r = e / kTile, c = e % kTile;
+        const int gi = I * kTile + r, gj = J * kTile + c;
+        T v;
+        if (I != J || r >= c) v = Wb[(size_t)gi * np + gj];
+        else v = Wb[(size_t)gj * np + gi];   // diagonal tile: mirror inside the tile
+        ts[r * (kTile + 1) + c] = -v;
+      }
     }
-    __syncthreads();
-    for (int e = tid; e < kTile * kTile; e += NT) {
-      const int r = e / kTile, c = e % kTile;
-      emit(I * kTile + r, J * kTile + c, ts[r][c]);
-      if (I != J) emit(J * kTile + r, I * kTile + c, ts[c][r]);   // transposed tile, coalesced along c
+    bar_sync(1 + g, kGroup);
+    if (J * kTile < n + m) {
+      for (int e = gt; e < kTile * kTile; e += kGroup) {
+        const int r = e / kTile, c = e % kTile;
+        emit(I * kTile + r, J * kTile + c, ts[r * (kTile + 1) + c]);
+        if (I != J) emit(J * kTile + r, I * kTile + c, ts[c * (kTile + 1) + r]);   // transposed tile, coalesced along c
+      }
     }
   }
   // zero the row padding so that padded columns never contribute
@@ -249,6 +505,7 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
       else g21[(size_t)(i - n) * ldd + j] = T(0);
     }
   }
+  PHASE_ADD(6);
   // c = K12 b~ = K21^T b~  (constant part of the x-update)
   if (a.c_out) {
     __syncthreads();
@@ -262,15 +519,34 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
   }
 }
 
-template <typename T>
-cudaError_t launch_gj_inverse(int B, const GjArgs<T>& a, cudaStream_t st) {
+template <typename T, bool LDL, bool RES>
+static cudaError_t launch_gj_res(int B, const GjArgs<T>& a, size_t smem, cudaStream_t st) {
   constexpr int NT = GjCfg<T>::NT;
-  const size_t smem = (size_t)2 * (NT / kGroup) * kTile * kMacro * sizeof(T);
-  cudaError_t e = cudaFuncSetAttribute(gj_inverse_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(gj_inverse_kernel<T, NT, LDL, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
   if (e != cudaSuccess) return e;
-  gj_inverse_kernel<T, NT><<<B, NT, smem, st>>>(a);
+  gj_inverse_kernel<T, NT, LDL, RES><<<B, NT, smem, st>>>(a);
   return cudaGetLastError();
 }
+template <bool LDL>
+static cudaError_t launch_gj(int B, const GjArgs<float>& a, cudaStream_t st) {
+  size_t res_elems = (size_t)2 * kTile * (a.np + 8);
+  const size_t grp_elems = (size_t)(GjCfg<float>::NT / kGroup) * GroupSmem<float>::value;
+  if (res_elems < grp_elems) res_elems = grp_elems;
+  const size_t res_smem = (res_elems + 2 * (size_t)a.np) * sizeof(float);
+  if (res_smem <= 200 * 1024) return launch_gj_res<float, LDL, true>(B, a, res_smem, st);
+  const size_t smem = ((size_t)(GjCfg<float>::NT / kGroup) * GroupSmem<float>::value + 2 * (size_t)a.np) * sizeof(float);
+  return launch_gj_res<float, LDL, false>(B, a, smem, st);
+}
+template <bool LDL>
+static cudaError_t launch_gj(int B, const GjArgs<double>& a, cudaStream_t st) {
+  const size_t smem = ((size_t)(GjCfg<double>::NT / kGroup) * GroupSmem<double>::value + 2 * (size_t)a.np) * sizeof(double);
+  return launch_gj_res<double, LDL, false>(B, a, smem, st);
+}
+template <typename T>
+cudaError_t launch_gj_inverse(int B, const GjArgs<T>& a, cudaStream_t st) { return launch_gj<false>(B, a, st); }
+template <typename T>
+cudaError_t launch_ldl_solve(int B, const GjArgs<T>& a, cudaStream_t st) { return launch_gj<true>(B, a, st); }
 
 // ---------------------------------------------------------------------------------------------
 // rho selection (:156-158, :200-203): rho = 0 if the whole batch is unbounded, the Frobenius
@@ -293,9 +569,22 @@ cudaError_t launch_select_rho(const lqpb_config& cfg, const FwdWs<T>& w, cudaStr
 
 #define INST(T)                                                                                \
   template cudaError_t launch_gj_inverse<T>(int, const GjArgs<T>&, cudaStream_t);              \
+  template cudaError_t launch_ldl_solve<T>(int, const GjArgs<T>&, cudaStream_t);               \
   template cudaError_t launch_select_rho<T>(const lqpb_config&, const FwdWs<T>&, cudaStream_t);
 INST(float)
 INST(double)
 #undef INST
 
 }  // namespace lqpb
+
+#ifdef LQPB_PHASE_TIMERS
+// developer aid (tools/gj_phases.py): per-phase clock64 totals of block 0
+extern "C" void lqpb_debug_phase_cycles(long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, lqpb::g_phase_cycles, sizeof(long long) * 16);
+  if (reset) {
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(lqpb::g_phase_cycles, z, sizeof(z));
+  }
+}
+#endif

@@ -72,12 +72,9 @@ inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
 template <typename T>
 struct BwdWs {
   int B, n, m, ld, np;
-  T* Minv;      // B*n*ld   inverse of the masked system matrix (symmetric)
-  T* W;         // B*np*np
+  T* W;         // B*np*np  LDL^T work matrix (lower triangle)
   T *Vg, *Wg;   // B*np*kTile
   T *mask, *dv; // B*ld
-  T* G21;       // B*m*ld   K21 of the masked KKT inverse
-  T* K22;       // B*m*m
   T* dnu;       // B*m
   size_t bytes;
 };
@@ -96,14 +93,11 @@ inline BwdWs<T> carve_bwd(void* base, int B, int n, int m) {
     return r;
   };
   const size_t Bn = (size_t)B;
-  w.Minv = (T*)take(Bn * n * w.ld, sizeof(T));
   w.W = (T*)take(Bn * w.np * w.np, sizeof(T));
   w.Vg = (T*)take(Bn * w.np * kTile, sizeof(T));
   w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
   w.mask = (T*)take(Bn * w.ld, sizeof(T));
   w.dv = (T*)take(Bn * w.ld, sizeof(T));
-  w.G21 = (T*)take(Bn * (m > 0 ? m : 1) * w.ld, sizeof(T));
-  w.K22 = (T*)take(Bn * (m > 0 ? m * m : 1), sizeof(T));
   w.dnu = (T*)take(Bn * (m > 0 ? m : 1), sizeof(T));
   w.bytes = off;
   return w;
@@ -130,9 +124,13 @@ struct GjArgs {
   T* G21;                         // K21 (B*m*ldd)
   T* K22;                         // K22 (B*m*m)
   const T* bt; T* c_out;          // optional: c = K21^T b~ (B*ldd)
+  // LDL-solve mode only (backward): right-hand side [-mask*rhs_g; 0], solution [sol_x (B*ldd); sol_nu (B*m)]
+  const T* rhs_g; T* sol_x; T* sol_nu;
 };
 template <typename T>
 cudaError_t launch_gj_inverse(int B, const GjArgs<T>& a, cudaStream_t st);
+template <typename T>
+cudaError_t launch_ldl_solve(int B, const GjArgs<T>& a, cudaStream_t st);
 template <typename T>
 cudaError_t launch_select_rho(const lqpb_config& cfg, const FwdWs<T>& w, cudaStream_t st);
 
@@ -146,8 +144,6 @@ cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho
 // backward.cu -- K5/K6
 template <typename T>
 cudaError_t launch_bwd_mask(const BwdWs<T>& w, const T* x, const T* u, const T* lb, const T* ub, cudaStream_t st);
-template <typename T>
-cudaError_t launch_bwd_solve(const BwdWs<T>& w, const T* dl_dz, cudaStream_t st);
 template <typename T>
 cudaError_t launch_bwd_grads(const BwdWs<T>& w, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
                              const T* Q, const T* A, const T* rho_dev, double rho_scalar, T* dQ, T* dp, T* dA, T* db,

@@ -84,12 +84,12 @@ template <typename T>
 int factor_forward(const FwdWs<T>& w, cudaStream_t st) {
   GjArgs<T> a{};
   a.n = w.n; a.m = w.m; a.np = w.np;
-  a.src = w.Qs; a.lds = w.ld;
+  a.src = w.Qp; a.lds = 0;          // packed symmetric Q~ (scale.cu)
   a.diag_shift = w.rho; a.diag_const = T(0);
   a.mask = nullptr; a.ldm = 0;
   a.Arows = w.At; a.lda = w.ld; a.a_diag = T(0);
   a.W = w.W; a.Vg = w.Vg; a.Wg = w.Wg;
-  a.dst = w.K; a.ldd = w.ld; a.G21 = w.Gt; a.K22 = w.Sinv;
+  a.dst = w.Kp; a.ldd = w.ld; a.G21 = w.Gt; a.K22 = w.Sinv;
   a.bt = w.bt; a.c_out = w.m > 0 ? w.c : nullptr;
   CK(launch_gj_inverse<T>(w.B, a, st), "gj_inverse (forward)");
   g_prof.launches += 1;

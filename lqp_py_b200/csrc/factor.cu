@@ -15,8 +15,8 @@
 // identity block); step k inverts the 32 x 32 pivot tile in shared memory, forms the column panels
 // V = A[:,k] and W = V * inv(A_kk) (stored k-major so the trailing update reads them as 16-byte
 // vectors), and applies the rank-32 update C -= W V^T to every 64 x 64 lower macro tile on the tensor
-// cores (3xTF32 mma.sync for fp32, DMMA for fp64).  After np/32 steps the buffer holds -(H^-1); the epilogue negates,
-// mirrors and compacts it into the row stride the iteration kernel streams.
+// cores (3xTF32 mma.sync for fp32, DMMA for fp64).  After np/32 steps the buffer holds -(M^-1); the epilogue negates
+// it and writes K11 in the packed symmetric layout (lower triangle, layout.cuh Pack<T>) the iteration kernel streams.
 #include "layout.cuh"
 
 namespace lqpb {
@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
   T* Wb = a.W + (size_t)b * np * np;
   T* Vb = RES ? tiles : a.Vg + (size_t)b * np * kTile;                      // k-major: Vb[c * lp + i]
   T* Wg = RES ? tiles + kTile * lp : a.Wg + (size_t)b * np * kTile;
-  const T* srcb = a.src + (size_t)b * n * a.lds;
+  const bool packed_src = a.lds == 0;
+  const int ntv_src = Pack<T>::nt(n);
+  const T* srcb = packed_src ? a.src + (size_t)b * Pack<T>::elems(n) : a.src + (size_t)b * n * a.lds;
   const T* maskb = a.mask ? a.mask + (size_t)b * a.ldm : nullptr;
   const T* Ab = (m > 0) ? a.Arows + (size_t)b * m * a.lda : nullptr;
   const T shift = (a.diag_shift ? a.diag_shift[b] : T(0)) + a.diag_const;
@@ -265,7 +267,15 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
       for (int j = lane; j <= i; j += 32) {
         const T fj = maskb ? maskb[j] : T(1);
         const bool keep = (fi != T(0)) && (fj != T(0));
-        T v = keep ? srow[j] : T(0);
+        T v = T(0);
+        if (keep) {
+          if (packed_src) {
+            v = srcb[Pack<T>::offset(i, j, ntv_src)];
+            if (i == j) v += v;                 // the packed layout stores the diagonal halved
+          } else {
+            v = srow[j];
+          }
+        }
         if (i == j) v = keep ? v + shift : T(1);
         wrow[j] = v;
       }
@@ -455,55 +465,41 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
     for (int l = tid; l < m; l += NT) a.sol_nu[(size_t)b * m + l] = wv[n + l];
     return;
   }
-  // ---- epilogue: -(Wb) = KKT^-1 = [[K11, K21^T], [K21, K22]]; K11 is mirrored to a full symmetric n x n
-  //      matrix with row stride ldd, K21 (m x n) and K22 (m x m) go to their own buffers.  Each group of
-  //      256 threads transposes its own 32 x 32 tiles through shared memory.
-  T* dstb = a.dst + (size_t)b * n * a.ldd;
-  T* g21 = (m > 0) ? a.G21 + (size_t)b * m * a.ldd : nullptr;
-  T* k22 = (m > 0) ? a.K22 + (size_t)b * m * m : nullptr;
-  const int ldd = a.ldd;
-  auto emit = [&](int gi, int gj, T val) {
-    if (gi < n) {
-      if (gj < n) dstb[(size_t)gi * ldd + gj] = val;
-    } else if (gi < n + m) {
-      if (gj < n) g21[(size_t)(gi - n) * ldd + gj] = val;
-      else if (gj < n + m) k22[(size_t)(gi - n) * m + (gj - n)] = val;
-    }
-  };
-  T* ts = tiles + g * kGroupSmem;     // [32][33] per group
-  const int ntl = nt * (nt + 1) / 2;
-  for (int t = g; t < ntl; t += NG) {
-    int I = (int)((sqrtf(8.f * t + 1.f) - 1.f) * 0.5f);
-    while ((I + 1) * (I + 2) / 2 <= t) ++I;
-    while (I * (I + 1) / 2 > t) --I;
-    const int J = t - I * (I + 1) / 2;
-    bar_sync(1 + g, kGroup);
-    if (J * kTile < n + m) {
-      for (int e = gt; e < kTile * kTile; e += kGroup) {
-        const int r = e / kTile, c = e % kTile;
-        const int gi = I * kTile + r, gj = J * kTile + c;
-        T v;
-        if (I != J || r >= c) v = Wb[(size_t)gi * np + gj];
-        else v = Wb[(size_t)gj * np + gi];   // diagonal tile: mirror inside the tile
-        ts[r * (kTile + 1) + c] = -v;
-      }
-    }
-    bar_sync(1 + g, kGroup);
-    if (J * kTile < n + m) {
-      for (int e = gt; e < kTile * kTile; e += kGroup) {
-        const int r = e / kTile, c = e % kTile;
-        emit(I * kTile + r, J * kTile + c, ts[r * (kTile + 1) + c]);
-        if (I != J) emit(J * kTile + r, I * kTile + c, ts[c * (kTile + 1) + r]);   // transposed tile, coalesced along c
+  // ---- epilogue: -(Wb) = KKT^-1 = [[K11, K21^T], [K21, K22]].  K11 goes out in the packed symmetric layout the
+  //      iteration kernel streams (lower triangle only, diagonal halved: Pack<T>), one warp per 4 KB tile with the
+  //      lanes along the tile columns (coalesced row segments in, full lines out); K21 (m x n, row stride ldd,
+  //      zero padded) and K22 (m x m) go to their own small buffers.
+  {
+    using P = Pack<T>;
+    T* dstb = a.dst + (size_t)b * P::elems(n);
+    const int ntv = P::nt(n), ntl = P::ntiles(n);
+    const int c = lane % P::TC, kc = c / P::VN, ec = c % P::VN;
+    for (int t = warp; t < ntl; t += NW) {
+      int Jc = 0, rem = t;
+      while (rem >= ntv - Jc / P::R) { rem -= ntv - Jc / P::R; ++Jc; }
+      const int I = Jc / P::R + rem;
+      T* tp = dstb + (size_t)t * P::TILE;
+      const int j = Jc * P::TC + c;
+#pragma unroll 4
+      for (int l0 = 0; l0 < kPackRows; l0 += P::R) {
+        const int l = l0 + lane / P::TC, i = I * kPackRows + l;
+        T v = T(0);
+        if (i < n && j <= i) {
+          v = -Wb[(size_t)i * np + j];
+          if (i == j) v *= T(0.5);
+        }
+        tp[l * P::TC + ((kc + l) & 7) * P::VN + ec] = v;
       }
     }
   }
-  // zero the row padding so that padded columns never contribute
-  if (ldd > n) {
-    for (int idx = tid; idx < (n + m) * (ldd - n); idx += NT) {
-      const int i = idx / (ldd - n), j = n + idx % (ldd - n);
-      if (i < n) dstb[(size_t)i * ldd + j] = T(0);
-      else g21[(size_t)(i - n) * ldd + j] = T(0);
-    }
+  T* g21 = (m > 0) ? a.G21 + (size_t)b * m * a.ldd : nullptr;
+  T* k22 = (m > 0) ? a.K22 + (size_t)b * m * m : nullptr;
+  const int ldd = a.ldd;
+  for (int r = warp; r < m; r += NW) {
+    const T* wrow = Wb + (size_t)(n + r) * np;
+    for (int j = lane; j < ldd; j += 32) g21[(size_t)r * ldd + j] = j < n ? -wrow[j] : T(0);
+    for (int q = lane; q < m; q += 32)
+      k22[(size_t)r * m + q] = q <= r ? -wrow[n + q] : -Wb[(size_t)(n + q) * np + n + r];
   }
   PHASE_ADD(6);
   // c = K12 b~ = K21^T b~  (constant part of the x-update)

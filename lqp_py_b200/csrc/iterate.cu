@@ -7,95 +7,95 @@
 //   :271-282  z = clamp(x + u), r = x - z, s = rho (z - z_prev), u += r
 //   :285-313  every check_solved iterations: six inf-norms (one needs Q~ x), tolerances, and the
 //             GLOBAL stop test "all problems optimal"
-//   :327      nus = (last KKT solve)[n:] * E   ->  here  nu = S^-1 (G^T rhs - b~) * E
+//   :327      nus = (last KKT solve)[n:] * E   ->  here  nu = K21 rhs + K22 b~, times E
 //
-// Design: one persistent CTA per problem (problems are strided over the grid when B exceeds the
-// number of resident CTAs).  A dedicated producer warp streams the symmetric operator K11 -- the
-// only O(n^2) data of an iteration -- from HBM into a shared-memory ring with 1-D bulk TMA copies
-// (cp.async.bulk + mbarrier complete_tx); it runs ahead across iteration boundaries because K11
-// does not change, so HBM never idles while the consumers do the O(n) vector update.  Because K11
-// is symmetric, a row panel is also a column panel: consumer thread (g, t) owns 16 bytes of
-// columns and accumulates  x[cols] += K[r][cols] * rhs[r]  over the panel rows r = g mod NG --
-// conflict-free 16-byte shared loads, no shuffles; the NG partial sums are combined once per
-// iteration.  All problems advance in lock step and stop together: every check_solved
-// iterations each CTA publishes its flags, a grid barrier (atomic counter) makes the decision
-// global, exactly like torch.all(is_optimal) in the reference.  No host round trip per iteration.
+// Design: one persistent CTA per problem (problems are strided over the grid when B exceeds the number
+// of resident CTAs).  The only O(n^2) data of an iteration is the symmetric operator K11 (and Q~ at the
+// checks); both are stored as packed lower triangles (layout.cuh Pack<T>: 4 KB tiles, block-column major,
+// chunk-rotated rows, halved diagonal), so an iteration streams n(n+32)/2 instead of n^2 elements -- at
+// dz=500, B=128 the fp32 operator set (70 MB) even stays resident in the 126 MB L2 across iterations.
+// The tile sequence of a matrix is cut into one contiguous run per warp.  Every warp owns a private ring
+// of `depth` 4 KB slots and feeds it itself with 1-D bulk TMA copies (cp.async.bulk + mbarrier
+// complete_tx): after consuming a slot, lane 0 immediately re-arms it with the tile `depth` positions
+// ahead in the warp's own stream -- which runs on across pass and iteration boundaries because the
+// operators do not change, so the memory system never idles during the O(n) vector phase and there is no
+// producer/consumer handshake between warps at all.  A tile T (block row I, block column J) is applied
+// symmetrically from shared memory: lane l reads row l (conflict-free thanks to the rotation) and
+// accumulates  x_I[l] += T[l,:] v_J  (one register) and  x_J[:] += T[l,:] v_I[l]  (TC registers, combined
+// across lanes with a butterfly of shuffles once per block column).  Partial sums go to a per-warp
+// slice of shared memory with a fixed summation order: results are deterministic and independent of the
+// position of a problem in the batch.  All problems advance in lock step and stop together: every
+// check_solved iterations each CTA publishes its flags and a grid barrier (atomic counter) makes the
+// decision global, exactly like torch.all(is_optimal) in the reference.  No host round trip per iteration.
+#include <cstdlib>
 #include "layout.cuh"
 
 namespace lqpb {
 
-constexpr int kIterConsumers = 512;
-constexpr int kIterThreads = kIterConsumers + 32;   // + one producer warp
-constexpr int kConsBar = 1;                         // named barrier of the consumer threads
-constexpr int kMaxChunks = 4;                       // max 16-byte column chunks per consumer thread
+constexpr int kIterMaxWarps = 16;
+constexpr int kIterMaxThreads = kIterMaxWarps * 32;
+constexpr int kIterMaxDepth = 8;
 
 struct IterGeom {
-  int tpr;          // threads per panel row (each owns `cpt` 16-byte chunks of columns)
-  int ng;           // row groups; group g owns the `rpg` contiguous panel rows [g*rpg, (g+1)*rpg)
-  int cpt;          // chunks per thread (template parameter of the kernel)
-  int rpg;          // rows per group and panel (1..8, dispatched to unrolled code)
-  int rows;         // rows per panel (stage) = ng * rpg; every panel is full: the last one is shifted
-                    // up to end at row n and the rows it shares with its predecessor are masked out
-  int panels;       // panels per matrix
-  int stages;       // ring depth
-  int stage_elems;  // elements per stage
+  int nwarps;       // warps per CTA (each owns a run of tiles and a private ring)
+  int depth;        // ring slots (4 KB tiles) per warp
+  int nt;           // block rows of the packed layout
+  int nbc;          // block columns
+  int ntiles;       // tiles per matrix
+  int np;           // padded vector length = 32 * nt
 };
 
-// One panel of the column sweep: acc[c][:] += sum_rr K[g*rpg + rr][cols_c] * v[g*rpg + rr].
-template <typename T, int CPT, int RPG>
-__device__ __forceinline__ void sweep_panel(const T* __restrict__ P, const T* __restrict__ vp, int skip, int row_base,
-                                            int ld, int col0, int col_stride, T (&acc)[CPT][Vec<T>::N]) {
-  constexpr int VN = Vec<T>::N;
-  using V4 = typename Vec<T>::type;
-  T vr[RPG];
+// Butterfly transpose-reduce: on entry lane l holds its own partial sums acc[0..TC) for the TC columns of a
+// block column; on exit acc[0] of lane l is the total (over the 32 lanes) of column (l mod TC).
+template <typename T, int TC>
+__device__ __forceinline__ void reduce_cols(T (&acc)[TC], int lane) {
+  if (TC == 16) {
 #pragma unroll
-  for (int rr = 0; rr < RPG; ++rr) vr[rr] = (row_base + rr >= skip) ? vp[row_base + rr] : T(0);
+    for (int k = 0; k < TC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
+  }
 #pragma unroll
-  for (int rr = 0; rr < RPG; ++rr) {
+  for (int s = (TC == 32 ? 16 : 8); s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const int col = col0 + c * col_stride;
-      if (CPT == 1 || col < ld) {
-        const V4 kv = *reinterpret_cast<const V4*>(P + (size_t)(row_base + rr) * ld + col);
-        const T* kp = reinterpret_cast<const T*>(&kv);
-#pragma unroll
-        for (int e = 0; e < VN; ++e) acc[c][e] += kp[e] * vr[rr];
-      }
+    for (int k = 0; k < s; ++k) {
+      const T send = up ? acc[k] : acc[k + s];
+      const T keep = up ? acc[k + s] : acc[k];
+      acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
     }
   }
 }
 
-template <typename T, int CPT>
-__global__ void __launch_bounds__(kIterThreads, 1)
+template <typename T>
+__global__ void __launch_bounds__(kIterMaxThreads, 1)
 iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, IterGeom geo) {
-  constexpr int VN = Vec<T>::N;
+  using P = Pack<T>;
+  constexpr int VN = P::VN, TC = P::TC, TILE = P::TILE;
   using V4 = typename Vec<T>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int n = w.n, m = w.m, ld = w.ld;
-  T* ring = reinterpret_cast<T*>(smem_raw);
-  T* part = ring + (size_t)geo.stages * geo.stage_elems;   // [ng][ld]
-  T* v = part + (size_t)geo.ng * ld;                        // [ld] rhs of the x-update
-  T* xs = v + ld;                                           // [ld] x~ of this iteration
-  T* Ds = xs + ld;                                          // [ld] D
-  T* tdot = Ds + ld;                                        // [max(m,1)] G^T rhs
+  const int n = w.n, m = w.m, ld = w.ld, np = geo.np;
+  const int nthreads = blockDim.x, nwarps = geo.nwarps, depth = geo.depth;
+  const int ntv = geo.nt, ntiles = geo.ntiles;
+  T* ring = reinterpret_cast<T*>(smem_raw);                 // [nwarps][depth][TILE]
+  T* xpart = ring + (size_t)nwarps * depth * TILE;          // [nwarps][np] per-warp partial sums of K v
+  T* v = xpart + (size_t)nwarps * np;                       // [np] rhs of the x-update (zero padded)
+  T* xs = v + np;                                           // [np] x~ of this iteration (zero padded)
+  T* Ds = xs + np;                                          // [np] D
+  T* tdot = Ds + np;                                        // [max(m,1)] K21 rhs
   T* red = tdot + (m > 0 ? round_up(m, 4) : 4);             // [6][16] reduction scratch
-  uint64_t* full = reinterpret_cast<uint64_t*>(red + 6 * 16 + 4);
-  uint64_t* empty = full + geo.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 6 * 16 + 4);   // [nwarps][depth]
   __shared__ int s_dec[4];
 
   const int tid = threadIdx.x;
   const int wid = tid >> 5, lane = tid & 31;
-  const bool is_producer = wid == (kIterConsumers >> 5);
   const int nprob = (w.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   Ctrl* ctrl = w.ctrl;
 
   if (tid == 0) {
-    for (int s = 0; s < geo.stages; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kIterConsumers >> 5);
-    }
+    for (int s = 0; s < nwarps * depth; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
+  for (int e = tid; e < nwarps * np; e += nthreads) xpart[e] = T(0);
+  for (int e = tid; e < np; e += nthreads) { v[e] = T(0); xs[e] = T(0); Ds[e] = T(1); }
   __syncthreads();
 
   const bool any_lb = ctrl->any_lb != 0, any_ub = ctrl->any_ub != 0;
@@ -104,15 +104,106 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
   const T eps_abs = (T)cfg.eps_abs, eps_rel = (T)cfg.eps_rel, zc = (T)cfg.zero_clamp;
   const T thr = (T)cfg.adaptive_rho_threshold, ar_tol = (T)cfg.adaptive_rho_tol, ar_tol_inv = (T)(1.0 / cfg.adaptive_rho_tol);
 
-  // consumer thread geometry
-  const int g = tid / geo.tpr, t = tid % geo.tpr;
-  const bool gemv_active = !is_producer && g < geo.ng && t * VN < ld;
-  const int nwc = kIterConsumers >> 5;
-  const int R = geo.rows;
-  const int last_start = n - R;      // first row of the (shifted) last panel
+  // ---- this warp's run of tiles (the same for every matrix) and the tile it starts with
+  const int run_lo = (int)((long long)wid * ntiles / nwarps);
+  const int run_len = (int)((long long)(wid + 1) * ntiles / nwarps) - run_lo;
+  int Jc_first = 0, I_first = 0;
+  {
+    int rem = run_lo;
+    while (Jc_first < geo.nbc && rem >= ntv - Jc_first / P::R) { rem -= ntv - Jc_first / P::R; ++Jc_first; }
+    I_first = Jc_first / P::R + rem;
+  }
+  T* const ring_w = ring + (size_t)wid * depth * TILE;
+  uint64_t* const full_w = full + wid * depth;
+  T* const xp = xpart + (size_t)wid * np;
 
-  int stage = 0;            // ring position and phase: same schedule in producer and consumers
-  uint32_t phase = 0;
+  // ---- the warp's tile stream: position of the next tile to fetch (p_*) and ring bookkeeping.  The stream
+  //      is  for i: for problem k: K11 run, then (check iterations) Q~ run;  it is fetched `depth` tiles ahead.
+  int p_i = i0, p_k = 0, p_pass = 0, p_r = 0, p_slot = 0;
+  int c_slot = 0;
+  uint32_t c_phase = 0;
+  int in_flight = 0;
+  uint64_t pol_keep = 0, pol_stream = 0;
+  if (lane == 0) { pol_keep = l2_policy_evict_last(); pol_stream = l2_policy_evict_first(); }
+  auto issue_next = [&]() {
+    if (run_len == 0 || p_i >= cfg.max_iters) return;
+    if (lane == 0) {
+      const int b = blockIdx.x + p_k * gridDim.x;
+      const T* src = (p_pass == 0 ? w.Kp : w.Qp) + ((size_t)b * ntiles + run_lo + p_r) * TILE;
+      mbar_arrive_expect_tx(&full_w[p_slot], (uint32_t)(TILE * sizeof(T)));
+      tma_load_1d_hint(ring_w + (size_t)p_slot * TILE, src, (uint32_t)(TILE * sizeof(T)), &full_w[p_slot],
+                       p_pass == 0 ? pol_keep : pol_stream);
+    }
+    ++in_flight;
+    if (++p_slot == depth) p_slot = 0;
+    if (++p_r == run_len) {
+      p_r = 0;
+      if (++p_pass == ((p_i % check) == 0 ? 2 : 1)) {
+        p_pass = 0;
+        if (++p_k == nprob) { p_k = 0; ++p_i; }
+      }
+    }
+  };
+  for (int d = 0; d < depth; ++d) issue_next();
+
+  // ---- one symmetric pass over the warp's run:  xp += (this warp's share of)  S vec,  S = K11 or Q~
+  auto sym_pass = [&](const T* vec) {
+    if (run_len == 0) return;
+    int Jc = Jc_first, I = I_first;
+    T vJ[TC], colacc[TC];
+    auto load_vJ = [&]() {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const V4 t4 = *reinterpret_cast<const V4*>(vec + Jc * TC + k * VN);
+        const T* tp = reinterpret_cast<const T*>(&t4);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) vJ[k * VN + e] = tp[e];
+      }
+#pragma unroll
+      for (int c = 0; c < TC; ++c) colacc[c] = T(0);
+    };
+    auto flush_cols = [&]() {
+      reduce_cols<T, TC>(colacc, lane);
+      __syncwarp();
+      if (lane < TC) xp[Jc * TC + lane] += colacc[0];
+      __syncwarp();
+    };
+    load_vJ();
+    bool dirty = false;
+    for (int r = 0; r < run_len; ++r) {
+      mbar_wait(&full_w[c_slot], c_phase);
+      const T* tp = ring_w + (size_t)c_slot * TILE + lane * TC;
+      V4 kv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) kv[k] = *reinterpret_cast<const V4*>(tp + ((k + lane) & 7) * VN);
+      const T vI = vec[I * kPackRows + lane];
+      T rs[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const T* kp = reinterpret_cast<const T*>(&kv[k]);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          rs[k & 3] += kp[e] * vJ[k * VN + e];
+          colacc[k * VN + e] += kp[e] * vI;
+        }
+      }
+      xp[I * kPackRows + lane] += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+      __syncwarp();                       // every lane has consumed the slot: it can be re-armed
+      if (++c_slot == depth) { c_slot = 0; c_phase ^= 1u; }
+      --in_flight;
+      issue_next();
+      dirty = true;
+      if (++I == ntv) {
+        flush_cols();
+        dirty = false;
+        ++Jc;
+        I = Jc / P::R;
+        if (r + 1 < run_len) load_vJ();
+      }
+    }
+    if (dirty) flush_cols();
+  };
+
   bool have_v = false;      // v already holds the rhs of this iteration (single-problem CTAs)
   int i = i0;
   int status = 0;
@@ -123,14 +214,12 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
     if (cfg.adaptive_rho && i > 0 && i < cfg.adaptive_rho_max_iter && (i % cfg.adaptive_rho_iter) == 0 &&
         !(i == i0 && skip_rho_check)) {
       if (last_wants && last_rout) {
-        if (!is_producer) {
-          for (int k = tid; k < nprob; k += kIterConsumers) {
-            const int b = blockIdx.x + k * gridDim.x;
-            if (w.wants[b]) {
-              T r = w.rho[b] * w.ratio[b];
-              r = t_min(t_max(r, (T)cfg.rho_min), (T)cfg.rho_max);
-              w.rho[b] = r;
-            }
+        for (int k = tid; k < nprob; k += nthreads) {
+          const int b = blockIdx.x + k * gridDim.x;
+          if (w.wants[b]) {
+            T r = w.rho[b] * w.ratio[b];
+            r = t_min(t_max(r, (T)cfg.rho_min), (T)cfg.rho_max);
+            w.rho[b] = r;
           }
         }
         status = 3;
@@ -141,200 +230,129 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
     const bool is_last = i == cfg.max_iters - 1;
     const bool maybe_final = is_check || is_last;
 
-    if (is_producer) {
-      // ======================= producer warp: stream K11 (and Q~ at checks) through the ring
-      if (lane == 0) {
-        for (int k = 0; k < nprob; ++k) {
-          const int b = blockIdx.x + k * gridDim.x;
-          for (int pass = 0; pass < (is_check ? 2 : 1); ++pass) {
-            const T* src = (pass == 0 ? w.K : w.Qs) + (size_t)b * n * ld;
-            const uint32_t bytes = (uint32_t)(R * ld * sizeof(T));
-            for (int pn = 0; pn < geo.panels; ++pn) {
-              mbar_wait(&empty[stage], phase ^ 1u);
-              const int start = min(pn * R, last_start);
-              mbar_arrive_expect_tx(&full[stage], bytes);
-              tma_load_1d(ring + (size_t)stage * geo.stage_elems, src + (size_t)start * ld, bytes, &full[stage]);
-              if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
-            }
-          }
-        }
+    int cta_notopt = 0, cta_wants = 0, cta_rout = 0;
+    for (int k = 0; k < nprob; ++k) {
+      const int b = blockIdx.x + k * gridDim.x;
+      const size_t vo = (size_t)b * ld;
+      const T rho = w.rho[b];
+      if (!have_v) {
+        for (int e = tid; e < n; e += nthreads) v[e] = -w.pt[vo + e] + rho * (w.z[vo + e] - w.u[vo + e]);
+        __syncthreads();
       }
-      __syncwarp();
-    } else {
-      // ======================= consumers
-      int cta_notopt = 0, cta_wants = 0, cta_rout = 0;
-      for (int k = 0; k < nprob; ++k) {
-        const int b = blockIdx.x + k * gridDim.x;
-        const size_t vo = (size_t)b * ld;
-        const T rho = w.rho[b];
-        if (!have_v) {
-          for (int e = tid; e < ld; e += kIterConsumers)
-            v[e] = e < n ? -w.pt[vo + e] + rho * (w.z[vo + e] - w.u[vo + e]) : T(0);
-          bar_sync(kConsBar, kIterConsumers);
+      // ---- x~ = K11 v (+ c below): symmetric sweep over the packed tiles
+      sym_pass(v);
+      __syncthreads();
+      // ---- K21 rhs for nu (:327), from the rhs of THIS solve (before v is overwritten)
+      if (maybe_final && m > 0) {
+        const T* Gt = w.Gt + (size_t)b * m * ld;
+        for (int l = wid; l < m; l += nwarps) {
+          T d = T(0);
+          for (int e = lane; e < n; e += 32) d += Gt[(size_t)l * ld + e] * v[e];
+          d = warp_sum(d);
+          if (lane == 0) tdot[l] = d;
         }
-        // ---- x~ = K11 v : column sweep over the streamed row panels
-        T acc[CPT][VN];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c)
-#pragma unroll
-          for (int e = 0; e < VN; ++e) acc[c][e] = T(0);
-        {
-          const int row_base = g * geo.rpg, col0 = t * VN, cstride = geo.tpr * VN;
-          for (int pn = 0; pn < geo.panels; ++pn) {
-            mbar_wait(&full[stage], phase);
-            if (gemv_active) {
-              const int start = min(pn * R, last_start);
-              const int skip = pn * R - start;          // rows already covered by the previous panel
-              const T* P = ring + (size_t)stage * geo.stage_elems;
-              const T* vp = v + start;
-              switch (geo.rpg) {
-                case 1: sweep_panel<T, CPT, 1>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
-                case 2: sweep_panel<T, CPT, 2>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
-                case 3: sweep_panel<T, CPT, 3>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
-                case 4: sweep_panel<T, CPT, 4>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
-                case 5: sweep_panel<T, CPT, 5>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
-                case 6: sweep_panel<T, CPT, 6>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
-                case 7: sweep_panel<T, CPT, 7>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
-                default: sweep_panel<T, CPT, 8>(P, vp, skip, row_base, ld, col0, cstride, acc); break;
-              }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
-          }
+        __syncthreads();
+      }
+      // ---- element-wise ADMM update (:271-282) and the rhs of the next iteration (:259-262)
+      T mx_p = T(0), mx_d = T(0), mx_x = T(0), mx_z = T(0), mx_y = T(0);
+      for (int e = tid; e < n; e += nthreads) {
+        T x = T(0);
+        for (int ww = 0; ww < nwarps; ++ww) {
+          x += xpart[(size_t)ww * np + e];
+          xpart[(size_t)ww * np + e] = T(0);
         }
-        if (gemv_active) {
-#pragma unroll
-          for (int c = 0; c < CPT; ++c) {
-            const int col = (t + c * geo.tpr) * VN;
-            if (CPT == 1 || col < ld) {
-#pragma unroll
-              for (int e = 0; e < VN; ++e) part[(size_t)g * ld + col + e] = acc[c][e];
-            }
-          }
-        }
-        bar_sync(kConsBar, kIterConsumers);
-        // ---- K21 rhs for nu (:327), from the rhs of THIS solve (before v is overwritten)
-        if (maybe_final && m > 0) {
-          const T* Gt = w.Gt + (size_t)b * m * ld;
-          for (int l = wid; l < m; l += nwc) {
-            T d = T(0);
-            for (int e = lane; e < n; e += 32) d += Gt[(size_t)l * ld + e] * v[e];
-            d = warp_sum(d);
-            if (lane == 0) tdot[l] = d;
-          }
-          bar_sync(kConsBar, kIterConsumers);
-        }
-        // ---- element-wise ADMM update (:271-282) and the rhs of the next iteration (:259-262)
-        T mx_p = T(0), mx_d = T(0), mx_x = T(0), mx_z = T(0), mx_y = T(0);
-        for (int e = tid; e < n; e += kIterConsumers) {
-          T x = T(0);
-          for (int gg = 0; gg < geo.ng; ++gg) x += part[(size_t)gg * ld + e];
-          x += w.c[vo + e];
-          const T z_prev = w.z[vo + e], u_prev = w.u[vo + e];
-          T zn = x + u_prev;
-          if (any_lb) zn = t_max(zn, w.lbt[vo + e]);
-          if (any_ub) zn = t_min(zn, w.ubt[vo + e]);
-          const T r = x - zn;
-          const T sres = rho * (zn - z_prev);
-          const T un = u_prev + r;
-          w.z[vo + e] = zn;
-          w.u[vo + e] = un;
-          v[e] = -w.pt[vo + e] + rho * (zn - un);
-          if (maybe_final) {
-            xs[e] = x;
-            w.xs[vo + e] = x;
-          }
-          if (is_check) {
-            const T d = w.D[vo + e];
-            Ds[e] = d;
-            mx_p = t_max(mx_p, t_abs(d * r));
-            mx_d = t_max(mx_d, t_abs(d * sres));
-            mx_x = t_max(mx_x, t_abs(d * x));
-            mx_z = t_max(mx_z, t_abs(d * zn));
-            mx_y = t_max(mx_y, t_abs(rho * d * un));
-          }
-        }
-        if (maybe_final)
-          for (int e = n + tid; e < ld; e += kIterConsumers) xs[e] = T(0);
-        have_v = (nprob == 1);
-        bar_sync(kConsBar, kIterConsumers);
-        if (maybe_final && m > 0 && tid < m) {     // nu = K21 rhs + K22 b~, unscaled by E (:327)
-          const T* K22 = w.Sinv + (size_t)b * m * m;
-          T a = tdot[tid];
-          for (int l = 0; l < m; ++l) a += K22[tid * m + l] * w.bt[(size_t)b * m + l];
-          nus_out[(size_t)b * m + tid] = a * w.E[(size_t)b * m + tid];
+        x += w.c[vo + e];
+        const T z_prev = w.z[vo + e], u_prev = w.u[vo + e];
+        T zn = x + u_prev;
+        if (any_lb) zn = t_max(zn, w.lbt[vo + e]);
+        if (any_ub) zn = t_min(zn, w.ubt[vo + e]);
+        const T r = x - zn;
+        const T sres = rho * (zn - z_prev);
+        const T un = u_prev + r;
+        w.z[vo + e] = zn;
+        w.u[vo + e] = un;
+        v[e] = -w.pt[vo + e] + rho * (zn - un);
+        if (maybe_final) {
+          xs[e] = x;
+          w.xs[vo + e] = x;
         }
         if (is_check) {
-          // ---- ||Q~ x~ / D||_inf (:299): row dots over the streamed Q~ panels, one warp per row
-          T mx_q = T(0);
-          for (int pn = 0; pn < geo.panels; ++pn) {
-            mbar_wait(&full[stage], phase);
-            const int start = min(pn * R, last_start);
-            const int skip = pn * R - start;
-            const T* P = ring + (size_t)stage * geo.stage_elems;
-            for (int r = skip + wid; r < R; r += nwc) {
-              T d = T(0);
-              for (int col = lane * VN; col < ld; col += 32 * VN) {
-                const V4 kv = *reinterpret_cast<const V4*>(P + (size_t)r * ld + col);
-                const V4 xv = *reinterpret_cast<const V4*>(xs + col);
-                const T* kp = reinterpret_cast<const T*>(&kv);
-                const T* xp = reinterpret_cast<const T*>(&xv);
-#pragma unroll
-                for (int e = 0; e < VN; ++e) d += kp[e] * xp[e];
-              }
-              d = warp_sum(d);
-              mx_q = t_max(mx_q, t_abs(d / Ds[start + r]));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);
-            if (++stage == geo.stages) { stage = 0; phase ^= 1u; }
-          }
-          // ---- block reduction of the six maxima
-          mx_p = warp_max(mx_p); mx_d = warp_max(mx_d); mx_x = warp_max(mx_x);
-          mx_z = warp_max(mx_z); mx_y = warp_max(mx_y); mx_q = warp_max(mx_q);
-          if (lane == 0) {
-            red[0 * 16 + wid] = mx_p; red[1 * 16 + wid] = mx_d; red[2 * 16 + wid] = mx_x;
-            red[3 * 16 + wid] = mx_z; red[4 * 16 + wid] = mx_y; red[5 * 16 + wid] = mx_q;
-          }
-          bar_sync(kConsBar, kIterConsumers);
-          if (tid == 0) {
-            T mm[6];
-            for (int a = 0; a < 6; ++a) {
-              T r = red[a * 16];
-              for (int ww = 1; ww < nwc; ++ww) r = t_max(r, red[a * 16 + ww]);
-              mm[a] = r;
-            }
-            const T primal = mm[0], dual = mm[1];
-            const T tol_p_rel = t_max(t_max(mm[2], mm[3]), zc);                      // :301
-            const T tol_p = eps_abs + eps_rel * tol_p_rel;                           // :302
-            const T tol_d_rel = t_max(t_max(t_max(mm[4], mm[5]), w.pnorm[b]), zc);   // :303
-            const T tol_d = eps_abs + eps_rel * tol_d_rel;                           // :304
-            const bool optimal = (primal < tol_p) && (dual < tol_d);                // :307-309
-            const bool wants = (primal > t_max(tol_p, thr)) || (dual > t_max(tol_d, thr));   // :310-311
-            const T num = t_max(primal / tol_p_rel, zc), den = t_max(dual / tol_d_rel, zc);  // :239-242
-            const T ratio = t_sqrt(num / den);                                       // :243
-            w.chk[4 * b + 0] = primal; w.chk[4 * b + 1] = dual;
-            w.chk[4 * b + 2] = tol_p_rel; w.chk[4 * b + 3] = tol_d_rel;
-            w.wants[b] = wants ? 1 : 0;
-            w.ratio[b] = ratio;
-            cta_notopt += optimal ? 0 : 1;
-            cta_wants |= wants ? 1 : 0;
-            cta_rout |= (ratio > ar_tol || ratio < ar_tol_inv) ? 1 : 0;              // :244-245
-            if (cfg.verbose) {
-              const int ci = i / check;
-              if (ci < LQPB_LOG_CAP) {
-                atomic_max_nonneg(&ctrl->log_primal[ci], (double)primal);
-                atomic_max_nonneg(&ctrl->log_dual[ci], (double)dual);
-                ctrl->log_iter[ci] = i;
-              }
-            }
-          }
-          bar_sync(kConsBar, kIterConsumers);   // red[] reusable
+          const T d = w.D[vo + e];
+          Ds[e] = d;
+          mx_p = t_max(mx_p, t_abs(d * r));
+          mx_d = t_max(mx_d, t_abs(d * sres));
+          mx_x = t_max(mx_x, t_abs(d * x));
+          mx_z = t_max(mx_z, t_abs(d * zn));
+          mx_y = t_max(mx_y, t_abs(rho * d * un));
         }
       }
-      // ---- publish this CTA's flags and make the decision global (:312 torch.all)
-      if (is_check && tid == 0) {
+      have_v = (nprob == 1);
+      __syncthreads();
+      if (maybe_final && m > 0 && tid < m) {     // nu = K21 rhs + K22 b~, unscaled by E (:327)
+        const T* K22 = w.Sinv + (size_t)b * m * m;
+        T a = tdot[tid];
+        for (int l = 0; l < m; ++l) a += K22[tid * m + l] * w.bt[(size_t)b * m + l];
+        nus_out[(size_t)b * m + tid] = a * w.E[(size_t)b * m + tid];
+      }
+      if (is_check) {
+        // ---- ||Q~ x~ / D||_inf (:299): the same symmetric sweep over the packed Q~ tiles
+        sym_pass(xs);
+        __syncthreads();
+        T mx_q = T(0);
+        for (int e = tid; e < n; e += nthreads) {
+          T y = T(0);
+          for (int ww = 0; ww < nwarps; ++ww) {
+            y += xpart[(size_t)ww * np + e];
+            xpart[(size_t)ww * np + e] = T(0);
+          }
+          mx_q = t_max(mx_q, t_abs(y / Ds[e]));
+        }
+        // ---- block reduction of the six maxima
+        mx_p = warp_max(mx_p); mx_d = warp_max(mx_d); mx_x = warp_max(mx_x);
+        mx_z = warp_max(mx_z); mx_y = warp_max(mx_y); mx_q = warp_max(mx_q);
+        if (lane == 0) {
+          red[0 * 16 + wid] = mx_p; red[1 * 16 + wid] = mx_d; red[2 * 16 + wid] = mx_x;
+          red[3 * 16 + wid] = mx_z; red[4 * 16 + wid] = mx_y; red[5 * 16 + wid] = mx_q;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          T mm[6];
+          for (int a = 0; a < 6; ++a) {
+            T r = red[a * 16];
+            for (int ww = 1; ww < nwarps; ++ww) r = t_max(r, red[a * 16 + ww]);
+            mm[a] = r;
+          }
+          const T primal = mm[0], dual = mm[1];
+          const T tol_p_rel = t_max(t_max(mm[2], mm[3]), zc);                      // :301
+          const T tol_p = eps_abs + eps_rel * tol_p_rel;                           // :302
+          const T tol_d_rel = t_max(t_max(t_max(mm[4], mm[5]), w.pnorm[b]), zc);   // :303
+          const T tol_d = eps_abs + eps_rel * tol_d_rel;                           // :304
+          const bool optimal = (primal < tol_p) && (dual < tol_d);                // :307-309
+          const bool wants = (primal > t_max(tol_p, thr)) || (dual > t_max(tol_d, thr));   // :310-311
+          const T num = t_max(primal / tol_p_rel, zc), den = t_max(dual / tol_d_rel, zc);  // :239-242
+          const T ratio = t_sqrt(num / den);                                       // :243
+          w.chk[4 * b + 0] = primal; w.chk[4 * b + 1] = dual;
+          w.chk[4 * b + 2] = tol_p_rel; w.chk[4 * b + 3] = tol_d_rel;
+          w.wants[b] = wants ? 1 : 0;
+          w.ratio[b] = ratio;
+          cta_notopt += optimal ? 0 : 1;
+          cta_wants |= wants ? 1 : 0;
+          cta_rout |= (ratio > ar_tol || ratio < ar_tol_inv) ? 1 : 0;              // :244-245
+          if (cfg.verbose) {
+            const int ci = i / check;
+            if (ci < LQPB_LOG_CAP) {
+              atomic_max_nonneg(&ctrl->log_primal[ci], (double)primal);
+              atomic_max_nonneg(&ctrl->log_dual[ci], (double)dual);
+              ctrl->log_iter[ci] = i;
+            }
+          }
+        }
+        __syncthreads();   // red[] reusable
+      }
+    }
+    // ---- publish this CTA's flags and make the decision global (:312 torch.all)
+    if (is_check) {
+      if (tid == 0) {
         int* slot = ctrl->slot[(i / check) & 3];
         if (cta_notopt) atomicAdd(&slot[0], cta_notopt);
         if (cta_wants) atomicOr(&slot[1], 1);
@@ -357,8 +375,6 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
           __threadfence();
         }
       }
-    }
-    if (is_check) {
       ++barrier_epoch;
       __syncthreads();
       const int notopt = s_dec[0];
@@ -369,6 +385,12 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
     }
     if (is_last) { status = 2; break; }
     ++i;
+  }
+  // ---- drain the tiles that were fetched ahead (a CTA must not exit with bulk copies in flight)
+  while (in_flight > 0) {
+    mbar_wait(&full_w[c_slot], c_phase);
+    if (++c_slot == depth) { c_slot = 0; c_phase ^= 1u; }
+    --in_flight;
   }
   if (blockIdx.x == 0 && tid == 0) {
     ctrl->status = status;
@@ -397,55 +419,47 @@ __global__ void finalize_kernel(FwdWs<T> w, T* x, T* z, T* u, T* lams, T* rho_ou
   if (e == 0) rho_out[b] = rho;
 }
 
-template <typename T>
-static IterGeom make_geom(const FwdWs<T>& w, size_t* smem_bytes, int max_smem) {
-  IterGeom g{};
-  const int vn = Vec<T>::N;
-  const int chunks = w.ld / vn;
-  int tpr;
-  if (chunks <= 32) { tpr = 1; while (tpr < chunks) tpr <<= 1; }
-  else tpr = round_up(chunks, 32);
-  if (tpr > kIterConsumers) tpr = kIterConsumers;
-  g.tpr = tpr;
-  g.cpt = (chunks + tpr - 1) / tpr;
-  const size_t row_bytes = (size_t)w.ld * sizeof(T);
-  int target = (int)(40960 / row_bytes);          // ~40 KB stages
-  if (target < 1) target = 1;
-  if (target > w.n) target = w.n;
-  int ng = kIterConsumers / tpr;
-  if (ng > 16) ng = 16;
-  while (ng > target) ng >>= 1;                    // power of two <= target rows
-  if (ng < 1) ng = 1;
-  g.ng = ng;
-  int rpg = target / ng;
-  if (rpg > 8) rpg = 8;
-  if (rpg < 1) rpg = 1;
-  // prefer a panel height that divides n (no shifted last panel), searching a little below the target
-  for (int cand = rpg; cand >= 1 && cand >= rpg - 2; --cand)
-    if (w.n % (cand * ng) == 0) { rpg = cand; break; }
-  g.rpg = rpg;
-  g.rows = rpg * ng;
-  g.panels = (w.n + g.rows - 1) / g.rows;
-  g.stage_elems = (int)(round_up_sz((size_t)g.rows * row_bytes, 128) / sizeof(T));
-  const size_t fixed = ((size_t)g.ng * w.ld + 3 * (size_t)w.ld + (w.m > 0 ? round_up(w.m, 4) : 4) + 6 * 16 + 4) * sizeof(T) +
-                       2 * 16 * sizeof(uint64_t) + 256;
-  const size_t stage_bytes = (size_t)g.stage_elems * sizeof(T);
-  int stages = (int)(((size_t)max_smem - fixed) / stage_bytes);
-  if (stages > 8) stages = 8;
-  g.stages = stages;
-  *smem_bytes = fixed + stages * stage_bytes;
-  return g;
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
 }
 
-template <typename T, int CPT>
-static cudaError_t launch_iterate_cpt(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check,
-                                      T* nus_out, IterGeom geo, size_t smem, int grid, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(iterate_kernel<T, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  lqpb_config c = cfg;
-  FwdWs<T> ww = w;
-  void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo};
-  return cudaLaunchCooperativeKernel((void*)iterate_kernel<T, CPT>, dim3(grid), dim3(kIterThreads), args, smem, st);
+// Shared-memory plan: `nwarps` private rings of `depth` 4 KB slots + the per-warp partial sums + vectors.
+// Default: as many warps as fit with at least two slots each (measured on B200: warps matter more than ring
+// depth -- 16 x 2 beats 12 x 4 and 8 x 6 at dz=500), then as many slots as fit; small problems get fewer,
+// busier warps.  LQPB_ITER_WARPS / LQPB_ITER_DEPTH override the plan (tuning aid, tools/iter_tune.py).
+template <typename T>
+static bool make_geom(const FwdWs<T>& w, int max_smem, IterGeom* out, size_t* smem_bytes) {
+  using P = Pack<T>;
+  IterGeom g{};
+  g.nt = P::nt(w.n);
+  g.nbc = P::nbc(w.n);
+  g.ntiles = P::ntiles(w.n);
+  g.np = kPackRows * g.nt;
+  const size_t tile_bytes = (size_t)P::TILE * sizeof(T);
+  auto fixed = [&](int nw) {
+    return ((size_t)nw * g.np + 3 * (size_t)g.np + (w.m > 0 ? round_up(w.m, 4) : 4) + 6 * 16 + 4) * sizeof(T) +
+           (size_t)nw * kIterMaxDepth * sizeof(uint64_t) + 128;
+  };
+  const int want_w = env_int("LQPB_ITER_WARPS", 0), want_d = env_int("LQPB_ITER_DEPTH", 0);
+  int nw_max = kIterMaxWarps;
+  if (!want_w && nw_max > round_up(g.ntiles, 4)) nw_max = round_up(g.ntiles, 4) < 4 ? 4 : round_up(g.ntiles, 4);
+  for (int nw = want_w ? want_w : nw_max; nw >= 4; nw -= 2) {
+    if (nw > kIterMaxWarps) continue;
+    if (fixed(nw) + 2 * nw * tile_bytes > (size_t)max_smem) {
+      if (want_w) return false;
+      continue;
+    }
+    int d = (int)(((size_t)max_smem - fixed(nw)) / (nw * tile_bytes));
+    if (d > kIterMaxDepth) d = kIterMaxDepth;
+    if (want_d && want_d >= 2 && want_d <= d) d = want_d;
+    g.nwarps = nw;
+    g.depth = d;
+    *smem_bytes = fixed(nw) + (size_t)nw * d * tile_bytes;
+    *out = g;
+    return true;
+  }
+  return false;
 }
 
 template <typename T>
@@ -457,14 +471,17 @@ cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, in
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   size_t smem = 0;
-  IterGeom geo = make_geom(w, &smem, max_smem - 1024);
-  if (geo.stages < 2 || geo.cpt > kMaxChunks) return cudaErrorInvalidConfiguration;
+  IterGeom geo{};
+  if (!make_geom(w, max_smem - 1024, &geo, &smem)) return cudaErrorInvalidConfiguration;
   const int grid = w.B < sms ? w.B : sms;   // one CTA per SM: all CTAs co-resident (needed by the grid barrier)
   e = cudaMemsetAsync(&w.ctrl->barrier, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  if (geo.cpt == 1) e = launch_iterate_cpt<T, 1>(cfg, w, i0, skip_rho_check, nus_out, geo, smem, grid, st);
-  else if (geo.cpt == 2) e = launch_iterate_cpt<T, 2>(cfg, w, i0, skip_rho_check, nus_out, geo, smem, grid, st);
-  else e = launch_iterate_cpt<T, 4>(cfg, w, i0, skip_rho_check, nus_out, geo, smem, grid, st);
+  e = cudaFuncSetAttribute(iterate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lqpb_config c = cfg;
+  FwdWs<T> ww = w;
+  void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo};
+  e = cudaLaunchCooperativeKernel((void*)iterate_kernel<T>, dim3(grid), dim3(geo.nwarps * 32), args, smem, st);
   if (launches) ++*launches;
   return e;
 }

@@ -12,11 +12,44 @@ constexpr int kTile = 32;      // Gauss-Jordan tile edge
 constexpr int kMacro = 64;     // macro tile edge of the trailing update (np is a multiple of it)
 constexpr int kMaxM = 64;      // max equality rows handled by the Schur-complement path
 
+// ------------------------------------------------------------------ packed symmetric storage
+// The two O(n^2) operands of the iteration kernel -- the x-update operator K11 and the scaled Q~ -- are
+// symmetric, so only the lower triangle is stored and streamed: half the bytes per ADMM iteration.
+// Layout: tiles of 32 rows x TC columns (TC = 32 floats / 16 doubles: 4 KB either way), ordered by
+// block column Jc and, inside a column, by block row I >= Jc / R (R = 32 / TC) -- a contiguous tile
+// sequence that is cut into per-warp runs and fetched with 1-D bulk TMA.  Inside a tile, row l holds its
+// 8 16-byte chunks rotated by l (chunk k at position (k + l) & 7), so that "lane l reads chunk k of row l"
+// is a bank-conflict-free shared-memory access.  Entries above the diagonal (inside diagonal tiles) and in
+// the padding rows/columns are zero and the diagonal is stored HALVED: every tile can then be applied
+// symmetrically ( x_I += T v_J  and  x_J += T^T v_I ) without a special case for diagonal tiles.
+constexpr int kPackRows = 32;
+template <typename T>
+struct Pack {
+  static constexpr int VN = Vec<T>::N;          // elements per 16-byte chunk
+  static constexpr int TC = 8 * VN;             // tile columns
+  static constexpr int R = kPackRows / TC;      // block columns per block row (1 or 2)
+  static constexpr int TILE = kPackRows * TC;   // elements per tile (4096 bytes)
+  __host__ __device__ static int nt(int n) { return (n + kPackRows - 1) / kPackRows; }
+  __host__ __device__ static int nbc(int n) { return nt(n) * R; }
+  __host__ __device__ static int col_start(int Jc, int ntv) {     // tiles in the block columns before Jc
+    const int q = Jc / R, rem = Jc % R;
+    return Jc * ntv - (R * (q * (q - 1) / 2) + rem * q);
+  }
+  __host__ __device__ static int ntiles(int n) { return col_start(nbc(n), nt(n)); }
+  __host__ __device__ static size_t elems(int n) { return (size_t)ntiles(n) * TILE; }
+  // offset of element (i, j), j <= i
+  __host__ __device__ static size_t offset(int i, int j, int ntv) {
+    const int Jc = j / TC, I = i / kPackRows, l = i % kPackRows, c = j % TC, k = c / VN, e = c % VN;
+    return (size_t)(col_start(Jc, ntv) + I - Jc / R) * TILE + l * TC + ((k + l) & 7) * VN + e;
+  }
+};
+
 template <typename T>
 struct FwdWs {
   int B, n, m, ld, np;
-  T* Qs;        // B*n*ld   scaled Q~ = D Q D            (read at every check: Q~ x~)
-  T* K;         // B*n*ld   x-update operator K11 (symmetric)  -- streamed every iteration
+  T* Qp;        // B*Pack::elems(n)  scaled Q~ = D Q D, packed lower triangle (read at every check: Q~ x~;
+                //                   also the source of the factorisation)
+  T* Kp;        // B*Pack::elems(n)  x-update operator K11, packed lower triangle -- streamed every iteration
   T* W;         // B*np*np  Gauss-Jordan work matrix (lower triangle)
   T* Vg;        // B*np*kTile   column panel before the sweep step
   T* Wg;        // B*np*kTile   column panel after the sweep step
@@ -46,8 +79,8 @@ inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
   };
   const size_t Bn = (size_t)B;
   w.ctrl = (Ctrl*)take(1, sizeof(Ctrl));
-  w.Qs = (T*)take(Bn * n * w.ld, sizeof(T));
-  w.K = (T*)take(Bn * n * w.ld, sizeof(T));
+  w.Qp = (T*)take(Bn * Pack<T>::elems(n), sizeof(T));
+  w.Kp = (T*)take(Bn * Pack<T>::elems(n), sizeof(T));
   w.W = (T*)take(Bn * w.np * w.np, sizeof(T));
   w.Vg = (T*)take(Bn * w.np * kTile, sizeof(T));
   w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
@@ -113,14 +146,15 @@ cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, 
 template <typename T>
 struct GjArgs {
   int n, m, np;
-  const T* src; int lds;          // B matrices, row stride lds, lower triangle read
+  const T* src; int lds;          // B matrices, row stride lds, lower triangle read; lds == 0: src is the packed
+                                  // symmetric layout (Pack<T>, diagonal stored halved)
   const T* diag_shift;            // per problem, may be null
   T diag_const;                   // added to the kept diagonal entries of H
   const T* mask; int ldm;         // 1 = keep, 0 = replace row/col of H by identity (and zero that column of A); may be null
   const T* Arows; int lda;        // B*m rows (row stride lda); unused when m == 0
   T a_diag;                       // diagonal of the (2,2) block
   T *W, *Vg, *Wg;                 // work: B*np*np, B*np*32, B*np*32
-  T* dst; int ldd;                // K11 (B*n*ldd, full symmetric)
+  T* dst; int ldd;                // K11 in the packed symmetric layout (B*Pack::elems(n)); ldd = row stride of G21 / c_out
   T* G21;                         // K21 (B*m*ldd)
   T* K22;                         // K22 (B*m*m)
   const T* bt; T* c_out;          // optional: c = K21^T b~ (B*ldd)

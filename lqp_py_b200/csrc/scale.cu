@@ -7,7 +7,8 @@
 //             Q~ = D Q D, p~ = D p, A~ = E (A D), b~ = E b, lb~ = lb / D, ub~ = ub / D
 //   :200-203  rho candidate = clamp(||Q~||_F / sqrt(n), rho_min, rho_max)
 //   :221-223  x = z = u = 0
-// HBM traffic: Q is read twice (column norms, then scaling), Q~ written once.
+// HBM traffic: Q is read 1.5 times (column norms over the full matrix, then the lower triangle for the
+// scaling), the packed lower triangle of Q~ written once.
 #include "layout.cuh"
 
 namespace lqpb {
@@ -57,35 +58,36 @@ __device__ __forceinline__ void col_absmax(const T* __restrict__ Qb, int n, T* c
   }
 }
 
-// Q~ = (D_i Q_ij) D_j written with row stride ld (== n when VW > 1); returns this thread's share of ||Q~||_F^2.
-template <typename T, int VW>
-__device__ __forceinline__ double scale_rows(const T* __restrict__ Qb, T* __restrict__ Qsb, int n, int ld,
-                                             const T* Ds, bool do_scale, int tid) {
-  const int chunks = ld / VW;                     // VW == 1: includes the zero padding columns
-  const int tpc = chunks < kScaleThreads ? round_up(chunks, 32) : kScaleThreads;
-  const int ng = kScaleThreads / tpc;
-  const int g = tid / tpc, t = tid % tpc;
+// Q~ = (D_i Q_ij) D_j for the lower triangle, written in the packed symmetric layout (Pack<T>: diagonal
+// halved, zero fill above the diagonal and in the padding); returns this thread's share of ||Q~||_F^2
+// (off-diagonal entries counted twice -- Q~ is symmetric).  One warp per tile: lanes run along the tile
+// columns, so the reads of Q are 128-byte row segments and every tile row is written as one full line.
+template <typename T>
+__device__ __forceinline__ double scale_pack(const T* __restrict__ Qb, T* __restrict__ Qpb, int n, const T* Ds,
+                                             bool do_scale, int tid) {
+  using P = Pack<T>;
+  const int ntv = P::nt(n), ntl = P::ntiles(n);
+  const int warp = tid >> 5, lane = tid & 31, nw = kScaleThreads / 32;
+  const int c = lane % P::TC, k = c / P::VN, e = c % P::VN;
   double fro = 0.0;
-  if (g >= ng) return fro;
-  for (int c = t; c < chunks; c += tpc) {
-    T dj[VW];
-#pragma unroll
-    for (int e = 0; e < VW; ++e) dj[e] = Ds[c * VW + e];
+  for (int t = warp; t < ntl; t += nw) {
+    int Jc = 0, rem = t;
+    while (rem >= ntv - Jc / P::R) { rem -= ntv - Jc / P::R; ++Jc; }
+    const int I = Jc / P::R + rem;
+    T* tp = Qpb + (size_t)t * P::TILE;
+    const int j = Jc * P::TC + c;
+    const T dj = j < n ? Ds[j] : T(0);
 #pragma unroll 4
-    for (int i = g; i < n; i += ng) {
-      alignas(16) T v[VW];
-      if (VW == 1) v[0] = (c < n) ? Qb[(size_t)i * n + c] : T(0);
-      else *reinterpret_cast<typename Vec<T>::type*>(v) =
-               *reinterpret_cast<const typename Vec<T>::type*>(Qb + (size_t)i * n + c * VW);
-      const T di = Ds[i];
-#pragma unroll
-      for (int e = 0; e < VW; ++e) {
-        if (do_scale) v[e] = (di * v[e]) * dj[e];
-        fro += (double)v[e] * (double)v[e];
+    for (int l0 = 0; l0 < kPackRows; l0 += P::R) {
+      const int l = l0 + lane / P::TC, i = I * kPackRows + l;
+      T v = T(0);
+      if (i < n && j <= i) {
+        v = Qb[(size_t)i * n + j];
+        if (do_scale) v = (Ds[i] * v) * dj;
+        fro += (i == j ? 1.0 : 2.0) * (double)v * (double)v;
+        if (i == j) v *= T(0.5);
       }
-      if (VW == 1) Qsb[(size_t)i * ld + c] = v[0];
-      else *reinterpret_cast<typename Vec<T>::type*>(Qsb + (size_t)i * ld + c * VW) =
-               *reinterpret_cast<typename Vec<T>::type*>(v);
+      tp[l * P::TC + ((k + l) & 7) * P::VN + e] = v;
     }
   }
   return fro;
@@ -108,7 +110,7 @@ scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __re
   const int n = w.n, m = w.m, ld = w.ld;
   const size_t vo = (size_t)b * ld;
   const T* Qb = Q + (size_t)b * n * n;
-  T* Qsb = w.Qs + (size_t)b * n * ld;
+  T* Qpb = w.Qp + (size_t)b * Pack<T>::elems(n);
 
   // ---- column inf-norms of Q (:163); thread layout: groups of rows x columns
   if (cfg.scale) {
@@ -173,13 +175,8 @@ scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __re
     __syncthreads();
   }
 
-  // ---- Q~ = (D_i Q_ij) D_j (:176), Frobenius norm (:201), written with the padded row stride
-  double fro;
-  {
-    const bool vec_ok = (n % Vec<T>::N) == 0 && ((uintptr_t)Q % 16) == 0;
-    if (vec_ok) fro = scale_rows<T, Vec<T>::N>(Qb, Qsb, n, ld, Ds, cfg.scale != 0, tid);
-    else fro = scale_rows<T, 1>(Qb, Qsb, n, ld, Ds, cfg.scale != 0, tid);
-  }
+  // ---- Q~ = (D_i Q_ij) D_j (:176), Frobenius norm (:201), written packed (lower triangle only)
+  const double fro = scale_pack<T>(Qb, Qpb, n, Ds, cfg.scale != 0, tid);
   const double fro_tot = group_sum(fro, dscratch, tid, kScaleThreads, 0);
 
   // ---- vectors: p~, lb~, ub~, state reset, flags, p_norm

@@ -53,8 +53,11 @@ def test_workspace_sizes(lib):
         g = getattr(lib, f"lqpb_backward_workspace_bytes_{sfx}")
         small, big = f(1, 10, 0), f(128, 500, 1)
         assert 0 < small < big
-        # at least Q~, K11 and the Gauss-Jordan work matrix
-        assert big >= 128 * s * (2 * 500 * 500 + 512 * 512)
+        # at least the packed lower triangles of Q~ and K11 (136 resp. 272 tiles of 4 KB at n = 500)
+        # and the Gauss-Jordan work matrix
+        tiles = 136 if sfx == "f32" else 272
+        assert big >= 128 * (2 * tiles * 4096 + s * 512 * 512)
+        assert big < 128 * s * (2 * 500 * 500 + 512 * 512)        # ... and less than two full matrices
         # backward: the LDL^T work matrix (no explicit inverse is formed)
         assert g(128, 500, 1) >= 128 * s * 512 * 512
 

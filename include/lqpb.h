@@ -139,6 +139,13 @@ int lqpb_lu_solve_f64(int B, int N, int nrhs, const double* LU, const int32_t* p
 int lqpb_outer_f32(int B, int N, int M, const float* a, const float* b, float* C, void* stream);
 int lqpb_outer_f64(int B, int N, int M, const double* a, const double* b, double* C, void* stream);
 
+/* ---- developer / diagnostic entry points (not part of the reference-facing surface) ----------
+ * Inverse of B symmetric (quasi-definite) N x N fp32 matrices, N a multiple of 128, through the
+ * tensor-core blocked sweep that lqpb_forward_f32 uses for n + m > 128 (csrc/tcfactor.cu); lets
+ * tools/tc_check.py and the GPU tests measure the tcgen05 3xTF32 path in isolation. */
+size_t lqpb_dev_tc_inverse_work_bytes(int B, int N);
+int lqpb_dev_tc_inverse_f32(int B, int N, const float* A, float* Ainv, void* work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

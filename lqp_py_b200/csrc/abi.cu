@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include "layout.cuh"
 
 namespace lqpb {
@@ -91,6 +92,15 @@ int factor_forward(const FwdWs<T>& w, cudaStream_t st) {
   a.W = w.W; a.Vg = w.Vg; a.Wg = w.Wg;
   a.dst = w.Kp; a.ldd = w.ld; a.G21 = w.Gt; a.K22 = w.Sinv;
   a.bt = w.bt; a.c_out = w.m > 0 ? w.c : nullptr;
+  if constexpr (std::is_same<T, float>::value) {
+    if (w.tc) {
+      int l = 0;
+      CK(launch_tc_inverse(w.B, a, w.Pb, w.nb, st, &l), "tensor-core inverse (forward)");
+      g_prof.launches += l;
+      g_prof.fac_launches += l;
+      return LQPB_OK;
+    }
+  }
   CK(launch_gj_inverse<T>(w.B, a, st), "gj_inverse (forward)");
   g_prof.launches += 1;
   g_prof.fac_launches += 1;
@@ -187,6 +197,7 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   if (prof) prof_init();
   g_prof.bwd_valid = false;
   g_prof.launches = 0;
+  int bwd_fac_launches = 0;
   if (prof) cudaEventRecord(g_prof.ev[4], st);
   CK(launch_bwd_mask<T>(w, x, u, lb, ub, st), "bwd_mask");
   {
@@ -200,14 +211,24 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
     a.dst = nullptr; a.ldd = w.ld; a.G21 = nullptr; a.K22 = nullptr;
     a.bt = nullptr; a.c_out = nullptr;
     a.rhs_g = dl_dz; a.sol_x = w.dv; a.sol_nu = w.dnu;
-    CK(launch_ldl_solve<T>(B, a, st), "ldl_solve (backward)");
+    bool done = false;
+    if constexpr (std::is_same<T, float>::value) {
+      if (w.tc) {
+        CK(launch_tc_ldl_solve(B, a, w.Pb, w.nb, st, &bwd_fac_launches), "tensor-core LDL solve (backward)");
+        done = true;
+      }
+    }
+    if (!done) {
+      CK(launch_ldl_solve<T>(B, a, st), "ldl_solve (backward)");
+      bwd_fac_launches = 1;
+    }
   }
   if (prof) cudaEventRecord(g_prof.ev[5], st);
   if (prof) cudaEventRecord(g_prof.ev[6], st);
   CK(launch_bwd_grads<T>(w, dl_dz, x, u, lams, nus, Q, A, rho_dev, rho_scalar, dQ, dp, dA, db, dlb, dub, st),
      "bwd_grads");
   if (prof) cudaEventRecord(g_prof.ev[7], st);
-  g_prof.launches = 3;
+  g_prof.launches = 2 + bwd_fac_launches;
   g_prof.bwd_valid = prof;
   return LQPB_OK;
 }
@@ -305,5 +326,19 @@ int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x,
   }
 LU_ENTRY(f32, float)
 LU_ENTRY(f64, double)
+
+// developer / diagnostic entry (tools/tc_check.py): inverse of B symmetric N x N matrices (N multiple of 128)
+// through the tensor-core sweep of tcfactor.cu.  work: lqpb_dev_tc_inverse_work_bytes(B, N) bytes of device memory.
+size_t lqpb_dev_tc_inverse_work_bytes(int B, int N) {
+  const size_t nb = (size_t)N / 128;
+  return (size_t)B * (nb * (nb + 1) / 2 + 3 * nb) * 128 * 128 * sizeof(float);
+}
+int lqpb_dev_tc_inverse_f32(int B, int N, const float* A, float* Ainv, void* work, void* stream) {
+  if (!A || !Ainv || !work || B <= 0 || N <= 0 || N % 128) return fail(LQPB_E_ARG, "bad argument");
+  int rc = check_device();
+  if (rc) return rc;
+  CK(launch_tc_dev_inverse(B, N, A, Ainv, (float*)work, (cudaStream_t)stream), "tc_dev_inverse");
+  return LQPB_OK;
+}
 
 }  // extern "C"

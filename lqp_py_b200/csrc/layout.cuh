@@ -3,6 +3,8 @@
 // (16-byte multiple so that rows are legal bulk-TMA sources), `np` the dimension padded to the
 // 32 x 32 tiles of the Gauss-Jordan inversion.
 #pragma once
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "../../include/lqpb.h"
 
@@ -11,6 +13,17 @@ namespace lqpb {
 constexpr int kTile = 32;      // Gauss-Jordan tile edge
 constexpr int kMacro = 64;     // macro tile edge of the trailing update (np is a multiple of it)
 constexpr int kMaxM = 64;      // max equality rows handled by the Schur-complement path
+constexpr int kTcBlock = 128;  // block edge of the tensor-core factorisation (tcfactor.cu)
+
+// fp32 problems with n + m > 128 are factorised on the tensor cores (tcfactor.cu: blocked sweep with
+// tcgen05 3xTF32 tile products); everything else (fp64, small problems) uses the Gauss-Jordan kernel of
+// factor.cu.  LQPB_FACTOR=gj in the environment forces the latter (A/B measurements).
+template <typename T> inline bool tc_factor_enabled(int, int) { return false; }
+template <> inline bool tc_factor_enabled<float>(int n, int m) {
+  const char* e = getenv("LQPB_FACTOR");
+  if (e && !strcmp(e, "gj")) return false;
+  return n + m > kTcBlock;
+}
 
 // ------------------------------------------------------------------ packed symmetric storage
 // The two O(n^2) operands of the iteration kernel -- the x-update operator K11 and the scaled Q~ -- are
@@ -47,6 +60,8 @@ struct Pack {
 template <typename T>
 struct FwdWs {
   int B, n, m, ld, np;
+  int tc, nb;   // tensor-core factorisation: W = block-lower tiles, Vg / Wg / Pb = nb tiles per problem
+  T* Pb;        // B*nb*128*128  pivot-block inverses (tc only)
   T* Qp;        // B*Pack::elems(n)  scaled Q~ = D Q D, packed lower triangle (read at every check: Q~ x~;
                 //                   also the source of the factorisation)
   T* Kp;        // B*Pack::elems(n)  x-update operator K11, packed lower triangle -- streamed every iteration
@@ -78,12 +93,23 @@ inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
     return r;
   };
   const size_t Bn = (size_t)B;
+  w.tc = tc_factor_enabled<T>(n, m) ? 1 : 0;
+  w.nb = (n + m + kTcBlock - 1) / kTcBlock;
+  const size_t tile_e = (size_t)kTcBlock * kTcBlock;
   w.ctrl = (Ctrl*)take(1, sizeof(Ctrl));
   w.Qp = (T*)take(Bn * Pack<T>::elems(n), sizeof(T));
   w.Kp = (T*)take(Bn * Pack<T>::elems(n), sizeof(T));
-  w.W = (T*)take(Bn * w.np * w.np, sizeof(T));
-  w.Vg = (T*)take(Bn * w.np * kTile, sizeof(T));
-  w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
+  if (w.tc) {
+    w.W = (T*)take(Bn * ((size_t)w.nb * (w.nb + 1) / 2) * tile_e, sizeof(T));
+    w.Vg = (T*)take(Bn * w.nb * tile_e, sizeof(T));
+    w.Wg = (T*)take(Bn * w.nb * tile_e, sizeof(T));
+    w.Pb = (T*)take(Bn * w.nb * tile_e, sizeof(T));
+  } else {
+    w.W = (T*)take(Bn * w.np * w.np, sizeof(T));
+    w.Vg = (T*)take(Bn * w.np * kTile, sizeof(T));
+    w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
+    w.Pb = nullptr;
+  }
   T** vecs[] = {&w.D, &w.pt, &w.lbt, &w.ubt, &w.c, &w.z, &w.u, &w.xs};
   for (auto v : vecs) *v = (T*)take(Bn * w.ld, sizeof(T));
   const size_t mm = m > 0 ? m : 1;
@@ -105,6 +131,8 @@ inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
 template <typename T>
 struct BwdWs {
   int B, n, m, ld, np;
+  int tc, nb;   // see FwdWs
+  T* Pb;
   T* W;         // B*np*np  LDL^T work matrix (lower triangle)
   T *Vg, *Wg;   // B*np*kTile
   T *mask, *dv; // B*ld
@@ -126,9 +154,20 @@ inline BwdWs<T> carve_bwd(void* base, int B, int n, int m) {
     return r;
   };
   const size_t Bn = (size_t)B;
-  w.W = (T*)take(Bn * w.np * w.np, sizeof(T));
-  w.Vg = (T*)take(Bn * w.np * kTile, sizeof(T));
-  w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
+  w.tc = tc_factor_enabled<T>(n, m) ? 1 : 0;
+  w.nb = (n + m + kTcBlock - 1) / kTcBlock;
+  if (w.tc) {
+    const size_t tile_e = (size_t)kTcBlock * kTcBlock;
+    w.W = (T*)take(Bn * ((size_t)w.nb * (w.nb + 1) / 2) * tile_e, sizeof(T));
+    w.Vg = (T*)take(Bn * w.nb * tile_e, sizeof(T));
+    w.Wg = (T*)take(Bn * w.nb * tile_e, sizeof(T));
+    w.Pb = (T*)take(Bn * w.nb * tile_e, sizeof(T));
+  } else {
+    w.W = (T*)take(Bn * w.np * w.np, sizeof(T));
+    w.Vg = (T*)take(Bn * w.np * kTile, sizeof(T));
+    w.Wg = (T*)take(Bn * w.np * kTile, sizeof(T));
+    w.Pb = nullptr;
+  }
   w.mask = (T*)take(Bn * w.ld, sizeof(T));
   w.dv = (T*)take(Bn * w.ld, sizeof(T));
   w.dnu = (T*)take(Bn * (m > 0 ? m : 1), sizeof(T));
@@ -167,6 +206,12 @@ template <typename T>
 cudaError_t launch_ldl_solve(int B, const GjArgs<T>& a, cudaStream_t st);
 template <typename T>
 cudaError_t launch_select_rho(const lqpb_config& cfg, const FwdWs<T>& w, cudaStream_t st);
+
+// tcfactor.cu -- K2 on the tensor cores (fp32): same arguments / outputs as launch_gj_inverse / launch_ldl_solve,
+// a.W = block-lower work matrix, a.Vg / a.Wg = panel tile buffers, Pbuf = pivot-block inverses
+cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches);
+cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches);
+cudaError_t launch_tc_dev_inverse(int B, int N, const float* A, float* Ainv, float* work, cudaStream_t st);
 
 // iterate.cu -- K3 (+K4): persistent ADMM loop and finalisation
 template <typename T>

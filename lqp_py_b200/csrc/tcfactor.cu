@@ -1,0 +1,651 @@
+// K2 (fp32, n + m > 128) -- the batched KKT factorisation on the 5th-generation tensor cores.
+//
+// Same mathematics as factor.cu (symmetric Gauss-Jordan "sweep" of the quasi-definite KKT matrix
+//     M = [[H, A^T], [A, d I]],  H = Q~ + rho I (forward, d = 0)  |  masked Q + 1e-8 I (backward, d = 1e-8),
+// replacing torch.linalg.lu_factor(M) of solve_box_qp_admm_torch.py:206-215, :252-254 and the fresh LU inside
+// torch.linalg.solve of the backward, :393), but blocked with 128 x 128 blocks so that every O(n^3) term is a
+// 128 x 128 x 128 product issued as tcgen05.mma (kind::tf32, accumulators in TMEM):
+//
+//   for k = 0 .. nb-1                                   (sweep of block k; nb = np / 128)
+//     P    = inv(M_kk)                 tc_pivot_kernel  (128 x 128 register-tiled sweep, FP32 pipe, one CTA / problem)
+//     W_i  = M_ik P       (i != k)     tc_tile_kernel<PANEL>   also keeps V_i = old M_ik and stores M_ik <- W_i
+//     M_ij = M_ij - W_i V_j^T (i,j!=k) tc_tile_kernel<TRAIL>
+//     M_kk = -P
+//   after nb sweeps the buffer holds -(M^-1); tc_extract_kernel writes K11 in the packed layout of the
+//   iteration kernel plus K21, K22 and c = K21^T b~.
+//   LDL mode (backward): only i, j > k are touched (block LDL^T, one third of the products), every P_k is kept,
+//   and tc_ldl_solve_kernel does the block forward / backward substitution for the single right-hand side.
+//
+// fp32 accuracy on TF32 tensor cores: every operand x is split as x = hi + lo with hi = rna_tf32(x) and
+// lo = rna_tf32(x - hi); a product is accumulated as hi*hi + lo*hi + hi*lo (fp32 accumulators in TMEM, zero
+// initialised; the C tile is added in registers by the epilogue).  The neglected lo*lo term is <= 2^-22 relative.
+//
+// Storage ("block lower"): only tiles (I, J) with I >= J are kept, tile index I (I + 1) / 2 + J, each 128 x 128
+// row-major and contiguous; diagonal tiles hold both triangles.  Operands are staged in shared memory by the
+// CTA's threads in the canonical K-major SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index
+// XOR row % 8), 32 k-columns (one 16 KB slab per operand part) at a time, while the previous slab's MMAs run.
+#include "layout.cuh"
+
+namespace lqpb {
+
+constexpr int kTB = 128;                 // block edge
+constexpr int kTBE = kTB * kTB;          // elements per tile
+constexpr int kSlabBytes = kTB * 128;    // 128 rows x 32 fp32
+constexpr int kTcThreads = 256;
+constexpr int kTcCols = 256;             // TMEM columns per CTA: hi*hi accumulator | cross-term accumulator
+constexpr int kTcSmem = 4 * kSlabBytes + 1024;   // Xhi | Xlo | Yhi | Ylo, manually aligned to 1024 B
+
+__host__ __device__ inline size_t bl_tile(int I, int J) { return (size_t)(I * (I + 1) / 2 + J) * kTBE; }
+__host__ __device__ inline size_t bl_off(int i, int j) {   // element (i, j), tile row >= tile column
+  return bl_tile(i >> 7, j >> 7) + (size_t)(i & 127) * kTB + (j & 127);
+}
+
+struct TcArgs {
+  float* M;       // B * nb(nb+1)/2 tiles
+  float* Wbuf;    // B * nb tiles : W_i of the current step
+  float* Vbuf;    // B * nb tiles : V_i = M_ik before the step
+  float* Pbuf;    // B * nb tiles : P_k = inv(M_kk) (all kept: the LDL solve needs them)
+  int nb, k, ldl;
+  int acc2;       // 1: cross terms (lo*hi + hi*lo) accumulate in their own TMEM tile (see tc_tile_kernel)
+};
+
+// ------------------------------------------------------------------ tcgen05 PTX wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, 128 x 128 x 8, TF32 inputs, FP32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 16 consecutive columns: thread `lane` of warp w reads TMEM lane 32 (w % 4) + lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// wait for the tcgen05.ld; the registers are in/out operands so that no use of them is scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
+// bits [0,14), leading byte offset (unused for swizzled K-major, canonical value 1) in [16,30), stride byte
+// offset = 1024 B between 8-row groups in [32,46), descriptor version 1 in [46,48), layout type 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2),
+// both K-major (bits 15, 16 = 0), N >> 3 in bits [17,23), M >> 4 in bits [24,29)
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// hi = x rounded to TF32 (10-bit mantissa, round to nearest / ties away: add half an ulp to the magnitude and
+// clear the 13 low bits -- 2 integer ops instead of cvt.rna.tf32.f32), lo = x - hi (exact, |lo| <= 2^-11 |x|)
+// rounded to TF32 the same way: the neglected part is <= 2^-22 |x|.
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
+  split_tf32(x.x, hi.x, lo.x);
+  split_tf32(x.y, hi.y, lo.y);
+  split_tf32(x.z, hi.z, lo.z);
+  split_tf32(x.w, hi.w, lo.w);
+}
+
+// ------------------------------------------------------------------ the tile product kernel
+// MODE 0 (PANEL): W_i = X P with X = M_ik (tile (i,k), or tile (k,i) read transposed when i < k), Y = P_k.
+//                 Side effects: V_i = X (raw copy), Wbuf_i = W_i, M_ik <- W_i (transposed store when i < k).
+// MODE 1 (TRAIL): M_ij <- M_ij - W_i V_j^T for the lower tiles i >= j (i, j != k; LDL: i >= j > k).
+// grid = B * jobs, one 128 x 128 output tile per CTA, 3 CTAs per SM (64 KB of operand slabs, 128 TMEM columns).
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 2) tc_tile_kernel(TcArgs a) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int k = a.k, nb = a.nb;
+
+  // ---- job decode
+  const int span = a.ldl ? nb - 1 - k : nb - 1;                  // block indices taking part (besides k)
+  const int jobs = MODE == 0 ? span : span * (span + 1) / 2;
+  const int b = blockIdx.x / jobs, job = blockIdx.x % jobs;
+  int i, j = 0;
+  if (MODE == 0) {
+    i = a.ldl ? k + 1 + job : (job < k ? job : job + 1);
+  } else {
+    int ii = (int)((sqrtf(8.f * job + 1.f) - 1.f) * 0.5f);
+    while ((ii + 1) * (ii + 2) / 2 <= job) ++ii;
+    while (ii * (ii + 1) / 2 > job) --ii;
+    const int jj = job - ii * (ii + 1) / 2;
+    if (a.ldl) { i = k + 1 + ii; j = k + 1 + jj; }
+    else { i = ii < k ? ii : ii + 1; j = jj < k ? jj : jj + 1; }
+  }
+  const size_t ntile = (size_t)nb * (nb + 1) / 2;
+  float* Mb = a.M + (size_t)b * ntile * kTBE;
+  float* Wb = a.Wbuf + (size_t)b * nb * kTBE;
+  float* Vb = a.Vbuf + (size_t)b * nb * kTBE;
+  const float* xsrc;
+  const float* ysrc;
+  bool xtrans = false;
+  if (MODE == 0) {
+    xtrans = i < k;
+    xsrc = Mb + (xtrans ? bl_tile(k, i) : bl_tile(i, k));
+    ysrc = a.Pbuf + ((size_t)b * nb + k) * kTBE;
+  } else {
+    xsrc = Wb + (size_t)i * kTBE;
+    ysrc = Vb + (size_t)j * kTBE;
+  }
+  float* vdst = Vb + (size_t)i * kTBE;   // MODE 0 only
+
+  // ---- shared memory carve (1024-byte aligned for the 128-byte swizzle), barrier, TMEM
+  const uint32_t sbase = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  unsigned char* sptr = tc_smem_raw + (sbase - smem_u32(tc_smem_raw));
+  unsigned char* sXh = sptr;
+  unsigned char* sXl = sptr + kSlabBytes;
+  unsigned char* sYh = sptr + 2 * kSlabBytes;
+  unsigned char* sYl = sptr + 3 * kSlabBytes;
+  if (warp == 0) tmem_alloc(&tmem_slot, kTcCols);
+  if (tid == 32) {
+    mbar_init(&mma_bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  float4 xr[4], yr[4];
+  auto gload = [&](int s) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int q = tid + kTcThreads * t, r = q >> 3, ch = q & 7;
+      if (!xtrans) {
+        xr[t] = *reinterpret_cast<const float4*>(xsrc + (size_t)r * kTB + 32 * s + 4 * ch);
+      } else {
+        const int r4 = 4 * (warp + 8 * t);      // logical rows r4 .. r4+3 at logical column 32 s + lane
+        xr[t] = *reinterpret_cast<const float4*>(xsrc + (size_t)(32 * s + lane) * kTB + r4);
+      }
+      yr[t] = *reinterpret_cast<const float4*>(ysrc + (size_t)r * kTB + 32 * s + 4 * ch);
+    }
+  };
+  auto sstore = [&](int s) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int q = tid + kTcThreads * t, r = q >> 3, ch = q & 7;
+      const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+      float4 hi, lo;
+      if (!xtrans) {
+        split4(xr[t], hi, lo);
+        *reinterpret_cast<float4*>(sXh + off) = hi;
+        *reinterpret_cast<float4*>(sXl + off) = lo;
+        if (MODE == 0) *reinterpret_cast<float4*>(vdst + (size_t)r * kTB + 32 * s + 4 * ch) = xr[t];
+      } else {
+        const int r4 = 4 * (warp + 8 * t);
+        const float xe[4] = {xr[t].x, xr[t].y, xr[t].z, xr[t].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int rr = r4 + e;
+          const uint32_t o = (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
+          float h1, l1;
+          split_tf32(xe[e], h1, l1);
+          *reinterpret_cast<float*>(sXh + o) = h1;
+          *reinterpret_cast<float*>(sXl + o) = l1;
+          if (MODE == 0) vdst[(size_t)rr * kTB + 32 * s + lane] = xe[e];
+        }
+      }
+      split4(yr[t], hi, lo);
+      *reinterpret_cast<float4*>(sYh + off) = hi;
+      *reinterpret_cast<float4*>(sYl + off) = lo;
+    }
+  };
+
+  gload(0);
+#pragma unroll 1
+  for (int s = 0; s < 4; ++s) {
+    if (s > 0) mbar_wait(&mma_bar, (uint32_t)((s - 1) & 1));   // MMAs of the previous slab have read smem
+    sstore(s);
+    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (s < 3) gload(s + 1);      // next slab's global loads fly while the MMAs run
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t ko = (uint32_t)kk * 32u;   // 8 tf32 = 32 bytes along K inside the swizzle atom
+        const uint64_t dXh = umma_desc(smem_u32(sXh) + ko), dXl = umma_desc(smem_u32(sXl) + ko);
+        const uint64_t dYh = umma_desc(smem_u32(sYh) + ko), dYl = umma_desc(smem_u32(sYl) + ko);
+        // The tensor core truncates the fp32 accumulator after every MMA, an error proportional to the
+        // accumulator's magnitude: the two small cross terms therefore get their own accumulator (columns
+        // 128..255), so that the large hi*hi sum sees 16 instead of 48 roundings; the epilogue adds the two.
+        const uint32_t tcross = tmem + (a.acc2 ? 128u : 0u);
+        umma_tf32(tcross, dXl, dYh, kIdescTf32, (s | kk) ? 1u : 0u);
+        umma_tf32(tcross, dXh, dYl, kIdescTf32, 1u);
+        umma_tf32(tmem, dXh, dYh, kIdescTf32, (a.acc2 && !(s | kk)) ? 0u : 1u);
+      }
+      umma_commit(&mma_bar);
+    }
+  }
+  mbar_wait(&mma_bar, 1u);        // 4th completion (phase parity 1)
+  tc_fence_after();
+
+  // ---- epilogue.  TMEM -> registers gives every thread 16 consecutive columns of ITS row (32 (warp % 4) + lane;
+  // warps 0-3 columns 0-63, warps 4-7 columns 64-127): written straight to global memory that is 32 different
+  // rows per instruction.  The 64 KB of operand slabs are free now, so the tile is staged there (16-byte chunk
+  // index XOR row: conflict-free both ways) and then moved with full-row 512-byte warp accesses.
+  float* stage = reinterpret_cast<float*>(sptr);
+  {
+    const int r = 32 * (warp & 3) + lane;
+    const uint32_t trow = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll 1
+    for (int g = 0; g < 4; ++g) {
+      const int c0 = (warp >> 2) * 64 + 16 * g;
+      uint32_t v[16];
+      float f[16];
+      tmem_ld16(trow + (uint32_t)c0, v);
+      tmem_ld_wait(v);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
+      if (a.acc2) {
+        tmem_ld16(trow + 128u + (uint32_t)c0, v);
+        tmem_ld_wait(v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] += __uint_as_float(v[e]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ch = (c0 >> 2) + q;
+        *reinterpret_cast<float4*>(stage + r * kTB + ((ch ^ (r & 31)) << 2)) =
+            make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+      }
+    }
+  }
+  __syncthreads();
+  if (MODE == 1) {
+    float* ct = Mb + bl_tile(i, j);
+#pragma unroll 4
+    for (int rr = warp; rr < kTB; rr += kTcThreads / 32) {
+      const float4 d = *reinterpret_cast<const float4*>(stage + rr * kTB + ((lane ^ (rr & 31)) << 2));
+      float4* cp = reinterpret_cast<float4*>(ct + (size_t)rr * kTB + 4 * lane);
+      float4 c = *cp;
+      c.x -= d.x; c.y -= d.y; c.z -= d.z; c.w -= d.w;
+      *cp = c;
+    }
+  } else {
+    float* wt = Wb + (size_t)i * kTBE;
+    if (!xtrans) {
+      float* mt = Mb + bl_tile(i, k);
+#pragma unroll 4
+      for (int rr = warp; rr < kTB; rr += kTcThreads / 32) {
+        const float4 d = *reinterpret_cast<const float4*>(stage + rr * kTB + ((lane ^ (rr & 31)) << 2));
+        *reinterpret_cast<float4*>(wt + (size_t)rr * kTB + 4 * lane) = d;
+        *reinterpret_cast<float4*>(mt + (size_t)rr * kTB + 4 * lane) = d;
+      }
+    } else {
+      // M_ki = W_i^T: thread (cc4 = 4 * lane .. +3 output columns = W rows, output row = W column c)
+      float* mt = Mb + bl_tile(k, i);
+#pragma unroll 4
+      for (int rr = warp; rr < kTB; rr += kTcThreads / 32) {
+        const float4 d = *reinterpret_cast<const float4*>(stage + rr * kTB + ((lane ^ (rr & 31)) << 2));
+        *reinterpret_cast<float4*>(wt + (size_t)rr * kTB + 4 * lane) = d;
+      }
+      // transposed read of the staged tile: output row c (= W column), 4 consecutive W rows per lane
+#pragma unroll 2
+      for (int c = warp; c < kTB; c += kTcThreads / 32) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int wr = 4 * lane + e;
+          o[e] = stage[wr * kTB + ((((c >> 2) ^ (wr & 31)) << 2) | (c & 3))];
+        }
+        *reinterpret_cast<float4*>(mt + (size_t)c * kTB + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTcCols);
+}
+
+// ------------------------------------------------------------------ pivot block inverse
+// One CTA (512 threads) per problem: symmetric sweep of the 128 x 128 pivot tile M_kk held in registers
+// (thread (ta, tb) of a 32 x 16 grid owns the 4 x 8 sub-block rows 4 ta.., columns 8 tb..); per sweep step the
+// pivot row and column are broadcast through double-buffered shared vectors, one __syncthreads per step, and
+// every thread applies the rank-1 update to its 32 entries.  The tile ends as -(M_kk)^-1: P = inv(M_kk) goes to
+// Pbuf[k], -P back into the matrix.
+constexpr int kPivThreads = 512;
+__global__ void __launch_bounds__(kPivThreads, 1) tc_pivot_kernel(TcArgs a) {
+  __shared__ __align__(16) float rowbuf[2][kTB];
+  __shared__ __align__(16) float colbuf[2][kTB];
+  const int b = blockIdx.x, tid = threadIdx.x, ta = tid >> 4, tb = tid & 15;   // rows 4 ta.., columns 8 tb..
+  const int k = a.k, nb = a.nb;
+  float* tile = a.M + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(k, k);
+  float acc[4][8];
+  // the lower triangle is the reference copy: entries above the diagonal are read transposed
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int r = 4 * ta + rr, c = 8 * tb + q;
+      acc[rr][q] = r >= c ? tile[(size_t)r * kTB + c] : tile[(size_t)c * kTB + r];
+    }
+  // the step loop is unrolled by 8 so that the row / column index inside the thread's tile is a
+  // compile-time constant: no dynamically indexed registers
+#pragma unroll 1
+  for (int sb = 0; sb < kTB / 8; ++sb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int s = 8 * sb + j, par = j & 1;
+      const int sr = j & 3, ra = 2 * sb + (j >> 2);   // pivot row s = 4 ra + sr ; pivot column s = 8 sb + j
+      if (ta == ra) {          // publish pivot row s
+        *reinterpret_cast<float4*>(&rowbuf[par][8 * tb]) = make_float4(acc[sr][0], acc[sr][1], acc[sr][2], acc[sr][3]);
+        *reinterpret_cast<float4*>(&rowbuf[par][8 * tb + 4]) = make_float4(acc[sr][4], acc[sr][5], acc[sr][6], acc[sr][7]);
+      }
+      if (tb == sb)            // publish pivot column s
+        *reinterpret_cast<float4*>(&colbuf[par][4 * ta]) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+      __syncthreads();
+      const float piv = __frcp_rn(rowbuf[par][s]);
+      const float4 a0 = *reinterpret_cast<const float4*>(&rowbuf[par][8 * tb]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&rowbuf[par][8 * tb + 4]);
+      const float4 c0 = *reinterpret_cast<const float4*>(&colbuf[par][4 * ta]);
+      const float asc[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float tr[4] = {c0.x * piv, c0.y * piv, c0.z * piv, c0.w * piv};
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[rr][q] = fmaf(-tr[rr], asc[q], acc[rr][q]);
+      if (tb == sb) {          // own column s: a[r][s] <- a[r][s] / piv
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) acc[rr][j] = tr[rr];
+      }
+      if (ta == ra) {          // own row s: a[s][c] <- a[s][c] / piv, a[s][s] <- -1 / piv
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[sr][q] = (tb == sb && q == j) ? -piv : asc[q] * piv;
+      }
+    }
+  }
+  float* P = a.Pbuf + ((size_t)b * nb + k) * kTBE;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const size_t o = (size_t)(4 * ta + rr) * kTB + 8 * tb;
+    *reinterpret_cast<float4*>(tile + o) = make_float4(acc[rr][0], acc[rr][1], acc[rr][2], acc[rr][3]);
+    *reinterpret_cast<float4*>(tile + o + 4) = make_float4(acc[rr][4], acc[rr][5], acc[rr][6], acc[rr][7]);
+    *reinterpret_cast<float4*>(P + o) = make_float4(-acc[rr][0], -acc[rr][1], -acc[rr][2], -acc[rr][3]);
+    *reinterpret_cast<float4*>(P + o + 4) = make_float4(-acc[rr][4], -acc[rr][5], -acc[rr][6], -acc[rr][7]);
+  }
+}
+
+// ------------------------------------------------------------------ assemble the KKT matrix (block-lower tiles)
+// Same embedding as the prologue of gj_inverse_kernel: H masked / shifted, the m equality rows right below it,
+// identity on the padding.  grid = (tiles, B).
+__global__ void __launch_bounds__(256) tc_assemble_kernel(GjArgs<float> a, float* __restrict__ Mout, int nb) {
+  const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+  int I = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
+  while ((I + 1) * (I + 2) / 2 <= tile) ++I;
+  while (I * (I + 1) / 2 > tile) --I;
+  const int J = tile - I * (I + 1) / 2;
+  const int n = a.n, m = a.m;
+  const bool packed_src = a.lds == 0;
+  const int ntv = Pack<float>::nt(n);
+  const float* srcb = packed_src ? a.src + (size_t)b * Pack<float>::elems(n) : a.src + (size_t)b * n * a.lds;
+  const float* maskb = a.mask ? a.mask + (size_t)b * a.ldm : nullptr;
+  const float* Ab = (m > 0) ? a.Arows + (size_t)b * m * a.lda : nullptr;
+  const float shift = (a.diag_shift ? a.diag_shift[b] : 0.f) + a.diag_const;
+  float* dst = Mout + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(I, J);
+  for (int e = tid; e < kTBE; e += 256) {
+    const int r = e >> 7, c = e & 127;
+    int i = I * kTB + r, j = J * kTB + c;
+    if (j > i) { const int t = i; i = j; j = t; }     // diagonal tiles: mirror the lower triangle
+    float v = 0.f;
+    if (i < n) {
+      const float fi = maskb ? maskb[i] : 1.f, fj = maskb ? maskb[j] : 1.f;
+      const bool keep = fi != 0.f && fj != 0.f;
+      if (keep) {
+        if (packed_src) {
+          v = srcb[Pack<float>::offset(i, j, ntv)];
+          if (i == j) v += v;                          // the packed layout stores the diagonal halved
+        } else {
+          v = srcb[(size_t)i * a.lds + j];
+        }
+      }
+      if (i == j) v = keep ? v + shift : 1.f;
+    } else if (i < n + m) {
+      if (j < n) {
+        const float av = Ab[(size_t)(i - n) * a.lda + j];
+        v = maskb ? av * maskb[j] : av;
+      } else if (j == i) {
+        v = a.a_diag;
+      }
+    } else {
+      v = (i == j) ? 1.f : 0.f;
+    }
+    dst[e] = v;
+  }
+}
+
+// ------------------------------------------------------------------ extract K11 (packed), K21, K22, c from -(M^-1)
+__global__ void __launch_bounds__(512) tc_extract_kernel(GjArgs<float> a, const float* __restrict__ Min, int nb) {
+  using P = Pack<float>;
+  constexpr int NW = 512 / 32;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.n, m = a.m;
+  const float* Mb = Min + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE;
+  float* dstb = a.dst + (size_t)b * P::elems(n);
+  const int ntv = P::nt(n), ntl = P::ntiles(n);
+  const int c = lane % P::TC, kc = c / P::VN, ec = c % P::VN;
+  for (int t = warp; t < ntl; t += NW) {
+    int Jc = 0, rem = t;
+    while (rem >= ntv - Jc / P::R) { rem -= ntv - Jc / P::R; ++Jc; }
+    const int I = Jc / P::R + rem;
+    float* tp = dstb + (size_t)t * P::TILE;
+    const int j = Jc * P::TC + c;
+#pragma unroll 4
+    for (int l0 = 0; l0 < kPackRows; l0 += P::R) {
+      const int l = l0 + lane / P::TC, i = I * kPackRows + l;
+      float v = 0.f;
+      if (i < n && j <= i) {
+        v = -Mb[bl_off(i, j)];
+        if (i == j) v *= 0.5f;
+      }
+      tp[l * P::TC + ((kc + l) & 7) * P::VN + ec] = v;
+    }
+  }
+  float* g21 = (m > 0) ? a.G21 + (size_t)b * m * a.ldd : nullptr;
+  float* k22 = (m > 0) ? a.K22 + (size_t)b * m * m : nullptr;
+  const int ldd = a.ldd;
+  for (int r = warp; r < m; r += NW) {
+    for (int j = lane; j < ldd; j += 32) g21[(size_t)r * ldd + j] = j < n ? -Mb[bl_off(n + r, j)] : 0.f;
+    for (int q = lane; q < m; q += 32)
+      k22[(size_t)r * m + q] = q <= r ? -Mb[bl_off(n + r, n + q)] : -Mb[bl_off(n + q, n + r)];
+  }
+  if (a.c_out) {
+    __syncthreads();
+    float* cb = a.c_out + (size_t)b * ldd;
+    for (int i = tid; i < ldd; i += 512) {
+      float acc = 0.f;
+      if (i < n)
+        for (int l = 0; l < m; ++l) acc += g21[(size_t)l * ldd + i] * a.bt[(size_t)b * m + l];
+      cb[i] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ block LDL^T solve (backward)
+// M = L D L^T with L_ik = W_i of step k (stored in tile (i,k)), D_k^-1 = P_k.  Solves M d = [-mask * dl_dz; 0]:
+// forward  y_i -= L_ik y_k,  z_k = P_k y_k,  backward d_k = z_k - sum_{i>k} L_ik^T d_i.  One CTA per problem.
+__global__ void __launch_bounds__(512) tc_ldl_solve_kernel(GjArgs<float> a, const float* __restrict__ Min,
+                                                           const float* __restrict__ Pin, int nb) {
+  extern __shared__ __align__(16) unsigned char ldl_smem[];
+  constexpr int NT = 512, NW = NT / 32;
+  const int np = nb * kTB, n = a.n, m = a.m;
+  float* y = reinterpret_cast<float*>(ldl_smem);   // [np]
+  float* z = y + np;                               // [np]
+  float* red = z + np;                             // [4][128]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* Mb = Min + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE;
+  const float* Pb = Pin + (size_t)b * nb * kTBE;
+  const float* maskb = a.mask + (size_t)b * a.ldm;
+  for (int i = tid; i < np; i += NT) y[i] = (i < n) ? -(maskb[i] * a.rhs_g[(size_t)b * n + i]) : 0.f;   // :368-375
+  __syncthreads();
+  for (int k = 0; k + 1 < nb; ++k) {
+    const float4 yk = *reinterpret_cast<const float4*>(y + k * kTB + 4 * lane);
+    for (int rr = warp; rr < (nb - 1 - k) * kTB; rr += NW) {
+      const int i = k + 1 + rr / kTB, r = rr % kTB;
+      const float4 l4 = *reinterpret_cast<const float4*>(Mb + bl_tile(i, k) + (size_t)r * kTB + 4 * lane);
+      float acc = l4.x * yk.x + l4.y * yk.y + l4.z * yk.z + l4.w * yk.w;
+      acc = warp_sum(acc);
+      if (lane == 0) y[i * kTB + r] -= acc;
+    }
+    __syncthreads();
+  }
+  for (int rr = warp; rr < np; rr += NW) {
+    const int k = rr / kTB, r = rr % kTB;
+    const float4 yk = *reinterpret_cast<const float4*>(y + k * kTB + 4 * lane);
+    const float4 p4 = *reinterpret_cast<const float4*>(Pb + (size_t)k * kTBE + (size_t)r * kTB + 4 * lane);
+    float acc = p4.x * yk.x + p4.y * yk.y + p4.z * yk.z + p4.w * yk.w;
+    acc = warp_sum(acc);
+    if (lane == 0) z[rr] = acc;
+  }
+  __syncthreads();
+  const int c = tid & 127, chunk = tid >> 7;        // 4 row chunks of 32
+  for (int k = nb - 2; k >= 0; --k) {
+    float acc = 0.f;
+    for (int i = k + 1; i < nb; ++i) {
+      const float* L = Mb + bl_tile(i, k);
+#pragma unroll 8
+      for (int r = chunk * 32; r < chunk * 32 + 32; ++r) acc += L[(size_t)r * kTB + c] * z[i * kTB + r];
+    }
+    red[chunk * kTB + c] = acc;
+    __syncthreads();
+    if (tid < kTB) z[k * kTB + tid] -= red[tid] + red[kTB + tid] + red[2 * kTB + tid] + red[3 * kTB + tid];
+    __syncthreads();
+  }
+  for (int i = tid; i < a.ldd; i += NT) a.sol_x[(size_t)b * a.ldd + i] = i < n ? z[i] : 0.f;
+  for (int l = tid; l < m; l += NT) a.sol_nu[(size_t)b * m + l] = z[n + l];
+}
+
+// ------------------------------------------------------------------ host orchestration
+static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st, int* launches) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(tc_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  TcArgs a = base;
+  a.ldl = ldl ? 1 : 0;
+  {
+    const char* e = getenv("LQPB_TC_ACC2");     // developer switch (accuracy A/B); default on
+    a.acc2 = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int nb = a.nb;
+  for (int k = 0; k < nb; ++k) {
+    a.k = k;
+    tc_pivot_kernel<<<B, kPivThreads, 0, st>>>(a);
+    ++*launches;
+    const int span = ldl ? nb - 1 - k : nb - 1;
+    if (span > 0) {
+      tc_tile_kernel<0><<<B * span, kTcThreads, kTcSmem, st>>>(a);
+      tc_tile_kernel<1><<<B * (span * (span + 1) / 2), kTcThreads, kTcSmem, st>>>(a);
+      *launches += 2;
+    }
+  }
+  return cudaGetLastError();
+}
+
+// forward: inverse of the KKT matrix, outputs as launch_gj_inverse (a.W = block-lower work matrix,
+// a.Vg / a.Wg = panel buffers (nb tiles per problem each), Pbuf = nb tiles per problem)
+cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches) {
+  dim3 ga(nb * (nb + 1) / 2, B);
+  tc_assemble_kernel<<<ga, 256, 0, st>>>(a, a.W, nb);
+  ++*launches;
+  TcArgs t{a.W, a.Wg, a.Vg, Pbuf, nb, 0, 0, 1};
+  cudaError_t e = tc_sweep(B, t, false, st, launches);
+  if (e != cudaSuccess) return e;
+  tc_extract_kernel<<<B, 512, 0, st>>>(a, a.W, nb);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+// backward: block LDL^T + solve, outputs as launch_ldl_solve
+cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches) {
+  dim3 ga(nb * (nb + 1) / 2, B);
+  tc_assemble_kernel<<<ga, 256, 0, st>>>(a, a.W, nb);
+  ++*launches;
+  TcArgs t{a.W, a.Wg, a.Vg, Pbuf, nb, 0, 1, 1};
+  cudaError_t e = tc_sweep(B, t, true, st, launches);
+  if (e != cudaSuccess) return e;
+  const size_t smem = ((size_t)2 * nb * kTB + 4 * kTB) * sizeof(float);
+  tc_ldl_solve_kernel<<<B, 512, smem, st>>>(a, a.W, Pbuf, nb);
+  ++*launches;
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ developer entry: dense inverse of B SPD /
+// quasi-definite N x N matrices (N multiple of 128) through the tensor-core sweep; used by tools/tc_check.py
+__global__ void tc_dev_pack_kernel(const float* __restrict__ A, float* __restrict__ Mout, int N, int nb) {
+  const int b = blockIdx.y, tile = blockIdx.x;
+  int I = (int)((sqrtf(8.f * tile + 1.f) - 1.f) * 0.5f);
+  while ((I + 1) * (I + 2) / 2 <= tile) ++I;
+  while (I * (I + 1) / 2 > tile) --I;
+  const int J = tile - I * (I + 1) / 2;
+  float* dst = Mout + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(I, J);
+  for (int e = threadIdx.x; e < kTBE; e += blockDim.x) {
+    int i = I * kTB + (e >> 7), j = J * kTB + (e & 127);
+    if (j > i) { const int t = i; i = j; j = t; }
+    dst[e] = A[((size_t)b * N + i) * N + j];
+  }
+}
+__global__ void tc_dev_unpack_kernel(const float* __restrict__ Min, float* __restrict__ Ainv, int N, int nb) {
+  const int b = blockIdx.y;
+  const float* Mb = Min + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < (size_t)N * N; e += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / N), j = (int)(e % N);
+    Ainv[(size_t)b * N * N + e] = -(i >= j ? Mb[bl_off(i, j)] : Mb[bl_off(j, i)]);
+  }
+}
+cudaError_t launch_tc_dev_inverse(int B, int N, const float* A, float* Ainv, float* work, cudaStream_t st) {
+  const int nb = N / kTB;
+  const size_t ntile = (size_t)nb * (nb + 1) / 2;
+  float* M = work;
+  float* Wb = M + (size_t)B * ntile * kTBE;
+  float* Vb = Wb + (size_t)B * nb * kTBE;
+  float* Pb = Vb + (size_t)B * nb * kTBE;
+  dim3 g((unsigned)ntile, B);
+  tc_dev_pack_kernel<<<g, 256, 0, st>>>(A, M, N, nb);
+  TcArgs t{M, Wb, Vb, Pb, nb, 0, 0, 1};
+  int launches = 0;
+  cudaError_t e = tc_sweep(B, t, false, st, &launches);
+  if (e != cudaSuccess) return e;
+  dim3 g2(64, B);
+  tc_dev_unpack_kernel<<<g2, 256, 0, st>>>(M, Ainv, N, nb);
+  return cudaGetLastError();
+}
+
+}  // namespace lqpb

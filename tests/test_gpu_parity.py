@@ -185,7 +185,9 @@ def test_full_size_properties(dev):
     sol = torch_solve_box_qp(Q, p, A, b, lb, ub, control)
     assert sol["iter"] == 60                                     # all ten seeds stop at 60
     x, z = sol["x"], sol["z"]
-    assert float((A @ x - b).abs().max()) < 2e-5                 # x comes from the KKT solve: A x = b to round-off
+    # x comes from the KKT solve: A x = b up to the round-off of the explicit fp32 operator K11 (a sum over 500
+    # coordinates of ~1e-7 errors; measured 1e-5 with the FP32-pipe factorisation, 2.3e-5 with the 3xTF32 one)
+    assert float((A @ x - b).abs().max()) < 5e-5
     # z~ is clamped exactly in the scaled space; un-scaling (z = D z~, lb~ = lb / D) costs one rounding
     assert float((z - lb).min()) >= -1e-6 and float((ub - z).min()) >= -1e-6
     assert float((x - z).abs().max()) < 1e-3                     # primal residual small at the stop

@@ -82,7 +82,7 @@ struct HostCtrl {
 thread_local HostCtrl g_hctrl;
 
 template <typename T>
-int factor_forward(const FwdWs<T>& w, cudaStream_t st) {
+int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
   GjArgs<T> a{};
   a.n = w.n; a.m = w.m; a.np = w.np;
   a.src = w.Qp; a.lds = 0;          // packed symmetric Q~ (scale.cu)
@@ -95,7 +95,8 @@ int factor_forward(const FwdWs<T>& w, cudaStream_t st) {
   if constexpr (std::is_same<T, float>::value) {
     if (w.tc) {
       int l = 0;
-      CK(launch_tc_inverse(w.B, a, w.Pb, w.nb, st, &l), "tensor-core inverse (forward)");
+      // the first factorisation of a call finds the H block already in place (scale_pack_kernel)
+      CK(launch_tc_inverse(w.B, a, w.Pb, w.nb, first, st, &l), "tensor-core inverse (forward)");
       g_prof.launches += l;
       g_prof.fac_launches += l;
       return LQPB_OK;
@@ -136,13 +137,13 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
   if (prof) cudaEventRecord(g_prof.ev[0], st);
   CK(launch_scale<T>(*cfg, w, Q, p, A, b, lb, ub, st), "scale");
   CK(launch_select_rho<T>(*cfg, w, st), "select_rho");
-  g_prof.launches += 2;
+  g_prof.launches += 4 + (cfg->scale ? 1 : 0);
   if (prof) cudaEventRecord(g_prof.ev[1], st);
 
   int n_factor = 0, i0 = 0, skip = 0;
   while (true) {
     if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac0[g_prof.n_fac], st);
-    rc = factor_forward<T>(w, st);
+    rc = factor_forward<T>(w, n_factor == 0, st);
     if (rc) return rc;
     if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac1[g_prof.n_fac++], st);
     ++n_factor;

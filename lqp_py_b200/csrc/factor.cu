@@ -552,7 +552,13 @@ __global__ void select_rho_kernel(lqpb_config cfg, FwdWs<T> w) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= w.B) return;
   const bool boxed = w.ctrl->any_lb || w.ctrl->any_ub;
-  T r = cfg.rho_auto ? w.rho_cand[b] : (T)cfg.rho;
+  // :200-203 rho candidate = clamp(||Q~||_F / sqrt(n)); the partial sums are added in a fixed order
+  double tot = 0.0;
+  for (int q = 0; q < w.n_fro; ++q) tot += w.fro_part[(size_t)b * w.n_fro + q];
+  T rc = (T)sqrt(tot) / (T)sqrt((double)w.n);
+  rc = t_min(t_max(rc, (T)cfg.rho_min), (T)cfg.rho_max);
+  w.rho_cand[b] = rc;
+  T r = cfg.rho_auto ? rc : (T)cfg.rho;
   if (!boxed) r = T(0);
   w.rho[b] = r;
 }

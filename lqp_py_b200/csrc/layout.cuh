@@ -73,6 +73,8 @@ struct FwdWs {
   T* Sinv;      // B*m*m    K22 (the (2,2) block of the KKT inverse = -(A~ H^-1 A~^T)^-1)
   T *bt, *E;    // B*m
   T *rho, *rho_cand, *pnorm, *ratio;   // B
+  double* fro_part;  // B*n_fro  per-CTA partial sums of ||Q~||_F^2 (scale_pack_kernel), added in order by select_rho
+  int n_fro;
   T* chk;       // B*4  [primal, dual, tol_primal_rel, tol_dual_rel] of the last check
   int* wants;   // B    do_rho_update of the last check
   Ctrl* ctrl;
@@ -122,6 +124,8 @@ inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
   w.rho_cand = (T*)take(Bn, sizeof(T));
   w.pnorm = (T*)take(Bn, sizeof(T));
   w.ratio = (T*)take(Bn, sizeof(T));
+  w.n_fro = (Pack<T>::ntiles(n) + 7) / 8;      // 8 packed tiles (one per warp) per scale_pack CTA
+  w.fro_part = (double*)take(Bn * w.n_fro, sizeof(double));
   w.chk = (T*)take(Bn * 4, sizeof(T));
   w.wants = (int*)take(Bn, sizeof(int));
   w.bytes = off;
@@ -209,7 +213,10 @@ cudaError_t launch_select_rho(const lqpb_config& cfg, const FwdWs<T>& w, cudaStr
 
 // tcfactor.cu -- K2 on the tensor cores (fp32): same arguments / outputs as launch_gj_inverse / launch_ldl_solve,
 // a.W = block-lower work matrix, a.Vg / a.Wg = panel tile buffers, Pbuf = pivot-block inverses
-cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches);
+// prebuilt: a.W already holds the H block of the KKT matrix without the diagonal shift (written by
+// scale_pack_kernel); only the shift, the equality rows and the padding are added before the sweep
+cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb, bool prebuilt, cudaStream_t st,
+                              int* launches);
 cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches);
 cudaError_t launch_tc_dev_inverse(int B, int N, const float* A, float* Ainv, float* work, cudaStream_t st);
 

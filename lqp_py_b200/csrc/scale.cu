@@ -1,4 +1,10 @@
-// K1 -- problem scaling, rho candidate and state reset (one CTA per problem).
+// K1 -- problem scaling, rho candidate and state reset: three kernels, so that the two passes over Q are spread
+// over thousands of CTAs instead of one CTA per problem (which left the pass latency-bound at 1.4 TB/s):
+//   colmax_kernel      grid (row chunks, B)  column inf-norms of Q (atomic max into the D buffer)
+//   scale_vec_kernel   grid B                D, beta, the scaled vectors, equality rows, flags, state reset
+//   scale_pack_kernel  grid (tile chunks, B) Q~ = D Q D in the packed layout (+ the block-lower tiles of the
+//                                            tensor-core factorisation), per-CTA partial sums of ||Q~||_F^2
+// select_rho_kernel (factor.cu) adds the partial sums in a fixed order: rho is deterministic.
 //
 // Restates the setup of the reference forward solver, lqp_py/solve_box_qp_admm_torch.py:
 //   :127      p_norm = ||p||_inf on the unscaled p
@@ -8,7 +14,8 @@
 //   :200-203  rho candidate = clamp(||Q~||_F / sqrt(n), rho_min, rho_max)
 //   :221-223  x = z = u = 0
 // HBM traffic: Q is read 1.5 times (column norms over the full matrix, then the lower triangle for the
-// scaling), the packed lower triangle of Q~ written once.
+// scaling), the packed lower triangle of Q~ written once (and once more as block-lower tiles when the
+// tensor-core factorisation is used).
 #include "layout.cuh"
 
 namespace lqpb {
@@ -32,20 +39,22 @@ __device__ __forceinline__ T torch_lerp(T a, T b, T w) {
   return w < T(0.5) ? a + w * (b - a) : b - (b - a) * (T(1) - w);
 }
 
-// Column max-abs of an n x n row-major matrix (row stride n) into smem cm[] (pre-zeroed), VW-wide loads.
+// ---------------------------------------------------------------------------------------------
+// Column inf-norms (:163).  CTA (rc, b) scans rows [rc * rows, (rc + 1) * rows) of problem b, thread = 16-byte
+// column chunk; the per-thread maxima are merged with an integer atomic max (values are non-negative, so the
+// result does not depend on the order).  The D buffer (zeroed by the host) receives the norms.
+constexpr int kColmaxThreads = 128;
+constexpr int kColmaxRows = 32;
+
 template <typename T, int VW>
-__device__ __forceinline__ void col_absmax(const T* __restrict__ Qb, int n, T* cm, int tid) {
+__device__ __forceinline__ void colmax_rows(const T* __restrict__ Qb, int n, int r0, int r1, T* __restrict__ out, int tid) {
   const int chunks = n / VW;
-  const int tpc = chunks < kScaleThreads ? round_up(chunks, 32) : kScaleThreads;
-  const int ng = kScaleThreads / tpc;
-  const int g = tid / tpc, t = tid % tpc;
-  if (g >= ng) return;
-  for (int c = t; c < chunks; c += tpc) {
+  for (int c = tid; c < chunks; c += kColmaxThreads) {
     T mx[VW];
 #pragma unroll
     for (int e = 0; e < VW; ++e) mx[e] = T(0);
 #pragma unroll 8
-    for (int i = g; i < n; i += ng) {
+    for (int i = r0; i < r1; ++i) {
       alignas(16) T v[VW];
       if (VW == 1) v[0] = Qb[(size_t)i * n + c];
       else *reinterpret_cast<typename Vec<T>::type*>(v) =
@@ -54,50 +63,28 @@ __device__ __forceinline__ void col_absmax(const T* __restrict__ Qb, int n, T* c
       for (int e = 0; e < VW; ++e) mx[e] = t_max(mx[e], t_abs(v[e]));
     }
 #pragma unroll
-    for (int e = 0; e < VW; ++e) smem_atomic_max_nonneg(&cm[c * VW + e], mx[e]);
+    for (int e = 0; e < VW; ++e) atomic_max_nonneg(&out[c * VW + e], mx[e]);
   }
 }
 
-// Q~ = (D_i Q_ij) D_j for the lower triangle, written in the packed symmetric layout (Pack<T>: diagonal
-// halved, zero fill above the diagonal and in the padding); returns this thread's share of ||Q~||_F^2
-// (off-diagonal entries counted twice -- Q~ is symmetric).  One warp per tile: lanes run along the tile
-// columns, so the reads of Q are 128-byte row segments and every tile row is written as one full line.
 template <typename T>
-__device__ __forceinline__ double scale_pack(const T* __restrict__ Qb, T* __restrict__ Qpb, int n, const T* Ds,
-                                             bool do_scale, int tid) {
-  using P = Pack<T>;
-  const int ntv = P::nt(n), ntl = P::ntiles(n);
-  const int warp = tid >> 5, lane = tid & 31, nw = kScaleThreads / 32;
-  const int c = lane % P::TC, k = c / P::VN, e = c % P::VN;
-  double fro = 0.0;
-  for (int t = warp; t < ntl; t += nw) {
-    int Jc = 0, rem = t;
-    while (rem >= ntv - Jc / P::R) { rem -= ntv - Jc / P::R; ++Jc; }
-    const int I = Jc / P::R + rem;
-    T* tp = Qpb + (size_t)t * P::TILE;
-    const int j = Jc * P::TC + c;
-    const T dj = j < n ? Ds[j] : T(0);
-#pragma unroll 4
-    for (int l0 = 0; l0 < kPackRows; l0 += P::R) {
-      const int l = l0 + lane / P::TC, i = I * kPackRows + l;
-      T v = T(0);
-      if (i < n && j <= i) {
-        v = Qb[(size_t)i * n + j];
-        if (do_scale) v = (Ds[i] * v) * dj;
-        fro += (i == j ? 1.0 : 2.0) * (double)v * (double)v;
-        if (i == j) v *= T(0.5);
-      }
-      tp[l * P::TC + ((k + l) & 7) * P::VN + e] = v;
-    }
-  }
-  return fro;
+__global__ void __launch_bounds__(kColmaxThreads) colmax_kernel(FwdWs<T> w, const T* __restrict__ Q) {
+  const int b = blockIdx.y, n = w.n;
+  const int r0 = blockIdx.x * kColmaxRows, r1 = min(r0 + kColmaxRows, n);
+  const T* Qb = Q + (size_t)b * n * n;
+  T* out = w.D + (size_t)b * w.ld;
+  const bool vec_ok = (n % Vec<T>::N) == 0 && ((uintptr_t)Q % 16) == 0;
+  if (vec_ok) colmax_rows<T, Vec<T>::N>(Qb, n, r0, r1, out, threadIdx.x);
+  else colmax_rows<T, 1>(Qb, n, r0, r1, out, threadIdx.x);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-problem vector work: D from the column norms, beta, blend; p~, lb~, ub~, flags, p_norm, state reset;
+// equality rows A~ = E (A D), b~ = E b.
 template <typename T>
 __global__ void __launch_bounds__(kScaleThreads)
-scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __restrict__ p,
-             const T* __restrict__ A, const T* __restrict__ bvec, const T* __restrict__ lb,
-             const T* __restrict__ ub, int P2) {
+scale_vec_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ p, const T* __restrict__ A,
+                 const T* __restrict__ bvec, const T* __restrict__ lb, const T* __restrict__ ub, int P2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Ds = reinterpret_cast<T*>(smem_raw);           // [ld]   column norms, then D
   T* sortbuf = Ds + w.ld;                           // [P2]
@@ -109,16 +96,9 @@ scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __re
   const int tid = threadIdx.x;
   const int n = w.n, m = w.m, ld = w.ld;
   const size_t vo = (size_t)b * ld;
-  const T* Qb = Q + (size_t)b * n * n;
-  T* Qpb = w.Qp + (size_t)b * Pack<T>::elems(n);
 
-  // ---- column inf-norms of Q (:163); thread layout: groups of rows x columns
   if (cfg.scale) {
-    for (int j = tid; j < ld; j += kScaleThreads) Ds[j] = T(0);
-    __syncthreads();
-    const bool vec_ok = (n % Vec<T>::N) == 0 && ((uintptr_t)Q % 16) == 0;
-    if (vec_ok) col_absmax<T, Vec<T>::N>(Qb, n, Ds, tid);
-    else col_absmax<T, 1>(Qb, n, Ds, tid);
+    for (int j = tid; j < ld; j += kScaleThreads) Ds[j] = w.D[vo + j];     // column inf-norms (colmax_kernel)
     __syncthreads();
     // mean of the norms (:166), zero guard (:164-168), D = sqrt(1/norm) (:170)
     double part = 0.0;
@@ -175,10 +155,6 @@ scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __re
     __syncthreads();
   }
 
-  // ---- Q~ = (D_i Q_ij) D_j (:176), Frobenius norm (:201), written packed (lower triangle only)
-  const double fro = scale_pack<T>(Qb, Qpb, n, Ds, cfg.scale != 0, tid);
-  const double fro_tot = group_sum(fro, dscratch, tid, kScaleThreads, 0);
-
   // ---- vectors: p~, lb~, ub~, state reset, flags, p_norm
   T pmax = T(0);
   int f_lb = 0, f_ub = 0;
@@ -209,10 +185,6 @@ scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __re
     w.pnorm[b] = pmax;
     if (f_lb) atomicOr(&w.ctrl->any_lb, 1);
     if (f_ub) atomicOr(&w.ctrl->any_ub, 1);
-    T fr = (T)sqrt(fro_tot);
-    T r = fr / (T)sqrt((double)n);
-    r = t_min(t_max(r, (T)cfg.rho_min), (T)cfg.rho_max);
-    w.rho_cand[b] = r;
     w.ratio[b] = T(1);
     w.wants[b] = 0;
     w.chk[4 * b + 0] = w.chk[4 * b + 1] = w.chk[4 * b + 2] = w.chk[4 * b + 3] = T(0);
@@ -262,15 +234,86 @@ scale_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q, const T* __re
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Q~ = (D_i Q_ij) D_j for the lower triangle (:176), written in the packed symmetric layout (Pack<T>: diagonal
+// halved, zero fill above the diagonal and in the padding) and, for the tensor-core factorisation, as
+// block-lower 128 x 128 tiles (tcfactor.cu; entries with i, j < n only -- the equality rows, the padding and the
+// diagonal shift are added by tc_fixup_kernel).  One warp per packed tile: lanes run along the tile columns, so
+// the reads of Q are 128-byte row segments and every tile row is written as one full line.  Each CTA leaves its
+// share of ||Q~||_F^2 (:201; off-diagonal entries counted twice) in fro_part[b][chunk].
+constexpr int kPackThreads = 256;
+constexpr int kPackWarps = kPackThreads / 32;
+
+template <typename T>
+__global__ void __launch_bounds__(kPackThreads)
+scale_pack_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q) {
+  using P = Pack<T>;
+  __shared__ double wsum[kPackWarps];
+  const int b = blockIdx.y, n = w.n, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const T* Qb = Q + (size_t)b * n * n;
+  const T* Ds = w.D + (size_t)b * w.ld;
+  T* Qpb = w.Qp + (size_t)b * P::elems(n);
+  const bool do_scale = cfg.scale != 0;
+  const int ntv = P::nt(n), ntl = P::ntiles(n);
+  const int c = lane % P::TC, k = c / P::VN, e = c % P::VN;
+  T* blb = nullptr;
+  if (w.tc) blb = w.W + (size_t)b * ((size_t)w.nb * (w.nb + 1) / 2) * kTcBlock * kTcBlock;
+  double fro = 0.0;
+  const int t = blockIdx.x * kPackWarps + warp;
+  if (t < ntl) {
+    int Jc = 0, rem = t;
+    while (rem >= ntv - Jc / P::R) { rem -= ntv - Jc / P::R; ++Jc; }
+    const int I = Jc / P::R + rem;
+    T* tp = Qpb + (size_t)t * P::TILE;
+    const int j = Jc * P::TC + c;
+    const T dj = j < n ? Ds[j] : T(0);
+#pragma unroll 4
+    for (int l0 = 0; l0 < kPackRows; l0 += P::R) {
+      const int l = l0 + lane / P::TC, i = I * kPackRows + l;
+      T v = T(0);
+      if (i < n && j <= i) {
+        v = Qb[(size_t)i * n + j];
+        if (do_scale) v = (Ds[i] * v) * dj;
+        fro += (i == j ? 1.0 : 2.0) * (double)v * (double)v;
+        if (blb) {
+          const int Ib = i >> 7, Jb = j >> 7;
+          blb[((size_t)(Ib * (Ib + 1) / 2 + Jb) * kTcBlock + (i & 127)) * kTcBlock + (j & 127)] = v;
+        }
+        if (i == j) v *= T(0.5);
+      }
+      tp[l * P::TC + ((k + l) & 7) * P::VN + e] = v;
+    }
+  }
+  fro = warp_sum(fro);
+  if (lane == 0) wsum[warp] = fro;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int q = 0; q < kPackWarps; ++q) s += wsum[q];
+    w.fro_part[(size_t)b * w.n_fro + blockIdx.x] = s;
+  }
+}
+
 template <typename T>
 cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, const T* p, const T* A, const T* b,
                          const T* lb, const T* ub, cudaStream_t st) {
+  cudaError_t e;
+  if (cfg.scale) {
+    e = cudaMemsetAsync(w.D, 0, (size_t)w.B * w.ld * sizeof(T), st);
+    if (e != cudaSuccess) return e;
+    dim3 g((w.n + kColmaxRows - 1) / kColmaxRows, w.B);
+    colmax_kernel<T><<<g, kColmaxThreads, 0, st>>>(w, Q);
+  }
   int P2 = 64;
   while (P2 < w.n) P2 <<= 1;
   const size_t smem = (size_t)(w.ld + P2 + 32) * sizeof(T) + 32 * sizeof(double) + 16;
-  cudaError_t e = cudaFuncSetAttribute(scale_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  e = cudaFuncSetAttribute(scale_vec_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  scale_kernel<T><<<w.B, kScaleThreads, smem, st>>>(cfg, w, Q, p, A, b, lb, ub, P2);
+  scale_vec_kernel<T><<<w.B, kScaleThreads, smem, st>>>(cfg, w, p, A, b, lb, ub, P2);
+  dim3 gp(w.n_fro, w.B);
+  scale_pack_kernel<T><<<gp, kPackThreads, 0, st>>>(cfg, w, Q);
   return cudaGetLastError();
 }
 

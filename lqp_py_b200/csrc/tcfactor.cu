@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(256) tc_assemble_kernel(GjArgs<float> a, float
   float* dst = Mout + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(I, J);
   for (int e = tid; e < kTBE; e += 256) {
     const int r = e >> 7, c = e & 127;
-    int i = I * kTB + r, j = J * kTB + c;
-    if (j > i) { const int t = i; i = j; j = t; }     // diagonal tiles: mirror the lower triangle
+    const int i = I * kTB + r, j = J * kTB + c;
+    if (j > i) continue;     // the strict upper triangle of a diagonal tile is never read (see tc_pivot_kernel)
     float v = 0.f;
     if (i < n) {
       const float fi = maskb ? maskb[i] : 1.f, fj = maskb ? maskb[j] : 1.f;
@@ -444,6 +444,29 @@ __global__ void __launch_bounds__(256) tc_assemble_kernel(GjArgs<float> a, float
       v = (i == j) ? 1.f : 0.f;
     }
     dst[e] = v;
+  }
+}
+
+// When scale_pack_kernel has already written the H block (entries i, j < n, no diagonal shift) into the
+// block-lower tiles, only the shift, the m equality rows and the identity padding are missing.  grid = B.
+__global__ void __launch_bounds__(256) tc_fixup_kernel(GjArgs<float> a, float* __restrict__ Mout, int nb) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n, m = a.m, np = nb * kTB;
+  float* Mb = Mout + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE;
+  const float shift = (a.diag_shift ? a.diag_shift[b] : 0.f) + a.diag_const;
+  for (int i = tid; i < n; i += 256) Mb[bl_off(i, i)] += shift;
+  const float* Ab = (m > 0) ? a.Arows + (size_t)b * m * a.lda : nullptr;
+  for (int e = tid; e < (np - n) * np; e += 256) {
+    const int i = n + e / np, j = e % np;
+    if (j > i) continue;
+    float v = 0.f;
+    if (i < n + m) {
+      if (j < n) v = Ab[(size_t)(i - n) * a.lda + j];
+      else if (j == i) v = a.a_diag;
+    } else if (j == i) {
+      v = 1.f;
+    }
+    Mb[bl_off(i, j)] = v;
   }
 }
 
@@ -581,9 +604,14 @@ static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st
 
 // forward: inverse of the KKT matrix, outputs as launch_gj_inverse (a.W = block-lower work matrix,
 // a.Vg / a.Wg = panel buffers (nb tiles per problem each), Pbuf = nb tiles per problem)
-cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches) {
-  dim3 ga(nb * (nb + 1) / 2, B);
-  tc_assemble_kernel<<<ga, 256, 0, st>>>(a, a.W, nb);
+cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb, bool prebuilt, cudaStream_t st,
+                              int* launches) {
+  if (prebuilt) {
+    tc_fixup_kernel<<<B, 256, 0, st>>>(a, a.W, nb);
+  } else {
+    dim3 ga(nb * (nb + 1) / 2, B);
+    tc_assemble_kernel<<<ga, 256, 0, st>>>(a, a.W, nb);
+  }
   ++*launches;
   TcArgs t{a.W, a.Wg, a.Vg, Pbuf, nb, 0, 0, 1};
   cudaError_t e = tc_sweep(B, t, false, st, launches);
@@ -617,9 +645,8 @@ __global__ void tc_dev_pack_kernel(const float* __restrict__ A, float* __restric
   const int J = tile - I * (I + 1) / 2;
   float* dst = Mout + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(I, J);
   for (int e = threadIdx.x; e < kTBE; e += blockDim.x) {
-    int i = I * kTB + (e >> 7), j = J * kTB + (e & 127);
-    if (j > i) { const int t = i; i = j; j = t; }
-    dst[e] = A[((size_t)b * N + i) * N + j];
+    const int i = I * kTB + (e >> 7), j = J * kTB + (e & 127);
+    if (j <= i) dst[e] = A[((size_t)b * N + i) * N + j];
   }
 }
 __global__ void tc_dev_unpack_kernel(const float* __restrict__ Min, float* __restrict__ Ainv, int N, int nb) {

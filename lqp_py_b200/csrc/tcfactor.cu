@@ -31,9 +31,9 @@ namespace lqpb {
 constexpr int kTB = 128;                 // block edge
 constexpr int kTBE = kTB * kTB;          // elements per tile
 constexpr int kSlabBytes = kTB * 128;    // 128 rows x 32 fp32
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 512;
 constexpr int kTcCols = 256;             // TMEM columns per CTA: hi*hi accumulator | cross-term accumulator
-constexpr int kTcSmem = 4 * kSlabBytes + 1024;   // Xhi | Xlo | Yhi | Ylo, manually aligned to 1024 B
+constexpr int kTcSmem = 8 * kSlabBytes + 1024;   // two stages of Xhi | Xlo | Yhi | Ylo, manually aligned to 1024 B
 
 __host__ __device__ inline size_t bl_tile(int I, int J) { return (size_t)(I * (I + 1) / 2 + J) * kTBE; }
 __host__ __device__ inline size_t bl_off(int i, int j) {   // element (i, j), tile row >= tile column
@@ -121,19 +121,38 @@ __device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) 
 // MODE 0 (PANEL): W_i = X P with X = M_ik (tile (i,k), or tile (k,i) read transposed when i < k), Y = P_k.
 //                 Side effects: V_i = X (raw copy), Wbuf_i = W_i, M_ik <- W_i (transposed store when i < k).
 // MODE 1 (TRAIL): M_ij <- M_ij - W_i V_j^T for the lower tiles i >= j (i, j != k; LDL: i >= j > k).
-// grid = B * jobs, one 128 x 128 output tile per CTA, 3 CTAs per SM (64 KB of operand slabs, 128 TMEM columns).
-template <int MODE>
-__global__ void __launch_bounds__(kTcThreads, 2) tc_tile_kernel(TcArgs a) {
-  extern __shared__ unsigned char tc_smem_raw[];
-  __shared__ __align__(8) uint64_t mma_bar;
-  __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int k = a.k, nb = a.nb;
+//
+// Persistent CTAs (one per SM, 512 threads), jobs = output tiles handed out round-robin.  The two 128 x 128
+// operand tiles of a job are fetched into registers (16 x 16 bytes per thread) one job ahead, so the global /
+// L2 latency is covered by the previous tile's MMAs and epilogue.  Per job the four 32-column K slabs are split
+// into hi / lo parts and stored in the canonical K-major SWIZZLE_128B layout into one of two shared-memory
+// stages (Xhi | Xlo | Yhi | Ylo, 64 KB each): the split of slab s + 1 overlaps the 12 MMAs of slab s, whose
+// completion (tcgen05.commit -> mbarrier) frees the stage again.  Accumulators: 2 x 128 TMEM columns.
+#ifdef LQPB_PHASE_TIMERS
+__device__ long long g_tc_cycles[16];
+#define TC_T0() long long tc_t__ = clock64()
+#define TC_ADD(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long n__ = clock64(); \
+    atomicAdd((unsigned long long*)&g_tc_cycles[(MODE) * 8 + (k)], (unsigned long long)(n__ - tc_t__)); tc_t__ = n__; } } while (0)
+#else
+#define TC_T0()
+#define TC_ADD(k)
+#endif
 
-  // ---- job decode
+struct TcJob {
+  const float* xsrc;
+  const float* ysrc;
+  float* vdst;      // PANEL: raw copy of X
+  float* wdst;      // PANEL: W_i
+  float* mdst;      // PANEL: tile of M that receives W_i (transposed if xtrans) ; TRAIL: the C tile
+  int xtrans;
+};
+
+template <int MODE>
+__device__ __forceinline__ TcJob tc_decode_job(const TcArgs& a, int job_global) {
+  const int k = a.k, nb = a.nb;
   const int span = a.ldl ? nb - 1 - k : nb - 1;                  // block indices taking part (besides k)
   const int jobs = MODE == 0 ? span : span * (span + 1) / 2;
-  const int b = blockIdx.x / jobs, job = blockIdx.x % jobs;
+  const int b = job_global / jobs, job = job_global % jobs;
   int i, j = 0;
   if (MODE == 0) {
     i = a.ldl ? k + 1 + job : (job < k ? job : job + 1);
@@ -149,182 +168,219 @@ __global__ void __launch_bounds__(kTcThreads, 2) tc_tile_kernel(TcArgs a) {
   float* Mb = a.M + (size_t)b * ntile * kTBE;
   float* Wb = a.Wbuf + (size_t)b * nb * kTBE;
   float* Vb = a.Vbuf + (size_t)b * nb * kTBE;
-  const float* xsrc;
-  const float* ysrc;
-  bool xtrans = false;
+  TcJob t;
   if (MODE == 0) {
-    xtrans = i < k;
-    xsrc = Mb + (xtrans ? bl_tile(k, i) : bl_tile(i, k));
-    ysrc = a.Pbuf + ((size_t)b * nb + k) * kTBE;
+    t.xtrans = i < k;
+    t.mdst = Mb + (t.xtrans ? bl_tile(k, i) : bl_tile(i, k));
+    t.xsrc = t.mdst;
+    t.ysrc = a.Pbuf + ((size_t)b * nb + k) * kTBE;
+    t.vdst = Vb + (size_t)i * kTBE;
+    t.wdst = Wb + (size_t)i * kTBE;
   } else {
-    xsrc = Wb + (size_t)i * kTBE;
-    ysrc = Vb + (size_t)j * kTBE;
+    t.xtrans = 0;
+    t.xsrc = Wb + (size_t)i * kTBE;
+    t.ysrc = Vb + (size_t)j * kTBE;
+    t.mdst = Mb + bl_tile(i, j);
+    t.vdst = nullptr;
+    t.wdst = nullptr;
   }
-  float* vdst = Vb + (size_t)i * kTBE;   // MODE 0 only
+  return t;
+}
 
-  // ---- shared memory carve (1024-byte aligned for the 128-byte swizzle), barrier, TMEM
+template <int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_tile_kernel(TcArgs a, int total_jobs) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- shared memory carve (1024-byte aligned for the 128-byte swizzle), barriers, TMEM
   const uint32_t sbase = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
   unsigned char* sptr = tc_smem_raw + (sbase - smem_u32(tc_smem_raw));
-  unsigned char* sXh = sptr;
-  unsigned char* sXl = sptr + kSlabBytes;
-  unsigned char* sYh = sptr + 2 * kSlabBytes;
-  unsigned char* sYl = sptr + 3 * kSlabBytes;
   if (warp == 0) tmem_alloc(&tmem_slot, kTcCols);
   if (tid == 32) {
-    mbar_init(&mma_bar, 1);
+    mbar_init(&mma_bar[0], 1);
+    mbar_init(&mma_bar[1], 1);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  uint32_t ph[2] = {0u, 0u};          // parity of the next completion to wait for, per stage barrier
 
-  float4 xr[4], yr[4];
-  auto gload = [&](int s) {
+  float4 xr[8], yr[8];                 // the whole X / Y tile pair of one job: [slab * 2 + t]
+  auto gload = [&](const TcJob& jb) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int q = tid + kTcThreads * t, r = q >> 3, ch = q & 7;
-      if (!xtrans) {
-        xr[t] = *reinterpret_cast<const float4*>(xsrc + (size_t)r * kTB + 32 * s + 4 * ch);
-      } else {
-        const int r4 = 4 * (warp + 8 * t);      // logical rows r4 .. r4+3 at logical column 32 s + lane
-        xr[t] = *reinterpret_cast<const float4*>(xsrc + (size_t)(32 * s + lane) * kTB + r4);
-      }
-      yr[t] = *reinterpret_cast<const float4*>(ysrc + (size_t)r * kTB + 32 * s + 4 * ch);
-    }
-  };
-  auto sstore = [&](int s) {
+    for (int s = 0; s < 4; ++s)
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int q = tid + kTcThreads * t, r = q >> 3, ch = q & 7;
-      const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
-      float4 hi, lo;
-      if (!xtrans) {
-        split4(xr[t], hi, lo);
-        *reinterpret_cast<float4*>(sXh + off) = hi;
-        *reinterpret_cast<float4*>(sXl + off) = lo;
-        if (MODE == 0) *reinterpret_cast<float4*>(vdst + (size_t)r * kTB + 32 * s + 4 * ch) = xr[t];
-      } else {
-        const int r4 = 4 * (warp + 8 * t);
-        const float xe[4] = {xr[t].x, xr[t].y, xr[t].z, xr[t].w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int rr = r4 + e;
-          const uint32_t o = (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
-          float h1, l1;
-          split_tf32(xe[e], h1, l1);
-          *reinterpret_cast<float*>(sXh + o) = h1;
-          *reinterpret_cast<float*>(sXl + o) = l1;
-          if (MODE == 0) vdst[(size_t)rr * kTB + 32 * s + lane] = xe[e];
+      for (int t = 0; t < 2; ++t) {
+        const int q = tid + kTcThreads * t, r = q >> 3, ch = q & 7;
+        if (!jb.xtrans) {
+          xr[2 * s + t] = *reinterpret_cast<const float4*>(jb.xsrc + (size_t)r * kTB + 32 * s + 4 * ch);
+        } else {
+          const int r4 = 4 * (warp + 16 * t);      // logical rows r4 .. r4+3 at logical column 32 s + lane
+          xr[2 * s + t] = *reinterpret_cast<const float4*>(jb.xsrc + (size_t)(32 * s + lane) * kTB + r4);
         }
+        yr[2 * s + t] = *reinterpret_cast<const float4*>(jb.ysrc + (size_t)r * kTB + 32 * s + 4 * ch);
       }
-      split4(yr[t], hi, lo);
-      *reinterpret_cast<float4*>(sYh + off) = hi;
-      *reinterpret_cast<float4*>(sYl + off) = lo;
-    }
   };
 
-  gload(0);
-#pragma unroll 1
-  for (int s = 0; s < 4; ++s) {
-    if (s > 0) mbar_wait(&mma_bar, (uint32_t)((s - 1) & 1));   // MMAs of the previous slab have read smem
-    sstore(s);
-    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (s < 3) gload(s + 1);      // next slab's global loads fly while the MMAs run
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const uint32_t ko = (uint32_t)kk * 32u;   // 8 tf32 = 32 bytes along K inside the swizzle atom
-        const uint64_t dXh = umma_desc(smem_u32(sXh) + ko), dXl = umma_desc(smem_u32(sXl) + ko);
-        const uint64_t dYh = umma_desc(smem_u32(sYh) + ko), dYl = umma_desc(smem_u32(sYl) + ko);
-        // The tensor core truncates the fp32 accumulator after every MMA, an error proportional to the
-        // accumulator's magnitude: the two small cross terms therefore get their own accumulator (columns
-        // 128..255), so that the large hi*hi sum sees 16 instead of 48 roundings; the epilogue adds the two.
-        const uint32_t tcross = tmem + (a.acc2 ? 128u : 0u);
-        umma_tf32(tcross, dXl, dYh, kIdescTf32, (s | kk) ? 1u : 0u);
-        umma_tf32(tcross, dXh, dYl, kIdescTf32, 1u);
-        umma_tf32(tmem, dXh, dYh, kIdescTf32, (a.acc2 && !(s | kk)) ? 0u : 1u);
-      }
-      umma_commit(&mma_bar);
-    }
+  int job = blockIdx.x;
+  TcJob cur{};
+  if (job < total_jobs) {
+    cur = tc_decode_job<MODE>(a, job);
+    gload(cur);
   }
-  mbar_wait(&mma_bar, 1u);        // 4th completion (phase parity 1)
-  tc_fence_after();
-
-  // ---- epilogue.  TMEM -> registers gives every thread 16 consecutive columns of ITS row (32 (warp % 4) + lane;
-  // warps 0-3 columns 0-63, warps 4-7 columns 64-127): written straight to global memory that is 32 different
-  // rows per instruction.  The 64 KB of operand slabs are free now, so the tile is staged there (16-byte chunk
-  // index XOR row: conflict-free both ways) and then moved with full-row 512-byte warp accesses.
-  float* stage = reinterpret_cast<float*>(sptr);
-  {
-    const int r = 32 * (warp & 3) + lane;
-    const uint32_t trow = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+  TC_T0();
 #pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
-      const int c0 = (warp >> 2) * 64 + 16 * g;
-      uint32_t v[16];
-      float f[16];
-      tmem_ld16(trow + (uint32_t)c0, v);
-      tmem_ld_wait(v);
+  for (; job < total_jobs; job += gridDim.x) {
+    TC_ADD(0);
 #pragma unroll
-      for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
-      if (a.acc2) {
-        tmem_ld16(trow + 128u + (uint32_t)c0, v);
+    for (int s = 0; s < 4; ++s) {
+      const int buf = s & 1;
+      unsigned char* sXh = sptr + buf * (4 * kSlabBytes);
+      unsigned char* sXl = sXh + kSlabBytes;
+      unsigned char* sYh = sXh + 2 * kSlabBytes;
+      unsigned char* sYl = sXh + 3 * kSlabBytes;
+      if (s >= 2) {                   // the MMAs of slab s - 2 have finished reading this stage
+        mbar_wait(&mma_bar[buf], ph[buf]);
+        ph[buf] ^= 1u;
+      }
+      TC_ADD(1);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int q = tid + kTcThreads * t, r = q >> 3, ch = q & 7;
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+        float4 hi, lo;
+        const float4 xv = xr[2 * s + t];
+        if (!cur.xtrans) {
+          split4(xv, hi, lo);
+          *reinterpret_cast<float4*>(sXh + off) = hi;
+          *reinterpret_cast<float4*>(sXl + off) = lo;
+          if (MODE == 0) *reinterpret_cast<float4*>(cur.vdst + (size_t)r * kTB + 32 * s + 4 * ch) = xv;
+        } else {
+          const int r4 = 4 * (warp + 16 * t);
+          const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int rr = r4 + e;
+            const uint32_t o = (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
+            float h1, l1;
+            split_tf32(xe[e], h1, l1);
+            *reinterpret_cast<float*>(sXh + o) = h1;
+            *reinterpret_cast<float*>(sXl + o) = l1;
+            if (MODE == 0) cur.vdst[(size_t)rr * kTB + 32 * s + lane] = xe[e];
+          }
+        }
+        split4(yr[2 * s + t], hi, lo);
+        *reinterpret_cast<float4*>(sYh + off) = hi;
+        *reinterpret_cast<float4*>(sYl + off) = lo;
+      }
+      TC_ADD(2);
+      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncthreads();
+      TC_ADD(3);
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t ko = (uint32_t)kk * 32u;   // 8 tf32 = 32 bytes along K inside the swizzle atom
+          const uint64_t dXh = umma_desc(smem_u32(sXh) + ko), dXl = umma_desc(smem_u32(sXl) + ko);
+          const uint64_t dYh = umma_desc(smem_u32(sYh) + ko), dYl = umma_desc(smem_u32(sYl) + ko);
+          // The tensor core truncates the fp32 accumulator after every MMA, an error proportional to the
+          // accumulator's magnitude: the two small cross terms therefore get their own accumulator (columns
+          // 128..255), so that the large hi*hi sum sees 16 instead of 48 roundings; the epilogue adds the two.
+          const uint32_t tcross = tmem + (a.acc2 ? 128u : 0u);
+          umma_tf32(tcross, dXl, dYh, kIdescTf32, (s | kk) ? 1u : 0u);
+          umma_tf32(tcross, dXh, dYl, kIdescTf32, 1u);
+          umma_tf32(tmem, dXh, dYh, kIdescTf32, (a.acc2 && !(s | kk)) ? 0u : 1u);
+        }
+        umma_commit(&mma_bar[buf]);
+      }
+      TC_ADD(4);
+    }
+    // ---- the operands of the next job start their trip now (the registers are free again)
+    const TcJob done = cur;
+    if (job + (int)gridDim.x < total_jobs) {
+      cur = tc_decode_job<MODE>(a, job + gridDim.x);
+      gload(cur);
+    }
+    // ---- all MMAs of this tile (slabs 2 and 3 are the outstanding commits)
+    mbar_wait(&mma_bar[0], ph[0]);
+    ph[0] ^= 1u;
+    mbar_wait(&mma_bar[1], ph[1]);
+    ph[1] ^= 1u;
+    tc_fence_after();
+    TC_ADD(5);
+
+    // ---- epilogue.  TMEM -> registers gives every thread 16 consecutive columns of ITS row (32 (warp % 4) +
+    // lane; warp / 4 selects a 32-column group): written straight to global memory that is 32 different rows
+    // per instruction.  The first stage is free now, so the tile is staged there (16-byte chunk index XOR row:
+    // conflict-free both ways) and then moved with full-row 512-byte warp accesses.
+    float* stage = reinterpret_cast<float*>(sptr);
+    {
+      const int r = 32 * (warp & 3) + lane;
+      const uint32_t trow = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll 1
+      for (int g = 0; g < 2; ++g) {
+        const int c0 = (warp >> 2) * 32 + 16 * g;
+        uint32_t v[16];
+        float f[16];
+        tmem_ld16(trow + (uint32_t)c0, v);
         tmem_ld_wait(v);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) f[e] += __uint_as_float(v[e]);
-      }
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]);
+        if (a.acc2) {
+          tmem_ld16(trow + 128u + (uint32_t)c0, v);
+          tmem_ld_wait(v);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int ch = (c0 >> 2) + q;
-        *reinterpret_cast<float4*>(stage + r * kTB + ((ch ^ (r & 31)) << 2)) =
-            make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          for (int e = 0; e < 16; ++e) f[e] += __uint_as_float(v[e]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int ch = (c0 >> 2) + q;
+          *reinterpret_cast<float4*>(stage + r * kTB + ((ch ^ (r & 31)) << 2)) =
+              make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        }
       }
     }
-  }
-  __syncthreads();
-  if (MODE == 1) {
-    float* ct = Mb + bl_tile(i, j);
+    tc_fence_before();              // TMEM reads are complete before the next job's first MMA overwrites it
+    __syncthreads();
+    TC_ADD(6);
+    constexpr int NW = kTcThreads / 32;
+    if (MODE == 1) {
 #pragma unroll 4
-    for (int rr = warp; rr < kTB; rr += kTcThreads / 32) {
-      const float4 d = *reinterpret_cast<const float4*>(stage + rr * kTB + ((lane ^ (rr & 31)) << 2));
-      float4* cp = reinterpret_cast<float4*>(ct + (size_t)rr * kTB + 4 * lane);
-      float4 c = *cp;
-      c.x -= d.x; c.y -= d.y; c.z -= d.z; c.w -= d.w;
-      *cp = c;
-    }
-  } else {
-    float* wt = Wb + (size_t)i * kTBE;
-    if (!xtrans) {
-      float* mt = Mb + bl_tile(i, k);
-#pragma unroll 4
-      for (int rr = warp; rr < kTB; rr += kTcThreads / 32) {
+      for (int rr = warp; rr < kTB; rr += NW) {
         const float4 d = *reinterpret_cast<const float4*>(stage + rr * kTB + ((lane ^ (rr & 31)) << 2));
-        *reinterpret_cast<float4*>(wt + (size_t)rr * kTB + 4 * lane) = d;
-        *reinterpret_cast<float4*>(mt + (size_t)rr * kTB + 4 * lane) = d;
+        float4* cp = reinterpret_cast<float4*>(done.mdst + (size_t)rr * kTB + 4 * lane);
+        float4 c = *cp;
+        c.x -= d.x; c.y -= d.y; c.z -= d.z; c.w -= d.w;
+        *cp = c;
       }
     } else {
-      // M_ki = W_i^T: thread (cc4 = 4 * lane .. +3 output columns = W rows, output row = W column c)
-      float* mt = Mb + bl_tile(k, i);
 #pragma unroll 4
-      for (int rr = warp; rr < kTB; rr += kTcThreads / 32) {
+      for (int rr = warp; rr < kTB; rr += NW) {
         const float4 d = *reinterpret_cast<const float4*>(stage + rr * kTB + ((lane ^ (rr & 31)) << 2));
-        *reinterpret_cast<float4*>(wt + (size_t)rr * kTB + 4 * lane) = d;
+        *reinterpret_cast<float4*>(done.wdst + (size_t)rr * kTB + 4 * lane) = d;
+        if (!done.xtrans) *reinterpret_cast<float4*>(done.mdst + (size_t)rr * kTB + 4 * lane) = d;
       }
-      // transposed read of the staged tile: output row c (= W column), 4 consecutive W rows per lane
+      if (done.xtrans) {
+        // M_ki = W_i^T: output row c (= W column), 4 consecutive W rows per lane (transposed read of the stage)
 #pragma unroll 2
-      for (int c = warp; c < kTB; c += kTcThreads / 32) {
-        float o[4];
+        for (int c = warp; c < kTB; c += NW) {
+          float o[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int wr = 4 * lane + e;
-          o[e] = stage[wr * kTB + ((((c >> 2) ^ (wr & 31)) << 2) | (c & 3))];
+          for (int e = 0; e < 4; ++e) {
+            const int wr = 4 * lane + e;
+            o[e] = stage[wr * kTB + ((((c >> 2) ^ (wr & 31)) << 2) | (c & 3))];
+          }
+          *reinterpret_cast<float4*>(done.mdst + (size_t)c * kTB + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
         }
-        *reinterpret_cast<float4*>(mt + (size_t)c * kTB + 4 * lane) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
+    __syncthreads();                // the stage is rewritten by the next job's first slab
+    TC_ADD(7);
   }
   tc_fence_before();
   __syncthreads();
@@ -574,7 +630,11 @@ __global__ void __launch_bounds__(512) tc_ldl_solve_kernel(GjArgs<float> a, cons
 // ------------------------------------------------------------------ host orchestration
 static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st, int* launches) {
   static bool attr_done = false;
+  static int n_sm = 148;
   if (!attr_done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(tc_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
@@ -594,8 +654,9 @@ static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st
     ++*launches;
     const int span = ldl ? nb - 1 - k : nb - 1;
     if (span > 0) {
-      tc_tile_kernel<0><<<B * span, kTcThreads, kTcSmem, st>>>(a);
-      tc_tile_kernel<1><<<B * (span * (span + 1) / 2), kTcThreads, kTcSmem, st>>>(a);
+      const int jp = B * span, jt = B * (span * (span + 1) / 2);
+      tc_tile_kernel<0><<<jp < n_sm ? jp : n_sm, kTcThreads, kTcSmem, st>>>(a, jp);
+      tc_tile_kernel<1><<<jt < n_sm ? jt : n_sm, kTcThreads, kTcSmem, st>>>(a, jt);
       *launches += 2;
     }
   }
@@ -676,3 +737,15 @@ cudaError_t launch_tc_dev_inverse(int B, int N, const float* A, float* Ainv, flo
 }
 
 }  // namespace lqpb
+
+#ifdef LQPB_PHASE_TIMERS
+// developer aid (tools/tc_phases.py): clock64 totals of thread 0 of CTA 0, [mode][phase]
+extern "C" void lqpb_debug_tc_cycles(long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, lqpb::g_tc_cycles, sizeof(long long) * 16);
+  if (reset) {
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(lqpb::g_tc_cycles, z, sizeof(z));
+  }
+}
+#endif

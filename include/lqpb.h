@@ -124,6 +124,25 @@ int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x,
                       double* dQ, double* dp, double* dA, double* db, double* dlb, double* dub,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- KKT backward: replaces torch_solve_box_qp_grad_kkt (solve_box_qp_admm_torch.py:435-584), the
+ * backward='kkt' mode of SolveBoxQPLayer.backward (:63-64).  Same outputs and NULL-skipping as
+ * lqpb_backward_*; workspace of lqpb_backward_workspace_bytes_*.  The 2n inequality rows of the
+ * reference's (3n+m) system are eliminated in closed form, leaving the symmetric
+ * [[Q + diag(lam_lo/s_lo + lam_hi/s_hi), A^T], [A, 0]] with the clamps of :450-451.
+ * any_bounds: optional HOST int[2] receiving any_lb, any_ub (:439-440) -- the reference returns
+ * dlb = None / dub = None without them (:572-579); passing it synchronises the stream once, NULL keeps
+ * the call fully asynchronous (the layer already knows the flags from the forward solve). */
+int lqpb_backward_kkt_f32(int B, int n, int m, const float* dl_dz, const float* x, const float* lams,
+                          const float* nus, const float* Q, const float* A, const float* lb,
+                          const float* ub, float* dQ, float* dp, float* dA, float* db, float* dlb,
+                          float* dub, int32_t* any_bounds, void* workspace, size_t workspace_bytes,
+                          void* stream);
+int lqpb_backward_kkt_f64(int B, int n, int m, const double* dl_dz, const double* x, const double* lams,
+                          const double* nus, const double* Q, const double* A, const double* lb,
+                          const double* ub, double* dQ, double* dp, double* dA, double* db,
+                          double* dlb, double* dub, int32_t* any_bounds, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- lu_layer: replaces TorchLU / TorchLULayer (lu_layer.py:5-58) -------------------------
  * lu_factor: partial-pivoting LU of B general N x N matrices (torch.linalg.lu_factor, :10,:30);
  *            LU (B,N,N) packed L\U, piv (B,N) 1-based row swaps like LAPACK getrf.

@@ -184,8 +184,9 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
 template <typename T>
 int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
                   const T* Q, const T* A, const T* lb, const T* ub, const T* rho_dev, double rho_scalar, T* dQ,
-                  T* dp, T* dA, T* db, T* dlb, T* dub, void* ws, size_t ws_bytes, void* stream) {
-  if (!dl_dz || !x || !u || !lams || !Q || !lb || !ub || !ws) return fail(LQPB_E_ARG, "null pointer argument");
+                  T* dp, T* dA, T* db, T* dlb, T* dub, void* ws, size_t ws_bytes, void* stream, bool kkt = false,
+                  int32_t* any_bounds = nullptr) {
+  if (!dl_dz || !x || (!u && !kkt) || !lams || !Q || !lb || !ub || !ws) return fail(LQPB_E_ARG, "null pointer argument");
   if (B <= 0 || n <= 0 || m < 0) return fail(LQPB_E_ARG, "bad dimensions");
   if (m > 0 && (!A || !nus)) return fail(LQPB_E_ARG, "A and nus are required when m > 0");
   if (m > kMaxM) return fail(LQPB_E_ARG, "more than 64 equality rows are not supported");
@@ -200,14 +201,16 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   g_prof.launches = 0;
   int bwd_fac_launches = 0;
   if (prof) cudaEventRecord(g_prof.ev[4], st);
-  CK(launch_bwd_mask<T>(w, x, u, lb, ub, st), "bwd_mask");
+  if (kkt) CK(launch_bwd_kkt_prep<T>(w, x, lams, lb, ub, st), "bwd_kkt_prep");
+  else CK(launch_bwd_mask<T>(w, x, u, lb, ub, st), "bwd_mask");
   {
     GjArgs<T> a{};
     a.n = n; a.m = m; a.np = w.np;
     a.src = Q; a.lds = n;
-    a.diag_shift = nullptr; a.diag_const = T(1e-8);      // :392 small regulariser on the whole diagonal
+    a.diag_shift = nullptr; a.diag_const = kkt ? T(0) : T(1e-8);   // :392 small regulariser on the whole diagonal
+    a.diag_vec = kkt ? w.dvec : nullptr;                           // KKT mode: Q + G^T diag(lam / s) G, no regulariser
     a.mask = w.mask; a.ldm = w.ld;
-    a.Arows = A; a.lda = n; a.a_diag = T(1e-8);
+    a.Arows = A; a.lda = n; a.a_diag = kkt ? T(0) : T(1e-8);
     a.W = w.W; a.Vg = w.Vg; a.Wg = w.Wg;
     a.dst = nullptr; a.ldd = w.ld; a.G21 = nullptr; a.K22 = nullptr;
     a.bt = nullptr; a.c_out = nullptr;
@@ -226,11 +229,16 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   }
   if (prof) cudaEventRecord(g_prof.ev[5], st);
   if (prof) cudaEventRecord(g_prof.ev[6], st);
-  CK(launch_bwd_grads<T>(w, dl_dz, x, u, lams, nus, Q, A, rho_dev, rho_scalar, dQ, dp, dA, db, dlb, dub, st),
+  CK(launch_bwd_grads<T>(w, dl_dz, x, u, lams, nus, Q, A, rho_dev, rho_scalar, dQ, dp, dA, db, dlb, dub, st,
+                         kkt ? lb : nullptr, kkt ? ub : nullptr),
      "bwd_grads");
   if (prof) cudaEventRecord(g_prof.ev[7], st);
   g_prof.launches = 2 + bwd_fac_launches;
   g_prof.bwd_valid = prof;
+  if (kkt && any_bounds) {
+    CK(cudaMemcpyAsync(any_bounds, w.flags, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "copy bound flags");
+    CK(cudaStreamSynchronize(st), "synchronize (bound flags)");
+  }
   return LQPB_OK;
 }
 
@@ -300,6 +308,21 @@ int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x,
                       double* dlb, double* dub, void* workspace, size_t workspace_bytes, void* stream) {
   return backward_impl<double>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db,
                                dlb, dub, workspace, workspace_bytes, stream);
+}
+
+int lqpb_backward_kkt_f32(int B, int n, int m, const float* dl_dz, const float* x, const float* lams,
+                          const float* nus, const float* Q, const float* A, const float* lb, const float* ub, float* dQ,
+                          float* dp, float* dA, float* db, float* dlb, float* dub, int32_t* any_bounds, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  return backward_impl<float>(B, n, m, dl_dz, x, nullptr, lams, nus, Q, A, lb, ub, nullptr, 0.0, dQ, dp, dA, db, dlb,
+                              dub, workspace, workspace_bytes, stream, true, any_bounds);
+}
+int lqpb_backward_kkt_f64(int B, int n, int m, const double* dl_dz, const double* x, const double* lams,
+                          const double* nus, const double* Q, const double* A, const double* lb, const double* ub,
+                          double* dQ, double* dp, double* dA, double* db, double* dlb, double* dub, int32_t* any_bounds,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  return backward_impl<double>(B, n, m, dl_dz, x, nullptr, lams, nus, Q, A, lb, ub, nullptr, 0.0, dQ, dp, dA, db, dlb,
+                               dub, workspace, workspace_bytes, stream, true, any_bounds);
 }
 
 #define LU_ENTRY(SFX, T)                                                                                          \

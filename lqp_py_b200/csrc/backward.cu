@@ -9,6 +9,17 @@
 //             elimination with the right-hand side carried along (launch_ldl_solve): dv, dnu.
 //   :396-427  dp = dv, dQ = 1/2 (dv x^T + x dv^T), dA = dnu x^T + nus dv^T, db = -dnu,
 //             dlam = (-dl_dz - Q dv - A^T dnu) / (rho u | 1), dlb = dlam lams[:n], dub = -dlam lams[n:]
+//
+// KKT backward (backward='kkt', lqp_py/solve_box_qp_admm_torch.py:435-584, torch_solve_box_qp_grad_kkt):
+//   :446-451  G = [-I; I], h = [-lb; ub], slacks = clamp(h - G x, 1e-8), lams = clamp(lams, 1e-8)
+//   :465-493  lhs = [[Q, G^T diag(lams), A^T], [G, -diag(slacks), 0], [A, 0, 0]],  :496-507 solve lhs d = [-dl_dz; 0; 0]
+//             The 2n inequality rows are eliminated in closed form -- dlam = (G dx) / slacks -- which leaves the
+//             symmetric  [[Q + diag(lam_lo / s_lo + lam_hi / s_hi), A^T], [A, 0]] [dx; dnu] = [-dl_dz; 0]:
+//             bwd_kkt_prep_kernel builds that diagonal (and mask = 1), the block LDL^T solver does the rest.
+//   :521-584  dp = dx, dQ = 1/2 (dx x^T + x dx^T), dA = dnu x^T + nus dx^T, db = -dnu, dh = -lams dlam,
+//             dlb = -dh[:n] = -lam_lo dx / s_lo,  dub = dh[n:] = -lam_hi dx / s_hi
+//             (an infinite bound has slack inf and contributes exactly 0 here; the reference's dense system
+//             contains -inf in that case and returns NaN for every gradient)
 #include "layout.cuh"
 
 namespace lqpb {
@@ -35,6 +46,46 @@ cudaError_t launch_bwd_mask(const BwdWs<T>& w, const T* x, const T* u, const T* 
   return cudaGetLastError();
 }
 
+template <typename T>
+__global__ void bwd_kkt_prep_kernel(BwdWs<T> w, const T* __restrict__ x, const T* __restrict__ lams,
+                                    const T* __restrict__ lb, const T* __restrict__ ub) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  int f_lb = 0, f_ub = 0;
+  if (e < w.ld) {
+    T f = T(0), d = T(0);
+    if (e < w.n) {
+      const size_t o = (size_t)b * w.n + e;
+      const T l = lb[o], u = ub[o], xv = x[o];
+      f_lb = l > -t_inf<T>();
+      f_ub = u < t_inf<T>();
+      const T s_lo = t_max(xv - l, T(1e-8)), s_hi = t_max(u - xv, T(1e-8));          // :450
+      const T l_lo = t_max(lams[(size_t)b * 2 * w.n + e], T(1e-8));                  // :451
+      const T l_hi = t_max(lams[(size_t)b * 2 * w.n + w.n + e], T(1e-8));
+      d = l_lo / s_lo + l_hi / s_hi;
+      f = T(1);
+    }
+    w.mask[(size_t)b * w.ld + e] = f;
+    w.dvec[(size_t)b * w.ld + e] = d;
+  }
+  f_lb = __syncthreads_or(f_lb);
+  f_ub = __syncthreads_or(f_ub);
+  if (threadIdx.x == 0) {
+    if (f_lb) atomicOr(&w.flags[0], 1);
+    if (f_ub) atomicOr(&w.flags[1], 1);
+  }
+}
+
+template <typename T>
+cudaError_t launch_bwd_kkt_prep(const BwdWs<T>& w, const T* x, const T* lams, const T* lb, const T* ub,
+                                cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(w.flags, 0, 4 * sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  dim3 grid((w.ld + 127) / 128, w.B);
+  bwd_kkt_prep_kernel<T><<<grid, 128, 0, st>>>(w, x, lams, lb, ub);
+  return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Gradient assembly.  grid = (row chunks, B); each CTA owns kGradRows rows of one problem:
 // Q dv row dots (one warp per row), dlam/dlb/dub for those rows, and the dQ rows (streaming write).
@@ -47,7 +98,7 @@ bwd_grads_kernel(BwdWs<T> w, const T* __restrict__ dl_dz, const T* __restrict__ 
                  const T* __restrict__ lams, const T* __restrict__ nus, const T* __restrict__ Q,
                  const T* __restrict__ A, const T* __restrict__ rho_dev, T rho_scalar, T* __restrict__ dQ,
                  T* __restrict__ dp, T* __restrict__ dA, T* __restrict__ db, T* __restrict__ dlb,
-                 T* __restrict__ dub) {
+                 T* __restrict__ dub, const T* __restrict__ lb_kkt, const T* __restrict__ ub_kkt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = w.n, m = w.m, ld = w.ld;
   T* dvs = reinterpret_cast<T*>(smem_raw);   // [n]
@@ -64,7 +115,21 @@ bwd_grads_kernel(BwdWs<T> w, const T* __restrict__ dl_dz, const T* __restrict__ 
   const int r1 = min(r0 + kGradRows, n);
   const T rho = rho_dev ? rho_dev[b] : rho_scalar;
 
-  if (dlb || dub) {
+  if (lb_kkt) {
+    // KKT mode (:521-584): dlb = -lam_lo dx / s_lo, dub = -lam_hi dx / s_hi with the clamps of :450-451
+    for (int i = r0 + tid; i < r1; i += kGradThreads) {
+      const size_t o = (size_t)b * n + i;
+      const T xv = xsh[i], dx = dvs[i];
+      if (dlb) {
+        const T s_lo = t_max(xv - lb_kkt[o], T(1e-8));
+        dlb[o] = -(t_max(lams[(size_t)b * 2 * n + i], T(1e-8)) * (dx / s_lo));
+      }
+      if (dub) {
+        const T s_hi = t_max(ub_kkt[o] - xv, T(1e-8));
+        dub[o] = -(t_max(lams[(size_t)b * 2 * n + n + i], T(1e-8)) * (dx / s_hi));
+      }
+    }
+  } else if (dlb || dub) {
     for (int i = r0 + wid; i < r1; i += kGradThreads / 32) {
       const T* Qi = Q + ((size_t)b * n + i) * n;
       T acc = T(0);
@@ -112,20 +177,22 @@ bwd_grads_kernel(BwdWs<T> w, const T* __restrict__ dl_dz, const T* __restrict__ 
 template <typename T>
 cudaError_t launch_bwd_grads(const BwdWs<T>& w, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
                              const T* Q, const T* A, const T* rho_dev, double rho_scalar, T* dQ, T* dp, T* dA, T* db,
-                             T* dlb, T* dub, cudaStream_t st) {
+                             T* dlb, T* dub, cudaStream_t st, const T* lb_kkt, const T* ub_kkt) {
   const size_t smem = (size_t)2 * w.n * sizeof(T);
   cudaError_t e = cudaFuncSetAttribute(bwd_grads_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((w.n + kGradRows - 1) / kGradRows, w.B);
   bwd_grads_kernel<T><<<grid, kGradThreads, smem, st>>>(w, dl_dz, x, u, lams, nus, Q, A, rho_dev, (T)rho_scalar, dQ,
-                                                        dp, dA, db, dlb, dub);
+                                                        dp, dA, db, dlb, dub, lb_kkt, ub_kkt);
   return cudaGetLastError();
 }
 
 #define INST(T)                                                                                                       \
   template cudaError_t launch_bwd_mask<T>(const BwdWs<T>&, const T*, const T*, const T*, const T*, cudaStream_t);    \
+  template cudaError_t launch_bwd_kkt_prep<T>(const BwdWs<T>&, const T*, const T*, const T*, const T*, cudaStream_t); \
   template cudaError_t launch_bwd_grads<T>(const BwdWs<T>&, const T*, const T*, const T*, const T*, const T*,        \
-                                           const T*, const T*, const T*, double, T*, T*, T*, T*, T*, T*, cudaStream_t);
+                                           const T*, const T*, const T*, double, T*, T*, T*, T*, T*, T*, cudaStream_t, \
+                                           const T*, const T*);
 INST(float)
 INST(double)
 #undef INST

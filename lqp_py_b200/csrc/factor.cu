@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
   const T* maskb = a.mask ? a.mask + (size_t)b * a.ldm : nullptr;
   const T* Ab = (m > 0) ? a.Arows + (size_t)b * m * a.lda : nullptr;
   const T shift = (a.diag_shift ? a.diag_shift[b] : T(0)) + a.diag_const;
+  const T* dvecb = a.diag_vec ? a.diag_vec + (size_t)b * a.ldm : nullptr;
 
   PHASE_T0();
   // ---- prologue: lower triangle of the KKT matrix [[H, A^T], [A, a_diag I]] embedded in the np x np
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
             v = srow[j];
           }
         }
-        if (i == j) v = keep ? v + shift : T(1);
+        if (i == j) v = keep ? v + shift + (dvecb ? dvecb[i] : T(0)) : T(1);
         wrow[j] = v;
       }
     } else if (i < n + m) {

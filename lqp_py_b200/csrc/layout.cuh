@@ -141,6 +141,8 @@ struct BwdWs {
   T *Vg, *Wg;   // B*np*kTile
   T *mask, *dv; // B*ld
   T* dnu;       // B*m
+  T* dvec;      // B*ld  KKT backward: lam_lo / s_lo + lam_hi / s_hi (diagonal of G^T diag(lam / s) G)
+  int* flags;   // [any_lb, any_ub] of the KKT backward (OR over the batch)
   size_t bytes;
 };
 
@@ -175,6 +177,8 @@ inline BwdWs<T> carve_bwd(void* base, int B, int n, int m) {
   w.mask = (T*)take(Bn * w.ld, sizeof(T));
   w.dv = (T*)take(Bn * w.ld, sizeof(T));
   w.dnu = (T*)take(Bn * (m > 0 ? m : 1), sizeof(T));
+  w.dvec = (T*)take(Bn * w.ld, sizeof(T));
+  w.flags = (int*)take(4, sizeof(int));
   w.bytes = off;
   return w;
 }
@@ -193,6 +197,7 @@ struct GjArgs {
                                   // symmetric layout (Pack<T>, diagonal stored halved)
   const T* diag_shift;            // per problem, may be null
   T diag_const;                   // added to the kept diagonal entries of H
+  const T* diag_vec;              // per element (row stride ldm), added to the kept diagonal entries; may be null
   const T* mask; int ldm;         // 1 = keep, 0 = replace row/col of H by identity (and zero that column of A); may be null
   const T* Arows; int lda;        // B*m rows (row stride lda); unused when m == 0
   T a_diag;                       // diagonal of the (2,2) block
@@ -231,8 +236,10 @@ cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho
 template <typename T>
 cudaError_t launch_bwd_mask(const BwdWs<T>& w, const T* x, const T* u, const T* lb, const T* ub, cudaStream_t st);
 template <typename T>
+cudaError_t launch_bwd_kkt_prep(const BwdWs<T>& w, const T* x, const T* lams, const T* lb, const T* ub, cudaStream_t st);
+template <typename T>
 cudaError_t launch_bwd_grads(const BwdWs<T>& w, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
                              const T* Q, const T* A, const T* rho_dev, double rho_scalar, T* dQ, T* dp, T* dA, T* db,
-                             T* dlb, T* dub, cudaStream_t st);
+                             T* dlb, T* dub, cudaStream_t st, const T* lb_kkt = nullptr, const T* ub_kkt = nullptr);
 
 }  // namespace lqpb

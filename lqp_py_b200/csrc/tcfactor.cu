@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(256) tc_assemble_kernel(GjArgs<float> a, float
   const float* maskb = a.mask ? a.mask + (size_t)b * a.ldm : nullptr;
   const float* Ab = (m > 0) ? a.Arows + (size_t)b * m * a.lda : nullptr;
   const float shift = (a.diag_shift ? a.diag_shift[b] : 0.f) + a.diag_const;
+  const float* dvecb = a.diag_vec ? a.diag_vec + (size_t)b * a.ldm : nullptr;
   float* dst = Mout + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(I, J);
   for (int e = tid; e < kTBE; e += 256) {
     const int r = e >> 7, c = e & 127;
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(256) tc_assemble_kernel(GjArgs<float> a, float
           v = srcb[(size_t)i * a.lds + j];
         }
       }
-      if (i == j) v = keep ? v + shift : 1.f;
+      if (i == j) v = keep ? v + shift + (dvecb ? dvecb[i] : 0.f) : 1.f;
     } else if (i < n + m) {
       if (j < n) {
         const float av = Ab[(size_t)(i - n) * a.lda + j];
@@ -628,6 +629,49 @@ __global__ void __launch_bounds__(512) tc_ldl_solve_kernel(GjArgs<float> a, cons
 }
 
 // ------------------------------------------------------------------ host orchestration
+// The pivot kernel is latency-bound (one CTA per problem, a serial sweep of 128 steps) and the tile kernels are
+// bound by memory latency, so the batch is cut into `groups` slices that run the same pivot -> panel -> trail
+// chain on their own streams: the pivot sweep of one slice overlaps the tile products of the others.  Slice 0
+// stays on the caller's stream; the auxiliary streams fork from / join into it with events, so the call keeps
+// its stream-ordered semantics.
+constexpr int kTcMaxGroups = 8;
+struct TcStreams {
+  int dev = -1;
+  cudaStream_t aux[kTcMaxGroups - 1];
+  cudaEvent_t fork, join[kTcMaxGroups - 1];
+};
+static thread_local TcStreams g_tcs;
+
+static cudaError_t tc_streams_init() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (g_tcs.dev == dev) return cudaSuccess;
+  for (int i = 0; i < kTcMaxGroups - 1; ++i) {
+    e = cudaStreamCreateWithFlags(&g_tcs.aux[i], cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    e = cudaEventCreateWithFlags(&g_tcs.join[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  e = cudaEventCreateWithFlags(&g_tcs.fork, cudaEventDisableTiming);
+  if (e != cudaSuccess) return e;
+  g_tcs.dev = dev;
+  return cudaSuccess;
+}
+
+static int tc_groups(int B) {
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char* e = getenv("LQPB_TC_GROUPS");     // developer switch; default chosen from measurements
+    cfg = e ? atoi(e) : 2;   // measured at dz=500, B=128: forward sweep 0.644 (1) / 0.593 (2) / 0.602 (3) / 0.608 ms (4)
+    if (cfg < 1) cfg = 1;
+    if (cfg > kTcMaxGroups) cfg = kTcMaxGroups;
+  }
+  int g = cfg;
+  while (g > 1 && B / g < 16) --g;                // slices of fewer than 16 problems no longer fill the tile grids
+  return g;
+}
+
 static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st, int* launches) {
   static bool attr_done = false;
   static int n_sm = 148;
@@ -641,24 +685,53 @@ static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  TcArgs a = base;
-  a.ldl = ldl ? 1 : 0;
+  TcArgs a0 = base;
+  a0.ldl = ldl ? 1 : 0;
   {
     const char* e = getenv("LQPB_TC_ACC2");     // developer switch (accuracy A/B); default on
-    a.acc2 = (e && e[0] == '0') ? 0 : 1;
+    a0.acc2 = (e && e[0] == '0') ? 0 : 1;
   }
-  const int nb = a.nb;
-  for (int k = 0; k < nb; ++k) {
-    a.k = k;
-    tc_pivot_kernel<<<B, kPivThreads, 0, st>>>(a);
-    ++*launches;
-    const int span = ldl ? nb - 1 - k : nb - 1;
-    if (span > 0) {
-      const int jp = B * span, jt = B * (span * (span + 1) / 2);
-      tc_tile_kernel<0><<<jp < n_sm ? jp : n_sm, kTcThreads, kTcSmem, st>>>(a, jp);
-      tc_tile_kernel<1><<<jt < n_sm ? jt : n_sm, kTcThreads, kTcSmem, st>>>(a, jt);
-      *launches += 2;
+  const int nb = a0.nb;
+  const int G = tc_groups(B);
+  if (G > 1) {
+    cudaError_t e = tc_streams_init();
+    if (e != cudaSuccess) return e;
+    e = cudaEventRecord(g_tcs.fork, st);
+    if (e != cudaSuccess) return e;
+    for (int g = 1; g < G; ++g) {
+      e = cudaStreamWaitEvent(g_tcs.aux[g - 1], g_tcs.fork, 0);
+      if (e != cudaSuccess) return e;
     }
+  }
+  const size_t ntile = (size_t)nb * (nb + 1) / 2;
+  // k outermost: the slices are enqueued round-robin, which is also the order the hardware should start them in
+  for (int k = 0; k < nb; ++k) {
+    for (int g = 0; g < G; ++g) {
+      const int b0 = (int)((long long)B * g / G), bc = (int)((long long)B * (g + 1) / G) - b0;
+      if (bc <= 0) continue;
+      cudaStream_t s = g == 0 ? st : g_tcs.aux[g - 1];
+      TcArgs a = a0;
+      a.M = a0.M + (size_t)b0 * ntile * kTBE;
+      a.Wbuf = a0.Wbuf + (size_t)b0 * nb * kTBE;
+      a.Vbuf = a0.Vbuf + (size_t)b0 * nb * kTBE;
+      a.Pbuf = a0.Pbuf + (size_t)b0 * nb * kTBE;
+      a.k = k;
+      tc_pivot_kernel<<<bc, kPivThreads, 0, s>>>(a);
+      ++*launches;
+      const int span = ldl ? nb - 1 - k : nb - 1;
+      if (span > 0) {
+        const int jp = bc * span, jt = bc * (span * (span + 1) / 2);
+        tc_tile_kernel<0><<<jp < n_sm ? jp : n_sm, kTcThreads, kTcSmem, s>>>(a, jp);
+        tc_tile_kernel<1><<<jt < n_sm ? jt : n_sm, kTcThreads, kTcSmem, s>>>(a, jt);
+        *launches += 2;
+      }
+    }
+  }
+  for (int g = 1; g < G; ++g) {
+    cudaError_t e = cudaEventRecord(g_tcs.join[g - 1], g_tcs.aux[g - 1]);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamWaitEvent(st, g_tcs.join[g - 1], 0);
+    if (e != cudaSuccess) return e;
   }
   return cudaGetLastError();
 }

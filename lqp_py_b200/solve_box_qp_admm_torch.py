@@ -9,6 +9,7 @@ Same module / autograd surface as the reference file of the same name
 * ``SolveBoxQPLayer.apply(Q, p, A, b, lb, ub, control)``                        (:21-67)
 * ``torch_solve_box_qp(Q, p, A, b, lb, ub, control) -> dict(x,z,u,lams,nus,rho,iter)`` (:108-333)
 * ``torch_solve_box_qp_grad(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho) -> 7-tuple``     (:349-432)
+* ``torch_solve_box_qp_grad_kkt(dl_dz, x, lams, nus, Q, A, lb, ub) -> 7-tuple``         (:435-462)
 
 but none of the arithmetic happens in torch: the functions flatten the settings into a POD
 struct and call the hand-written sm_100a kernels through the C ABI of ``include/lqpb.h``
@@ -55,6 +56,7 @@ class SolveBoxQPLayer(torch.autograd.Function):
             control['rho'] = 0
         ctx.rho = sol["rho"]
         ctx.backward_method = control.get('backward', 'fixed_point')
+        ctx.any_bounds = (sol["_any_lb"], sol["_any_ub"])
         ctx.out_device = out_device
         ctx.input_devices = tuple(None if t is None else t.device for t in (Q, p, A, b, lb, ub))
         # saved tensors are the CUDA-resident copies: the backward never re-uploads Q
@@ -66,11 +68,11 @@ class SolveBoxQPLayer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dl_dz):
         x, u, lams, nus, Q, A, lb, ub = ctx.saved_tensors
-        if ctx.backward_method == 'kkt':
-            raise NotImplementedError(
-                "backward='kkt' (reference :435-584) is outside this build's hot path; use 'fixed_point'")
         need = ctx.needs_input_grad[:6]
-        grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need)
+        if ctx.backward_method == 'kkt':       # reference :63-64
+            grads = _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, ctx.any_bounds)
+        else:
+            grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need)
         out = []
         for g, dev in zip(grads, ctx.input_devices):
             out.append(None if g is None else _to_device_of(g, dev))
@@ -99,6 +101,19 @@ def torch_solve_box_qp_grad(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho):
     rho_d = rho.to(dv["x"].device) if torch.is_tensor(rho) else rho
     grads = _grad_device(dv["dl_dz"], dv["x"], dv["u"], dv["lams"], dv["nus"], dv["Q"], dv["A"], dv["lb"], dv["ub"],
                          rho_d, (True,) * 6)
+    out = [None if g is None else _to_device_of(g, d) for g, d in zip(grads, devs)]
+    return (*out, None)
+
+
+def torch_solve_box_qp_grad_kkt(dl_dz, x, lams, nus, Q, A, lb, ub):
+    """KKT backward (reference :435-462 and helpers :465-584).  Returns ``(dQ, dp, dA, db, dlb, dub, None)``
+    with ``dlb`` / ``dub`` = ``None`` when the batch has no finite lower / upper bound (:572-579).  With a
+    one-sided or partly infinite box the reference's dense system contains ``-inf`` and every gradient comes out
+    NaN; here an infinite bound contributes exactly zero."""
+    devs = [t.device for t in (Q, x, A if A is not None else x, A if A is not None else x, lb, ub)]
+    dv = _stage(dict(dl_dz=dl_dz, x=x, lams=lams, nus=nus, Q=Q, A=A, lb=lb, ub=ub))
+    grads = _grad_kkt_device(dv["dl_dz"], dv["x"], dv["lams"], dv["nus"], dv["Q"], dv["A"], dv["lb"], dv["ub"],
+                             (True,) * 6, None)
     out = [None if g is None else _to_device_of(g, d) for g, d in zip(grads, devs)]
     return (*out, None)
 
@@ -269,4 +284,45 @@ def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need):
             _abi.ptr(lb), _abi.ptr(ub), _abi.ptr(rho_dev), rho_scalar, _abi.ptr(dQ), _abi.ptr(dp), _abi.ptr(dA),
             _abi.ptr(db), _abi.ptr(dlb), _abi.ptr(dub), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
         _abi.check(rc, "lqpb_backward")
+    return dQ, dp, dA, db, dlb, dub
+
+
+def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds):
+    """KKT backward on one CUDA device.  ``any_bounds`` = ``(any_lb, any_ub)`` when the caller already knows the
+    flags (the layer does, from the forward solve: the call stays asynchronous) or ``None`` to have them
+    evaluated on the device (one stream synchronisation)."""
+    L = _abi.lib()
+    dev, dt = x.device, x.dtype
+    sfx = _abi.suffix(dt)
+    B, n = Q.shape[0], Q.shape[1]
+    m = get_ncon(A, dim=1)
+    g = dl_dz.detach()
+    if g.dtype != dt:
+        raise TypeError(f"dl_dz has dtype {g.dtype}, expected {dt}")
+    if g.device != dev:
+        g = g.to(dev, non_blocking=True)
+    g = g.contiguous()
+    nQ, np_, nA, nb, nlb, nub = need
+    flags = (C.c_int32 * 2)()
+    with torch.cuda.device(dev):
+        new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+        dQ = new(B, n, n) if nQ else None
+        dp = new(B, n, 1) if np_ else None
+        dA = new(B, m, n) if (nA and m > 0) else None
+        db = new(B, m, 1) if (nb and m > 0) else None
+        dlb = new(B, n, 1) if (nlb and (any_bounds is None or any_bounds[0])) else None
+        dub = new(B, n, 1) if (nub and (any_bounds is None or any_bounds[1])) else None
+        ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{sfx}")(B, n, m)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = getattr(L, f"lqpb_backward_kkt_{sfx}")(
+            B, n, m, _abi.ptr(g), _abi.ptr(x), _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A), _abi.ptr(lb),
+            _abi.ptr(ub), _abi.ptr(dQ), _abi.ptr(dp), _abi.ptr(dA), _abi.ptr(db), _abi.ptr(dlb), _abi.ptr(dub),
+            flags if any_bounds is None else None, _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
+        _abi.check(rc, "lqpb_backward_kkt")
+    if any_bounds is None:                      # reference :572-579
+        if not flags[0]:
+            dlb = None
+        if not flags[1]:
+            dub = None
     return dQ, dp, dA, db, dlb, dub

@@ -10,6 +10,7 @@ the timing of this port is representative of the reference's CPU path) of
 
 * the forward ADMM solver   reference ``lqp_py/solve_box_qp_admm_torch.py:108-333``
 * the fixed-point backward  reference ``lqp_py/solve_box_qp_admm_torch.py:349-432``
+* the KKT backward          reference ``lqp_py/solve_box_qp_admm_torch.py:435-584``
 * the cached-factor LU op   reference ``lqp_py/lu_layer.py:5-58``
 * the experiment generators reference ``experiments/utils.py:35-61,64-131``
 
@@ -286,6 +287,65 @@ def grad(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho):
         dlb = dlam * lams[:, :n, :]                                 # :426
         dub = -dlam * lams[:, n:2 * n, :]                           # :427
     return dQ, dv, dA, db, dlb, dub
+
+
+# --------------------------------------------------------------------------
+# backward, KKT mode (implicit differentiation of the optimality conditions)
+# --------------------------------------------------------------------------
+def grad_kkt(dl_dz, x, lams, nus, Q, A, lb, ub):
+    """reference :435-584 (``torch_solve_box_qp_grad_kkt`` and its helpers).  Returns
+    (dQ, dp, dA, db, dlb, dub); dlb / dub are None without finite lower / upper bounds.
+    Builds the same dense (n + 2n + m) system as the reference, so a one-sided box (infinite
+    slacks) yields NaN exactly like the reference does."""
+    with torch.no_grad():
+        B, n = Q.shape[0], Q.shape[1]
+        m = 0 if A is None else A.shape[1]
+        has_lb = bool(lb.max() > -INF)                              # :439-441
+        has_ub = bool(ub.min() < INF)
+        boxed = has_lb or has_ub
+        xt = x.transpose(1, 2)
+        rows = [Q]
+        k = 0
+        if boxed:                                                   # :444-451
+            k = 2 * n
+            eye = torch.eye(n)
+            G = torch.cat((-eye, eye)).unsqueeze(0) * torch.ones(B, 1, 1)
+            slack = torch.clamp(torch.cat((-lb, ub), 1) - torch.matmul(G, x), 10 ** -8)
+            lams = torch.clamp(lams, 10 ** -8)
+            rows.append(G.transpose(1, 2) * lams.transpose(1, 2))   # :477 / :485
+        if m:
+            rows.append(A.transpose(1, 2))
+        lhs = torch.cat(rows, 2)
+        if boxed:                                                   # :478 / :486
+            blk = [G, torch.diag_embed(-slack.squeeze(2))]
+            if m:
+                blk.append(torch.zeros(B, k, m))
+            lhs = torch.cat((lhs, torch.cat(blk, 2)), 1)
+        if m:                                                       # :482 / :487
+            blk = [A]
+            if boxed:
+                blk.append(torch.zeros(B, m, k))
+            blk.append(torch.zeros(B, m, m))
+            lhs = torch.cat((lhs, torch.cat(blk, 2)), 1)
+        rhs = torch.cat((-dl_dz, torch.zeros(B, k + m, 1)), 1)       # :500-504
+        d = torch.linalg.solve(lhs, rhs)
+        dx = d[:, :n, :]
+        half = torch.matmul(0.5 * dx, xt)                           # :536-537
+        dQ = half + half.transpose(1, 2)
+        dA = db = dlb = dub = None
+        if m:                                                       # :550-552
+            dnu = d[:, n + k:, :]
+            dA = torch.matmul(dnu, xt) + torch.matmul(nus, dx.transpose(1, 2))
+            db = -dnu
+        if boxed:
+            dh = -lams * d[:, n:n + k, :]                           # :545
+            if has_lb and has_ub:                                   # :572-579
+                dlb, dub = -dh[:, :n, :], dh[:, n:, :]
+            elif has_lb:
+                dlb = -dh[:, :n, :]
+            else:
+                dub = dh[:, :n, :]
+    return dQ, dx, dA, db, dlb, dub
 
 
 def solve_and_grad(Q, p, A, b, lb, ub, control, dl_dz):

@@ -97,3 +97,69 @@ def compare(case: Case, sol: dict, grads, tol: dict, skip=()):
                 chk("dQ_probe", torch.matmul(dQ.cpu(), w))
                 chk("dQ_fro", torch.linalg.matrix_norm(dQ.cpu()))
     return errs
+
+
+# ---------------------------------------------------------------------------------- KKT backward fixtures
+KKT_DIR = os.path.join(GOLDEN_DIR, "kkt")
+
+
+def kkt_case_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(KKT_DIR, "*.npz")))
+
+
+def compare_kkt(case: Case, grads, tol: dict):
+    """grads = (dQ, dp, dA, db, dlb, dub) of the KKT backward evaluated at the REFERENCE's forward solution
+    (case.t('x'), 'lams', 'nus'); compared with tests/golden/kkt/<case>.npz (make_golden_kkt.py)."""
+    z = np.load(os.path.join(KKT_DIR, case.name + ".npz"), allow_pickle=False)
+    assert not bool(z["reference_nan"])
+    dQ, dp, dA, db, dlb, dub = grads
+    assert (dlb is not None) == bool(z["has_dlb"]) and (dub is not None) == bool(z["has_dub"]), case.name
+    errs = {}
+
+    def chk(key, val):
+        e = rel_err(val.detach().cpu().numpy(), z[key])
+        errs[key] = e
+        lim = tol.get(key, tol["default"])
+        assert e <= lim, f"kkt/{case.name}: {key} rel err {e:.3e} > {lim:.1e}"
+
+    for k, v in (("dp", dp), ("dA", dA), ("db", db), ("dlb", dlb), ("dub", dub)):
+        if v is not None:
+            chk(k, v)
+    if "dQ" in z.files:
+        chk("dQ", dQ)
+    else:
+        gen = torch.Generator().manual_seed(4321)
+        w = torch.randn(dQ.shape[0], dQ.shape[1], 2, generator=gen, dtype=case.dtype)
+        chk("dQ_probe", torch.matmul(dQ.cpu(), w))
+        chk("dQ_fro", torch.linalg.matrix_norm(dQ.cpu()))
+    return errs
+
+
+def kkt_reference_is_nan(name):
+    return bool(np.load(os.path.join(KKT_DIR, name + ".npz"), allow_pickle=False)["reference_nan"])
+
+
+def kkt_reduced_fp64(dl_dz, x, lams, nus, Q, A, lb, ub):
+    """The KKT adjoint with the 2n inequality rows eliminated in closed form (what csrc/backward.cu solves),
+    evaluated in fp64 on the CPU.  Equal to the reference's dense (3n+m) solve wherever that is finite; used
+    as the yardstick for the one-sided boxes where the reference returns NaN."""
+    dl_dz, x, lams, Q, lb, ub = (t.double().cpu() for t in (dl_dz, x, lams, Q, lb, ub))
+    B, n = Q.shape[0], Q.shape[1]
+    lam = lams.clamp(min=1e-8)
+    s_lo, s_hi = (x - lb).clamp(min=1e-8), (ub - x).clamp(min=1e-8)
+    H = Q + torch.diag_embed((lam[:, :n] / s_lo + lam[:, n:] / s_hi).squeeze(2))
+    if A is not None:
+        A, nus = A.double().cpu(), nus.double().cpu()
+        m = A.shape[1]
+        K = torch.cat((torch.cat((H, A.transpose(1, 2)), 2), torch.cat((A, torch.zeros(B, m, m, dtype=torch.float64)), 2)), 1)
+        rhs = torch.cat((-dl_dz, torch.zeros(B, m, 1, dtype=torch.float64)), 1)
+    else:
+        K, rhs = H, -dl_dz
+    d = torch.linalg.solve(K, rhs)
+    dx = d[:, :n]
+    half = 0.5 * dx @ x.transpose(1, 2)
+    dA = db = None
+    if A is not None:
+        dnu = d[:, n:]
+        dA, db = dnu @ x.transpose(1, 2) + nus @ dx.transpose(1, 2), -dnu
+    return half + half.transpose(1, 2), dx, dA, db, -lam[:, :n] * dx / s_lo, -lam[:, n:] * dx / s_hi

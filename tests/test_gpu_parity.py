@@ -18,7 +18,8 @@ import pytest
 import torch
 
 from oracle import box_qp_oracle as orc
-from tests._golden import Case, case_names, compare, rel_err, GOLDEN_DIR
+from tests._golden import (Case, case_names, compare, rel_err, GOLDEN_DIR, kkt_case_names, compare_kkt,
+                           kkt_reference_is_nan, kkt_reduced_fp64)
 
 pytestmark = pytest.mark.gpu
 
@@ -115,6 +116,67 @@ def test_against_oracle_fresh_seeds(n, B, dtype, seed, dev):
         t = max(t, 4 * gap.get(k, 0.0))
         e = rel_err(mine.cpu().numpy(), theirs.numpy())
         assert e <= t, f"{k}: {e:.2e} > {t:.1e}"
+
+
+@pytest.mark.parametrize("name", kkt_case_names())
+def test_kkt_backward_golden(name, dev):
+    """backward='kkt' (reference :435-584) through lqpb_backward_kkt_*, evaluated at the reference's forward
+    solution and compared with the reference's own KKT gradients (tests/golden/kkt).  fp64 1e-8; fp32 1e-5
+    except nus-driven db (2e-4, as for the fixed-point mode).  One-sided / partly infinite boxes: the reference
+    returns NaN (its dense system holds -inf); here they must be finite and equal the closed-form reduced
+    adjoint evaluated in fp64."""
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp_grad_kkt
+    case = Case(name)
+    Q, p, A, b, lb, ub = case.inputs()
+    to = lambda t: None if t is None else t.to(dev)
+    grads = torch_solve_box_qp_grad_kkt(to(case.t("dl_dz")), to(case.t("x")), to(case.t("lams")), to(case.t("nus")),
+                                        to(Q), to(A), to(lb), to(ub))
+    assert len(grads) == 7 and grads[6] is None
+    grads = [None if g is None else g.cpu() for g in grads[:6]]
+    f64 = case.dtype == torch.float64
+    if kkt_reference_is_nan(name):
+        red = kkt_reduced_fp64(case.t("dl_dz"), case.t("x"), case.t("lams"), case.t("nus"), Q, A, lb, ub)
+        has_lb, has_ub = bool(lb.max() > -float("inf")), bool(ub.min() < float("inf"))
+        assert (grads[4] is not None) == has_lb and (grads[5] is not None) == has_ub
+        for g, r, nm in zip(grads, red, ("dQ", "dp", "dA", "db", "dlb", "dub")):
+            if g is not None:
+                assert torch.isfinite(g).all(), nm
+                assert rel_err(g.numpy(), r.numpy()) <= 1e-8, nm
+        return
+    tol = {"default": 1e-8 if f64 else 1e-5}
+    if not f64:
+        tol.update(db=2e-4, dA=2e-5)
+    compare_kkt(case, grads, tol)
+
+
+def test_kkt_backward_through_the_layer(dev):
+    """control['backward'] = 'kkt' (reference :63-64): forward on the GPU, KKT gradients on the leaves; checked
+    against the oracle pipeline (forward + grad_kkt on the CPU).  The KKT adjoint divides by slacks clamped at
+    1e-8, so it amplifies the 1e-15 forward differences a little: 1e-6 here, 1e-8 in the golden test above."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    dtype = torch.float64
+    Q, p, A, b, lb, ub = orc.make_exp1_data(48, 6, seed=11, dtype=dtype)
+    control = box_qp_control(eps_abs=1e-6, eps_rel=1e-6, backward='kkt')
+    g = torch.randn(p.shape, generator=torch.Generator().manual_seed(5), dtype=dtype)
+    torch.set_default_dtype(dtype)
+    try:
+        ref = orc.solve(Q, p, A, b, lb, ub, dict(control))
+        rg = orc.grad_kkt(g, ref["x"], ref["lams"], ref["nus"], Q, A, lb, ub)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    ins = [t.to(dev).requires_grad_(True) for t in (Q, p, A, b, lb, ub)]
+    x = SolveBoxQP(control=control).forward(*ins)
+    x.backward(g.to(dev))
+    for t, r, name in zip(ins, rg, ("dQ", "dp", "dA", "db", "dlb", "dub")):
+        assert t.grad is not None and t.grad.shape == t.shape
+        assert rel_err(t.grad.cpu().numpy(), r.numpy()) <= 1e-6, name
+    # no finite bound at all: dlb / dub are None like in the reference (:572-579)
+    inf = float("inf")
+    ins = [t.to(dev).requires_grad_(True) for t in (Q, p, A, b, torch.full_like(lb, -inf), torch.full_like(ub, inf))]
+    x = SolveBoxQP(control=box_qp_control(backward='kkt')).forward(*ins)
+    x.backward(g.to(dev))
+    assert ins[4].grad is None and ins[5].grad is None and ins[0].grad is not None
 
 
 def test_module_autograd_and_needs_input_grad(dev):

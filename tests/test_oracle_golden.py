@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from oracle import box_qp_oracle as orc
-from tests._golden import Case, case_names, compare, GOLDEN_DIR
+from tests._golden import (Case, case_names, compare, GOLDEN_DIR, kkt_case_names, compare_kkt,
+                           kkt_reference_is_nan, kkt_reduced_fp64, rel_err)
 import os
 
 
@@ -23,6 +24,31 @@ def test_oracle_matches_reference(name):
     # same LAPACK/BLAS calls in the same order -> agreement to round-off
     tol = {"default": 1e-12 if case.dtype == torch.float64 else 2e-5}
     compare(case, sol, grads, tol)
+
+
+@pytest.mark.parametrize("name", kkt_case_names())
+def test_oracle_kkt_backward_matches_reference(name):
+    """oracle.grad_kkt against the reference's torch_solve_box_qp_grad_kkt (:435-584), both evaluated at the
+    reference's forward solution; the reduced closed form the CUDA path solves is checked alongside."""
+    case = Case(name)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(case.dtype)
+    try:
+        Q, p, A, b, lb, ub = case.inputs()
+        grads = orc.grad_kkt(case.t("dl_dz"), case.t("x"), case.t("lams"), case.t("nus"), Q, A, lb, ub)
+    finally:
+        torch.set_default_dtype(prev)
+    if kkt_reference_is_nan(name):           # one-sided / partly infinite box: the dense system holds -inf
+        assert torch.isnan(grads[1]).any()
+        red = kkt_reduced_fp64(case.t("dl_dz"), case.t("x"), case.t("lams"), case.t("nus"), Q, A, lb, ub)
+        assert all(torch.isfinite(g).all() for g in red if g is not None)
+        return
+    compare_kkt(case, grads, {"default": 1e-12 if case.dtype == torch.float64 else 2e-5})
+    red = kkt_reduced_fp64(case.t("dl_dz"), case.t("x"), case.t("lams"), case.t("nus"), Q, A, lb, ub)
+    lim = 1e-9 if case.dtype == torch.float64 else 2e-5
+    for g, r in zip(grads, red):
+        if g is not None:
+            assert rel_err(g.numpy(), r.numpy()) <= lim
 
 
 def test_oracle_lu_layer():

@@ -289,7 +289,8 @@ def run_b200(a):
         pin_sets = [[t.pin_memory() for t in d] for d in host_sets]
         g_host = torch.ones(B, n, 1, dtype=dtype).pin_memory()
         def step_host(k):
-            ins = [t.detach().requires_grad_(True) for t in pin_sets[k % len(pin_sets)]]
+            # leaves as experiments/utils.py:41-50 creates them: Q and p require grad, A, b, lb, ub do not
+            ins = [t.detach().requires_grad_(j < 2) for j, t in enumerate(pin_sets[k % len(pin_sets)])]
             x = QP.forward(*ins)
             x.backward(g_host)
             return x, ins
@@ -314,7 +315,8 @@ def run_b200(a):
         d2h = (x.numel() + sum(t.grad.numel() for t in ins if t.grad is not None)) * s
         e2e = {"value": B * world * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": Ke, "ms_per_step": dt / Ke * 1e3,
-               "how": "SolveBoxQP.forward + x.backward on pinned CPU tensors; copies in the timed region"}
+               "how": "SolveBoxQP.forward + x.backward on pinned CPU tensors (Q, p require grad as in "
+                      "experiments/utils.py:41-50; x, dQ, dp come back to the host); copies in the timed region"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

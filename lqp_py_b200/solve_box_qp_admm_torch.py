@@ -50,7 +50,7 @@ class SolveBoxQPLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Q, p, A, b, lb, ub, control):
         out_device = p.device
-        sol = _solve_device(Q, p, A, b, lb, ub, control)
+        sol = _solve_device(Q, p, A, b, lb, ub, control, host_keys=("x",))
         # reference :33-38 -- with no finite bound the caller's dict is switched to rho = 0
         if not (sol["_any_lb"] or sol["_any_ub"]):
             control['rho'] = 0
@@ -73,10 +73,7 @@ class SolveBoxQPLayer(torch.autograd.Function):
             grads = _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, ctx.any_bounds)
         else:
             grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need)
-        out = []
-        for g, dev in zip(grads, ctx.input_devices):
-            out.append(None if g is None else _to_device_of(g, dev))
-        return (*out, None)
+        return (*_to_devices(grads, ctx.input_devices), None)
 
 
 # ------------------------------------------------------------------------------------------
@@ -101,8 +98,7 @@ def torch_solve_box_qp_grad(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho):
     rho_d = rho.to(dv["x"].device) if torch.is_tensor(rho) else rho
     grads = _grad_device(dv["dl_dz"], dv["x"], dv["u"], dv["lams"], dv["nus"], dv["Q"], dv["A"], dv["lb"], dv["ub"],
                          rho_d, (True,) * 6)
-    out = [None if g is None else _to_device_of(g, d) for g, d in zip(grads, devs)]
-    return (*out, None)
+    return (*_to_devices(grads, devs), None)
 
 
 def torch_solve_box_qp_grad_kkt(dl_dz, x, lams, nus, Q, A, lb, ub):
@@ -114,8 +110,7 @@ def torch_solve_box_qp_grad_kkt(dl_dz, x, lams, nus, Q, A, lb, ub):
     dv = _stage(dict(dl_dz=dl_dz, x=x, lams=lams, nus=nus, Q=Q, A=A, lb=lb, ub=ub))
     grads = _grad_kkt_device(dv["dl_dz"], dv["x"], dv["lams"], dv["nus"], dv["Q"], dv["A"], dv["lb"], dv["ub"],
                              (True,) * 6, None)
-    out = [None if g is None else _to_device_of(g, d) for g, d in zip(grads, devs)]
-    return (*out, None)
+    return (*_to_devices(grads, devs), None)
 
 
 # ------------------------------------------------------------------------------------------
@@ -147,15 +142,28 @@ def _stage(tensors):
     return out
 
 
+def _to_devices(tensors, devices):
+    """Return every tensor of ``tensors`` on the matching device of ``devices`` (``None`` entries pass through).
+    Device -> host copies go to pinned staging memory, are all enqueued first and waited for with ONE stream
+    synchronisation."""
+    out, pending = [], None
+    for t, device in zip(tensors, devices):
+        if t is None or device is None or t.device == device:
+            out.append(t)
+        elif device.type == "cpu":
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host.copy_(t, non_blocking=True)
+            pending = t.device
+            out.append(host)
+        else:
+            out.append(t.to(device))
+    if pending is not None:
+        torch.cuda.current_stream(pending).synchronize()
+    return out
+
+
 def _to_device_of(t, device):
-    if device is None or t.device == device:
-        return t
-    if device.type == "cpu":
-        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        host.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(t.device).synchronize()
-        return host
-    return t.to(device)
+    return _to_devices([t], [device])[0]
 
 
 def _default_dtype_value(v):
@@ -197,7 +205,7 @@ def _derive_config(control, n_x):
     return cfg
 
 
-def _solve_device(Q, p, A, b, lb, ub, control):
+def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
     L = _abi.lib()
     out_device = p.device
     dv = _stage(dict(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub))
@@ -235,9 +243,13 @@ def _solve_device(Q, p, A, b, lb, ub, control):
         rho = rho_t                               # :200-203 / :248-250
     else:
         rho = user_rho
-    host = lambda t: None if t is None else _to_device_of(t, out_device)
-    rho_out = host(rho) if torch.is_tensor(rho) else rho
-    return {"x": host(x), "z": host(z), "u": host(u), "lams": host(lams), "nus": host(nus), "rho": rho_out,
+    # results go back to where the caller's tensors live; the layer only hands x to autograd (host_keys)
+    keys = ("x", "z", "u", "lams", "nus", "rho")
+    vals = [x, z, u, lams, nus, rho if torch.is_tensor(rho) else None]
+    want = [out_device if (host_keys is None or k in host_keys) else None for k in keys]
+    hx, hz, hu, hlams, hnus, hrho = _to_devices(vals, want)
+    rho_out = hrho if torch.is_tensor(rho) else rho
+    return {"x": hx, "z": hz, "u": hu, "lams": hlams, "nus": hnus, "rho": rho_out,
             "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor),
             "_any_lb": bool(info.any_lb), "_any_ub": bool(info.any_ub), "_dev": dv,
             "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus,

@@ -34,6 +34,7 @@ constexpr int kSlabBytes = kTB * 128;    // 128 rows x 32 fp32
 constexpr int kTcThreads = 512;
 constexpr int kTcCols = 256;             // TMEM columns per CTA: hi*hi accumulator | cross-term accumulator
 constexpr int kTcSmem = 8 * kSlabBytes + 1024;   // two stages of Xhi | Xlo | Yhi | Ylo, manually aligned to 1024 B
+constexpr int kTcSmemTrail = kTcSmem + kTBE * 4; // + the C tile of the job, fetched by one bulk TMA copy
 
 __host__ __device__ inline size_t bl_tile(int I, int J) { return (size_t)(I * (I + 1) / 2 + J) * kTBE; }
 __host__ __device__ inline size_t bl_off(int i, int j) {   // element (i, j), tile row >= tile column
@@ -191,6 +192,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_tile_kernel(TcArgs a, int total_jobs) {
   extern __shared__ unsigned char tc_smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar[2];
+  __shared__ __align__(8) uint64_t c_bar;      // TRAIL: the C tile has landed in shared memory
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_tile_kernel(TcArgs a, int to
   if (tid == 32) {
     mbar_init(&mma_bar[0], 1);
     mbar_init(&mma_bar[1], 1);
+    mbar_init(&c_bar, 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -208,6 +211,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_tile_kernel(TcArgs a, int to
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   uint32_t ph[2] = {0u, 0u};          // parity of the next completion to wait for, per stage barrier
+  uint32_t c_ph = 0u;
+  // TRAIL: the 64 KB C tile of a job (contiguous in the block-lower storage) is fetched by ONE bulk TMA copy at
+  // the start of the job and waits in shared memory until the epilogue: the read-modify-write of C then has no
+  // global-load latency left (it used to queue behind the 128 KB operand prefetch of the next job).
+  float* cbuf = reinterpret_cast<float*>(sptr + 8 * kSlabBytes);
 
   float4 xr[8], yr[8];                 // the whole X / Y tile pair of one job: [slab * 2 + t]
   auto gload = [&](const TcJob& jb) {
@@ -235,6 +243,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_tile_kernel(TcArgs a, int to
   TC_T0();
 #pragma unroll 1
   for (; job < total_jobs; job += gridDim.x) {
+    if (MODE == 1 && tid == 0) {      // the previous job's reads of cbuf ended before its closing __syncthreads
+      mbar_arrive_expect_tx(&c_bar, (uint32_t)(kTBE * sizeof(float)));
+      tma_load_1d(cbuf, cur.mdst, (uint32_t)(kTBE * sizeof(float)), &c_bar);
+    }
     TC_ADD(0);
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
@@ -350,13 +362,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_tile_kernel(TcArgs a, int to
     TC_ADD(6);
     constexpr int NW = kTcThreads / 32;
     if (MODE == 1) {
+      mbar_wait(&c_bar, c_ph);
+      c_ph ^= 1u;
 #pragma unroll 4
       for (int rr = warp; rr < kTB; rr += NW) {
         const float4 d = *reinterpret_cast<const float4*>(stage + rr * kTB + ((lane ^ (rr & 31)) << 2));
-        float4* cp = reinterpret_cast<float4*>(done.mdst + (size_t)rr * kTB + 4 * lane);
-        float4 c = *cp;
+        float4 c = *reinterpret_cast<const float4*>(cbuf + rr * kTB + 4 * lane);
         c.x -= d.x; c.y -= d.y; c.z -= d.z; c.w -= d.w;
-        *cp = c;
+        *reinterpret_cast<float4*>(done.mdst + (size_t)rr * kTB + 4 * lane) = c;
       }
     } else {
 #pragma unroll 4
@@ -877,7 +890,7 @@ static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(tc_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+    e = cudaFuncSetAttribute(tc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemTrail);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -920,7 +933,7 @@ static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st
       if (span > 0) {
         const int jp = bc * span, jt = bc * (span * (span + 1) / 2);
         tc_tile_kernel<0><<<jp < n_sm ? jp : n_sm, kTcThreads, kTcSmem, s>>>(a, jp);
-        tc_tile_kernel<1><<<jt < n_sm ? jt : n_sm, kTcThreads, kTcSmem, s>>>(a, jt);
+        tc_tile_kernel<1><<<jt < n_sm ? jt : n_sm, kTcThreads, kTcSmemTrail, s>>>(a, jt);
         *launches += 2;
       }
     }

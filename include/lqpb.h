@@ -143,6 +143,44 @@ int lqpb_backward_kkt_f64(int B, int n, int m, const double* dl_dz, const double
                           double* dlb, double* dub, int32_t* any_bounds, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- host-buffer forms of the two calls above: what a caller of the reference holds are CPU tensors
+ * (experiments/experiment_1.py:58-77 builds Q, p, ... on the host, calls .forward and .backward and reads
+ * x and the .grad fields on the host).  h* pointers are HOST memory (page-locked memory keeps the copies
+ * asynchronous; pageable memory works, slower); the unprefixed pointers are DEVICE buffers of the same
+ * shapes supplied by the caller: forward_host fills Q, p, A, b, lb, ub with the device copies (keep them
+ * for the backward, like ctx.save_for_backward in :48) and x, z, u, lams, nus, rho_out with the results;
+ * hx (may be NULL) receives x.  backward_host uploads h_dl_dz into dl_dz, leaves every requested gradient
+ * in its device buffer and copies it to the matching h* pointer (NULL = not wanted on the host); kkt != 0
+ * selects the KKT backward (u, rho_dev unused).  The batch is cut into `chunks` (0 = choose) slices of
+ * whole problems: a copy stream uploads Q slice c + 1 while slice c is scaled and factorised, and returns
+ * the dQ rows of slice c while slice c + 1 is differentiated.  Both calls return after `stream` and the
+ * copy stream have drained (the host buffers are valid on return). */
+int lqpb_forward_host_f32(const lqpb_config* cfg, int B, int n, int m, const float* hQ, const float* hp,
+                          const float* hA, const float* hb, const float* hlb, const float* hub, float* Q,
+                          float* p, float* A, float* b, float* lb, float* ub, float* x, float* z, float* u,
+                          float* lams, float* nus, float* rho_out, float* hx, lqpb_info* info,
+                          void* workspace, size_t workspace_bytes, void* stream, int chunks);
+int lqpb_forward_host_f64(const lqpb_config* cfg, int B, int n, int m, const double* hQ, const double* hp,
+                          const double* hA, const double* hb, const double* hlb, const double* hub,
+                          double* Q, double* p, double* A, double* b, double* lb, double* ub, double* x,
+                          double* z, double* u, double* lams, double* nus, double* rho_out, double* hx,
+                          lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream,
+                          int chunks);
+int lqpb_backward_host_f32(int B, int n, int m, int kkt, const float* h_dl_dz, float* dl_dz, const float* x,
+                           const float* u, const float* lams, const float* nus, const float* Q,
+                           const float* A, const float* lb, const float* ub, const float* rho_dev,
+                           double rho_scalar, float* dQ, float* dp, float* dA, float* db, float* dlb,
+                           float* dub, float* hdQ, float* hdp, float* hdA, float* hdb, float* hdlb,
+                           float* hdub, int32_t* any_bounds, void* workspace, size_t workspace_bytes,
+                           void* stream, int chunks);
+int lqpb_backward_host_f64(int B, int n, int m, int kkt, const double* h_dl_dz, double* dl_dz,
+                           const double* x, const double* u, const double* lams, const double* nus,
+                           const double* Q, const double* A, const double* lb, const double* ub,
+                           const double* rho_dev, double rho_scalar, double* dQ, double* dp, double* dA,
+                           double* db, double* dlb, double* dub, double* hdQ, double* hdp, double* hdA,
+                           double* hdb, double* hdlb, double* hdub, int32_t* any_bounds, void* workspace,
+                           size_t workspace_bytes, void* stream, int chunks);
+
 /* ---- lu_layer: replaces TorchLU / TorchLULayer (lu_layer.py:5-58) -------------------------
  * lu_factor: partial-pivoting LU of B general N x N matrices (torch.linalg.lu_factor, :10,:30);
  *            LU (B,N,N) packed L\U, piv (B,N) 1-based row swaps like LAPACK getrf.

@@ -81,6 +81,111 @@ struct HostCtrl {
 };
 thread_local HostCtrl g_hctrl;
 
+// ---- host-buffer calls (lqpb_forward_host_* / lqpb_backward_host_*): the batch is cut into chunks of whole
+// problems; a copy stream moves chunk c + 1 over PCIe while the compute stream runs the per-problem setup
+// (forward) or the whole adjoint chain (backward) of chunk c.
+constexpr int kMaxChunks = 16;
+struct HostPipe {
+  int dev = -1;
+  cudaStream_t cs;
+  cudaEvent_t fork, vec, done, ev[kMaxChunks];
+};
+thread_local HostPipe g_pipe;
+
+cudaError_t pipe_init() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess || g_pipe.dev == dev) return e;
+  if ((e = cudaStreamCreateWithFlags(&g_pipe.cs, cudaStreamNonBlocking)) != cudaSuccess) return e;
+  cudaEvent_t* evs[] = {&g_pipe.fork, &g_pipe.vec, &g_pipe.done};
+  for (auto p : evs)
+    if ((e = cudaEventCreateWithFlags(p, cudaEventDisableTiming)) != cudaSuccess) return e;
+  for (auto& p : g_pipe.ev)
+    if ((e = cudaEventCreateWithFlags(&p, cudaEventDisableTiming)) != cudaSuccess) return e;
+  g_pipe.dev = dev;
+  return cudaSuccess;
+}
+
+int pick_chunks(int requested, int B) {
+  static const int env_chunks = [] { const char* e = getenv("LQPB_HOST_CHUNKS"); return e ? atoi(e) : 0; }();
+  int c = requested > 0 ? requested : (env_chunks > 0 ? env_chunks : 4);
+  if (c > kMaxChunks) c = kMaxChunks;
+  while (c > 1 && B / c < 16) --c;       // chunks of fewer than 16 problems are pure launch latency
+  return c < 1 ? 1 : c;
+}
+
+// chunk c of C covers problems [chunk_lo(c), chunk_lo(c + 1)): equal sizes (the per-chunk kernel chains are latency-
+// bound, ~0.45 ms for 32 problems at dz=500; smaller first / last chunks were measured and did not pay)
+int chunk_lo(int B, int C, int c) { return (int)((long long)B * c / C); }
+
+template <typename T>
+struct HostFwd {      // host side of a forward call
+  const T *Q, *p, *A, *b, *lb, *ub;
+  T* x;
+  int chunks;
+};
+template <typename T>
+struct HostBwd {      // host side of a backward call
+  const T* dl_dz;
+  T *dQ, *dp, *dA, *db, *dlb, *dub;
+  int chunks;
+};
+
+// problems [b0, b0 + bc) of a carved workspace (every array is per-problem contiguous; ctrl / flags are shared)
+template <typename T>
+FwdWs<T> slice_fwd(const FwdWs<T>& w, int b0, int bc) {
+  FwdWs<T> s = w;
+  s.B = bc;
+  const size_t o = (size_t)b0, te = (size_t)kTcBlock * kTcBlock, mm = w.m > 0 ? w.m : 1;
+  s.Qp += o * Pack<T>::elems(w.n);
+  s.Kp += o * Pack<T>::elems(w.n);
+  if (w.tc) {
+    s.W += o * ((size_t)w.nb * (w.nb + 1) / 2) * te;
+    s.Vg += o * w.nb * te;
+    s.Wg += o * w.nb * te;
+    s.Pb += o * w.nb * te;
+  } else {
+    s.W += o * w.np * w.np;
+    s.Vg += o * w.np * kTile;
+    s.Wg += o * w.np * kTile;
+  }
+  T** vecs[] = {&s.D, &s.pt, &s.lbt, &s.ubt, &s.c, &s.z, &s.u, &s.xs};
+  for (auto v : vecs) *v += o * w.ld;
+  s.At += o * mm * w.ld;
+  s.Gt += o * mm * w.ld;
+  s.Sinv += o * mm * mm;
+  s.bt += o * mm;
+  s.E += o * mm;
+  s.rho += o; s.rho_cand += o; s.pnorm += o; s.ratio += o;
+  s.fro_part += o * w.n_fro;
+  s.chk += 4 * o;
+  s.wants += o;
+  return s;
+}
+template <typename T>
+BwdWs<T> slice_bwd(const BwdWs<T>& w, int b0, int bc) {
+  BwdWs<T> s = w;
+  s.B = bc;
+  const size_t o = (size_t)b0, te = (size_t)kTcBlock * kTcBlock;
+  if (w.tc) {
+    s.W += o * ((size_t)w.nb * (w.nb + 1) / 2) * te;
+    s.Vg += o * w.nb * te;
+    s.Wg += o * w.nb * te;
+    s.Pb += o * w.nb * te;
+  } else {
+    s.W += o * w.np * w.np;
+    s.Vg += o * w.np * kTile;
+    s.Wg += o * w.np * kTile;
+  }
+  s.mask += o * w.ld;
+  s.dv += o * w.ld;
+  s.dvec += o * w.ld;
+  s.dnu += o * (w.m > 0 ? w.m : 1);
+  return s;
+}
+template <typename P>
+P* off(P* p, size_t elems) { return p ? p + elems : nullptr; }
+
 template <typename T>
 int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
   GjArgs<T> a{};
@@ -111,7 +216,9 @@ int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
 template <typename T>
 int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A, const T* b,
                  const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, lqpb_info* info, void* ws,
-                 size_t ws_bytes, void* stream) {
+                 size_t ws_bytes, void* stream, const HostFwd<T>* host = nullptr) {
+  if (host && (!host->Q || !host->p || !host->lb || !host->ub || (m > 0 && (!host->A || !host->b))))
+    return fail(LQPB_E_ARG, "null host pointer argument");
   if (!cfg || !Q || !p || !lb || !ub || !x || !z || !u || !lams || !rho_out || !info || !ws)
     return fail(LQPB_E_ARG, "null pointer argument");
   if (B <= 0 || n <= 0 || m < 0) return fail(LQPB_E_ARG, "bad dimensions");
@@ -135,17 +242,63 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
 
   CK(cudaMemsetAsync(w.ctrl, 0, sizeof(Ctrl), st), "memset ctrl");
   if (prof) cudaEventRecord(g_prof.ev[0], st);
-  CK(launch_scale<T>(*cfg, w, Q, p, A, b, lb, ub, st), "scale");
-  CK(launch_select_rho<T>(*cfg, w, st), "select_rho");
-  g_prof.launches += 4 + (cfg->scale ? 1 : 0);
-  if (prof) cudaEventRecord(g_prof.ev[1], st);
+  bool factored = false;
+  if (host) {
+    // ---- inputs on the host: the vectors first (they decide any_lb / any_ub for the whole batch), then Q chunk
+    //      by chunk on the copy stream; scaling + rho + factorisation of a chunk start as soon as it has landed
+    const int C = pick_chunks(host->chunks, B);
+    CK(pipe_init(), "copy stream");
+    cudaStream_t cs = g_pipe.cs;
+    CK(cudaEventRecord(g_pipe.fork, st), "fork");
+    CK(cudaStreamWaitEvent(cs, g_pipe.fork, 0), "fork wait");
+    const size_t sv = (size_t)B * n * sizeof(T);
+    CK(cudaMemcpyAsync((void*)p, host->p, sv, cudaMemcpyHostToDevice, cs), "H2D p");
+    CK(cudaMemcpyAsync((void*)lb, host->lb, sv, cudaMemcpyHostToDevice, cs), "H2D lb");
+    CK(cudaMemcpyAsync((void*)ub, host->ub, sv, cudaMemcpyHostToDevice, cs), "H2D ub");
+    if (m > 0) {
+      CK(cudaMemcpyAsync((void*)A, host->A, (size_t)B * m * n * sizeof(T), cudaMemcpyHostToDevice, cs), "H2D A");
+      CK(cudaMemcpyAsync((void*)b, host->b, (size_t)B * m * sizeof(T), cudaMemcpyHostToDevice, cs), "H2D b");
+    }
+    CK(cudaEventRecord(g_pipe.vec, cs), "vec event");
+    for (int c = 0; c < C; ++c) {
+      const int b0 = chunk_lo(B, C, c), bc = chunk_lo(B, C, c + 1) - b0;
+      CK(cudaMemcpyAsync((void*)(Q + (size_t)b0 * n * n), host->Q + (size_t)b0 * n * n, (size_t)bc * n * n * sizeof(T),
+                         cudaMemcpyHostToDevice, cs), "H2D Q");
+      CK(cudaEventRecord(g_pipe.ev[c], cs), "chunk event");
+    }
+    CK(cudaStreamWaitEvent(st, g_pipe.vec, 0), "vec wait");
+    CK(launch_bound_flags<T>(w, lb, ub, st), "bound_flags");
+    if (prof) cudaEventRecord(g_prof.ev[1], st);
+    if (prof) cudaEventRecord(g_prof.fac0[0], st);
+    for (int c = 0; c < C; ++c) {
+      const int b0 = chunk_lo(B, C, c), bc = chunk_lo(B, C, c + 1) - b0;
+      const FwdWs<T> wc = slice_fwd(w, b0, bc);
+      CK(cudaStreamWaitEvent(st, g_pipe.ev[c], 0), "chunk wait");
+      CK(launch_scale<T>(*cfg, wc, Q + (size_t)b0 * n * n, p + (size_t)b0 * n, off(A, (size_t)b0 * m * n),
+                         off(b, (size_t)b0 * m), lb + (size_t)b0 * n, ub + (size_t)b0 * n, st), "scale");
+      CK(launch_select_rho<T>(*cfg, wc, st), "select_rho");
+      g_prof.launches += 4 + (cfg->scale ? 1 : 0);
+      rc = factor_forward<T>(wc, true, st);
+      if (rc) return rc;
+    }
+    if (prof) cudaEventRecord(g_prof.fac1[0], st);
+    g_prof.n_fac = 1;
+    factored = true;
+  } else {
+    CK(launch_scale<T>(*cfg, w, Q, p, A, b, lb, ub, st), "scale");
+    CK(launch_select_rho<T>(*cfg, w, st), "select_rho");
+    g_prof.launches += 4 + (cfg->scale ? 1 : 0);
+    if (prof) cudaEventRecord(g_prof.ev[1], st);
+  }
 
   int n_factor = 0, i0 = 0, skip = 0;
   while (true) {
-    if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac0[g_prof.n_fac], st);
-    rc = factor_forward<T>(w, n_factor == 0, st);
-    if (rc) return rc;
-    if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac1[g_prof.n_fac++], st);
+    if (!(factored && n_factor == 0)) {
+      if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac0[g_prof.n_fac], st);
+      rc = factor_forward<T>(w, n_factor == 0, st);
+      if (rc) return rc;
+      if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac1[g_prof.n_fac++], st);
+    }
     ++n_factor;
     if (prof && g_prof.n_it < kMaxSeg) cudaEventRecord(g_prof.it0[g_prof.n_it], st);
     CK(launch_iterate<T>(*cfg, w, i0, skip, nus, &g_prof.it_launches, st), "iterate");
@@ -155,6 +308,8 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
     if (prof) cudaEventRecord(g_prof.ev[3], st);
     g_prof.launches += 2;
     CK(cudaMemcpyAsync(hc, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st), "copy ctrl");
+    if (host && host->x)     // wasted (and overwritten later) only in the rare segment that ends in a refactorisation
+      CK(cudaMemcpyAsync(host->x, x, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToHost, st), "D2H x");
     CK(cudaStreamSynchronize(st), "synchronize (segment end)");
     if (hc->status == 3) {
       i0 = hc->next_i;
@@ -185,7 +340,8 @@ template <typename T>
 int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
                   const T* Q, const T* A, const T* lb, const T* ub, const T* rho_dev, double rho_scalar, T* dQ,
                   T* dp, T* dA, T* db, T* dlb, T* dub, void* ws, size_t ws_bytes, void* stream, bool kkt = false,
-                  int32_t* any_bounds = nullptr) {
+                  int32_t* any_bounds = nullptr, const HostBwd<T>* host = nullptr) {
+  if (host && !host->dl_dz) return fail(LQPB_E_ARG, "null host pointer argument");
   if (!dl_dz || !x || (!u && !kkt) || !lams || !Q || !lb || !ub || !ws) return fail(LQPB_E_ARG, "null pointer argument");
   if (B <= 0 || n <= 0 || m < 0) return fail(LQPB_E_ARG, "bad dimensions");
   if (m > 0 && (!A || !nus)) return fail(LQPB_E_ARG, "A and nus are required when m > 0");
@@ -201,40 +357,83 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   g_prof.launches = 0;
   int bwd_fac_launches = 0;
   if (prof) cudaEventRecord(g_prof.ev[4], st);
-  if (kkt) CK(launch_bwd_kkt_prep<T>(w, x, lams, lb, ub, st), "bwd_kkt_prep");
-  else CK(launch_bwd_mask<T>(w, x, u, lb, ub, st), "bwd_mask");
-  {
-    GjArgs<T> a{};
-    a.n = n; a.m = m; a.np = w.np;
-    a.src = Q; a.lds = n;
-    a.diag_shift = nullptr; a.diag_const = kkt ? T(0) : T(1e-8);   // :392 small regulariser on the whole diagonal
-    a.diag_vec = kkt ? w.dvec : nullptr;                           // KKT mode: Q + G^T diag(lam / s) G, no regulariser
-    a.mask = w.mask; a.ldm = w.ld;
-    a.Arows = A; a.lda = n; a.a_diag = kkt ? T(0) : T(1e-8);
-    a.W = w.W; a.Vg = w.Vg; a.Wg = w.Wg;
-    a.dst = nullptr; a.ldd = w.ld; a.G21 = nullptr; a.K22 = nullptr;
-    a.bt = nullptr; a.c_out = nullptr;
-    a.rhs_g = dl_dz; a.sol_x = w.dv; a.sol_nu = w.dnu;
-    bool done = false;
-    if constexpr (std::is_same<T, float>::value) {
-      if (w.tc) {
-        CK(launch_tc_ldl_solve(B, a, w.Pb, w.nb, st, &bwd_fac_launches), "tensor-core LDL solve (backward)");
-        done = true;
+  if (kkt) CK(cudaMemsetAsync(w.flags, 0, 4 * sizeof(int), st), "memset flags");
+  // device-buffer call: one chunk = the whole batch.  Host-buffer call: the adjoint chain of chunk c runs on the
+  // compute stream while the copy stream returns the dQ rows of chunk c - 1 to the host.
+  const int C = host ? pick_chunks(host->chunks, B) : 1;
+  cudaStream_t cs = nullptr;
+  if (host) {
+    CK(pipe_init(), "copy stream");
+    cs = g_pipe.cs;
+    CK(cudaMemcpyAsync((void*)dl_dz, host->dl_dz, (size_t)B * n * sizeof(T), cudaMemcpyHostToDevice, st), "H2D dl_dz");
+  }
+  for (int c = 0; c < C; ++c) {
+    const int b0 = chunk_lo(B, C, c), bc = chunk_lo(B, C, c + 1) - b0;
+    const size_t o = (size_t)b0;
+    const BwdWs<T> wc = C > 1 ? slice_bwd(w, b0, bc) : w;
+    const T *xc = x + o * n, *uc = off(u, o * n), *lamc = lams + o * 2 * n, *nuc = off(nus, o * m);
+    const T *Qc = Q + o * n * n, *Ac = off(A, o * m * n), *lbc = lb + o * n, *ubc = ub + o * n, *gc = dl_dz + o * n;
+    if (kkt) CK(launch_bwd_kkt_prep<T>(wc, xc, lamc, lbc, ubc, st), "bwd_kkt_prep");
+    else CK(launch_bwd_mask<T>(wc, xc, uc, lbc, ubc, st), "bwd_mask");
+    {
+      GjArgs<T> a{};
+      a.n = n; a.m = m; a.np = wc.np;
+      a.src = Qc; a.lds = n;
+      a.diag_shift = nullptr; a.diag_const = kkt ? T(0) : T(1e-8);   // :392 small regulariser on the whole diagonal
+      a.diag_vec = kkt ? wc.dvec : nullptr;                          // KKT mode: Q + G^T diag(lam / s) G, no regulariser
+      a.mask = wc.mask; a.ldm = wc.ld;
+      a.Arows = Ac; a.lda = n; a.a_diag = kkt ? T(0) : T(1e-8);
+      a.W = wc.W; a.Vg = wc.Vg; a.Wg = wc.Wg;
+      a.dst = nullptr; a.ldd = wc.ld; a.G21 = nullptr; a.K22 = nullptr;
+      a.bt = nullptr; a.c_out = nullptr;
+      a.rhs_g = gc; a.sol_x = wc.dv; a.sol_nu = wc.dnu;
+      bool done = false;
+      if constexpr (std::is_same<T, float>::value) {
+        if (wc.tc) {
+          int l = 0;
+          CK(launch_tc_ldl_solve(bc, a, wc.Pb, wc.nb, st, &l), "tensor-core LDL solve (backward)");
+          bwd_fac_launches += l;
+          done = true;
+        }
+      }
+      if (!done) {
+        CK(launch_ldl_solve<T>(bc, a, st), "ldl_solve (backward)");
+        bwd_fac_launches += 1;
       }
     }
-    if (!done) {
-      CK(launch_ldl_solve<T>(B, a, st), "ldl_solve (backward)");
-      bwd_fac_launches = 1;
+    if (prof && c == C - 1) cudaEventRecord(g_prof.ev[5], st);
+    if (prof && c == C - 1) cudaEventRecord(g_prof.ev[6], st);
+    CK(launch_bwd_grads<T>(wc, gc, xc, uc, lamc, nuc, Qc, Ac, off(rho_dev, o), rho_scalar, off(dQ, o * n * n),
+                           off(dp, o * n), off(dA, o * m * n), off(db, o * m), off(dlb, o * n), off(dub, o * n), st,
+                           kkt ? lbc : nullptr, kkt ? ubc : nullptr),
+       "bwd_grads");
+    if (host && host->dQ && dQ) {
+      CK(cudaEventRecord(g_pipe.ev[c], st), "chunk event");
+      CK(cudaStreamWaitEvent(cs, g_pipe.ev[c], 0), "chunk wait");
+      CK(cudaMemcpyAsync(host->dQ + o * n * n, dQ + o * n * n, (size_t)bc * n * n * sizeof(T), cudaMemcpyDeviceToHost,
+                         cs), "D2H dQ");
     }
   }
-  if (prof) cudaEventRecord(g_prof.ev[5], st);
-  if (prof) cudaEventRecord(g_prof.ev[6], st);
-  CK(launch_bwd_grads<T>(w, dl_dz, x, u, lams, nus, Q, A, rho_dev, rho_scalar, dQ, dp, dA, db, dlb, dub, st,
-                         kkt ? lb : nullptr, kkt ? ub : nullptr),
-     "bwd_grads");
   if (prof) cudaEventRecord(g_prof.ev[7], st);
-  g_prof.launches = 2 + bwd_fac_launches;
+  g_prof.launches = 2 * C + bwd_fac_launches;
   g_prof.bwd_valid = prof;
+  if (host) {
+    // the small gradients follow the last chunk on the compute stream; then wait for both streams
+    const size_t sv = (size_t)B * n * sizeof(T);
+    if (host->dp && dp) CK(cudaMemcpyAsync(host->dp, dp, sv, cudaMemcpyDeviceToHost, st), "D2H dp");
+    if (host->dlb && dlb) CK(cudaMemcpyAsync(host->dlb, dlb, sv, cudaMemcpyDeviceToHost, st), "D2H dlb");
+    if (host->dub && dub) CK(cudaMemcpyAsync(host->dub, dub, sv, cudaMemcpyDeviceToHost, st), "D2H dub");
+    if (m > 0 && host->dA && dA)
+      CK(cudaMemcpyAsync(host->dA, dA, (size_t)B * m * n * sizeof(T), cudaMemcpyDeviceToHost, st), "D2H dA");
+    if (m > 0 && host->db && db)
+      CK(cudaMemcpyAsync(host->db, db, (size_t)B * m * sizeof(T), cudaMemcpyDeviceToHost, st), "D2H db");
+    if (kkt && any_bounds)
+      CK(cudaMemcpyAsync(any_bounds, w.flags, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "copy bound flags");
+    CK(cudaEventRecord(g_pipe.done, cs), "copy done");
+    CK(cudaStreamWaitEvent(st, g_pipe.done, 0), "join");
+    CK(cudaStreamSynchronize(st), "synchronize (host gradients)");
+    return LQPB_OK;
+  }
   if (kkt && any_bounds) {
     CK(cudaMemcpyAsync(any_bounds, w.flags, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "copy bound flags");
     CK(cudaStreamSynchronize(st), "synchronize (bound flags)");
@@ -309,6 +508,27 @@ int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x,
   return backward_impl<double>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db,
                                dlb, dub, workspace, workspace_bytes, stream);
 }
+
+#define HOST_ENTRY(SFX, T)                                                                                         \
+  int lqpb_forward_host_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* hQ, const T* hp, const T* hA,  \
+                              const T* hb, const T* hlb, const T* hub, T* Q, T* p, T* A, T* b, T* lb, T* ub, T* x, \
+                              T* z, T* u, T* lams, T* nus, T* rho_out, T* hx, lqpb_info* info, void* workspace,    \
+                              size_t workspace_bytes, void* stream, int chunks) {                                  \
+    HostFwd<T> h{hQ, hp, hA, hb, hlb, hub, hx, chunks};                                                            \
+    return forward_impl<T>(cfg, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, workspace,         \
+                           workspace_bytes, stream, &h);                                                           \
+  }                                                                                                                \
+  int lqpb_backward_host_##SFX(int B, int n, int m, int kkt, const T* h_dl_dz, T* dl_dz, const T* x, const T* u,  \
+                               const T* lams, const T* nus, const T* Q, const T* A, const T* lb, const T* ub,     \
+                               const T* rho_dev, double rho_scalar, T* dQ, T* dp, T* dA, T* db, T* dlb, T* dub,   \
+                               T* hdQ, T* hdp, T* hdA, T* hdb, T* hdlb, T* hdub, int32_t* any_bounds,             \
+                               void* workspace, size_t workspace_bytes, void* stream, int chunks) {               \
+    HostBwd<T> h{h_dl_dz, hdQ, hdp, hdA, hdb, hdlb, hdub, chunks};                                                 \
+    return backward_impl<T>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db,   \
+                            dlb, dub, workspace, workspace_bytes, stream, kkt != 0, any_bounds, &h);               \
+  }
+HOST_ENTRY(f32, float)
+HOST_ENTRY(f64, double)
 
 int lqpb_backward_kkt_f32(int B, int n, int m, const float* dl_dz, const float* x, const float* lams,
                           const float* nus, const float* Q, const float* A, const float* lb, const float* ub, float* dQ,

@@ -79,8 +79,7 @@ __global__ void bwd_kkt_prep_kernel(BwdWs<T> w, const T* __restrict__ x, const T
 template <typename T>
 cudaError_t launch_bwd_kkt_prep(const BwdWs<T>& w, const T* x, const T* lams, const T* lb, const T* ub,
                                 cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(w.flags, 0, 4 * sizeof(int), st);
-  if (e != cudaSuccess) return e;
+  // w.flags is zeroed once per call by the C ABI (abi.cu): the batch may arrive here in several chunks
   dim3 grid((w.ld + 127) / 128, w.B);
   bwd_kkt_prep_kernel<T><<<grid, 128, 0, st>>>(w, x, lams, lb, ub);
   return cudaGetLastError();

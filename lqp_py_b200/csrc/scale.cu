@@ -296,6 +296,33 @@ scale_pack_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q) {
   }
 }
 
+// any_lb / any_ub (:129-130) over the WHOLE batch, for the chunked host-buffer forward: the per-chunk
+// scale_vec_kernel only sees its own problems, but rho = 0 (:157-158) is a decision about all of them.
+template <typename T>
+__global__ void bound_flags_kernel(FwdWs<T> w, const T* __restrict__ lb, const T* __restrict__ ub) {
+  const size_t total = (size_t)w.B * w.n;
+  int f_lb = 0, f_ub = 0;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    f_lb |= lb[e] > -t_inf<T>();
+    f_ub |= ub[e] < t_inf<T>();
+  }
+  f_lb = __syncthreads_or(f_lb);
+  f_ub = __syncthreads_or(f_ub);
+  if (threadIdx.x == 0) {
+    if (f_lb) atomicOr(&w.ctrl->any_lb, 1);
+    if (f_ub) atomicOr(&w.ctrl->any_ub, 1);
+  }
+}
+
+template <typename T>
+cudaError_t launch_bound_flags(const FwdWs<T>& w, const T* lb, const T* ub, cudaStream_t st) {
+  const size_t total = (size_t)w.B * w.n;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 296) blocks = 296;
+  bound_flags_kernel<T><<<blocks, 256, 0, st>>>(w, lb, ub);
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, const T* p, const T* A, const T* b,
                          const T* lb, const T* ub, cudaStream_t st) {
@@ -317,6 +344,8 @@ cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, 
   return cudaGetLastError();
 }
 
+template cudaError_t launch_bound_flags<float>(const FwdWs<float>&, const float*, const float*, cudaStream_t);
+template cudaError_t launch_bound_flags<double>(const FwdWs<double>&, const double*, const double*, cudaStream_t);
 template cudaError_t launch_scale<float>(const lqpb_config&, const FwdWs<float>&, const float*, const float*,
                                          const float*, const float*, const float*, const float*, cudaStream_t);
 template cudaError_t launch_scale<double>(const lqpb_config&, const FwdWs<double>&, const double*, const double*,

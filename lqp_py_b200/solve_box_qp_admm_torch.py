@@ -69,7 +69,11 @@ class SolveBoxQPLayer(torch.autograd.Function):
     def backward(ctx, dl_dz):
         x, u, lams, nus, Q, A, lb, ub = ctx.saved_tensors
         need = ctx.needs_input_grad[:6]
-        if ctx.backward_method == 'kkt':       # reference :63-64
+        kkt = ctx.backward_method == 'kkt'       # reference :63-64
+        if dl_dz.device.type == "cpu" and _all_on_host_devices(ctx.input_devices):
+            # the caller lives on the host: gradients stream back chunk by chunk while the next chunk is differentiated
+            return (*_grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need, kkt, ctx.any_bounds), None)
+        if kkt:
             grads = _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, ctx.any_bounds)
         else:
             grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need)
@@ -205,10 +209,38 @@ def _derive_config(control, n_x):
     return cfg
 
 
+def _all_on_host_devices(devices):
+    ds = [d for d in devices if d is not None]
+    return len(ds) > 0 and all(d.type == "cpu" for d in ds)
+
+
+def _all_on_host(tensors):
+    ts = [t for t in tensors if t is not None]
+    return len(ts) > 0 and all(t.device.type == "cpu" for t in ts)
+
+
+def _host_view(t):
+    """Contiguous, detached host tensor (no copy for the usual contiguous inputs)."""
+    return None if t is None else t.detach().contiguous()
+
+
 def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
     L = _abi.lib()
     out_device = p.device
-    dv = _stage(dict(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub))
+    host_mode = _all_on_host((Q, p, A, b, lb, ub))
+    hx = None
+    if host_mode:
+        # CPU tensors in (the reference's callers): lqpb_forward_host_* uploads Q in chunks on a copy stream and
+        # overlaps the per-problem setup with the transfer; the device copies it fills are kept for the backward
+        hv = {k: _host_view(t) for k, t in dict(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub).items()}
+        dt = hv["p"].dtype
+        for k, t in hv.items():
+            if t is not None and t.dtype != dt:
+                raise TypeError(f"all tensors must share one dtype, got {dt} and {t.dtype} ({k})")
+        dev = _cuda_device(hv["p"])
+        dv = {k: (None if t is None else torch.empty(t.shape, dtype=dt, device=dev)) for k, t in hv.items()}
+    else:
+        dv = _stage(dict(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub))
     Qd, pd = dv["Q"], dv["p"]
     dev, dt = pd.device, pd.dtype
     sfx = _abi.suffix(dt)
@@ -225,11 +257,21 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         info = _abi.Info()
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = getattr(L, f"lqpb_forward_{sfx}")(
-            C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
-            _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u), _abi.ptr(lams),
-            _abi.ptr(nus), _abi.ptr(rho_t), C.byref(info), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
-        _abi.check(rc, "lqpb_forward")
+        if host_mode:
+            hx = torch.empty((B, n, 1), dtype=dt, pin_memory=True)
+            rc = getattr(L, f"lqpb_forward_host_{sfx}")(
+                C.byref(cfg), B, n, m, _abi.ptr(hv["Q"]), _abi.ptr(hv["p"]), _abi.ptr(hv["A"]), _abi.ptr(hv["b"]),
+                _abi.ptr(hv["lb"]), _abi.ptr(hv["ub"]), _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]),
+                _abi.ptr(dv["b"]), _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u),
+                _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(rho_t), _abi.ptr(hx), C.byref(info), _abi.ptr(ws), ws_bytes,
+                C.c_void_p(stream), 0)
+            _abi.check(rc, "lqpb_forward_host")
+        else:
+            rc = getattr(L, f"lqpb_forward_{sfx}")(
+                C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
+                _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u), _abi.ptr(lams),
+                _abi.ptr(nus), _abi.ptr(rho_t), C.byref(info), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
+            _abi.check(rc, "lqpb_forward")
     if cfg.verbose:
         for k in range(info.n_log):          # same text as the reference prints (:289-294)
             print(f'iteration = {info.log_iter[k]}')
@@ -247,7 +289,10 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
     keys = ("x", "z", "u", "lams", "nus", "rho")
     vals = [x, z, u, lams, nus, rho if torch.is_tensor(rho) else None]
     want = [out_device if (host_keys is None or k in host_keys) else None for k in keys]
-    hx, hz, hu, hlams, hnus, hrho = _to_devices(vals, want)
+    if hx is not None:
+        want[0] = None                            # x already came back inside lqpb_forward_host_*
+    x_out, hz, hu, hlams, hnus, hrho = _to_devices(vals, want)
+    hx = hx if hx is not None else x_out
     rho_out = hrho if torch.is_tensor(rho) else rho
     return {"x": hx, "z": hz, "u": hu, "lams": hlams, "nus": hnus, "rho": rho_out,
             "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor),
@@ -338,3 +383,48 @@ def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds):
         if not flags[1]:
             dub = None
     return dQ, dp, dA, db, dlb, dub
+
+
+def _grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, kkt, any_bounds):
+    """Backward for host callers: saved tensors are the device copies of the forward, ``dl_dz`` is a CPU tensor and
+    the gradients are returned as (pinned) CPU tensors through ``lqpb_backward_host_*``.  ``any_bounds`` is the
+    (any_lb, any_ub) pair of the forward solve (KKT mode: dlb / dub are None without such bounds, :572-579)."""
+    L = _abi.lib()
+    dev, dt = x.device, x.dtype
+    sfx = _abi.suffix(dt)
+    B, n = Q.shape[0], Q.shape[1]
+    m = get_ncon(A, dim=1)
+    g = dl_dz.detach()
+    if g.dtype != dt:
+        raise TypeError(f"dl_dz has dtype {g.dtype}, expected {dt}")
+    g = g.contiguous()
+    rho_dev, rho_scalar = None, 0.0
+    if not kkt:
+        if rho is None:
+            rho = 1.0                              # :356-357
+        if torch.is_tensor(rho):
+            rho_dev = rho.detach().to(device=dev, dtype=dt).reshape(-1).contiguous()
+            if rho_dev.numel() == 1 and B > 1:
+                rho_dev = rho_dev.expand(B).contiguous()
+        else:
+            rho_scalar = float(rho)
+    nQ, np_, nA, nb, nlb, nub = need
+    if kkt:
+        nlb = nlb and any_bounds[0]
+        nub = nub and any_bounds[1]
+    shapes = [(B, n, n) if nQ else None, (B, n, 1) if np_ else None, (B, m, n) if (nA and m > 0) else None,
+              (B, m, 1) if (nb and m > 0) else None, (B, n, 1) if nlb else None, (B, n, 1) if nub else None]
+    with torch.cuda.device(dev):
+        dbuf = [None if s is None else torch.empty(s, dtype=dt, device=dev) for s in shapes]
+        hbuf = [None if s is None else torch.empty(s, dtype=dt, pin_memory=True) for s in shapes]
+        g_dev = torch.empty((B, n, 1), dtype=dt, device=dev)
+        ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{sfx}")(B, n, m)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = getattr(L, f"lqpb_backward_host_{sfx}")(
+            B, n, m, 1 if kkt else 0, _abi.ptr(g), _abi.ptr(g_dev), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams),
+            _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A), _abi.ptr(lb), _abi.ptr(ub), _abi.ptr(rho_dev), rho_scalar,
+            *[_abi.ptr(t) for t in dbuf], *[_abi.ptr(t) for t in hbuf], None, _abi.ptr(ws), ws_bytes,
+            C.c_void_p(stream), 0)
+        _abi.check(rc, "lqpb_backward_host")
+    return tuple(hbuf)

@@ -225,6 +225,36 @@ def test_cpu_tensors_drop_in(dev):
     assert Q.grad.device.type == "cpu" and p.grad.shape == p.shape
 
 
+@pytest.mark.parametrize("n,B,dtype,backward", [(40, 70, torch.float64, "fixed_point"), (200, 64, torch.float32, "fixed_point"),
+                                                (40, 70, torch.float64, "kkt"), (500, 128, torch.float32, "fixed_point")])
+def test_host_buffer_pipeline_equals_device_path(n, B, dtype, backward, dev):
+    """CPU tensors go through lqpb_forward_host_* / lqpb_backward_host_* (Q uploaded and dQ returned in chunks that
+    overlap the per-problem setup / adjoint chains).  Problems are independent and every kernel is deterministic
+    per problem, so the results must be BIT-identical to the device-tensor path (one chunk = whole batch)."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    data = orc.make_exp1_data(n, B, seed=21, dtype=dtype)
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5, backward=backward)
+    g = torch.randn(B, n, 1, generator=torch.Generator().manual_seed(9), dtype=dtype)
+    host = [t.clone().pin_memory().requires_grad_(True) for t in data]
+    xh = SolveBoxQP(control=control).forward(*host)
+    assert xh.device.type == "cpu"
+    xh.backward(g)
+    devs = [t.to(dev).requires_grad_(True) for t in data]
+    xd = SolveBoxQP(control=control).forward(*devs)
+    xd.backward(g.to(dev))
+    assert torch.equal(xh.detach(), xd.detach().cpu())
+    for th, td, name in zip(host, devs, ("dQ", "dp", "dA", "db", "dlb", "dub")):
+        assert th.grad is not None and th.grad.device.type == "cpu", name
+        assert torch.equal(th.grad, td.grad.cpu()), name
+    # pageable (not pinned) host tensors take the same path
+    host2 = [t.clone().requires_grad_(k < 2) for k, t in enumerate(data)]
+    x2 = SolveBoxQP(control=control).forward(*host2)
+    x2.backward(g)
+    assert torch.equal(x2.detach(), xh.detach()) and torch.equal(host2[0].grad, host[0].grad)
+    assert host2[2].grad is None and host2[4].grad is None
+
+
 def test_unbounded_batch_mutates_control_like_reference(dev):
     from lqp_py_b200.control import box_qp_control
     from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP

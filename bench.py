@@ -111,6 +111,8 @@ def run_reference(a):
     if rank != 0:
         return
     from oracle import box_qp_oracle as orc
+    # torchrun exports OMP_NUM_THREADS=1; this arm is the CPU path with every host thread it can use
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     dtype = torch.float32 if a.dtype == "f32" else torch.float64
     K = a.steps if a.steps is not None else 3
     W = a.warmup if a.warmup is not None else 1
@@ -129,7 +131,8 @@ def run_reference(a):
     val = a.batch * K / dt
     cores = torch.get_num_threads()
     sample = f"{K} steps of the full batch ({a.batch} problems, dz={a.dz}), {W} warm-up, ADMM iter={iters}"
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "steps": K, "warmup": W,
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "launched_as_gpus": a.gpus,
+           "steps": K, "warmup": W,
            "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": a.dtype, "data": "synthetic", "config": {"workload": workload_name(a)},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
@@ -140,6 +143,7 @@ def run_reference(a):
 
 def cpu_baseline(a, dtype):
     from oracle import box_qp_oracle as orc
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     prev = torch.get_default_dtype()
     torch.set_default_dtype(dtype)
     try:

@@ -246,7 +246,9 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
   if (host) {
     // ---- inputs on the host: the vectors first (they decide any_lb / any_ub for the whole batch), then Q chunk
     //      by chunk on the copy stream; scaling + rho + factorisation of a chunk start as soon as it has landed
-    const int C = pick_chunks(host->chunks, B);
+    // (the one-CTA-per-problem Gauss-Jordan kernel of the fp64 / small-problem path takes as long for 32 problems as
+    // for 128, so its chains do not pipeline: one chunk there)
+    const int C = w.tc ? pick_chunks(host->chunks, B) : 1;
     CK(pipe_init(), "copy stream");
     cudaStream_t cs = g_pipe.cs;
     CK(cudaEventRecord(g_pipe.fork, st), "fork");
@@ -360,7 +362,7 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   if (kkt) CK(cudaMemsetAsync(w.flags, 0, 4 * sizeof(int), st), "memset flags");
   // device-buffer call: one chunk = the whole batch.  Host-buffer call: the adjoint chain of chunk c runs on the
   // compute stream while the copy stream returns the dQ rows of chunk c - 1 to the host.
-  const int C = host ? pick_chunks(host->chunks, B) : 1;
+  const int C = (host && w.tc) ? pick_chunks(host->chunks, B) : 1;
   cudaStream_t cs = nullptr;
   if (host) {
     CK(pipe_init(), "copy stream");

@@ -1,0 +1,26 @@
+#!/bin/bash
+# One GPU-box session that produces the round's tracked evidence (tools/make_profiles.py <tag> afterwards):
+# smoke, parity suite, bench (fp32 headline, fp64, reference arm), ncu launch list of the bench command,
+# ncu --set full captures of the dominant kernels.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+python -c "import __graft_entry__ as e; e.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log gpurun_out/smoke.log
+timeout 600 python bench.py > gpurun_out/bench_f32.json 2> gpurun_out/bench_f32.err
+timeout 600 python bench.py --dtype f64 --no-cpu-baseline > gpurun_out/bench_f64.json 2> gpurun_out/bench_f64.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+cat gpurun_out/bench_f32.json gpurun_out/bench_f64.json gpurun_out/bench_ref.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_f32.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_launch.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'iterate_kernel' -s 3 -c 1 -o gpurun_out/iterate_f32 -f \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_iter32.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'iterate_kernel' -s 3 -c 1 -o gpurun_out/iterate_f64 -f \
+  python bench.py --steps 1 --warmup 3 --dtype f64 --no-cpu-baseline --no-e2e > gpurun_out/ncu_iter64.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_tile_kernel' -s 24 -c 2 -o gpurun_out/tc_tile_f32 -f \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_tile32.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_pivot8' -s 12 -c 1 -o gpurun_out/tc_pivot_f32 -f \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_pivot32.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gj_inverse_kernel' -s 6 -c 1 -o gpurun_out/gj_f64 -f \
+  python bench.py --steps 1 --warmup 3 --dtype f64 --no-cpu-baseline --no-e2e > gpurun_out/ncu_gj64.log 2>&1
+ls -la gpurun_out

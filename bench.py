@@ -97,6 +97,33 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def log(msg):
+    """progress marker on stderr (stdout carries only the JSON line)"""
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def usable_cpus():
+    """Host threads this process can really use: the affinity mask, capped by the cgroup CPU quota (a box can
+    show 200 CPUs and grant 16; sizing the BLAS pool by os.cpu_count() there oversubscribes by 10x)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        try:                                        # cgroup v1
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, int(quota / period + 0.5)))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def gen_data(a, seed, dtype):
     from lqp_py_b200.datasets import create_qp_data
     Q, p, A, b, lb, ub, _, _ = create_qp_data(a.dz, a.batch, 2 * a.dz, seed=seed, requires_grad=False, dtype=dtype)
@@ -112,7 +139,7 @@ def run_reference(a):
         return
     from oracle import box_qp_oracle as orc
     # torchrun exports OMP_NUM_THREADS=1; this arm is the CPU path with every host thread it can use
-    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
+    torch.set_num_threads(usable_cpus())
     dtype = torch.float32 if a.dtype == "f32" else torch.float64
     K = a.steps if a.steps is not None else 3
     W = a.warmup if a.warmup is not None else 1
@@ -120,13 +147,15 @@ def run_reference(a):
     data = gen_data(a, 0, dtype)
     control = orc.default_control(eps_abs=1e-5, eps_rel=1e-5)
     g = torch.ones(a.batch, a.dz, 1, dtype=dtype)            # experiment_1.py:75
+    log(f"reference arm: {torch.get_num_threads()} threads, {W} warm-up + {K} steps of {a.batch} problems")
     for _ in range(W):
         orc.solve_and_grad(*data, control, g)
     t0 = time.perf_counter()
     iters = None
-    for _ in range(K):
+    for k in range(K):
         sol, _ = orc.solve_and_grad(*data, control, g)
         iters = sol["iter"]
+        log(f"reference arm: step {k + 1}/{K} at {time.perf_counter() - t0:.1f} s")
     dt = time.perf_counter() - t0
     val = a.batch * K / dt
     cores = torch.get_num_threads()
@@ -143,28 +172,37 @@ def run_reference(a):
 
 def cpu_baseline(a, dtype):
     from oracle import box_qp_oracle as orc
-    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
+    torch.set_num_threads(usable_cpus())
     prev = torch.get_default_dtype()
     torch.set_default_dtype(dtype)
     try:
         data = gen_data(a, 0, dtype)
         control = orc.default_control(eps_abs=1e-5, eps_rel=1e-5)
         g = torch.ones(a.batch, a.dz, 1, dtype=dtype)
-        small = [t[:8] for t in data]
-        orc.solve_and_grad(*small, control, g[:8])             # warm up LAPACK / thread pool
+        # bounded sample: time 8 problems first, then as much of the batch as fits in ~10 s per pass
+        nb0 = min(8, a.batch)
+        small = [t[:nb0] for t in data]
+        orc.solve_and_grad(*small, control, g[:nb0])           # warm up LAPACK / thread pool
+        t0 = time.perf_counter()
+        orc.solve_and_grad(*small, control, g[:nb0])
+        per_problem = (time.perf_counter() - t0) / nb0
+        nb = int(max(nb0, min(a.batch, 10.0 / max(per_problem, 1e-9))))
+        log(f"cpu baseline: {torch.get_num_threads()} threads, {per_problem * 1e3:.1f} ms per problem on a batch of "
+            f"{nb0} -> sample of {nb} problems per pass")
+        sample = [t[:nb] for t in data]
         t0 = time.perf_counter()
         reps = 0
         iters = None
-        while reps < 2 or (time.perf_counter() - t0 < 8.0 and reps < 6):
-            sol, _ = orc.solve_and_grad(*data, control, g)
+        while reps < 1 or (time.perf_counter() - t0 < 8.0 and reps < 6):
+            sol, _ = orc.solve_and_grad(*sample, control, g[:nb])
             iters = sol["iter"]
             reps += 1
         dt = time.perf_counter() - t0
     finally:
         torch.set_default_dtype(prev)
-    return {"value": a.batch * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": nb * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "host_cpus": os.cpu_count(),
-            "sample": f"{reps} forward+backward passes of the full batch ({a.batch} problems, dz={a.dz}, {a.dtype}) "
+            "sample": f"{reps} forward+backward passes of {nb} of the {a.batch} problems (dz={a.dz}, {a.dtype}) "
                       f"with the oracle port (torch CPU, batched LAPACK), ADMM iter={iters}, {dt:.1f} s"}
 
 
@@ -234,9 +272,11 @@ def run_b200(a):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    log(f"rank {rank}: data on {dev}, {W} warm-up + {K} timed steps")
     for k in range(W):
         step(k, False)
     sync_all()
+    log("warm-up done")
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -249,6 +289,7 @@ def run_b200(a):
     sync_all()
     ms = e0.elapsed_time(e1)
     add_prof(BWD)            # the last step's backward
+    log(f"timed region done: {ms / K:.3f} ms per step")
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -317,6 +358,7 @@ def run_b200(a):
         dt = float(tt.item())
         h2d = sum(t.numel() for t in pin_sets[0]) * s + g_host.numel() * s
         d2h = (x.numel() + sum(t.grad.numel() for t in ins if t.grad is not None)) * s
+        log(f"e2e done: {dt / Ke * 1e3:.3f} ms per step")
         e2e = {"value": B * world * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": Ke, "ms_per_step": dt / Ke * 1e3,
                "how": "SolveBoxQP.forward + x.backward on pinned CPU tensors (Q, p require grad as in "

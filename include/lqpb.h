@@ -181,6 +181,37 @@ int lqpb_backward_host_f64(int B, int n, int m, int kkt, const double* h_dl_dz, 
                            double* hdb, double* hdlb, double* hdub, int32_t* any_bounds, void* workspace,
                            size_t workspace_bytes, void* stream, int chunks);
 
+/* ---- unrolled mode: control['unroll'] = True (solve_box_qp_admm_torch.py:13-15) lets autograd differentiate
+ * every ADMM iteration (:259-282), each KKT solve through TorchLULayer (lu_layer.py:18-58: dx = M^-1 (-g),
+ * dl_dA = dx xv^T, dl_db = -dx).  Here the loop is recorded and swept backwards by two calls that work on the
+ * operators a preceding lqpb_forward_* call left in its `workspace` (which the caller keeps alive; the solve must
+ * have ended with info.n_factor == 1, i.e. without an adaptive-rho refactorisation):
+ * unroll_record:   re-runs the n_iter = info.iter + 1 iterations from z = u = 0 with identical arithmetic and writes,
+ *                  per problem and iteration k, the scaled iterate x~_k, z_k, u_k into tape_x/z/u (B, n_iter, n) and
+ *                  the equality part nu_k of the KKT solve into tape_nu (B, n_iter, m) (unused when m == 0).
+ *                  Synchronises the stream once (it checks that the pass ended at iteration n_iter - 1).
+ * unroll_backward: g_x (B, n) is the adjoint of the last x~.  Runs the reverse sweep (one symmetric GEMV with the
+ *                  cached K11 per recorded iteration, the same operator stream as the forward loop) and returns the
+ *                  adjoints of the SCALED problem data: gp (B,n), gb (B,m), glb, gub (B,n), grho (B) and, when the
+ *                  pointers are not NULL, gQ (B,n,n) = -sum_k w_k x_k^T (not symmetric, like the reference's) and
+ *                  gA (B,m,n); tape_w (B,n_iter,n) / tape_wnu (B,n_iter,m) are scratch for the adjoint solves.
+ *                  The adapter maps them to the caller's Q, p, A, b, lb, ub through the scaling (:161-203).
+ *                  Fully asynchronous on `stream`. */
+int lqpb_unroll_record_f32(const lqpb_config* cfg, int B, int n, int m, int n_iter, void* workspace,
+                           size_t workspace_bytes, float* tape_x, float* tape_z, float* tape_u, float* tape_nu,
+                           void* stream);
+int lqpb_unroll_record_f64(const lqpb_config* cfg, int B, int n, int m, int n_iter, void* workspace,
+                           size_t workspace_bytes, double* tape_x, double* tape_z, double* tape_u, double* tape_nu,
+                           void* stream);
+int lqpb_unroll_backward_f32(int B, int n, int m, int n_iter, void* workspace, size_t workspace_bytes,
+                             const float* g_x, const float* tape_x, const float* tape_z, const float* tape_u,
+                             const float* tape_nu, float* tape_w, float* tape_wnu, float* gQ, float* gp, float* gA,
+                             float* gb, float* glb, float* gub, float* grho, void* stream);
+int lqpb_unroll_backward_f64(int B, int n, int m, int n_iter, void* workspace, size_t workspace_bytes,
+                             const double* g_x, const double* tape_x, const double* tape_z, const double* tape_u,
+                             const double* tape_nu, double* tape_w, double* tape_wnu, double* gQ, double* gp,
+                             double* gA, double* gb, double* glb, double* gub, double* grho, void* stream);
+
 /* ---- lu_layer: replaces TorchLU / TorchLULayer (lu_layer.py:5-58) -------------------------
  * lu_factor: partial-pivoting LU of B general N x N matrices (torch.linalg.lu_factor, :10,:30);
  *            LU (B,N,N) packed L\U, piv (B,N) 1-based row swaps like LAPACK getrf.

@@ -20,6 +20,7 @@ EXPORTS = (
     "lqpb_backward_workspace_bytes_f32", "lqpb_backward_workspace_bytes_f64",
     "lqpb_backward_f32", "lqpb_backward_f64", "lqpb_backward_kkt_f32", "lqpb_backward_kkt_f64",
     "lqpb_forward_host_f32", "lqpb_forward_host_f64", "lqpb_backward_host_f32", "lqpb_backward_host_f64",
+    "lqpb_unroll_record_f32", "lqpb_unroll_record_f64", "lqpb_unroll_backward_f32", "lqpb_unroll_backward_f64",
     "lqpb_lu_factor_f32", "lqpb_lu_factor_f64", "lqpb_lu_solve_f32", "lqpb_lu_solve_f64",
     "lqpb_outer_f32", "lqpb_outer_f64",
     "lqpb_dev_tc_inverse_work_bytes", "lqpb_dev_tc_inverse_f32",
@@ -102,6 +103,10 @@ def lib():
         f.argtypes = ([i32, i32, i32, i32] + [vp] * 2 + [vp] * 8 + [vp, dbl] + [vp] * 6 + [vp] * 6
                       + [C.POINTER(C.c_int32), vp, sz, vp, i32])
         f.restype = i32
+        f = getattr(L, f"lqpb_unroll_record_{sfx}")
+        f.argtypes, f.restype = [C.POINTER(Config), i32, i32, i32, i32, vp, sz] + [vp] * 4 + [vp], i32
+        f = getattr(L, f"lqpb_unroll_backward_{sfx}")
+        f.argtypes, f.restype = [i32, i32, i32, i32, vp, sz] + [vp] * 5 + [vp] * 2 + [vp] * 7 + [vp], i32
         f = getattr(L, f"lqpb_lu_factor_{sfx}")
         f.argtypes, f.restype = [i32, i32, vp, vp, vp, vp], i32
         f = getattr(L, f"lqpb_lu_solve_{sfx}")

@@ -1,5 +1,6 @@
 // C ABI (include/lqpb.h): argument validation, workspace carving, kernel orchestration, profiling.
 // Host code only; every kernel lives in scale.cu / factor.cu / iterate.cu / backward.cu / lu.cu.
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -443,6 +444,59 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   return LQPB_OK;
 }
 
+// ---- unrolled mode: recording pass and reverse sweep on the operators a forward call left in its workspace
+template <typename T>
+int unroll_record_impl(const lqpb_config* cfg, int B, int n, int m, int n_iter, void* ws, size_t ws_bytes, T* tx,
+                       T* tz, T* tu, T* tnu, void* stream) {
+  if (!cfg || !ws || !tx || !tz || !tu || (m > 0 && !tnu)) return fail(LQPB_E_ARG, "null pointer argument");
+  if (B <= 0 || n <= 0 || m < 0 || m > kMaxM || n_iter < 1) return fail(LQPB_E_ARG, "bad dimensions");
+  int rc = check_device();
+  if (rc) return rc;
+  FwdWs<T> w = carve_fwd<T>(ws, B, n, m);
+  if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!g_hctrl.pinned) CK(cudaMallocHost(&g_hctrl.pinned, sizeof(Ctrl)), "cudaMallocHost");
+  Ctrl* hc = g_hctrl.pinned;
+  // same start as the forward solve: z = u = 0, no check results yet; any_lb / any_ub are kept
+  CK(cudaMemsetAsync(w.ctrl, 0, offsetof(Ctrl, any_lb), st), "reset ctrl");
+  CK(cudaMemsetAsync((char*)w.ctrl + offsetof(Ctrl, n_log), 0, sizeof(Ctrl) - offsetof(Ctrl, n_log), st), "reset ctrl");
+  CK(cudaMemsetAsync(w.z, 0, (size_t)B * w.ld * sizeof(T), st), "reset z");
+  CK(cudaMemsetAsync(w.u, 0, (size_t)B * w.ld * sizeof(T), st), "reset u");
+  CK(cudaMemsetAsync(w.wants, 0, (size_t)B * sizeof(int), st), "reset wants");
+  lqpb_config c = *cfg;
+  c.max_iters = n_iter;
+  c.verbose = 0;
+  Tape<T> tape{n_iter, tx, tz, tu, tnu};
+  int l = 0;
+  CK(launch_iterate<T>(c, w, 0, 0, (T*)nullptr, &l, st, &tape), "iterate (recording pass)");
+  CK(cudaMemcpyAsync(hc, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st), "copy ctrl");
+  CK(cudaStreamSynchronize(st), "synchronize (recording pass)");
+  if (hc->status == 3) return fail(LQPB_E_ARG, "recording pass hit an adaptive-rho update (the forward solve must have n_factor == 1)");
+  if ((hc->status != LQPB_STATUS_CONVERGED && hc->status != LQPB_STATUS_MAX_ITERS) || hc->iter != n_iter - 1)
+    return fail(LQPB_E_CUDA, "recording pass did not reproduce the forward solve");
+  return LQPB_OK;
+}
+
+template <typename T>
+int unroll_backward_impl(int B, int n, int m, int n_iter, void* ws, size_t ws_bytes, const T* gx, const T* tx,
+                         const T* tz, const T* tu, const T* tnu, T* tw, T* twnu, T* gQ, T* gp, T* gA, T* gb, T* glb,
+                         T* gub, T* grho, void* stream) {
+  if (!ws || !gx || !tx || !tz || !tu || !tw || !gp || !glb || !gub || !grho)
+    return fail(LQPB_E_ARG, "null pointer argument");
+  if (m > 0 && (!tnu || !twnu || !gb)) return fail(LQPB_E_ARG, "tape_nu, tape_wnu and gb are required when m > 0");
+  if (B <= 0 || n <= 0 || m < 0 || m > kMaxM || n_iter < 1) return fail(LQPB_E_ARG, "bad dimensions");
+  int rc = check_device();
+  if (rc) return rc;
+  FwdWs<T> w = carve_fwd<T>(ws, B, n, m);
+  if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
+  Tape<T> tape{n_iter, (T*)tx, (T*)tz, (T*)tu, (T*)tnu};
+  UnrollGrads<T> g{gx, tw, twnu, gQ, gp, gA, gb, glb, gub, grho};
+  int l = 0;
+  CK(launch_unroll_reverse<T>(w, tape, g, &l, (cudaStream_t)stream), "unroll reverse sweep");
+  g_prof.launches = l;
+  return LQPB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -546,6 +600,22 @@ int lqpb_backward_kkt_f64(int B, int n, int m, const double* dl_dz, const double
   return backward_impl<double>(B, n, m, dl_dz, x, nullptr, lams, nus, Q, A, lb, ub, nullptr, 0.0, dQ, dp, dA, db, dlb,
                                dub, workspace, workspace_bytes, stream, true, any_bounds);
 }
+
+#define UNROLL_ENTRY(SFX, T)                                                                                       \
+  int lqpb_unroll_record_##SFX(const lqpb_config* cfg, int B, int n, int m, int n_iter, void* workspace,            \
+                               size_t workspace_bytes, T* tape_x, T* tape_z, T* tape_u, T* tape_nu, void* stream) { \
+    return unroll_record_impl<T>(cfg, B, n, m, n_iter, workspace, workspace_bytes, tape_x, tape_z, tape_u,          \
+                                 tape_nu, stream);                                                                  \
+  }                                                                                                                \
+  int lqpb_unroll_backward_##SFX(int B, int n, int m, int n_iter, void* workspace, size_t workspace_bytes,         \
+                                 const T* g_x, const T* tape_x, const T* tape_z, const T* tape_u,                  \
+                                 const T* tape_nu, T* tape_w, T* tape_wnu, T* gQ, T* gp, T* gA, T* gb, T* glb,     \
+                                 T* gub, T* grho, void* stream) {                                                  \
+    return unroll_backward_impl<T>(B, n, m, n_iter, workspace, workspace_bytes, g_x, tape_x, tape_z, tape_u,       \
+                                   tape_nu, tape_w, tape_wnu, gQ, gp, gA, gb, glb, gub, grho, stream);             \
+  }
+UNROLL_ENTRY(f32, float)
+UNROLL_ENTRY(f64, double)
 
 #define LU_ENTRY(SFX, T)                                                                                          \
   int lqpb_lu_factor_##SFX(int B, int N, const T* A, T* LU, int32_t* piv, void* stream) {                          \

@@ -27,47 +27,15 @@
 // position of a problem in the batch.  All problems advance in lock step and stop together: every
 // check_solved iterations each CTA publishes its flags and a grid barrier (atomic counter) makes the
 // decision global, exactly like torch.all(is_optimal) in the reference.  No host round trip per iteration.
-#include <cstdlib>
-#include "layout.cuh"
+#include "itergeom.cuh"
 
 namespace lqpb {
 
-constexpr int kIterMaxWarps = 16;
-constexpr int kIterMaxThreads = kIterMaxWarps * 32;
-constexpr int kIterMaxDepth = 8;
-
-struct IterGeom {
-  int nwarps;       // warps per CTA (each owns a run of tiles and a private ring)
-  int depth;        // ring slots (4 KB tiles) per warp
-  int nt;           // block rows of the packed layout
-  int nbc;          // block columns
-  int ntiles;       // tiles per matrix
-  int np;           // padded vector length = 32 * nt
-};
-
-// Butterfly transpose-reduce: on entry lane l holds its own partial sums acc[0..TC) for the TC columns of a
-// block column; on exit acc[0] of lane l is the total (over the 32 lanes) of column (l mod TC).
-template <typename T, int TC>
-__device__ __forceinline__ void reduce_cols(T (&acc)[TC], int lane) {
-  if (TC == 16) {
-#pragma unroll
-    for (int k = 0; k < TC; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 16);
-  }
-#pragma unroll
-  for (int s = (TC == 32 ? 16 : 8); s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int k = 0; k < s; ++k) {
-      const T send = up ? acc[k] : acc[k + s];
-      const T keep = up ? acc[k + s] : acc[k];
-      acc[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-}
-
-template <typename T>
+// TAPE = true is the recording pass of the unrolled mode (lqpb_unroll_record_*): identical arithmetic and
+// decisions, plus x~_i, z_i, u_i and the equality part nu_i of EVERY KKT solve written to the tape.
+template <typename T, bool TAPE>
 __global__ void __launch_bounds__(kIterMaxThreads, 1)
-iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, IterGeom geo) {
+iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, IterGeom geo, Tape<T> tape) {
   using P = Pack<T>;
   constexpr int VN = P::VN, TC = P::TC, TILE = P::TILE;
   using V4 = typename Vec<T>::type;
@@ -228,7 +196,7 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
     }
     const bool is_check = (i % check) == 0;
     const bool is_last = i == cfg.max_iters - 1;
-    const bool maybe_final = is_check || is_last;
+    const bool maybe_final = TAPE || is_check || is_last;
 
     int cta_notopt = 0, cta_wants = 0, cta_rout = 0;
     for (int k = 0; k < nprob; ++k) {
@@ -276,6 +244,12 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
           xs[e] = x;
           w.xs[vo + e] = x;
         }
+        if (TAPE) {
+          const size_t to = ((size_t)b * tape.n_iter + i) * n + e;
+          tape.x[to] = x;
+          tape.z[to] = zn;
+          tape.u[to] = un;
+        }
         if (is_check) {
           const T d = w.D[vo + e];
           Ds[e] = d;
@@ -292,7 +266,8 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
         const T* K22 = w.Sinv + (size_t)b * m * m;
         T a = tdot[tid];
         for (int l = 0; l < m; ++l) a += K22[tid * m + l] * w.bt[(size_t)b * m + l];
-        nus_out[(size_t)b * m + tid] = a * w.E[(size_t)b * m + tid];
+        if (!TAPE || nus_out) nus_out[(size_t)b * m + tid] = a * w.E[(size_t)b * m + tid];
+        if (TAPE) tape.nu[((size_t)b * tape.n_iter + i) * m + tid] = a;
       }
       if (is_check) {
         // ---- ||Q~ x~ / D||_inf (:299): the same symmetric sweep over the packed Q~ tiles
@@ -419,52 +394,9 @@ __global__ void finalize_kernel(FwdWs<T> w, T* x, T* z, T* u, T* lams, T* rho_ou
   if (e == 0) rho_out[b] = rho;
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return (s && *s) ? atoi(s) : dflt;
-}
-
-// Shared-memory plan: `nwarps` private rings of `depth` 4 KB slots + the per-warp partial sums + vectors.
-// Default: as many warps as fit with at least two slots each (measured on B200: warps matter more than ring
-// depth -- 16 x 2 beats 12 x 4 and 8 x 6 at dz=500), then as many slots as fit; small problems get fewer,
-// busier warps.  LQPB_ITER_WARPS / LQPB_ITER_DEPTH override the plan (tuning aid, tools/iter_tune.py).
-template <typename T>
-static bool make_geom(const FwdWs<T>& w, int max_smem, IterGeom* out, size_t* smem_bytes) {
-  using P = Pack<T>;
-  IterGeom g{};
-  g.nt = P::nt(w.n);
-  g.nbc = P::nbc(w.n);
-  g.ntiles = P::ntiles(w.n);
-  g.np = kPackRows * g.nt;
-  const size_t tile_bytes = (size_t)P::TILE * sizeof(T);
-  auto fixed = [&](int nw) {
-    return ((size_t)nw * g.np + 3 * (size_t)g.np + (w.m > 0 ? round_up(w.m, 4) : 4) + 6 * 16 + 4) * sizeof(T) +
-           (size_t)nw * kIterMaxDepth * sizeof(uint64_t) + 128;
-  };
-  const int want_w = env_int("LQPB_ITER_WARPS", 0), want_d = env_int("LQPB_ITER_DEPTH", 0);
-  int nw_max = kIterMaxWarps;
-  if (!want_w && nw_max > round_up(g.ntiles, 4)) nw_max = round_up(g.ntiles, 4) < 4 ? 4 : round_up(g.ntiles, 4);
-  for (int nw = want_w ? want_w : nw_max; nw >= 4; nw -= 2) {
-    if (nw > kIterMaxWarps) continue;
-    if (fixed(nw) + 2 * nw * tile_bytes > (size_t)max_smem) {
-      if (want_w) return false;
-      continue;
-    }
-    int d = (int)(((size_t)max_smem - fixed(nw)) / (nw * tile_bytes));
-    if (d > kIterMaxDepth) d = kIterMaxDepth;
-    if (want_d && want_d >= 2 && want_d <= d) d = want_d;
-    g.nwarps = nw;
-    g.depth = d;
-    *smem_bytes = fixed(nw) + (size_t)nw * d * tile_bytes;
-    *out = g;
-    return true;
-  }
-  return false;
-}
-
 template <typename T>
 cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
-                           int* launches, cudaStream_t st) {
+                           int* launches, cudaStream_t st, const Tape<T>* tape) {
   int dev = 0, max_smem = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -476,12 +408,14 @@ cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, in
   const int grid = w.B < sms ? w.B : sms;   // one CTA per SM: all CTAs co-resident (needed by the grid barrier)
   e = cudaMemsetAsync(&w.ctrl->barrier, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(iterate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  void* kern = tape ? (void*)iterate_kernel<T, true> : (void*)iterate_kernel<T, false>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   lqpb_config c = cfg;
   FwdWs<T> ww = w;
-  void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo};
-  e = cudaLaunchCooperativeKernel((void*)iterate_kernel<T>, dim3(grid), dim3(geo.nwarps * 32), args, smem, st);
+  Tape<T> tp = tape ? *tape : Tape<T>{};
+  void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo, &tp};
+  e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(geo.nwarps * 32), args, smem, st);
   if (launches) ++*launches;
   return e;
 }
@@ -494,7 +428,8 @@ cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho
 }
 
 #define INST(T)                                                                                            \
-  template cudaError_t launch_iterate<T>(const lqpb_config&, const FwdWs<T>&, int, int, T*, int*, cudaStream_t); \
+  template cudaError_t launch_iterate<T>(const lqpb_config&, const FwdWs<T>&, int, int, T*, int*, cudaStream_t, \
+                                         const Tape<T>*);                                                  \
   template cudaError_t launch_finalize<T>(const FwdWs<T>&, T*, T*, T*, T*, T*, cudaStream_t);
 INST(float)
 INST(double)

@@ -228,10 +228,29 @@ cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb
 cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches);
 cudaError_t launch_tc_dev_inverse(int B, int N, const float* A, float* Ainv, float* work, cudaStream_t st);
 
-// iterate.cu -- K3 (+K4): persistent ADMM loop and finalisation
+// Tape of the unrolled mode: per problem and ADMM iteration k the scaled iterate x~_k, z_k, u_k ((B, n_iter, n),
+// unpadded rows) and the equality part nu_k of the KKT solve ((B, n_iter, m), before the E un-scaling).
+template <typename T>
+struct Tape {
+  int n_iter;
+  T *x, *z, *u, *nu;
+};
+
+// iterate.cu -- K3 (+K4): persistent ADMM loop and finalisation (tape != nullptr: recording pass of the unrolled mode)
 template <typename T>
 cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
-                           int* launches, cudaStream_t st);
+                           int* launches, cudaStream_t st, const Tape<T>* tape = nullptr);
+
+// unroll.cu -- reverse sweep of the unrolled mode and the rank-n_iter products that form dQ~ and dA~
+template <typename T>
+struct UnrollGrads {
+  const T* gx;              // (B, n)  adjoint of the last x~
+  T *tw, *twnu;             // (B, n_iter, n), (B, n_iter, max(m,1))  adjoint solves w_k = K11 gx_k, K21 gx_k (scratch)
+  T *gQ, *gp, *gA, *gb, *glb, *gub, *grho;   // adjoints of Q~, p~, A~, b~, lb~, ub~, rho (gQ / gA may be null)
+};
+template <typename T>
+cudaError_t launch_unroll_reverse(const FwdWs<T>& w, const Tape<T>& tape, const UnrollGrads<T>& g, int* launches,
+                                  cudaStream_t st);
 template <typename T>
 cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho_out, cudaStream_t st);
 

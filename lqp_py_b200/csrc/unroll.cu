@@ -1,0 +1,328 @@
+// Unrolled mode (control['unroll'] = True): the reverse sweep through the recorded ADMM iterations.
+//
+// The reference differentiates the loop of lqp_py/solve_box_qp_admm_torch.py:259-282 with autograd; every linear
+// solve goes through TorchLULayer (lqp_py/lu_layer.py:18-58), whose backward is
+//     dx = M^-1 (-g),   dl_dA = dx xv^T,   dl_db = -dx                                   (lu_layer.py:52-54)
+// With (z_k, u_k) the state after iteration k, xv_k = [x_k; nu_k] = M^-1 [-p~ + rho (z_{k-1} - u_{k-1}); b~],
+// z_k = clamp(x_k + u_{k-1}), u_k = u_{k-1} + x_k - z_k, the adjoint recursion from the last iteration down is
+//     h    = gz - gu                       (adjoint of z_k once u_k = u_{k-1} + x_k - z_k is undone)
+//     t    = h where z_k is strictly inside the box, else 0;  the clamped entries send h to lb~ / ub~
+//     gx   = gu + t  (+ the incoming adjoint of the returned x~ at the last iteration)
+//     [w; wnu] = M^-1 [gx; 0] = [K11 gx; K21 gx]          <- the same symmetric GEMV the forward iteration streams
+//     gp~ -= w,  gb~ += wnu,  grho += w . (z_{k-1} - u_{k-1}) - w . x_k   (rhs term and the trace of dM = -w xv^T)
+//     gz   = rho w,   gu = gu + t - rho w
+// and the matrix adjoints are rank-n_iter products over the tape, formed once at the end instead of one dense
+// N x N outer product per iteration as in the reference:
+//     dQ~ = - sum_k w_k x_k^T   (NOT symmetric, like the reference's),   dA~ = - sum_k (wnu_k x_k^T + nu_k w_k^T).
+// Problems are independent here (no stop test): one persistent CTA per problem, K11 streamed from its packed lower
+// triangle through the per-warp bulk-TMA rings of the forward kernel (itergeom.cuh), prefetching across iterations.
+#include "itergeom.cuh"
+
+namespace lqpb {
+
+template <typename T>
+__global__ void __launch_bounds__(kIterMaxThreads, 1)
+unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) {
+  using P = Pack<T>;
+  constexpr int VN = P::VN, TC = P::TC, TILE = P::TILE;
+  using V4 = typename Vec<T>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = w.n, m = w.m, ld = w.ld, np = geo.np, K = tape.n_iter;
+  const int nthreads = blockDim.x, nwarps = geo.nwarps, depth = geo.depth;
+  const int ntv = geo.nt, ntiles = geo.ntiles;
+  T* ring = reinterpret_cast<T*>(smem_raw);                 // [nwarps][depth][TILE]
+  T* xpart = ring + (size_t)nwarps * depth * TILE;          // [nwarps][np] per-warp partial sums of K11 gx
+  T* v = xpart + (size_t)nwarps * np;                       // [np] gx of this iteration (zero padded)
+  T* gz = v + np;                                           // [np] adjoint of z_k
+  T* gu = gz + np;                                          // [np] adjoint of u_k
+  T* tdot = gu + np;                                        // [max(m,1)] K21 gx
+  T* red = tdot + (m > 0 ? round_up(m, 4) : 4);             // [6][16] reduction scratch
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 6 * 16 + 4);   // [nwarps][depth]
+
+  const int tid = threadIdx.x;
+  const int wid = tid >> 5, lane = tid & 31;
+  const int nprob = (w.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < nwarps * depth; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  for (int e = tid; e < nwarps * np; e += nthreads) xpart[e] = T(0);
+  for (int e = tid; e < np; e += nthreads) { v[e] = T(0); gz[e] = T(0); gu[e] = T(0); }
+  __syncthreads();
+
+  const bool any_lb = w.ctrl->any_lb != 0, any_ub = w.ctrl->any_ub != 0;
+
+  const int run_lo = (int)((long long)wid * ntiles / nwarps);
+  const int run_len = (int)((long long)(wid + 1) * ntiles / nwarps) - run_lo;
+  int Jc_first = 0, I_first = 0;
+  {
+    int rem = run_lo;
+    while (Jc_first < geo.nbc && rem >= ntv - Jc_first / P::R) { rem -= ntv - Jc_first / P::R; ++Jc_first; }
+    I_first = Jc_first / P::R + rem;
+  }
+  T* const ring_w = ring + (size_t)wid * depth * TILE;
+  uint64_t* const full_w = full + wid * depth;
+  T* const xp = xpart + (size_t)wid * np;
+
+  // ---- tile stream of this warp: for problem: for iteration: its K11 run; fetched `depth` tiles ahead
+  int p_k = 0, p_it = 0, p_r = 0, p_slot = 0;
+  int c_slot = 0;
+  uint32_t c_phase = 0;
+  int in_flight = 0;
+  uint64_t pol_keep = 0;
+  if (lane == 0) pol_keep = l2_policy_evict_last();
+  auto issue_next = [&]() {
+    if (run_len == 0 || p_k >= nprob) return;
+    if (lane == 0) {
+      const int b = blockIdx.x + p_k * gridDim.x;
+      const T* src = w.Kp + ((size_t)b * ntiles + run_lo + p_r) * TILE;
+      mbar_arrive_expect_tx(&full_w[p_slot], (uint32_t)(TILE * sizeof(T)));
+      tma_load_1d_hint(ring_w + (size_t)p_slot * TILE, src, (uint32_t)(TILE * sizeof(T)), &full_w[p_slot], pol_keep);
+    }
+    ++in_flight;
+    if (++p_slot == depth) p_slot = 0;
+    if (++p_r == run_len) {
+      p_r = 0;
+      if (++p_it == K) { p_it = 0; ++p_k; }
+    }
+  };
+  for (int d = 0; d < depth; ++d) issue_next();
+
+  auto sym_pass = [&](const T* vec) {
+    if (run_len == 0) return;
+    int Jc = Jc_first, I = I_first;
+    T vJ[TC], colacc[TC];
+    auto load_vJ = [&]() {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const V4 t4 = *reinterpret_cast<const V4*>(vec + Jc * TC + k * VN);
+        const T* tp = reinterpret_cast<const T*>(&t4);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) vJ[k * VN + e] = tp[e];
+      }
+#pragma unroll
+      for (int c = 0; c < TC; ++c) colacc[c] = T(0);
+    };
+    auto flush_cols = [&]() {
+      reduce_cols<T, TC>(colacc, lane);
+      __syncwarp();
+      if (lane < TC) xp[Jc * TC + lane] += colacc[0];
+      __syncwarp();
+    };
+    load_vJ();
+    bool dirty = false;
+    for (int r = 0; r < run_len; ++r) {
+      mbar_wait(&full_w[c_slot], c_phase);
+      const T* tp = ring_w + (size_t)c_slot * TILE + lane * TC;
+      V4 kv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) kv[k] = *reinterpret_cast<const V4*>(tp + ((k + lane) & 7) * VN);
+      const T vI = vec[I * kPackRows + lane];
+      T rs[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const T* kp = reinterpret_cast<const T*>(&kv[k]);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          rs[k & 3] += kp[e] * vJ[k * VN + e];
+          colacc[k * VN + e] += kp[e] * vI;
+        }
+      }
+      xp[I * kPackRows + lane] += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+      __syncwarp();
+      if (++c_slot == depth) { c_slot = 0; c_phase ^= 1u; }
+      --in_flight;
+      issue_next();
+      dirty = true;
+      if (++I == ntv) {
+        flush_cols();
+        dirty = false;
+        ++Jc;
+        I = Jc / P::R;
+        if (r + 1 < run_len) load_vJ();
+      }
+    }
+    if (dirty) flush_cols();
+  };
+
+  for (int kp = 0; kp < nprob; ++kp) {
+    const int b = blockIdx.x + kp * gridDim.x;
+    const size_t vo = (size_t)b * ld, go = (size_t)b * n;
+    const size_t tb = (size_t)b * K * n;
+    const T rho = w.rho[b];
+    const T* lbt = w.lbt + vo;
+    const T* ubt = w.ubt + vo;
+    T grho_acc = T(0), gb_acc = T(0);
+
+    // adjoint of (x_k, z_k, u_k) folded into gx: the elementwise head of iteration k (needs gz, gu of k + 1)
+    auto head = [&](int k, int e, T gz_e, T gu_e) {
+      const T zk = tape.z[tb + (size_t)k * n + e];
+      const T h = gz_e - gu_e;
+      const bool at_ub = any_ub && zk == ubt[e];              // z = min(max(x + u, lb), ub)  (:272-276)
+      const bool at_lb = !at_ub && any_lb && zk == lbt[e];
+      const T t = (at_ub || at_lb) ? T(0) : h;
+      if (at_ub) g.gub[go + e] += h;
+      if (at_lb) g.glb[go + e] += h;
+      v[e] = gu_e + t + (k == K - 1 ? g.gx[go + e] : T(0));
+      gu[e] = gu_e + t;
+    };
+    for (int e = tid; e < n; e += nthreads) {
+      g.gp[go + e] = T(0);
+      g.glb[go + e] = T(0);
+      g.gub[go + e] = T(0);
+      head(K - 1, e, T(0), T(0));
+    }
+    __syncthreads();
+
+    for (int k = K - 1; k >= 0; --k) {
+      sym_pass(v);                                            // xpart += K11 gx
+      if (m > 0) {                                            // wnu = K21 gx
+        const T* Gt = w.Gt + (size_t)b * m * ld;
+        for (int l = wid; l < m; l += nwarps) {
+          T d = T(0);
+          for (int e = lane; e < n; e += 32) d += Gt[(size_t)l * ld + e] * v[e];
+          d = warp_sum(d);
+          if (lane == 0) tdot[l] = d;
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < n; e += nthreads) {
+        T we = T(0);
+        for (int ww = 0; ww < nwarps; ++ww) {
+          we += xpart[(size_t)ww * np + e];
+          xpart[(size_t)ww * np + e] = T(0);
+        }
+        g.tw[tb + (size_t)k * n + e] = we;
+        g.gp[go + e] -= we;
+        T zu = T(0);
+        if (k > 0) zu = tape.z[tb + (size_t)(k - 1) * n + e] - tape.u[tb + (size_t)(k - 1) * n + e];
+        grho_acc += we * (zu - tape.x[tb + (size_t)k * n + e]);
+        const T gz_e = rho * we;
+        const T gu_e = gu[e] - rho * we;
+        if (k > 0) head(k - 1, e, gz_e, gu_e);
+      }
+      if (m > 0 && tid < m) {
+        g.twnu[((size_t)b * K + k) * m + tid] = tdot[tid];
+        gb_acc += tdot[tid];
+      }
+      __syncthreads();
+    }
+    // ---- per-problem scalars
+    grho_acc = warp_sum(grho_acc);
+    if (lane == 0) red[wid] = grho_acc;
+    __syncthreads();
+    if (tid == 0) {
+      T s = T(0);
+      for (int ww = 0; ww < nwarps; ++ww) s += red[ww];
+      g.grho[b] = s;
+    }
+    if (m > 0 && tid < m) g.gb[(size_t)b * m + tid] = gb_acc;
+    for (int e = tid; e < np; e += nthreads) { gz[e] = T(0); gu[e] = T(0); v[e] = T(0); }
+    __syncthreads();
+  }
+  while (in_flight > 0) {
+    mbar_wait(&full_w[c_slot], c_phase);
+    if (++c_slot == depth) { c_slot = 0; c_phase ^= 1u; }
+    --in_flight;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[b][i][j] = - sum_k ( U[b][k][i] V[b][k][j] + U2[b][k][i] V2[b][k][j] ),  i < rows, j < cols, k < K.
+// 64 x 64 output tile per CTA, 4 x 4 per thread, the K dimension staged through shared memory 16 at a time.
+template <typename T>
+__global__ void __launch_bounds__(256)
+tape_outer_kernel(const T* __restrict__ U, int su, const T* __restrict__ V, int sv, const T* __restrict__ U2, int su2,
+                  const T* __restrict__ V2, int sv2, int rows, int cols, int K, T* __restrict__ out) {
+  constexpr int TB = 64, KC = 16;
+  __shared__ T us[KC][TB + 4], vs[KC][TB + 4];
+  const int b = blockIdx.z;
+  const int i0 = blockIdx.y * TB, j0 = blockIdx.x * TB;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = T(0);
+  const int npairs = U2 ? 2 : 1;
+  for (int pr = 0; pr < npairs; ++pr) {
+    const T* Ub = pr == 0 ? U + (size_t)b * K * su : U2 + (size_t)b * K * su2;
+    const T* Vb = pr == 0 ? V + (size_t)b * K * sv : V2 + (size_t)b * K * sv2;
+    const int s_u = pr == 0 ? su : su2, s_v = pr == 0 ? sv : sv2;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+      for (int t = threadIdx.x; t < KC * TB; t += 256) {
+        const int kk = t / TB, c = t % TB;
+        const bool kin = k0 + kk < K;
+        us[kk][c] = (kin && i0 + c < rows) ? Ub[(size_t)(k0 + kk) * s_u + i0 + c] : T(0);
+        vs[kk][c] = (kin && j0 + c < cols) ? Vb[(size_t)(k0 + kk) * s_v + j0 + c] : T(0);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk) {
+        T ua[4], va[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { ua[a] = us[kk][ty * 4 + a]; va[a] = vs[kk][tx * 4 + a]; }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[a][c] += ua[a] * va[c];
+      }
+      __syncthreads();
+    }
+  }
+  T* ob = out + (size_t)b * rows * cols;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int i = i0 + ty * 4 + a;
+    if (i >= rows) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = j0 + tx * 4 + c;
+      if (j < cols) ob[(size_t)i * cols + j] = -acc[a][c];
+    }
+  }
+}
+
+template <typename T>
+cudaError_t launch_unroll_reverse(const FwdWs<T>& w, const Tape<T>& tape, const UnrollGrads<T>& g, int* launches,
+                                  cudaStream_t st) {
+  int dev = 0, max_smem = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t smem = 0;
+  IterGeom geo{};
+  if (!make_geom(w, max_smem - 1024, &geo, &smem)) return cudaErrorInvalidConfiguration;
+  const int grid = w.B < sms ? w.B : sms;
+  e = cudaFuncSetAttribute(unroll_reverse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  unroll_reverse_kernel<T><<<grid, geo.nwarps * 32, smem, st>>>(w, tape, g, geo);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (launches) ++*launches;
+  const int n = w.n, m = w.m, K = tape.n_iter;
+  if (g.gQ) {       // dQ~ = - sum_k w_k x_k^T
+    dim3 grid2((n + 63) / 64, (n + 63) / 64, w.B);
+    tape_outer_kernel<T><<<grid2, 256, 0, st>>>(g.tw, n, tape.x, n, (const T*)nullptr, 0, (const T*)nullptr, 0, n, n, K,
+                                                g.gQ);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (launches) ++*launches;
+  }
+  if (g.gA && m > 0) {   // dA~ = - sum_k (wnu_k x_k^T + nu_k w_k^T)
+    dim3 grid2((n + 63) / 64, (m + 63) / 64, w.B);
+    tape_outer_kernel<T><<<grid2, 256, 0, st>>>(g.twnu, m, tape.x, n, tape.nu, m, g.tw, n, m, n, K, g.gA);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (launches) ++*launches;
+  }
+  return cudaSuccess;
+}
+
+#define INST(T)                                                                                                   \
+  template cudaError_t launch_unroll_reverse<T>(const FwdWs<T>&, const Tape<T>&, const UnrollGrads<T>&, int*, \
+                                                cudaStream_t);
+INST(float)
+INST(double)
+#undef INST
+
+}  // namespace lqpb

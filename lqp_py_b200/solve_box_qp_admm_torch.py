@@ -88,9 +88,7 @@ def torch_solve_box_qp(Q, p, A, b, lb, ub, control):
     ``{"x","z","u","lams","nus","rho","iter"}``; ``rho`` is a ``(B,1,1)`` tensor when it was
     selected automatically or adapted and the caller's scalar otherwise, ``iter`` a Python int."""
     if control.get('unroll', False):
-        raise NotImplementedError(
-            "unroll=True (differentiating through the loop, reference :13-15, :264-265) is outside this build's "
-            "hot path; use the default implicit fixed-point backward")
+        return _solve_unrolled(Q, p, A, b, lb, ub, control)           # :328-329 -- a bare x, connected to autograd
     sol = _solve_device(Q, p, A, b, lb, ub, control)
     return {k: sol[k] for k in ("x", "z", "u", "lams", "nus", "rho", "iter")}
 
@@ -297,8 +295,144 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
     return {"x": hx, "z": hz, "u": hu, "lams": hlams, "nus": hnus, "rho": rho_out,
             "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor),
             "_any_lb": bool(info.any_lb), "_any_ub": bool(info.any_ub), "_dev": dv,
-            "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus,
+            "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus, "_ws": ws, "_cfg": cfg,
             "rho_dev": rho if torch.is_tensor(rho) else None}
+
+
+# ------------------------------------------------------------------------------------------
+# unrolled mode (control['unroll'] = True)
+# ------------------------------------------------------------------------------------------
+def _solve_unrolled(Q, p, A, b, lb, ub, control):
+    """``unroll=True`` (reference :13-15): ``x`` comes back attached to an autograd graph that differentiates the
+    scaling (:161-197), the rho selection (:200-203), every ADMM iteration (:259-282) and the un-scaling (:316).
+
+    The T iterations -- all the O(T n^2) work -- are ONE autograd node, ``_UnrolledLoop``: its forward records the
+    iterates of the CUDA loop (``lqpb_unroll_record_*``), its backward is the reverse-sweep kernel
+    (``lqpb_unroll_backward_*``: one symmetric K11 GEMV per recorded iteration, then dQ~ / dA~ as rank-T products
+    over the tape instead of the reference's dense ``dx xv^T`` per iteration, lu_layer.py:53).  The O(n^2), T-
+    independent map between the caller's tensors and the scaled problem (D, E, Q~ = D Q D, rho = ||Q~||_F / sqrt(n))
+    is written below with the torch operators the reference itself uses, on the CUDA copies, so that autograd
+    applies exactly the reference's (sub)gradient conventions for ``norm(inf)``, ``quantile`` and ``clamp``.
+
+    An adaptive-rho update inside the unrolled loop (reference :246-256, where ``rho_new = rho * ratio`` stays in
+    the graph) is not supported and raises: none occurs on the reference's experiment data."""
+    out_device = p.device
+    for t in (Q, p, A, b, lb, ub):
+        if t is not None and t.dtype != p.dtype:
+            raise TypeError(f"all tensors must share one dtype, got {p.dtype} and {t.dtype}")
+    dev = _cuda_device(next((t for t in (Q, p, A, b, lb, ub) if t is not None and t.is_cuda), p))
+    # device copies that stay connected to the caller's leaves (``.to`` is differentiable)
+    Qd, pd, Ad, bd, lbd, ubd = (None if t is None else t.to(dev).contiguous() for t in (Q, p, A, b, lb, ub))
+    plain = dict(control)
+    plain['unroll'] = False
+    sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=())
+    if sol["n_factor"] != 1:
+        raise NotImplementedError(
+            "unroll=True with an adaptive-rho update inside the loop (reference :246-256) is not supported: "
+            "set adaptive_rho=False or choose rho so that no update triggers")
+    any_lb, any_ub = sol["_any_lb"], sol["_any_ub"]
+    n = pd.shape[1]
+    m = get_ncon(Ad, dim=1)
+    Qt, pt, At, bt, lbt, ubt, D, rho = _scaled_problem(Qd, pd, Ad, bd, lbd, ubd, control, any_lb, any_ub)
+    state = dict(ws=sol["_ws"], cfg=sol["_cfg"], n_iter=sol["iter"] + 1, B=Qd.shape[0], n=n, m=m)
+    xt = _UnrolledLoop.apply(Qt, pt, At, bt, lbt if any_lb else None, ubt if any_ub else None,
+                             rho if torch.is_tensor(rho) else None, state)
+    x = D * xt                                                           # :316
+    return x if x.device == out_device else x.to(out_device)
+
+
+def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub):
+    """Scaling and rho selection of the reference (:156-203) as differentiable torch expressions of the device
+    copies.  Returns ``(Q~, p~, A~, b~, lb~, ub~, D, rho)``; ``D`` is ``(B,n,1)`` (or 1.0 without scaling) and ``rho``
+    a ``(B,1,1)`` tensor when it is selected from ``||Q~||_F``, otherwise the caller's number."""
+    n = p.shape[1]
+    any_ineq = any_lb or any_ub
+    rho = control.get('rho', None) if any_ineq else 0                   # :157-158
+    D = 1.0
+    if control.get('scale', False):
+        colmax = torch.linalg.norm(Q, ord=_INF, dim=1)                   # :163
+        bad = colmax <= 0.0
+        if bool(bad.any()):                                              # :164-168
+            floor = colmax.mean(dim=1).clamp(min=1e-6).unsqueeze(1)
+            colmax = torch.where(bad, torch.maximum(colmax, floor), colmax)
+        D = torch.sqrt(1 / colmax)                                       # :170
+        beta = control.get('beta')
+        if beta is None:                                                 # :171-174
+            q = torch.quantile(D, torch.tensor([0.10, 0.90], dtype=D.dtype, device=D.device), dim=1)
+            beta = (1 - q[0] / q[1]).unsqueeze(1)
+        D = (1 - beta) * D + beta * D.mean(dim=1, keepdim=True)          # :175
+        Q = D.unsqueeze(2) * Q * D.unsqueeze(1)                          # :176
+        p = D.unsqueeze(2) * p                                           # :177
+        if A is not None:
+            A = A * D.unsqueeze(1)                                       # :180
+            rown = torch.linalg.norm(A, ord=_INF, dim=2)                 # :181
+            bad = rown <= 0.0
+            if bool(bad.any()):                                          # :182-186
+                floor = rown.mean(dim=1).clamp(min=1e-6).unsqueeze(1)
+                rown = torch.where(bad, torch.maximum(rown, floor), rown)
+            E = (1 / rown).unsqueeze(2)                                  # :187-188
+            A, b = E * A, E * b                                          # :189-190
+        D = D.unsqueeze(2)
+        if any_ineq:
+            lb, ub = lb / D, ub / D                                      # :193-194
+    if rho is None:                                                      # :200-203
+        rho = torch.linalg.matrix_norm(Q, keepdim=True) / n ** 0.5
+        rho = torch.clamp(rho, min=control.get('rho_min', 1e-6), max=control.get('rho_max', 1e6))
+    return Q, p, A, b, lb, ub, D, rho
+
+
+class _UnrolledLoop(torch.autograd.Function):
+    """The T recorded ADMM iterations as one autograd node: scaled problem data -> last x~ (reference :259-282 with
+    every KKT solve differentiated as in lu_layer.py:41-58)."""
+
+    @staticmethod
+    def forward(ctx, Qt, pt, At, bt, lbt, ubt, rho, state):
+        L = _abi.lib()
+        B, n, m, K = state["B"], state["n"], state["m"], state["n_iter"]
+        dev, dt = pt.device, pt.dtype
+        sfx = _abi.suffix(dt)
+        ws = state["ws"]
+        with torch.cuda.device(dev):
+            tape = [torch.empty((B, K, n), dtype=dt, device=dev) for _ in range(3)]
+            tape_nu = torch.empty((B, K, m), dtype=dt, device=dev) if m > 0 else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = getattr(L, f"lqpb_unroll_record_{sfx}")(
+                C.byref(state["cfg"]), B, n, m, K, _abi.ptr(ws), ws.numel(), _abi.ptr(tape[0]), _abi.ptr(tape[1]),
+                _abi.ptr(tape[2]), _abi.ptr(tape_nu), C.c_void_p(stream))
+            _abi.check(rc, "lqpb_unroll_record")
+        ctx.state = state
+        ctx.tape = (*tape, tape_nu)
+        ctx.shapes = tuple(None if t is None else t.shape for t in (Qt, pt, At, bt, lbt, ubt, rho))
+        return tape[0][:, K - 1, :].unsqueeze(2).clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _abi.lib()
+        st = ctx.state
+        B, n, m, K = st["B"], st["n"], st["m"], st["n_iter"]
+        tx, tz, tu, tnu = ctx.tape
+        dev, dt = tx.device, tx.dtype
+        sfx = _abi.suffix(dt)
+        ws = st["ws"]
+        need = ctx.needs_input_grad
+        g = g.detach().to(device=dev, dtype=dt).contiguous()
+        with torch.cuda.device(dev):
+            new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+            tw = new(B, K, n)
+            twnu = new(B, K, m) if m > 0 else None
+            gQ = new(B, n, n) if need[0] else None
+            gA = new(B, m, n) if (m > 0 and need[2]) else None
+            gp, glb, gub, grho = new(B, n, 1), new(B, n, 1), new(B, n, 1), new(B, 1, 1)
+            gb = new(B, m, 1) if m > 0 else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = getattr(L, f"lqpb_unroll_backward_{sfx}")(
+                B, n, m, K, _abi.ptr(ws), ws.numel(), _abi.ptr(g), _abi.ptr(tx), _abi.ptr(tz), _abi.ptr(tu),
+                _abi.ptr(tnu), _abi.ptr(tw), _abi.ptr(twnu), _abi.ptr(gQ), _abi.ptr(gp), _abi.ptr(gA), _abi.ptr(gb),
+                _abi.ptr(glb), _abi.ptr(gub), _abi.ptr(grho), C.c_void_p(stream))
+            _abi.check(rc, "lqpb_unroll_backward")
+        outs = [gQ, gp, gA, gb, glb, gub, grho]
+        outs = [o if (shape is not None and nd) else None for o, shape, nd in zip(outs, ctx.shapes, need[:7])]
+        return (*outs, None)
 
 
 def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need):

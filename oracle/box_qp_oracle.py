@@ -184,6 +184,7 @@ def iterate(w: dict, st: Settings):
                 if bool((ratio > st.adaptive_tol).any()) or bool((ratio < 1 / st.adaptive_tol).any()):
                     rho = torch.where(wants_update, rho * ratio, rho * torch.ones_like(ratio))
                     rho = rho.clamp(st.rho_min, st.rho_max)         # :248-250
+                    K = K.clone()                                   # (no in-place write into a tensor autograd saved)
                     K[:, :n, :n] = Q + rho * w["eye"]               # :252
                     LU, piv = torch.linalg.lu_factor(K)             # :254
                     factorisations += 1
@@ -241,6 +242,18 @@ def solve(Q, p, A, b, lb, ub, control: dict) -> dict:
         out = conclude(w, x, z, u, sol, i)
     out["factorisations"] = nfac
     return out
+
+
+def solve_unrolled(Q, p, A, b, lb, ub, control: dict):
+    """``unroll=True`` (reference :13-15, :216-217, :264-265, :328-329): the same three stages with autograd
+    recording, returning only ``x``.  The reference differentiates each linear solve with ``TorchLULayer``
+    (lu_layer.py:41-58: ``dx = M^-1 (-g)``, ``dl_dA = dx x^T``, ``dl_db = -dx``), which is the exact adjoint of
+    ``M^-1 rhs`` for the symmetric KKT matrix, so letting torch differentiate ``lu_factor`` / ``lu_solve`` here
+    gives the same gradients to round-off (pinned by tests/golden/unroll/*.npz)."""
+    st = derive_settings(control, p.shape[1])
+    w = prepare(Q, p, A, b, lb, ub, st)
+    x, z, u, sol, i, nfac = iterate(w, st)
+    return w["D"] * x                                               # :316, :328-329
 
 
 # --------------------------------------------------------------------------

@@ -43,7 +43,7 @@ class Case:
         Q, p, A, b, lb, ub = orc.make_exp1_data(n, B, seed=seed, dtype=self.dtype)
         chk = np.array([float(Q.double().sum()), float(p.double().sum()),
                         float(lb.double().sum()), float(ub.double().sum())])
-        np.testing.assert_allclose(chk, self.z["input_checksum"], rtol=1e-9)
+        np.testing.assert_allclose(chk, self.z["input_checksum"], rtol=1e-9 if self.dtype == torch.float64 else 1e-6)
         return Q, p, A, b, lb, ub
 
     def control_dict(self):
@@ -163,3 +163,67 @@ def kkt_reduced_fp64(dl_dz, x, lams, nus, Q, A, lb, ub):
         dnu = d[:, n:]
         dA, db = dnu @ x.transpose(1, 2) + nus @ dx.transpose(1, 2), -dnu
     return half + half.transpose(1, 2), dx, dA, db, -lam[:, :n] * dx / s_lo, -lam[:, n:] * dx / s_hi
+
+
+# ---------------------------------------------------------------------------------- unrolled mode fixtures
+UNROLL_DIR = os.path.join(GOLDEN_DIR, "unroll")
+
+
+def unroll_case_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(UNROLL_DIR, "*.npz")))
+
+
+class UnrollCase:
+    """tests/golden/unroll/<name>.npz (make_golden_unroll.py): reference run with control['unroll'] = True."""
+
+    def __init__(self, name):
+        self.name = name
+        z = np.load(os.path.join(UNROLL_DIR, name + ".npz"), allow_pickle=False)
+        self.z = z
+        self.dtype = getattr(torch, str(z["dtype"]))
+        self.control = json.loads(str(z["control"]))
+        self.adaptive_update = name.startswith("adapt")     # an adaptive-rho refactorisation happens inside the loop
+
+    def inputs(self):
+        z = self.z
+        if "Q" in z.files:
+            return tuple(torch.from_numpy(z[k]) if k in z.files else None for k in ("Q", "p", "A", "b", "lb", "ub"))
+        n, B = (int(v) for v in z["gen_shape"])
+        Q, p, A, b, lb, ub = orc.make_exp1_data(n, B, seed=int(z["gen_seed"]), dtype=self.dtype)
+        chk = np.array([float(Q.double().sum()), float(p.double().sum()), float(lb.double().sum()), float(ub.double().sum())])
+        # fp32 generation (randn -> bmm) rounds differently from one host CPU to the next: pin the stream, not the bits
+        np.testing.assert_allclose(chk, z["input_checksum"], rtol=1e-9 if self.dtype == torch.float64 else 1e-6)
+        return Q, p, A, b, lb, ub
+
+    def compare(self, x, grads, tol):
+        """x and grads = (dQ, dp, dA, db, dlb, dub) as CPU tensors (None where autograd produced no gradient).
+        A gradient the reference left at None (lb without a finite lower bound, ...) must be None or zero here;
+        entries where the reference itself is NaN (0 * inf in the scaling of an infinite bound) are not compared."""
+        z = self.z
+        errs = {}
+
+        def chk(key, val, ref):
+            ref = np.asarray(ref)
+            val = val.detach().cpu().numpy()
+            ok = np.isfinite(ref)
+            if not ok.all():
+                val, ref = np.where(ok, val, 0.0), np.where(ok, ref, 0.0)
+            e = rel_err(val, ref)
+            errs[key] = e
+            lim = tol.get(key, tol["default"])
+            assert e <= lim, f"unroll/{self.name}: {key} rel err {e:.3e} > {lim:.1e}"
+
+        chk("x", x, z["x"])
+        for k, g in zip(("dQ", "dp", "dA", "db", "dlb", "dub"), grads):
+            if k == "dQ" and "dQ" not in z.files:
+                gen = torch.Generator().manual_seed(4321)
+                w = torch.randn(g.shape[0], g.shape[1], 2, generator=gen, dtype=self.dtype)
+                chk("dQ_probe", torch.matmul(g.cpu(), w), z["dQ_probe"])
+                chk("dQT_probe", torch.matmul(g.cpu().transpose(1, 2), w), z["dQT_probe"])
+                chk("dQ_fro", torch.linalg.matrix_norm(g.cpu()), z["dQ_fro"])
+            elif k in z.files:
+                assert g is not None, f"unroll/{self.name}: {k} missing"
+                chk(k, g, z[k])
+            else:
+                assert g is None or float(g.abs().max()) == 0.0, f"unroll/{self.name}: {k} should be None"
+        return errs

@@ -19,7 +19,7 @@ import torch
 
 from oracle import box_qp_oracle as orc
 from tests._golden import (Case, case_names, compare, rel_err, GOLDEN_DIR, kkt_case_names, compare_kkt,
-                           kkt_reference_is_nan, kkt_reduced_fp64)
+                           kkt_reference_is_nan, kkt_reduced_fp64, UnrollCase, unroll_case_names)
 
 pytestmark = pytest.mark.gpu
 
@@ -348,3 +348,82 @@ def test_verbose_prints_like_reference(dev, capsys):
     ours = [float(l.split("=")[1]) for l in out.splitlines() if "error" in l]
     theirs = [float(l.split("=")[1]) for l in ref_out.splitlines() if "error" in l]
     assert len(ours) == len(theirs) and np.allclose(ours, theirs, rtol=0, atol=2e-9)
+
+
+# ------------------------------------------------------------------------------------------ unrolled mode
+@pytest.mark.parametrize("name", unroll_case_names())
+@pytest.mark.parametrize("where", ["cuda", "cpu"])
+def test_unrolled_golden_case(name, where, dev):
+    """control['unroll'] = True (reference :13-15): x and the six input gradients of the recorded loop + reverse
+    sweep kernels against the reference's autograd-through-the-loop run.  fp64 1e-8; fp32 1e-5 except where the
+    reference's own fp32 noise is larger (its fp32-vs-fp64 gap on these cases is up to 3e-5 in dA)."""
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    case = UnrollCase(name)
+    if where == "cpu" and not name.startswith("exp1_n50"):
+        pytest.skip("CPU-tensor drop-in is exercised on two cases")
+    target = dev if where == "cuda" else torch.device("cpu")
+    leaves = [None if t is None else t.to(target).requires_grad_(True) for t in case.inputs()]
+    control = dict(case.control)
+    if case.adaptive_update:
+        with pytest.raises(NotImplementedError):
+            SolveBoxQP(control=control).forward(*leaves)
+        return
+    x = SolveBoxQP(control=control).forward(*leaves)
+    assert torch.is_tensor(x) and x.device.type == target.type and x.requires_grad
+    x.backward(torch.from_numpy(case.z["dl_dz"]).to(target))
+    grads = [None if t is None else (None if t.grad is None else t.grad.cpu()) for t in leaves]
+    f64 = case.dtype == torch.float64
+    tol = {"default": 1e-8 if f64 else 1e-5}
+    if not f64:
+        tol.update(dA=1e-4, db=1e-4, dQ=3e-5, dQ_probe=3e-5, dQT_probe=3e-5)
+    case.compare(x.detach().cpu(), grads, tol)
+
+
+def test_unrolled_matches_oracle_fresh_seed_and_needs_input_grad(dev):
+    """Fresh inputs (not in the fixtures), B > 148 so that persistent CTAs sweep several problems, only p and lb
+    require a gradient (dQ~ / dA~ products are skipped)."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    dtype = torch.float64
+    Q, p, A, b, lb, ub = orc.make_exp1_data(48, 160, seed=21, dtype=dtype)
+    g = torch.randn(p.shape, generator=torch.Generator().manual_seed(5), dtype=dtype)
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5, unroll=True)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        leaves = [t.clone().requires_grad_(True) for t in (Q, p, A, b, lb, ub)]
+        xr = orc.solve_unrolled(*leaves, dict(control))
+        xr.backward(g)
+    finally:
+        torch.set_default_dtype(prev)
+    ins = [t.to(dev) for t in (Q, p, A, b, lb, ub)]
+    ins[1].requires_grad_(True)
+    ins[4].requires_grad_(True)
+    x = SolveBoxQP(control=control).forward(*ins)
+    x.backward(g.to(dev))
+    assert ins[0].grad is None and ins[2].grad is None
+    assert rel_err(x.detach().cpu().numpy(), xr.detach().numpy()) <= 1e-8
+    assert rel_err(ins[1].grad.cpu().numpy(), leaves[1].grad.numpy()) <= 1e-8
+    assert rel_err(ins[4].grad.cpu().numpy(), leaves[4].grad.numpy()) <= 1e-8
+
+
+def test_unrolled_full_size_fp32(dev):
+    """dz=500, B=128 (the headline shape) in unrolled mode: x equals the implicit layer's x (same kernels; the final
+    un-scaling D x~ is a torch multiply there, hence not bit for bit), the unrolled dp approaches the fixed-point dp (the ADMM map is contractive; the reference's own gap
+    between the two modes is ~1e-3 relative at tol 1e-5), dQ is finite and NOT symmetric (lu_layer.py:53)."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    Q, p, A, b, lb, ub = orc.make_exp1_data(500, 128, seed=0, dtype=torch.float32)
+    g = torch.randn(p.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float32).to(dev)
+    outs = {}
+    for unroll in (False, True):
+        ins = [t.to(dev).requires_grad_(True) for t in (Q, p, A, b, lb, ub)]
+        x = SolveBoxQP(control=box_qp_control(eps_abs=1e-5, eps_rel=1e-5, unroll=unroll)).forward(*ins)
+        x.backward(g)
+        outs[unroll] = (x.detach(), [t.grad for t in ins])
+    assert float((outs[True][0] - outs[False][0]).abs().max()) <= 1e-6 * float(outs[False][0].abs().max())
+    dp_u, dp_f = outs[True][1][1], outs[False][1][1]
+    assert float((dp_u - dp_f).abs().max() / dp_f.abs().max()) < 2e-2
+    dQ = outs[True][1][0]
+    assert torch.isfinite(dQ).all()
+    assert float((dQ - dQ.transpose(1, 2)).abs().max()) > 1e-3 * float(dQ.abs().max())

@@ -6,7 +6,7 @@ import torch
 
 from oracle import box_qp_oracle as orc
 from tests._golden import (Case, case_names, compare, GOLDEN_DIR, kkt_case_names, compare_kkt,
-                           kkt_reference_is_nan, kkt_reduced_fp64, rel_err)
+                           kkt_reference_is_nan, kkt_reduced_fp64, rel_err, UnrollCase, unroll_case_names)
 import os
 
 
@@ -49,6 +49,23 @@ def test_oracle_kkt_backward_matches_reference(name):
     for g, r in zip(grads, red):
         if g is not None:
             assert rel_err(g.numpy(), r.numpy()) <= lim
+
+
+@pytest.mark.parametrize("name", unroll_case_names())
+def test_oracle_unrolled_matches_reference(name):
+    """oracle.solve_unrolled (autograd through the restated loop) against the reference run with
+    control['unroll'] = True: x and all six gradients, including the adaptive-rho cases."""
+    case = UnrollCase(name)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(case.dtype)
+    try:
+        leaves = [None if t is None else t.clone().requires_grad_(True) for t in case.inputs()]
+        x = orc.solve_unrolled(*leaves, dict(case.control))
+        x.backward(torch.from_numpy(case.z["dl_dz"]))
+    finally:
+        torch.set_default_dtype(prev)
+    grads = [None if t is None else t.grad for t in leaves]
+    case.compare(x.detach(), grads, {"default": 1e-11 if case.dtype == torch.float64 else 2e-5})
 
 
 def test_oracle_lu_layer():

@@ -31,7 +31,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-child"])
+    ap.add_argument("--threads", type=int, default=1, help="(reference-child) torch / BLAS threads")
+    ap.add_argument("--nprob", type=int, default=8, help="(reference-child) problems per pass")
     ap.add_argument("--dz", type=int, default=500)
     ap.add_argument("--batch", type=int, default=128, help="problems per GPU (weak scaling)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="f32 = the reference experiments' dtype")
@@ -55,13 +57,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
+        self.lines = []          # (host time of arrival, csv line)
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -69,22 +71,31 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
 
-    def stop(self):
+    def count(self, t_lo):
+        return sum(1 for t, _ in self.lines if t >= t_lo)
+
+    def stop(self, t_lo=0.0, t_hi=float("inf"), t_timed_hi=None):
+        """Statistics over the samples that arrived in [t_lo, t_hi] (host clock): the timed region plus, when
+        that region is shorter than a few nvidia-smi periods, the identical steps run right after it."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        in_timed = 0
+        for t, ln in self.lines:
+            if t < t_lo or t > t_hi:
+                continue
             f = [s.strip() for s in ln.split(",")]
             if len(f) < 9:
                 continue
+            if t_timed_hi is not None and t <= t_timed_hi:
+                in_timed += 1
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
@@ -94,7 +105,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_in_timed_region": in_timed, "reasons": sorted(reasons)}
 
 
 def log(msg):
@@ -131,79 +142,119 @@ def gen_data(a, seed, dtype):
 
 
 # ------------------------------------------------------------------------------------------------
+def reference_child(a):
+    """One bounded run of the oracle port in THIS process (spawned by cpu_arm with the thread count in the
+    environment): W warm-up + K timed forward+backward passes over the first --nprob problems of the workload."""
+    from oracle import box_qp_oracle as orc
+    dtype = torch.float32 if a.dtype == "f32" else torch.float64
+    # the pool size comes from OMP_NUM_THREADS (set by the parent).  torch.set_num_threads(k > 1) is NOT used: with
+    # this torch / oneMKL build it makes the threaded sgetrf fail ("Parameter 6 was incorrect on entry to SLASWP")
+    # and spin for minutes, on every host tried.
+    torch.set_default_dtype(dtype)
+    data = [t[:a.nprob] for t in gen_data(a, 0, dtype)]
+    control = orc.default_control(eps_abs=1e-5, eps_rel=1e-5)
+    g = torch.ones(a.nprob, a.dz, 1, dtype=dtype)            # experiment_1.py:75
+    for _ in range(a.warmup or 0):
+        orc.solve_and_grad(*data, control, g)
+    t0 = time.perf_counter()
+    sol = None
+    for _ in range(a.steps or 1):
+        sol, grads = orc.solve_and_grad(*data, control, g)
+    dt = time.perf_counter() - t0
+    ok = bool(torch.isfinite(sol["x"]).all()) and all(bool(torch.isfinite(t).all()) for t in grads if t is not None)
+    print(json.dumps({"seconds": dt, "iter": int(sol["iter"]), "finite": ok, "threads": torch.get_num_threads()}),
+          flush=True)
+
+
+def _spawn_child(a, threads, nprob, steps, warmup, timeout):
+    """Run reference_child in a fresh interpreter with a hard wall-clock limit.  Returns the child's dict or None
+    (time-out, crash, non-finite results or LAPACK complaints on stderr)."""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(threads)                     # torchrun exports OMP_NUM_THREADS=1
+    env.pop("MKL_NUM_THREADS", None)
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-child", "--threads", str(threads),
+           "--nprob", str(nprob), "--steps", str(steps), "--warmup", str(warmup), "--dz", str(a.dz),
+           "--batch", str(a.batch), "--dtype", a.dtype]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    except subprocess.TimeoutExpired:
+        log(f"cpu arm: {threads} threads x {nprob} problems did not finish in {timeout} s")
+        return None
+    bad = r.stderr.count("MKL ERROR")
+    try:
+        out = json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        out = None
+    if r.returncode != 0 or out is None or not out.get("finite") or bad:
+        log(f"cpu arm: {threads} threads x {nprob} problems failed (rc {r.returncode}, {bad} LAPACK errors)")
+        return None
+    return out
+
+
+def cpu_arm(a, steps, warmup, budget_s):
+    """The reference's CPU path (oracle port: the same batched torch.linalg LAPACK calls in the same order) on the
+    host cores, bounded: every run happens in a subprocess with a time limit, the thread count is the fastest of
+    {all usable CPUs, half, 1} on an 8-problem probe (batched getrs does not scale with threads and an over-
+    subscribed BLAS pool crawls), and a step covers as many problems of the batch as fit the time budget."""
+    ncpu = usable_cpus()
+    cands = sorted({ncpu, max(1, ncpu // 2), 1}, reverse=True)
+    nb0 = min(16, a.batch)
+    best = None
+    for t in cands:
+        out = _spawn_child(a, t, nb0, 1, 1, 60)
+        if out is None:
+            continue
+        log(f"cpu arm probe: {t} threads, {nb0} problems: {out['seconds']:.2f} s")
+        if best is None or out["seconds"] < best[1]:
+            best = (t, out["seconds"])
+    if best is None:
+        return None
+    threads, probe_s = best
+    per_problem = probe_s / nb0
+    nb = int(max(nb0, min(a.batch, budget_s / max(per_problem * (steps + warmup), 1e-9))))
+    for attempt in range(3):
+        out = _spawn_child(a, threads, nb, steps, warmup, 60 + 4 * budget_s)
+        if out is not None:
+            break
+        nb = max(nb0, nb // 4)                    # shrink the sample (and, last resort, the thread pool) and retry
+        if attempt == 1:
+            threads = 1
+    if out is None:
+        return None
+    val = nb * steps / out["seconds"]
+    sample = (f"{steps} forward+backward passes ({warmup} warm-up) over {nb} of the {a.batch} problems (dz={a.dz}, "
+              f"{a.dtype}) with the oracle port (torch CPU, batched LAPACK), ADMM iter={out['iter']}, "
+              f"{out['seconds']:.1f} s, {threads} threads chosen from {cands} by an {nb0}-problem probe")
+    return {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+            "host_cpus": os.cpu_count(), "usable_cpus": ncpu, "seconds": out["seconds"], "problems_per_step": nb}
+
+
 def run_reference(a):
     """CPU arm: the oracle port of the reference's torch path (oracle/box_qp_oracle.py -- same batched
-    LAPACK calls through torch.linalg as the reference), all host threads."""
+    LAPACK calls through torch.linalg as the reference) on the host cores; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import box_qp_oracle as orc
-    # torchrun exports OMP_NUM_THREADS=1; this arm is the CPU path with every host thread it can use
-    torch.set_num_threads(usable_cpus())
-    dtype = torch.float32 if a.dtype == "f32" else torch.float64
     K = a.steps if a.steps is not None else 3
     W = a.warmup if a.warmup is not None else 1
-    torch.set_default_dtype(dtype)
-    data = gen_data(a, 0, dtype)
-    control = orc.default_control(eps_abs=1e-5, eps_rel=1e-5)
-    g = torch.ones(a.batch, a.dz, 1, dtype=dtype)            # experiment_1.py:75
-    log(f"reference arm: {torch.get_num_threads()} threads, {W} warm-up + {K} steps of {a.batch} problems")
-    for _ in range(W):
-        orc.solve_and_grad(*data, control, g)
-    t0 = time.perf_counter()
-    iters = None
-    for k in range(K):
-        sol, _ = orc.solve_and_grad(*data, control, g)
-        iters = sol["iter"]
-        log(f"reference arm: step {k + 1}/{K} at {time.perf_counter() - t0:.1f} s")
-    dt = time.perf_counter() - t0
-    val = a.batch * K / dt
-    cores = torch.get_num_threads()
-    sample = f"{K} steps of the full batch ({a.batch} problems, dz={a.dz}), {W} warm-up, ADMM iter={iters}"
+    cpu = cpu_arm(a, K, W, budget_s=40.0)
+    if cpu is None:
+        print(json.dumps({"impl": "reference", "unavailable": "the oracle port did not complete on this host "
+                                                             "(time-out or LAPACK failure in every configuration)"}), flush=True)
+        return
+    val = cpu["value"]
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "launched_as_gpus": a.gpus,
            "steps": K, "warmup": W,
-           "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "ms_per_step": cpu["seconds"] / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": a.dtype, "data": "synthetic", "config": {"workload": workload_name(a)},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                            "host_cpus": os.cpu_count()},
+           "cpu_baseline": cpu,
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
 def cpu_baseline(a, dtype):
-    from oracle import box_qp_oracle as orc
-    torch.set_num_threads(usable_cpus())
-    prev = torch.get_default_dtype()
-    torch.set_default_dtype(dtype)
-    try:
-        data = gen_data(a, 0, dtype)
-        control = orc.default_control(eps_abs=1e-5, eps_rel=1e-5)
-        g = torch.ones(a.batch, a.dz, 1, dtype=dtype)
-        # bounded sample: time 8 problems first, then as much of the batch as fits in ~10 s per pass
-        nb0 = min(8, a.batch)
-        small = [t[:nb0] for t in data]
-        orc.solve_and_grad(*small, control, g[:nb0])           # warm up LAPACK / thread pool
-        t0 = time.perf_counter()
-        orc.solve_and_grad(*small, control, g[:nb0])
-        per_problem = (time.perf_counter() - t0) / nb0
-        nb = int(max(nb0, min(a.batch, 10.0 / max(per_problem, 1e-9))))
-        log(f"cpu baseline: {torch.get_num_threads()} threads, {per_problem * 1e3:.1f} ms per problem on a batch of "
-            f"{nb0} -> sample of {nb} problems per pass")
-        sample = [t[:nb] for t in data]
-        t0 = time.perf_counter()
-        reps = 0
-        iters = None
-        while reps < 1 or (time.perf_counter() - t0 < 8.0 and reps < 6):
-            sol, _ = orc.solve_and_grad(*sample, control, g[:nb])
-            iters = sol["iter"]
-            reps += 1
-        dt = time.perf_counter() - t0
-    finally:
-        torch.set_default_dtype(prev)
-    return {"value": nb * reps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "host_cpus": os.cpu_count(),
-            "sample": f"{reps} forward+backward passes of {nb} of the {a.batch} problems (dz={a.dz}, {a.dtype}) "
-                      f"with the oracle port (torch CPU, batched LAPACK), ADMM iter={iters}, {dt:.1f} s"}
+    return cpu_arm(a, steps=2, warmup=1, budget_s=15.0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -273,14 +324,15 @@ def run_b200(a):
             torch.cuda.synchronize(dev)
 
     log(f"rank {rank}: data on {dev}, {W} warm-up + {K} timed steps")
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()          # started before the warm-up: nvidia-smi needs ~0.2 s to deliver its first line
     for k in range(W):
         step(k, False)
     sync_all()
     log("warm-up done")
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     sync_all()
+    t_host0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(K):
@@ -288,9 +340,22 @@ def run_b200(a):
     e1.record()
     sync_all()
     ms = e0.elapsed_time(e1)
+    t_host1 = time.perf_counter()
     add_prof(BWD)            # the last step's backward
     log(f"timed region done: {ms / K:.3f} ms per step")
-    clocks = sampler.stop() if sampler else None
+    clocks = None
+    if sampler:
+        # K steps last tens of ms, a handful of nvidia-smi periods at best: keep the GPU under the SAME load (the
+        # same steps, untimed) until at least 8 samples have been taken since the timed region began
+        k, t_end = 0, time.perf_counter() + 3.0
+        while sampler.proc and sampler.count(t_host0) < 8 and time.perf_counter() < t_end:
+            step(W + K + k, False)
+            k += 1
+            if k % 8 == 0:
+                torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
+        clocks = sampler.stop(t_host0, time.perf_counter(), t_host1)
+        clocks["extra_load_steps"] = k
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -385,7 +450,9 @@ def run_b200(a):
 
 if __name__ == "__main__":
     args = parse()
-    if args.impl == "reference":
+    if args.impl == "reference-child":
+        reference_child(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -183,34 +183,63 @@ int lqpb_backward_host_f64(int B, int n, int m, int kkt, const double* h_dl_dz, 
 
 /* ---- unrolled mode: control['unroll'] = True (solve_box_qp_admm_torch.py:13-15) lets autograd differentiate
  * every ADMM iteration (:259-282), each KKT solve through TorchLULayer (lu_layer.py:18-58: dx = M^-1 (-g),
- * dl_dA = dx xv^T, dl_db = -dx).  Here the loop is recorded and swept backwards by two calls that work on the
- * operators a preceding lqpb_forward_* call left in its `workspace` (which the caller keeps alive; the solve must
- * have ended with info.n_factor == 1, i.e. without an adaptive-rho refactorisation):
- * unroll_record:   re-runs the n_iter = info.iter + 1 iterations from z = u = 0 with identical arithmetic and writes,
- *                  per problem and iteration k, the scaled iterate x~_k, z_k, u_k into tape_x/z/u (B, n_iter, n) and
- *                  the equality part nu_k of the KKT solve into tape_nu (B, n_iter, m) (unused when m == 0).
- *                  Synchronises the stream once (it checks that the pass ended at iteration n_iter - 1).
- * unroll_backward: g_x (B, n) is the adjoint of the last x~.  Runs the reverse sweep (one symmetric GEMV with the
- *                  cached K11 per recorded iteration, the same operator stream as the forward loop) and returns the
- *                  adjoints of the SCALED problem data: gp (B,n), gb (B,m), glb, gub (B,n), grho (B) and, when the
- *                  pointers are not NULL, gQ (B,n,n) = -sum_k w_k x_k^T (not symmetric, like the reference's) and
- *                  gA (B,m,n); tape_w (B,n_iter,n) / tape_wnu (B,n_iter,m) are scratch for the adjoint solves.
- *                  The adapter maps them to the caller's Q, p, A, b, lb, ub through the scaling (:161-203).
- *                  Fully asynchronous on `stream`. */
+ * dl_dA = dx xv^T, dl_db = -dx).  Here the loop is recorded on a tape and swept backwards by a kernel.  All calls
+ * follow a plain lqpb_forward_* solve of the same problem, which tells n_iter = info.iter + 1 and
+ * n_seg = info.n_factor (operator segments: 1 + adaptive-rho updates, :246-256).
+ *
+ * tapes: tape_x / tape_z / tape_u (B, n_iter, n) hold the scaled iterate x~_k, z_k, u_k after iteration k,
+ *        tape_nu (B, n_iter, m) the equality part of the KKT solve of iteration k (unused when m == 0).
+ * unroll_record:   n_seg == 1 only.  Re-runs the n_iter iterations from z = u = 0 on the operators still held in
+ *                  the forward call's `workspace` (identical arithmetic) and fills the tapes.
+ * unroll_forward:  any n_seg.  A complete recording solve (same arguments / outputs as lqpb_forward_*) that also
+ *                  keeps, per operator segment s, a snapshot of (K11, K21, K22, c, rho) in `snapshots`
+ *                  (n_seg x lqpb_unroll_snapshot_bytes_*), writes the first iteration of every segment and n_iter
+ *                  into the HOST array seg_start[n_seg + 1], and the do_rho_update flags (:310-311) each update
+ *                  applied into the DEVICE array wants (n_seg - 1, B).
+ *                  Both recording calls synchronise the stream (they verify the run ended at iteration n_iter - 1).
+ * unroll_backward: reverse sweep over the iterations k_hi .. k_lo (inclusive) of ONE operator segment: operators from
+ *                  `snapshot` (one snapshot of unroll_forward) or, when NULL, from `workspace`.  In: adjoints of
+ *                  x~_{k_hi}, z_{k_hi}, u_{k_hi}, z_{k_hi - 1} (g_x, g_z, g_u, g_zprev, (B, n) each, NULL = zero).
+ *                  Out: the adjoints of the SCALED problem data accumulated over the range -- gp (B,n), gb (B,m), glb,
+ *                  gub (B,n), grho (B) and, when not NULL, gQ (B,n,n) = -sum_k w_k x_k^T (not symmetric, like the
+ *                  reference's) and gA (B,m,n) -- and those of the state the range started from, gz_in / gu_in
+ *                  (z_{k_lo - 1}, u_{k_lo - 1}; may be NULL).  tape_w (B,n_iter,n) / tape_wnu (B,n_iter,m) are
+ *                  scratch for the adjoint solves.  One symmetric GEMV with the cached K11 per iteration -- the
+ *                  operator stream of the forward loop.  Fully asynchronous on `stream`.
+ * The adapter (lqp_py_b200/solve_box_qp_admm_torch.py) chains the ranges around each adaptive-rho update and maps
+ * the scaled adjoints to the caller's Q, p, A, b, lb, ub through the scaling (:161-203). */
+size_t lqpb_unroll_snapshot_bytes_f32(int B, int n, int m);
+size_t lqpb_unroll_snapshot_bytes_f64(int B, int n, int m);
 int lqpb_unroll_record_f32(const lqpb_config* cfg, int B, int n, int m, int n_iter, void* workspace,
                            size_t workspace_bytes, float* tape_x, float* tape_z, float* tape_u, float* tape_nu,
                            void* stream);
 int lqpb_unroll_record_f64(const lqpb_config* cfg, int B, int n, int m, int n_iter, void* workspace,
                            size_t workspace_bytes, double* tape_x, double* tape_z, double* tape_u, double* tape_nu,
                            void* stream);
-int lqpb_unroll_backward_f32(int B, int n, int m, int n_iter, void* workspace, size_t workspace_bytes,
-                             const float* g_x, const float* tape_x, const float* tape_z, const float* tape_u,
-                             const float* tape_nu, float* tape_w, float* tape_wnu, float* gQ, float* gp, float* gA,
-                             float* gb, float* glb, float* gub, float* grho, void* stream);
-int lqpb_unroll_backward_f64(int B, int n, int m, int n_iter, void* workspace, size_t workspace_bytes,
-                             const double* g_x, const double* tape_x, const double* tape_z, const double* tape_u,
-                             const double* tape_nu, double* tape_w, double* tape_wnu, double* gQ, double* gp,
-                             double* gA, double* gb, double* glb, double* gub, double* grho, void* stream);
+int lqpb_unroll_forward_f32(const lqpb_config* cfg, int B, int n, int m, int n_iter, int n_seg, const float* Q,
+                            const float* p, const float* A, const float* b, const float* lb, const float* ub,
+                            float* x, float* z, float* u, float* lams, float* nus, float* rho_out, float* tape_x,
+                            float* tape_z, float* tape_u, float* tape_nu, void* snapshots, size_t snapshot_bytes,
+                            int32_t* seg_start, int32_t* wants, lqpb_info* info, void* workspace,
+                            size_t workspace_bytes, void* stream);
+int lqpb_unroll_forward_f64(const lqpb_config* cfg, int B, int n, int m, int n_iter, int n_seg, const double* Q,
+                            const double* p, const double* A, const double* b, const double* lb, const double* ub,
+                            double* x, double* z, double* u, double* lams, double* nus, double* rho_out,
+                            double* tape_x, double* tape_z, double* tape_u, double* tape_nu, void* snapshots,
+                            size_t snapshot_bytes, int32_t* seg_start, int32_t* wants, lqpb_info* info,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int lqpb_unroll_backward_f32(int B, int n, int m, int n_iter, int k_lo, int k_hi, void* workspace,
+                             size_t workspace_bytes, const void* snapshot, const float* g_x, const float* g_z,
+                             const float* g_u, const float* g_zprev, const float* tape_x, const float* tape_z,
+                             const float* tape_u, const float* tape_nu, float* tape_w, float* tape_wnu, float* gQ,
+                             float* gp, float* gA, float* gb, float* glb, float* gub, float* grho, float* gz_in,
+                             float* gu_in, void* stream);
+int lqpb_unroll_backward_f64(int B, int n, int m, int n_iter, int k_lo, int k_hi, void* workspace,
+                             size_t workspace_bytes, const void* snapshot, const double* g_x, const double* g_z,
+                             const double* g_u, const double* g_zprev, const double* tape_x, const double* tape_z,
+                             const double* tape_u, const double* tape_nu, double* tape_w, double* tape_wnu,
+                             double* gQ, double* gp, double* gA, double* gb, double* glb, double* gub, double* grho,
+                             double* gz_in, double* gu_in, void* stream);
 
 /* ---- lu_layer: replaces TorchLU / TorchLULayer (lu_layer.py:5-58) -------------------------
  * lu_factor: partial-pivoting LU of B general N x N matrices (torch.linalg.lu_factor, :10,:30);

@@ -9,13 +9,13 @@ Sub-modules keep the reference's names so imports translate one-to-one:
 from .control import box_qp_control
 from .utils import get_ncon
 
-__all__ = ["box_qp_control", "get_ncon", "SolveBoxQP", "SolveBoxQPLayer", "torch_solve_box_qp",
+__all__ = ["box_qp_control", "get_ncon", "SolveBoxQP", "SolveBoxQPLayer", "BoxQPTH", "torch_solve_box_qp",
            "torch_solve_box_qp_grad", "torch_solve_box_qp_grad_kkt", "TorchLU", "TorchLULayer"]
 
 
 def __getattr__(name):
     # torch is imported lazily so that `import lqp_py_b200.build` works in a bare interpreter
-    if name in ("SolveBoxQP", "SolveBoxQPLayer", "torch_solve_box_qp", "torch_solve_box_qp_grad",
+    if name in ("SolveBoxQP", "SolveBoxQPLayer", "BoxQPTH", "torch_solve_box_qp", "torch_solve_box_qp_grad",
                 "torch_solve_box_qp_grad_kkt"):
         from . import solve_box_qp_admm_torch as m
         return getattr(m, name)

@@ -20,7 +20,9 @@ EXPORTS = (
     "lqpb_backward_workspace_bytes_f32", "lqpb_backward_workspace_bytes_f64",
     "lqpb_backward_f32", "lqpb_backward_f64", "lqpb_backward_kkt_f32", "lqpb_backward_kkt_f64",
     "lqpb_forward_host_f32", "lqpb_forward_host_f64", "lqpb_backward_host_f32", "lqpb_backward_host_f64",
-    "lqpb_unroll_record_f32", "lqpb_unroll_record_f64", "lqpb_unroll_backward_f32", "lqpb_unroll_backward_f64",
+    "lqpb_unroll_snapshot_bytes_f32", "lqpb_unroll_snapshot_bytes_f64",
+    "lqpb_unroll_record_f32", "lqpb_unroll_record_f64", "lqpb_unroll_forward_f32", "lqpb_unroll_forward_f64",
+    "lqpb_unroll_backward_f32", "lqpb_unroll_backward_f64",
     "lqpb_lu_factor_f32", "lqpb_lu_factor_f64", "lqpb_lu_solve_f32", "lqpb_lu_solve_f64",
     "lqpb_outer_f32", "lqpb_outer_f64",
     "lqpb_dev_tc_inverse_work_bytes", "lqpb_dev_tc_inverse_f32",
@@ -105,8 +107,15 @@ def lib():
         f.restype = i32
         f = getattr(L, f"lqpb_unroll_record_{sfx}")
         f.argtypes, f.restype = [C.POINTER(Config), i32, i32, i32, i32, vp, sz] + [vp] * 4 + [vp], i32
+        f = getattr(L, f"lqpb_unroll_snapshot_bytes_{sfx}")
+        f.argtypes, f.restype = [i32, i32, i32], sz
+        f = getattr(L, f"lqpb_unroll_forward_{sfx}")
+        f.argtypes = ([C.POINTER(Config), i32, i32, i32, i32, i32] + [vp] * 6 + [vp] * 6 + [vp] * 4 + [vp, sz]
+                      + [C.POINTER(C.c_int32), vp, C.POINTER(Info), vp, sz, vp])
+        f.restype = i32
         f = getattr(L, f"lqpb_unroll_backward_{sfx}")
-        f.argtypes, f.restype = [i32, i32, i32, i32, vp, sz] + [vp] * 5 + [vp] * 2 + [vp] * 7 + [vp], i32
+        f.argtypes = [i32] * 6 + [vp, sz, vp] + [vp] * 4 + [vp] * 4 + [vp] * 2 + [vp] * 7 + [vp] * 2 + [vp]
+        f.restype = i32
         f = getattr(L, f"lqpb_lu_factor_{sfx}")
         f.argtypes, f.restype = [i32, i32, vp, vp, vp, vp], i32
         f = getattr(L, f"lqpb_lu_solve_{sfx}")

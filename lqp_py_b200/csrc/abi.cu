@@ -187,6 +187,40 @@ BwdWs<T> slice_bwd(const BwdWs<T>& w, int b0, int bc) {
 template <typename P>
 P* off(P* p, size_t elems) { return p ? p + elems : nullptr; }
 
+// ---- unrolled mode: what a reverse sweep needs of one operator segment (rho and the KKT inverse it belongs to)
+template <typename T>
+struct Snap {
+  T *Kp, *Gt, *Sinv, *c, *rho;
+  size_t bytes;
+};
+template <typename T>
+Snap<T> carve_snap(void* base, int B, int n, int m) {
+  Snap<T> s;
+  char* p = static_cast<char*>(base);
+  size_t o = 0;
+  auto take = [&](size_t count) {
+    void* r = p ? p + o : nullptr;
+    o = round_up_sz(o + count * sizeof(T), 256);
+    return (T*)r;
+  };
+  const size_t Bn = (size_t)B, mm = m > 0 ? m : 1, ld = round_up(n, Vec<T>::N);
+  s.Kp = take(Bn * Pack<T>::elems(n));
+  s.Gt = take(Bn * mm * ld);
+  s.Sinv = take(Bn * mm * mm);
+  s.c = take(Bn * ld);
+  s.rho = take(Bn);
+  s.bytes = o;
+  return s;
+}
+template <typename T>
+struct UnrollRec {        // recording run of a forward solve (lqpb_unroll_forward_*)
+  Tape<T> tape;
+  void* snap;             // max_seg snapshots of carve_snap().bytes each
+  int max_seg;
+  int32_t* seg_start;     // host, max_seg + 1 entries: first iteration of every operator segment, then n_iter
+  int32_t* wants;         // device, (max_seg - 1, B): do_rho_update flags applied by each adaptive-rho update
+};
+
 template <typename T>
 int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
   GjArgs<T> a{};
@@ -217,7 +251,7 @@ int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
 template <typename T>
 int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A, const T* b,
                  const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, lqpb_info* info, void* ws,
-                 size_t ws_bytes, void* stream, const HostFwd<T>* host = nullptr) {
+                 size_t ws_bytes, void* stream, const HostFwd<T>* host = nullptr, const UnrollRec<T>* rec = nullptr) {
   if (host && (!host->Q || !host->p || !host->lb || !host->ub || (m > 0 && (!host->A || !host->b))))
     return fail(LQPB_E_ARG, "null host pointer argument");
   if (!cfg || !Q || !p || !lb || !ub || !x || !z || !u || !lams || !rho_out || !info || !ws)
@@ -302,9 +336,20 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
       if (rc) return rc;
       if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac1[g_prof.n_fac++], st);
     }
+    if (rec) {      // keep the operators of this segment for its reverse sweep
+      if (n_factor >= rec->max_seg) return fail(LQPB_E_ARG, "recording run needs more operator segments than announced");
+      const Snap<T> sn = carve_snap<T>((char*)rec->snap + (size_t)n_factor * carve_snap<T>(nullptr, B, n, m).bytes, B, n, m);
+      const size_t mm = m > 0 ? m : 1, sz = sizeof(T);
+      CK(cudaMemcpyAsync(sn.Kp, w.Kp, (size_t)B * Pack<T>::elems(n) * sz, cudaMemcpyDeviceToDevice, st), "snapshot K11");
+      CK(cudaMemcpyAsync(sn.Gt, w.Gt, (size_t)B * mm * w.ld * sz, cudaMemcpyDeviceToDevice, st), "snapshot K21");
+      CK(cudaMemcpyAsync(sn.Sinv, w.Sinv, (size_t)B * mm * mm * sz, cudaMemcpyDeviceToDevice, st), "snapshot K22");
+      CK(cudaMemcpyAsync(sn.c, w.c, (size_t)B * w.ld * sz, cudaMemcpyDeviceToDevice, st), "snapshot c");
+      CK(cudaMemcpyAsync(sn.rho, w.rho, (size_t)B * sz, cudaMemcpyDeviceToDevice, st), "snapshot rho");
+      rec->seg_start[n_factor] = i0;
+    }
     ++n_factor;
     if (prof && g_prof.n_it < kMaxSeg) cudaEventRecord(g_prof.it0[g_prof.n_it], st);
-    CK(launch_iterate<T>(*cfg, w, i0, skip, nus, &g_prof.it_launches, st), "iterate");
+    CK(launch_iterate<T>(*cfg, w, i0, skip, nus, &g_prof.it_launches, st, rec ? &rec->tape : nullptr), "iterate");
     if (prof && g_prof.n_it < kMaxSeg) cudaEventRecord(g_prof.it1[g_prof.n_it++], st);
     if (prof) cudaEventRecord(g_prof.ev[2], st);
     CK(launch_finalize<T>(w, x, z, u, lams, rho_out, st), "finalize");
@@ -317,6 +362,9 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
     if (hc->status == 3) {
       i0 = hc->next_i;
       skip = 1;
+      if (rec && n_factor < rec->max_seg)     // the flags the kernel just applied to rho (w.wants is rewritten at the next check)
+        CK(cudaMemcpyAsync(rec->wants + (size_t)(n_factor - 1) * B, w.wants, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice,
+                           st), "snapshot wants");
       CK(cudaMemsetAsync(&w.ctrl->status, 0, sizeof(int), st), "reset status");
       continue;
     }
@@ -324,6 +372,11 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
   }
   if (hc->status != LQPB_STATUS_CONVERGED && hc->status != LQPB_STATUS_MAX_ITERS)
     return fail(LQPB_E_CUDA, "iteration kernel ended without a status");
+  if (rec) {
+    if (n_factor != rec->max_seg || hc->iter != rec->tape.n_iter - 1)
+      return fail(LQPB_E_CUDA, "recording run did not reproduce the forward solve");
+    rec->seg_start[n_factor] = rec->tape.n_iter;
+  }
   info->iter = hc->iter;
   info->status = hc->status;
   info->n_factor = n_factor;
@@ -478,19 +531,42 @@ int unroll_record_impl(const lqpb_config* cfg, int B, int n, int m, int n_iter, 
 }
 
 template <typename T>
-int unroll_backward_impl(int B, int n, int m, int n_iter, void* ws, size_t ws_bytes, const T* gx, const T* tx,
-                         const T* tz, const T* tu, const T* tnu, T* tw, T* twnu, T* gQ, T* gp, T* gA, T* gb, T* glb,
-                         T* gub, T* grho, void* stream) {
-  if (!ws || !gx || !tx || !tz || !tu || !tw || !gp || !glb || !gub || !grho)
+int unroll_forward_impl(const lqpb_config* cfg, int B, int n, int m, int n_iter, int n_seg, const T* Q, const T* p,
+                        const T* A, const T* b, const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out,
+                        T* tx, T* tz, T* tu, T* tnu, void* snap, size_t snap_bytes, int32_t* seg_start, int32_t* wants,
+                        lqpb_info* info, void* ws, size_t ws_bytes, void* stream) {
+  if (!cfg || !tx || !tz || !tu || (m > 0 && !tnu) || !snap || !seg_start || (n_seg > 1 && !wants))
     return fail(LQPB_E_ARG, "null pointer argument");
+  if (n_iter < 1 || n_seg < 1) return fail(LQPB_E_ARG, "bad dimensions");
+  if (B > 0 && n > 0 && m >= 0 && carve_snap<T>(nullptr, B, n, m).bytes * (size_t)n_seg > snap_bytes)
+    return fail(LQPB_E_WORKSPACE, "snapshot buffer too small");
+  lqpb_config c = *cfg;
+  if (c.max_iters > n_iter) c.max_iters = n_iter;      // the tape has n_iter rows: the run can never write past them
+  c.verbose = 0;
+  UnrollRec<T> rec{Tape<T>{n_iter, tx, tz, tu, tnu}, snap, n_seg, seg_start, wants};
+  return forward_impl<T>(&c, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, ws, ws_bytes, stream, nullptr,
+                         &rec);
+}
+
+template <typename T>
+int unroll_backward_impl(int B, int n, int m, int n_iter, int k_lo, int k_hi, void* ws, size_t ws_bytes, const void* snap,
+                         const T* gx, const T* gz_last, const T* gu_last, const T* gzprev_last, const T* tx, const T* tz,
+                         const T* tu, const T* tnu, T* tw, T* twnu, T* gQ, T* gp, T* gA, T* gb, T* glb, T* gub, T* grho,
+                         T* gz_in, T* gu_in, void* stream) {
+  if (!ws || !tx || !tz || !tu || !tw || !gp || !glb || !gub || !grho) return fail(LQPB_E_ARG, "null pointer argument");
   if (m > 0 && (!tnu || !twnu || !gb)) return fail(LQPB_E_ARG, "tape_nu, tape_wnu and gb are required when m > 0");
-  if (B <= 0 || n <= 0 || m < 0 || m > kMaxM || n_iter < 1) return fail(LQPB_E_ARG, "bad dimensions");
+  if (B <= 0 || n <= 0 || m < 0 || m > kMaxM || n_iter < 1 || k_lo < 0 || k_hi < k_lo || k_hi >= n_iter)
+    return fail(LQPB_E_ARG, "bad dimensions");
   int rc = check_device();
   if (rc) return rc;
   FwdWs<T> w = carve_fwd<T>(ws, B, n, m);
   if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
+  if (snap) {                       // operators of an earlier segment; bounds and flags stay those of the workspace
+    const Snap<T> sn = carve_snap<T>(const_cast<void*>(snap), B, n, m);
+    w.Kp = sn.Kp; w.Gt = sn.Gt; w.Sinv = sn.Sinv; w.c = sn.c; w.rho = sn.rho;
+  }
   Tape<T> tape{n_iter, (T*)tx, (T*)tz, (T*)tu, (T*)tnu};
-  UnrollGrads<T> g{gx, tw, twnu, gQ, gp, gA, gb, glb, gub, grho};
+  UnrollGrads<T> g{k_lo, k_hi, gx, gz_last, gu_last, gzprev_last, gz_in, gu_in, tw, twnu, gQ, gp, gA, gb, glb, gub, grho};
   int l = 0;
   CK(launch_unroll_reverse<T>(w, tape, g, &l, (cudaStream_t)stream), "unroll reverse sweep");
   g_prof.launches = l;
@@ -602,17 +678,29 @@ int lqpb_backward_kkt_f64(int B, int n, int m, const double* dl_dz, const double
 }
 
 #define UNROLL_ENTRY(SFX, T)                                                                                       \
+  size_t lqpb_unroll_snapshot_bytes_##SFX(int B, int n, int m) { return carve_snap<T>(nullptr, B, n, m).bytes; }    \
   int lqpb_unroll_record_##SFX(const lqpb_config* cfg, int B, int n, int m, int n_iter, void* workspace,            \
                                size_t workspace_bytes, T* tape_x, T* tape_z, T* tape_u, T* tape_nu, void* stream) { \
     return unroll_record_impl<T>(cfg, B, n, m, n_iter, workspace, workspace_bytes, tape_x, tape_z, tape_u,          \
                                  tape_nu, stream);                                                                  \
   }                                                                                                                \
-  int lqpb_unroll_backward_##SFX(int B, int n, int m, int n_iter, void* workspace, size_t workspace_bytes,         \
-                                 const T* g_x, const T* tape_x, const T* tape_z, const T* tape_u,                  \
-                                 const T* tape_nu, T* tape_w, T* tape_wnu, T* gQ, T* gp, T* gA, T* gb, T* glb,     \
-                                 T* gub, T* grho, void* stream) {                                                  \
-    return unroll_backward_impl<T>(B, n, m, n_iter, workspace, workspace_bytes, g_x, tape_x, tape_z, tape_u,       \
-                                   tape_nu, tape_w, tape_wnu, gQ, gp, gA, gb, glb, gub, grho, stream);             \
+  int lqpb_unroll_forward_##SFX(const lqpb_config* cfg, int B, int n, int m, int n_iter, int n_seg, const T* Q,     \
+                                const T* p, const T* A, const T* b, const T* lb, const T* ub, T* x, T* z, T* u,     \
+                                T* lams, T* nus, T* rho_out, T* tape_x, T* tape_z, T* tape_u, T* tape_nu,           \
+                                void* snapshots, size_t snapshot_bytes, int32_t* seg_start, int32_t* wants,         \
+                                lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream) {           \
+    return unroll_forward_impl<T>(cfg, B, n, m, n_iter, n_seg, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out,     \
+                                  tape_x, tape_z, tape_u, tape_nu, snapshots, snapshot_bytes, seg_start, wants,     \
+                                  info, workspace, workspace_bytes, stream);                                        \
+  }                                                                                                                \
+  int lqpb_unroll_backward_##SFX(int B, int n, int m, int n_iter, int k_lo, int k_hi, void* workspace,             \
+                                 size_t workspace_bytes, const void* snapshot, const T* g_x, const T* g_z,         \
+                                 const T* g_u, const T* g_zprev, const T* tape_x, const T* tape_z,                 \
+                                 const T* tape_u, const T* tape_nu, T* tape_w, T* tape_wnu, T* gQ, T* gp, T* gA,   \
+                                 T* gb, T* glb, T* gub, T* grho, T* gz_in, T* gu_in, void* stream) {               \
+    return unroll_backward_impl<T>(B, n, m, n_iter, k_lo, k_hi, workspace, workspace_bytes, snapshot, g_x, g_z,    \
+                                   g_u, g_zprev, tape_x, tape_z, tape_u, tape_nu, tape_w, tape_wnu, gQ, gp, gA,    \
+                                   gb, glb, gub, grho, gz_in, gu_in, stream);                                      \
   }
 UNROLL_ENTRY(f32, float)
 UNROLL_ENTRY(f64, double)

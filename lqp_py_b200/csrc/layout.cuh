@@ -244,7 +244,10 @@ cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, in
 // unroll.cu -- reverse sweep of the unrolled mode and the rank-n_iter products that form dQ~ and dA~
 template <typename T>
 struct UnrollGrads {
-  const T* gx;              // (B, n)  adjoint of the last x~
+  int k_lo, k_hi;           // iterations swept (inclusive), all with the operators / rho of `w`
+  const T* gx;              // (B, n)  adjoint of x~_{k_hi} (may be null)
+  const T *gz_last, *gu_last, *gzprev_last;   // (B, n) adjoints of z_{k_hi}, u_{k_hi}, z_{k_hi - 1} (may be null)
+  T *gz_in, *gu_in;         // (B, n) out: adjoints of z_{k_lo - 1}, u_{k_lo - 1} (may be null)
   T *tw, *twnu;             // (B, n_iter, n), (B, n_iter, max(m,1))  adjoint solves w_k = K11 gx_k, K21 gx_k (scratch)
   T *gQ, *gp, *gA, *gb, *glb, *gub, *grho;   // adjoints of Q~, p~, A~, b~, lb~, ub~, rho (gQ / gA may be null)
 };

@@ -14,6 +14,9 @@
 // and the matrix adjoints are rank-n_iter products over the tape, formed once at the end instead of one dense
 // N x N outer product per iteration as in the reference:
 //     dQ~ = - sum_k w_k x_k^T   (NOT symmetric, like the reference's),   dA~ = - sum_k (wnu_k x_k^T + nu_k w_k^T).
+// A sweep covers the iteration range [k_lo, k_hi] of one operator segment (rho and K11 constant): it takes the
+// adjoints of (x, z, u)_{k_hi} and z_{k_hi - 1} and returns those of (z, u)_{k_lo - 1}, so that the host can chain
+// segments around an adaptive-rho update (reference :237-256), whose ratio reads the state of the last check.
 // Problems are independent here (no stop test): one persistent CTA per problem, K11 streamed from its packed lower
 // triangle through the per-warp bulk-TMA rings of the forward kernel (itergeom.cuh), prefetching across iterations.
 #include "itergeom.cuh"
@@ -27,7 +30,8 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
   constexpr int VN = P::VN, TC = P::TC, TILE = P::TILE;
   using V4 = typename Vec<T>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int n = w.n, m = w.m, ld = w.ld, np = geo.np, K = tape.n_iter;
+  const int n = w.n, m = w.m, ld = w.ld, np = geo.np, K = tape.n_iter;     // K: rows of the tape per problem
+  const int k_lo = g.k_lo, k_hi = g.k_hi, nk = g.k_hi - g.k_lo + 1;            // iterations swept here, k_hi down to k_lo
   const int nthreads = blockDim.x, nwarps = geo.nwarps, depth = geo.depth;
   const int ntv = geo.nt, ntiles = geo.ntiles;
   T* ring = reinterpret_cast<T*>(smem_raw);                 // [nwarps][depth][TILE]
@@ -84,7 +88,7 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
     if (++p_slot == depth) p_slot = 0;
     if (++p_r == run_len) {
       p_r = 0;
-      if (++p_it == K) { p_it = 0; ++p_k; }
+      if (++p_it == nk) { p_it = 0; ++p_k; }
     }
   };
   for (int d = 0; d < depth; ++d) issue_next();
@@ -164,18 +168,18 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
       const T t = (at_ub || at_lb) ? T(0) : h;
       if (at_ub) g.gub[go + e] += h;
       if (at_lb) g.glb[go + e] += h;
-      v[e] = gu_e + t + (k == K - 1 ? g.gx[go + e] : T(0));
+      v[e] = gu_e + t + ((k == k_hi && g.gx) ? g.gx[go + e] : T(0));
       gu[e] = gu_e + t;
     };
     for (int e = tid; e < n; e += nthreads) {
       g.gp[go + e] = T(0);
       g.glb[go + e] = T(0);
       g.gub[go + e] = T(0);
-      head(K - 1, e, T(0), T(0));
+      head(k_hi, e, g.gz_last ? g.gz_last[go + e] : T(0), g.gu_last ? g.gu_last[go + e] : T(0));
     }
     __syncthreads();
 
-    for (int k = K - 1; k >= 0; --k) {
+    for (int k = k_hi; k >= k_lo; --k) {
       sym_pass(v);                                            // xpart += K11 gx
       if (m > 0) {                                            // wnu = K21 gx
         const T* Gt = w.Gt + (size_t)b * m * ld;
@@ -198,9 +202,15 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
         T zu = T(0);
         if (k > 0) zu = tape.z[tb + (size_t)(k - 1) * n + e] - tape.u[tb + (size_t)(k - 1) * n + e];
         grho_acc += we * (zu - tape.x[tb + (size_t)k * n + e]);
-        const T gz_e = rho * we;
+        T gz_e = rho * we;
+        if (k == k_hi && g.gzprev_last) gz_e += g.gzprev_last[go + e];   // z_{k_hi - 1} is also an output of the segment
         const T gu_e = gu[e] - rho * we;
-        if (k > 0) head(k - 1, e, gz_e, gu_e);
+        if (k > k_lo) {
+          head(k - 1, e, gz_e, gu_e);
+        } else {                                                        // adjoints of the state the segment started from
+          if (g.gz_in) g.gz_in[go + e] = gz_e;
+          if (g.gu_in) g.gu_in[go + e] = gu_e;
+        }
       }
       if (m > 0 && tid < m) {
         g.twnu[((size_t)b * K + k) * m + tid] = tdot[tid];
@@ -234,7 +244,8 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
 template <typename T>
 __global__ void __launch_bounds__(256)
 tape_outer_kernel(const T* __restrict__ U, int su, const T* __restrict__ V, int sv, const T* __restrict__ U2, int su2,
-                  const T* __restrict__ V2, int sv2, int rows, int cols, int K, T* __restrict__ out) {
+                  const T* __restrict__ V2, int sv2, int rows, int cols, int kb, int k_lo, int K, T* __restrict__ out) {
+  // kb = tape rows per problem (batch stride), the sum runs over the K rows k_lo .. k_lo + K - 1
   constexpr int TB = 64, KC = 16;
   __shared__ T us[KC][TB + 4], vs[KC][TB + 4];
   const int b = blockIdx.z;
@@ -247,8 +258,8 @@ tape_outer_kernel(const T* __restrict__ U, int su, const T* __restrict__ V, int 
     for (int c = 0; c < 4; ++c) acc[a][c] = T(0);
   const int npairs = U2 ? 2 : 1;
   for (int pr = 0; pr < npairs; ++pr) {
-    const T* Ub = pr == 0 ? U + (size_t)b * K * su : U2 + (size_t)b * K * su2;
-    const T* Vb = pr == 0 ? V + (size_t)b * K * sv : V2 + (size_t)b * K * sv2;
+    const T* Ub = pr == 0 ? U + ((size_t)b * kb + k_lo) * su : U2 + ((size_t)b * kb + k_lo) * su2;
+    const T* Vb = pr == 0 ? V + ((size_t)b * kb + k_lo) * sv : V2 + ((size_t)b * kb + k_lo) * sv2;
     const int s_u = pr == 0 ? su : su2, s_v = pr == 0 ? sv : sv2;
     for (int k0 = 0; k0 < K; k0 += KC) {
       for (int t = threadIdx.x; t < KC * TB; t += 256) {
@@ -301,17 +312,17 @@ cudaError_t launch_unroll_reverse(const FwdWs<T>& w, const Tape<T>& tape, const 
   unroll_reverse_kernel<T><<<grid, geo.nwarps * 32, smem, st>>>(w, tape, g, geo);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (launches) ++*launches;
-  const int n = w.n, m = w.m, K = tape.n_iter;
+  const int n = w.n, m = w.m, kb = tape.n_iter, K = g.k_hi - g.k_lo + 1;
   if (g.gQ) {       // dQ~ = - sum_k w_k x_k^T
     dim3 grid2((n + 63) / 64, (n + 63) / 64, w.B);
-    tape_outer_kernel<T><<<grid2, 256, 0, st>>>(g.tw, n, tape.x, n, (const T*)nullptr, 0, (const T*)nullptr, 0, n, n, K,
-                                                g.gQ);
+    tape_outer_kernel<T><<<grid2, 256, 0, st>>>(g.tw, n, tape.x, n, (const T*)nullptr, 0, (const T*)nullptr, 0, n, n, kb,
+                                                g.k_lo, K, g.gQ);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) ++*launches;
   }
   if (g.gA && m > 0) {   // dA~ = - sum_k (wnu_k x_k^T + nu_k w_k^T)
     dim3 grid2((n + 63) / 64, (m + 63) / 64, w.B);
-    tape_outer_kernel<T><<<grid2, 256, 0, st>>>(g.twnu, m, tape.x, n, tape.nu, m, g.tw, n, m, n, K, g.gA);
+    tape_outer_kernel<T><<<grid2, 256, 0, st>>>(g.twnu, m, tape.x, n, tape.nu, m, g.tw, n, m, n, kb, g.k_lo, K, g.gA);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) ++*launches;
   }

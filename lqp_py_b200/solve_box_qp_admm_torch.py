@@ -14,7 +14,10 @@ Same module / autograd surface as the reference file of the same name
 but none of the arithmetic happens in torch: the functions flatten the settings into a POD
 struct and call the hand-written sm_100a kernels through the C ABI of ``include/lqpb.h``
 (scaling + Gauss-Jordan operator setup, the persistent TMA-streamed ADMM kernel, the
-masked-inverse backward).  PyTorch only owns device memory and the CUDA stream.
+masked-inverse backward).  PyTorch only owns device memory and the CUDA stream.  The one exception
+is ``unroll=True``: its iterations run in the same kernels (recorded, then swept backwards), but the
+T-independent scaling / rho-update expressions around them are torch operators on the CUDA copies so
+that autograd reproduces the reference's subgradient conventions (see ``_solve_unrolled``).
 
 Tensors may live on the GPU (zero copy) or on the CPU like in the reference's experiments;
 CPU tensors are staged to the current CUDA device and the results are returned on the CPU.
@@ -78,6 +81,33 @@ class SolveBoxQPLayer(torch.autograd.Function):
         else:
             grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need)
         return (*_to_devices(grads, ctx.input_devices), None)
+
+
+class BoxQPTH:
+    """Stateful holder of one batch of problems (reference :70-105): ``solve()`` runs the forward solver on the
+    stored data, keeps the solution dict in ``self.sol`` and returns ``x``; ``update(...)`` replaces stored fields.
+    Like the reference's, ``update`` stores ``None`` -- not the new tensor -- when ``lb`` / ``ub`` are passed
+    (:99-102), so a caller that relied on that sees the same behaviour.  No autograd (the functional solver)."""
+
+    def __init__(self, Q, p, A, b, lb, ub, control):
+        self.Q, self.p, self.A, self.b, self.lb, self.ub = Q, p, A, b, lb, ub
+        self.control = control
+        self.sol = {}
+
+    def solve(self):
+        sol = torch_solve_box_qp(Q=self.Q, p=self.p, A=self.A, b=self.b, lb=self.lb, ub=self.ub, control=self.control)
+        self.sol = sol
+        return sol.get('x')
+
+    def update(self, Q=None, p=None, A=None, b=None, lb=None, ub=None, control=None):
+        for name, val in (("Q", Q), ("p", p), ("A", A), ("b", b), ("control", control)):
+            if val is not None:
+                setattr(self, name, val)
+        if lb is not None:
+            self.lb = None                                           # :99-100
+        if ub is not None:
+            self.ub = None                                           # :101-102
+        return None
 
 
 # ------------------------------------------------------------------------------------------
@@ -304,18 +334,20 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
 # ------------------------------------------------------------------------------------------
 def _solve_unrolled(Q, p, A, b, lb, ub, control):
     """``unroll=True`` (reference :13-15): ``x`` comes back attached to an autograd graph that differentiates the
-    scaling (:161-197), the rho selection (:200-203), every ADMM iteration (:259-282) and the un-scaling (:316).
+    scaling (:161-197), the rho selection (:200-203), every ADMM iteration (:259-282), every adaptive-rho update
+    (:237-256, where ``rho_new = rho * ratio`` stays in the graph) and the un-scaling (:316).
 
-    The T iterations -- all the O(T n^2) work -- are ONE autograd node, ``_UnrolledLoop``: its forward records the
-    iterates of the CUDA loop (``lqpb_unroll_record_*``), its backward is the reverse-sweep kernel
-    (``lqpb_unroll_backward_*``: one symmetric K11 GEMV per recorded iteration, then dQ~ / dA~ as rank-T products
-    over the tape instead of the reference's dense ``dx xv^T`` per iteration, lu_layer.py:53).  The O(n^2), T-
-    independent map between the caller's tensors and the scaled problem (D, E, Q~ = D Q D, rho = ||Q~||_F / sqrt(n))
-    is written below with the torch operators the reference itself uses, on the CUDA copies, so that autograd
-    applies exactly the reference's (sub)gradient conventions for ``norm(inf)``, ``quantile`` and ``clamp``.
-
-    An adaptive-rho update inside the unrolled loop (reference :246-256, where ``rho_new = rho * ratio`` stays in
-    the graph) is not supported and raises: none occurs on the reference's experiment data."""
+    The iterations -- all the O(T n^2) work -- are autograd nodes backed by CUDA kernels (``_UnrolledSegment``): the
+    loop is recorded on a tape (``lqpb_unroll_record_*`` / ``lqpb_unroll_forward_*``) and a node's backward is the
+    reverse-sweep kernel over its iteration range (``lqpb_unroll_backward_*``: one symmetric K11 GEMV per recorded
+    iteration, then dQ~ / dA~ as rank-T products over the tape instead of the reference's dense ``dx xv^T`` per
+    iteration, lu_layer.py:53).  Without an adaptive-rho update the whole loop is ONE node.  An update at iteration
+    i reads the residual norms of the last check (iteration c = i - check_solved), so the loop is cut after c and
+    before i and the T-independent pieces in between -- like the O(n^2) map between the caller's tensors and the
+    scaled problem (D, E, Q~ = D Q D, rho = ||Q~||_F / sqrt(n)) -- are written with the torch operators the
+    reference itself uses, on the CUDA copies, so that autograd applies exactly the reference's (sub)gradient
+    conventions for ``norm(inf)``, ``quantile``, ``maximum`` and ``clamp``."""
+    L = _abi.lib()
     out_device = p.device
     for t in (Q, p, A, b, lb, ub):
         if t is not None and t.dtype != p.dtype:
@@ -326,19 +358,84 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
     plain = dict(control)
     plain['unroll'] = False
     sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=())
-    if sol["n_factor"] != 1:
-        raise NotImplementedError(
-            "unroll=True with an adaptive-rho update inside the loop (reference :246-256) is not supported: "
-            "set adaptive_rho=False or choose rho so that no update triggers")
     any_lb, any_ub = sol["_any_lb"], sol["_any_ub"]
-    n = pd.shape[1]
+    B, n, dt = Qd.shape[0], pd.shape[1], pd.dtype
     m = get_ncon(Ad, dim=1)
+    sfx = _abi.suffix(dt)
+    K, S = sol["iter"] + 1, sol["n_factor"]
+    cfg, ws = sol["_cfg"], sol["_ws"]
+    state = dict(ws=ws, B=B, n=n, m=m, n_iter=K, snaps=None, snap_each=0)
+    with torch.cuda.device(dev):
+        tape = [torch.empty((B, K, n), dtype=dt, device=dev) for _ in range(3)]
+        tape_nu = torch.empty((B, K, m), dtype=dt, device=dev) if m > 0 else None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        wants = None
+        if S == 1:
+            rc = getattr(L, f"lqpb_unroll_record_{sfx}")(
+                C.byref(cfg), B, n, m, K, _abi.ptr(ws), ws.numel(), _abi.ptr(tape[0]), _abi.ptr(tape[1]),
+                _abi.ptr(tape[2]), _abi.ptr(tape_nu), C.c_void_p(stream))
+            _abi.check(rc, "lqpb_unroll_record")
+            seg_start = [0, K]
+        else:
+            # adaptive-rho updates: a full recording solve that also keeps the operators of every segment
+            d = sol["_dev"]
+            each = getattr(L, f"lqpb_unroll_snapshot_bytes_{sfx}")(B, n, m)
+            snaps = torch.empty(S * each, dtype=torch.uint8, device=dev)
+            wants = torch.empty((S - 1, B), dtype=torch.int32, device=dev)
+            segs = (C.c_int32 * (S + 1))()
+            info = _abi.Info()
+            scratch = [sol["_x_dev"], torch.empty_like(sol["_x_dev"]), sol["_u_dev"], sol["_lams_dev"], sol["_nus_dev"],
+                       torch.empty((B, 1, 1), dtype=dt, device=dev)]
+            rc = getattr(L, f"lqpb_unroll_forward_{sfx}")(
+                C.byref(cfg), B, n, m, K, S, _abi.ptr(d["Q"]), _abi.ptr(d["p"]), _abi.ptr(d["A"]), _abi.ptr(d["b"]),
+                _abi.ptr(d["lb"]), _abi.ptr(d["ub"]), *[_abi.ptr(t) for t in scratch], _abi.ptr(tape[0]),
+                _abi.ptr(tape[1]), _abi.ptr(tape[2]), _abi.ptr(tape_nu), _abi.ptr(snaps), snaps.numel(), segs,
+                _abi.ptr(wants), C.byref(info), _abi.ptr(ws), ws.numel(), C.c_void_p(stream))
+            _abi.check(rc, "lqpb_unroll_forward")
+            seg_start = list(segs)
+            state.update(snaps=snaps, snap_each=each)
+    state["tape"] = (*tape, tape_nu)
+
     Qt, pt, At, bt, lbt, ubt, D, rho = _scaled_problem(Qd, pd, Ad, bd, lbd, ubd, control, any_lb, any_ub)
-    state = dict(ws=sol["_ws"], cfg=sol["_cfg"], n_iter=sol["iter"] + 1, B=Qd.shape[0], n=n, m=m)
-    xt = _UnrolledLoop.apply(Qt, pt, At, bt, lbt if any_lb else None, ubt if any_ub else None,
-                             rho if torch.is_tensor(rho) else None, state)
-    x = D * xt                                                           # :316
+    check = cfg.check_solved
+    z_in = u_in = x_l = None
+    for s_idx in range(S):
+        lo, hi = seg_start[s_idx], seg_start[s_idx + 1] - 1
+        pieces = [(lo, hi)]
+        if s_idx < S - 1:                       # the update at hi + 1 reads the last check before it, iteration c (:239-243)
+            c = (hi // check) * check
+            if c < lo:
+                raise NotImplementedError("unroll=True with adaptive_rho_iter < check_solved: an adaptive-rho update "
+                                          "would read a check made before the previous update")
+            pieces = [(lo, c)] + ([(c + 1, hi)] if c < hi else [])
+        for (k_lo, k_hi) in pieces:
+            x_l, z_l, u_l, zp_l = _UnrolledSegment.apply(
+                Qt, pt, At, bt, lbt if any_lb else None, ubt if any_ub else None, rho if torch.is_tensor(rho) else None,
+                z_in, u_in, state, k_lo, k_hi, s_idx)
+            z_in, u_in = z_l, u_l
+            if s_idx < S - 1 and k_hi == pieces[0][1]:
+                at_check = (x_l, z_l, u_l, zp_l)
+        if s_idx < S - 1:
+            rho = _adapted_rho(rho, at_check, wants[s_idx].view(B, 1, 1) != 0, Qt, pd, D, cfg, control)
+    x = D * x_l                                                          # :316
     return x if x.device == out_device else x.to(out_device)
+
+
+def _adapted_rho(rho, at_check, wants, Qt, p, D, cfg, control):
+    """rho after an adaptive update (reference :239-250) as a differentiable function of the state recorded at the
+    last check (:286-304).  ``wants`` is the kernel's do_rho_update mask (:310-311), a decision, not differentiated."""
+    x, z, u, z_prev = at_check
+    ninf = lambda t: torch.linalg.norm(t, ord=_INF, dim=1, keepdim=True)
+    tiny = torch.full((1,), cfg.zero_clamp, dtype=x.dtype, device=x.device)                    # :229-230
+    r, s = x - z, rho * (z - z_prev)                                                          # :279-280
+    primal, dual = ninf(D * r), ninf(D * s)                                                  # :286-287
+    scale_p = torch.maximum(torch.maximum(ninf(D * x), ninf(D * z)), tiny)                   # :296-301
+    scale_d = torch.maximum(torch.maximum(torch.maximum(ninf(rho * D * u), ninf(torch.matmul(Qt, x) / D)), ninf(p)), tiny)
+    num = torch.clamp(primal / scale_p, min=cfg.zero_clamp)                                  # :239-242
+    den = torch.clamp(dual / scale_d, min=cfg.zero_clamp)
+    ratio = (num / den) ** 0.5                                                               # :243
+    rho = rho * torch.logical_not(wants) + (rho * ratio) * wants                             # :248-249
+    return torch.clamp(rho, min=control.get('rho_min', 1e-6), max=control.get('rho_max', 1e6))
 
 
 def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub):
@@ -381,58 +478,58 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub):
     return Q, p, A, b, lb, ub, D, rho
 
 
-class _UnrolledLoop(torch.autograd.Function):
-    """The T recorded ADMM iterations as one autograd node: scaled problem data -> last x~ (reference :259-282 with
-    every KKT solve differentiated as in lu_layer.py:41-58)."""
+class _UnrolledSegment(torch.autograd.Function):
+    """Iterations k_lo .. k_hi of the recorded loop (one operator segment: rho and K11 fixed) as one autograd node:
+    (scaled problem data, rho, z_{k_lo-1}, u_{k_lo-1}) -> (x~, z, u at k_hi, z at k_hi - 1), reference :259-282 with
+    every KKT solve differentiated as in lu_layer.py:41-58.  The forward only reads the tape."""
 
     @staticmethod
-    def forward(ctx, Qt, pt, At, bt, lbt, ubt, rho, state):
-        L = _abi.lib()
-        B, n, m, K = state["B"], state["n"], state["m"], state["n_iter"]
-        dev, dt = pt.device, pt.dtype
-        sfx = _abi.suffix(dt)
-        ws = state["ws"]
-        with torch.cuda.device(dev):
-            tape = [torch.empty((B, K, n), dtype=dt, device=dev) for _ in range(3)]
-            tape_nu = torch.empty((B, K, m), dtype=dt, device=dev) if m > 0 else None
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = getattr(L, f"lqpb_unroll_record_{sfx}")(
-                C.byref(state["cfg"]), B, n, m, K, _abi.ptr(ws), ws.numel(), _abi.ptr(tape[0]), _abi.ptr(tape[1]),
-                _abi.ptr(tape[2]), _abi.ptr(tape_nu), C.c_void_p(stream))
-            _abi.check(rc, "lqpb_unroll_record")
-        ctx.state = state
-        ctx.tape = (*tape, tape_nu)
-        ctx.shapes = tuple(None if t is None else t.shape for t in (Qt, pt, At, bt, lbt, ubt, rho))
-        return tape[0][:, K - 1, :].unsqueeze(2).clone()
+    def forward(ctx, Qt, pt, At, bt, lbt, ubt, rho, z_in, u_in, state, k_lo, k_hi, seg):
+        tx, tz, tu, _ = state["tape"]
+        ctx.set_materialize_grads(False)
+        ctx.state, ctx.range, ctx.seg = state, (k_lo, k_hi), seg
+        ctx.shapes = tuple(None if t is None else t.shape for t in (Qt, pt, At, bt, lbt, ubt, rho, z_in, u_in))
+        pick = lambda t, k: t[:, k, :].unsqueeze(2).clone()
+        z_prev = pick(tz, k_hi - 1) if k_hi > 0 else torch.zeros_like(pick(tz, 0))
+        return pick(tx, k_hi), pick(tz, k_hi), pick(tu, k_hi), z_prev
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, gx, gz, gu, gzp):
         L = _abi.lib()
         st = ctx.state
         B, n, m, K = st["B"], st["n"], st["m"], st["n_iter"]
-        tx, tz, tu, tnu = ctx.tape
+        k_lo, k_hi = ctx.range
+        tx, tz, tu, tnu = st["tape"]
         dev, dt = tx.device, tx.dtype
         sfx = _abi.suffix(dt)
         ws = st["ws"]
         need = ctx.needs_input_grad
-        g = g.detach().to(device=dev, dtype=dt).contiguous()
+        prep = lambda t: None if t is None else t.detach().to(device=dev, dtype=dt).contiguous()
+        gx, gz, gu, gzp = prep(gx), prep(gz), prep(gu), prep(gzp)
+        snap = None
+        if st["snaps"] is not None:
+            snap = C.c_void_p(st["snaps"].data_ptr() + ctx.seg * st["snap_each"])
         with torch.cuda.device(dev):
             new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
-            tw = new(B, K, n)
-            twnu = new(B, K, m) if m > 0 else None
+            if "tw" not in st:                        # scratch for the adjoint solves, shared by all segments
+                st["tw"] = new(B, K, n)
+                st["twnu"] = new(B, K, m) if m > 0 else None
             gQ = new(B, n, n) if need[0] else None
             gA = new(B, m, n) if (m > 0 and need[2]) else None
             gp, glb, gub, grho = new(B, n, 1), new(B, n, 1), new(B, n, 1), new(B, 1, 1)
             gb = new(B, m, 1) if m > 0 else None
+            gz_in = new(B, n, 1) if need[7] else None
+            gu_in = new(B, n, 1) if need[8] else None
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = getattr(L, f"lqpb_unroll_backward_{sfx}")(
-                B, n, m, K, _abi.ptr(ws), ws.numel(), _abi.ptr(g), _abi.ptr(tx), _abi.ptr(tz), _abi.ptr(tu),
-                _abi.ptr(tnu), _abi.ptr(tw), _abi.ptr(twnu), _abi.ptr(gQ), _abi.ptr(gp), _abi.ptr(gA), _abi.ptr(gb),
-                _abi.ptr(glb), _abi.ptr(gub), _abi.ptr(grho), C.c_void_p(stream))
+                B, n, m, K, k_lo, k_hi, _abi.ptr(ws), ws.numel(), snap, _abi.ptr(gx), _abi.ptr(gz), _abi.ptr(gu),
+                _abi.ptr(gzp), _abi.ptr(tx), _abi.ptr(tz), _abi.ptr(tu), _abi.ptr(tnu), _abi.ptr(st["tw"]),
+                _abi.ptr(st["twnu"]), _abi.ptr(gQ), _abi.ptr(gp), _abi.ptr(gA), _abi.ptr(gb), _abi.ptr(glb), _abi.ptr(gub),
+                _abi.ptr(grho), _abi.ptr(gz_in), _abi.ptr(gu_in), C.c_void_p(stream))
             _abi.check(rc, "lqpb_unroll_backward")
-        outs = [gQ, gp, gA, gb, glb, gub, grho]
-        outs = [o if (shape is not None and nd) else None for o, shape, nd in zip(outs, ctx.shapes, need[:7])]
-        return (*outs, None)
+        outs = [gQ, gp, gA, gb, glb, gub, grho, gz_in, gu_in]
+        outs = [o if (shape is not None and nd) else None for o, shape, nd in zip(outs, ctx.shapes, need[:9])]
+        return (*outs, None, None, None, None)
 
 
 def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need):

@@ -445,3 +445,128 @@ def test_boxqpth_stateful_wrapper(dev):
     assert rel_err(x2.cpu().numpy(), ref["x"].numpy()) <= 1e-8
     holder.update(lb=lb, ub=ub)
     assert holder.lb is None and holder.ub is None
+
+
+# ------------------------------------------------------------------------------------------ sizes at the seams
+def _oracle_run(data, control, g, dtype):
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        return orc.solve_and_grad(*data, control, g)
+    finally:
+        torch.set_default_dtype(prev)
+
+
+@pytest.mark.parametrize("n,B,dtype", [(1, 1, torch.float64), (2, 3, torch.float64), (5, 1, torch.float32),
+                                       (127, 3, torch.float32), (128, 3, torch.float32), (129, 2, torch.float64),
+                                       (255, 2, torch.float32), (257, 2, torch.float32), (384, 2, torch.float32),
+                                       (640, 2, torch.float32), (33, 150, torch.float32)])
+def test_sizes_at_the_seams(n, B, dtype, dev):
+    """Single problems, n = 1, and the sizes either side of every internal switch: n + m = 128 / 129 (Gauss-Jordan
+    kernel vs tensor-core block sweep), block counts 2..6 of the sweep, tile padding of the packed operator
+    (n = 33, 255, 257), more problems than SMs."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp, torch_solve_box_qp_grad
+    data = orc.make_exp1_data(n, B, seed=n, dtype=dtype)
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5)
+    g = torch.randn(B, n, 1, generator=torch.Generator().manual_seed(n), dtype=dtype)
+    ref, rg = _oracle_run(data, control, g, dtype)
+    ins = [t.to(dev) for t in data]
+    sol = torch_solve_box_qp(*ins, control)
+    grads = torch_solve_box_qp_grad(g.to(dev), sol["x"], sol["u"], sol["lams"], sol["nus"], ins[0], ins[2], ins[4],
+                                    ins[5], sol["rho"])
+    assert abs(sol["iter"] - ref["iter"]) <= 2
+    f64 = dtype == torch.float64
+    if sol["iter"] != ref["iter"]:
+        return                                  # a check decided at round-off level: states are one check apart
+    lim = 1e-8 if f64 else 2e-5
+    for k in ("x", "z", "lams"):
+        assert rel_err(sol[k].cpu().numpy(), ref[k].numpy()) <= lim, k
+    for k, a, r in zip(("dQ", "dp"), grads[:2], rg[:2]):
+        assert rel_err(a.cpu().numpy(), r.numpy()) <= (1e-7 if f64 else 1e-4), k
+
+
+def test_equality_row_limits(dev):
+    """m = 64 general equality rows (the most the Schur path takes) against the oracle; m = 65 is refused loudly."""
+    from lqp_py_b200 import _abi
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp
+    dtype = torch.float64
+    n, B = 160, 3
+    Q, p, _, _, lb, ub = orc.make_exp1_data(n, B, seed=5, dtype=dtype)
+    gen = torch.Generator().manual_seed(8)
+    control = box_qp_control(eps_abs=1e-6, eps_rel=1e-6)
+    for m in (64, 65):
+        A = torch.randn(B, m, n, generator=gen, dtype=dtype)
+        x0 = torch.rand(B, n, 1, generator=gen, dtype=dtype) - 0.5           # a point inside the box: feasible b
+        b = A @ x0
+        ins = [t.to(dev) for t in (Q, p, A, b, lb, ub)]
+        if m == 65:
+            with pytest.raises(_abi.LqpbError, match="64 equality rows"):
+                torch_solve_box_qp(*ins, control)
+            continue
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(dtype)
+        try:
+            ref = orc.solve(Q, p, A, b, lb, ub, control)
+        finally:
+            torch.set_default_dtype(prev)
+        sol = torch_solve_box_qp(*ins, control)
+        assert abs(sol["iter"] - ref["iter"]) <= 2
+        if sol["iter"] == ref["iter"]:
+            assert rel_err(sol["x"].cpu().numpy(), ref["x"].numpy()) <= 1e-8
+            assert rel_err(sol["nus"].cpu().numpy(), ref["nus"].numpy()) <= 1e-7
+
+
+def test_single_iteration_and_noncontiguous_inputs(dev):
+    """max_iters = 1 (the loop exits on its first pass, iter = 0) and inputs that are views (transposed Q, strided
+    vectors): the adapter makes them contiguous, results equal the contiguous call bit for bit."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import torch_solve_box_qp
+    dtype = torch.float64
+    Q, p, A, b, lb, ub = orc.make_exp1_data(40, 6, seed=12, dtype=dtype)
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5, max_iters=1)
+    ref = _oracle_run((Q, p, A, b, lb, ub), control, torch.zeros_like(p), dtype)[0]
+    ins = [t.to(dev) for t in (Q, p, A, b, lb, ub)]
+    sol = torch_solve_box_qp(*ins, control)
+    assert sol["iter"] == ref["iter"] == 0
+    assert rel_err(sol["x"].cpu().numpy(), ref["x"].numpy()) <= 1e-8
+    control = box_qp_control(eps_abs=1e-5, eps_rel=1e-5)
+    base = torch_solve_box_qp(*ins, control)
+    Qv = ins[0].transpose(1, 2)                                   # symmetric: same matrix, non-contiguous view
+    wide = torch.stack((ins[1], ins[1] + 1), dim=3)               # (B, n, 1, 2): [..., 0] is a strided view of p
+    pv = wide[..., 0]
+    assert not Qv.is_contiguous() and not pv.is_contiguous()
+    sol = torch_solve_box_qp(Qv, pv, ins[2], ins[3], ins[4], ins[5], control)
+    assert sol["iter"] == base["iter"] and rel_err(sol["x"].cpu().numpy(), base["x"].cpu().numpy()) <= 1e-12
+
+
+def test_experiment2_learning_loop_matches_oracle_layer(dev):
+    """Experiment 2 (experiments/experiment_2.py:52-99; BASELINE config 5 scaled down): Linear(5, n) -> p_hat ->
+    SolveBoxQP -> true cost -> backward -> SGD, 6 epochs.  The loop with the CUDA layer must trace the same loss
+    curve and end at the same weights as the same loop with the layer built on the CPU oracle."""
+    from lqp_py_b200 import sharding
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    from tests.test_sharding_cpu import _OracleLayer
+    dtype = torch.float64
+    n, B, nf = 60, 24, 5
+    Q, _, A, b, lb, ub = orc.make_exp1_data(n, B, seed=2, dtype=dtype)
+    gen = torch.Generator().manual_seed(4)
+    feats = torch.randn(B, nf, generator=gen, dtype=dtype)
+    p_true = (feats @ torch.randn(nf, n, generator=gen, dtype=dtype)).unsqueeze(2)
+    control = box_qp_control(eps_abs=1e-8, eps_rel=1e-8)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        oracle_layer = lambda *a: _OracleLayer.apply(*a, dict(control))
+        m_ref, h_ref = sharding.train_learn_p(oracle_layer, Q, p_true, A, b, lb, ub, feats, n_epochs=6, n_mini_batch=8,
+                                              lr=5e-3, seed=1)
+        qp = SolveBoxQP(control=dict(control))
+        on = [t.to(dev) for t in (Q, p_true, A, b, lb, ub, feats)]
+        m_gpu, h_gpu = sharding.train_learn_p(qp, *on, n_epochs=6, n_mini_batch=8, lr=5e-3, seed=1)
+    finally:
+        torch.set_default_dtype(prev)
+    assert rel_err(np.array(h_gpu), np.array(h_ref)) <= 1e-7
+    for a, r in zip(m_gpu.parameters(), m_ref.parameters()):
+        assert rel_err(a.detach().cpu().numpy(), r.detach().numpy()) <= 1e-7

@@ -6,7 +6,7 @@
 // With (z_k, u_k) the state after iteration k, xv_k = [x_k; nu_k] = M^-1 [-p~ + rho (z_{k-1} - u_{k-1}); b~],
 // z_k = clamp(x_k + u_{k-1}), u_k = u_{k-1} + x_k - z_k, the adjoint recursion from the last iteration down is
 //     h    = gz - gu                       (adjoint of z_k once u_k = u_{k-1} + x_k - z_k is undone)
-//     t    = h where z_k is strictly inside the box, else 0;  the clamped entries send h to lb~ / ub~
+//     t    = h where z_k is strictly inside the box, else 0;  the clamped entries send h to lb~ / ub~ (ties: halves)
 //     gx   = gu + t  (+ the incoming adjoint of the returned x~ at the last iteration)
 //     [w; wnu] = M^-1 [gx; 0] = [K11 gx; K21 gx]          <- the same symmetric GEMV the forward iteration streams
 //     gp~ -= w,  gb~ += wnu,  grho += w . (z_{k-1} - u_{k-1}) - w . x_k   (rhs term and the trace of dM = -w xv^T)
@@ -161,13 +161,28 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
 
     // adjoint of (x_k, z_k, u_k) folded into gx: the elementwise head of iteration k (needs gz, gu of k + 1)
     auto head = [&](int k, int e, T gz_e, T gu_e) {
-      const T zk = tape.z[tb + (size_t)k * n + e];
+      // z_k = min(max(v, lb), ub), v = x_k + u_{k-1} (:272-276), with torch's rule for ties: maximum / minimum send
+      // half of the gradient to each argument when they are equal (a pinned variable has lb == ub)
+      const size_t to = tb + (size_t)k * n + e;
+      const T vk = tape.x[to] + (k > 0 ? tape.u[to - n] : T(0));
       const T h = gz_e - gu_e;
-      const bool at_ub = any_ub && zk == ubt[e];              // z = min(max(x + u, lb), ub)  (:272-276)
-      const bool at_lb = !at_ub && any_lb && zk == lbt[e];
-      const T t = (at_ub || at_lb) ? T(0) : h;
-      if (at_ub) g.gub[go + e] += h;
-      if (at_lb) g.glb[go + e] += h;
+      T z1 = vk, c_v = T(1), c_lb = T(0), c_ub = T(0);
+      if (any_lb) {
+        const T l = lbt[e];
+        c_v = vk > l ? T(1) : (vk == l ? T(0.5) : T(0));
+        c_lb = T(1) - c_v;
+        z1 = t_max(vk, l);
+      }
+      if (any_ub) {
+        const T ub_e = ubt[e];
+        const T c_z1 = z1 < ub_e ? T(1) : (z1 == ub_e ? T(0.5) : T(0));
+        c_ub = T(1) - c_z1;
+        c_v *= c_z1;
+        c_lb *= c_z1;
+      }
+      const T t = c_v * h;
+      if (c_ub != T(0)) g.gub[go + e] += c_ub * h;
+      if (c_lb != T(0)) g.glb[go + e] += c_lb * h;
       v[e] = gu_e + t + ((k == k_hi && g.gx) ? g.gx[go + e] : T(0));
       gu[e] = gu_e + t;
     };

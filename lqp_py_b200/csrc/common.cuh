@@ -25,6 +25,14 @@ template <typename T> __device__ __forceinline__ T t_inf();
 template <> __device__ __forceinline__ float t_inf<float>() { return __int_as_float(0x7f800000); }
 template <> __device__ __forceinline__ double t_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 
+// packed FP32 FMA (Blackwell FFMA2: two IEEE fused multiply-adds per issued instruction), d = a * b + c per half
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 // ---------------------------------------------------------------- warp / block reductions
 template <typename T> __device__ __forceinline__ T warp_max(T v) {
 #pragma unroll

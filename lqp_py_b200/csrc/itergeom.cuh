@@ -39,6 +39,46 @@ __device__ __forceinline__ void reduce_cols(T (&acc)[TC], int lane) {
   }
 }
 
+// Register state of a warp's symmetric pass over packed tiles: the TC entries v_J of the current block column and the
+// TC running column sums.  apply() consumes one tile row (8 rotated 16-byte chunks, lane = row): returns the row
+// sum  T[l,:] v_J  and adds  T[l,:] v_I[l]  to the column sums.  (Packed FFMA2 was measured for fp32 and lost:
+// 9.5 vs 9.3 us per ADMM iteration at dz=500 -- the pass waits on the tile stream, not on instruction issue.)
+template <typename T>
+struct SymAcc {
+  static constexpr int TC = Pack<T>::TC, VN = Pack<T>::VN;
+  using V4 = typename Vec<T>::type;
+  T vJ[TC], colacc[TC];
+  __device__ __forceinline__ void load_vJ(const T* src) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const V4 t4 = *reinterpret_cast<const V4*>(src + k * VN);
+      const T* tp = reinterpret_cast<const T*>(&t4);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) vJ[k * VN + e] = tp[e];
+    }
+#pragma unroll
+    for (int c = 0; c < TC; ++c) colacc[c] = T(0);
+  }
+  __device__ __forceinline__ T apply(const V4 (&kv)[8], T vI) {
+    T rs[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const T* kp = reinterpret_cast<const T*>(&kv[k]);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        rs[k & 3] += kp[e] * vJ[k * VN + e];
+        colacc[k * VN + e] += kp[e] * vI;
+      }
+    }
+    return (rs[0] + rs[1]) + (rs[2] + rs[3]);
+  }
+  // column totals: on exit the return value of lane l is the sum over the 32 lanes of column (l mod TC)
+  __device__ __forceinline__ T reduce(int lane) {
+    reduce_cols<T, TC>(colacc, lane);
+    return colacc[0];
+  }
+};
+
 inline int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;

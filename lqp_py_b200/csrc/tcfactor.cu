@@ -616,11 +616,19 @@ __global__ void __launch_bounds__(kPiv8Threads, 1) tc_pivot8_kernel(TcArgs a) {
         const float4 r0 = *reinterpret_cast<const float4*>(&rowbuf[s][4 * tb]);
         const float4 r1 = *reinterpret_cast<const float4*>(&rowbuf[s][64 + 4 * tb]);
         const float uu[4] = {ur[s].x, ur[s].y, ur[s].z, ur[s].w};
-        const float rc[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const float2 rc[4] = {make_float2(r0.x, r0.y), make_float2(r0.z, r0.w), make_float2(r1.x, r1.y),
+                              make_float2(r1.z, r1.w)};
+        // packed FFMA2: two of the thread's 32 entries per issued instruction (the update is issue-bound)
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr)
+        for (int rr = 0; rr < 4; ++rr) {
+          const float2 nu = make_float2(-uu[rr], -uu[rr]);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) acc[rr][q] = fmaf(-uu[rr], rc[q], acc[rr][q]);
+          for (int j = 0; j < 4; ++j) {
+            const float2 t = ffma2(nu, rc[j], make_float2(acc[rr][2 * j], acc[rr][2 * j + 1]));
+            acc[rr][2 * j] = t.x;
+            acc[rr][2 * j + 1] = t.y;
+          }
+        }
       }
       if (tb == tS || tb == tS + 1) {     // columns S of the thread's rows:  A_rS <- U^T
         const bool hi = tb != tS;         // local columns 4..7 of S

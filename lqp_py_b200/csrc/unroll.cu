@@ -96,25 +96,15 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
   auto sym_pass = [&](const T* vec) {
     if (run_len == 0) return;
     int Jc = Jc_first, I = I_first;
-    T vJ[TC], colacc[TC];
-    auto load_vJ = [&]() {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const V4 t4 = *reinterpret_cast<const V4*>(vec + Jc * TC + k * VN);
-        const T* tp = reinterpret_cast<const T*>(&t4);
-#pragma unroll
-        for (int e = 0; e < VN; ++e) vJ[k * VN + e] = tp[e];
-      }
-#pragma unroll
-      for (int c = 0; c < TC; ++c) colacc[c] = T(0);
-    };
+    SymAcc<T> sa;
     auto flush_cols = [&]() {
-      reduce_cols<T, TC>(colacc, lane);
+      const T tot = sa.reduce(lane);
       __syncwarp();
-      if (lane < TC) xp[Jc * TC + lane] += colacc[0];
+      if (lane < TC) xp[Jc * TC + lane] += tot;
       __syncwarp();
     };
-    load_vJ();
+    sa.load_vJ(vec + Jc * TC);
+    auto load_vJ = [&]() { sa.load_vJ(vec + Jc * TC); };
     bool dirty = false;
     for (int r = 0; r < run_len; ++r) {
       mbar_wait(&full_w[c_slot], c_phase);
@@ -123,17 +113,7 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
 #pragma unroll
       for (int k = 0; k < 8; ++k) kv[k] = *reinterpret_cast<const V4*>(tp + ((k + lane) & 7) * VN);
       const T vI = vec[I * kPackRows + lane];
-      T rs[4] = {T(0), T(0), T(0), T(0)};
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const T* kp = reinterpret_cast<const T*>(&kv[k]);
-#pragma unroll
-        for (int e = 0; e < VN; ++e) {
-          rs[k & 3] += kp[e] * vJ[k * VN + e];
-          colacc[k * VN + e] += kp[e] * vI;
-        }
-      }
-      xp[I * kPackRows + lane] += (rs[0] + rs[1]) + (rs[2] + rs[3]);
+      xp[I * kPackRows + lane] += sa.apply(kv, vI);
       __syncwarp();
       if (++c_slot == depth) { c_slot = 0; c_phase ^= 1u; }
       --in_flight;

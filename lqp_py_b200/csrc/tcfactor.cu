@@ -672,297 +672,12 @@ __global__ void __launch_bounds__(kPiv8Threads, 1) tc_pivot8_kernel(TcArgs a) {
   }
 }
 
-// ------------------------------------------------------------------ pivot block inverse on the tensor cores
-// The FP32-pipe sweeps above spend 128^3 FMAs per problem on one SM (8.6 us at the FFMA peak of an SM, 41 us
-// measured).  Here the 16 rank-8 updates of the blocked sweep are tcgen05.mma instructions (M = N = 128, K = 8 --
-// exactly one TF32 instruction per split term) that accumulate  Sigma = sum_steps X^T Y  in TMEM; the threads only
-// produce the two 8 x 128 operands of a step.  With S the 8 pivots of a step, R = A_S: (current rows S),
-// P = inv(A_SS), U = P R, the whole sweep of S -- including the pivot rows and columns -- is ONE rank-8 update
-//     A <- A - X^T Y,   X[s][r] = U[s][r] (r not in S),  delta(s, r) - P[r][s] (r in S);   Y[s][c] = R[s][c] - delta(c, S[s])
-// which leaves rows S = U, columns S = U^T and the S x S block = -P + 2 I.  That block is never read again by the
-// sweep (later pivot rows S' only cross it in columns that belong to rows S'), so the 16 diagonal 8 x 8 blocks are
-// kept exactly, in fp32, in a small side buffer (-P at their own step, the rank-8 updates of the later steps) and
-// the TMEM copy of those 64-entry blocks is ignored.  Current rows are read back as  A0[S,:] - Sigma[S,:]
-// (A0 = the original tile, kept in shared memory): 8 TMEM lanes per step.  As in tc_pivot8_kernel a 17th warp
-// inverts the NEXT 8 x 8 diagonal block (look-ahead) while the MMAs of the step and the next read-back are in
-// flight.  Accuracy as in tc_tile_kernel: 3-term hi/lo split, cross terms in their own accumulator (16 MMAs per
-// accumulator chain, like one 128 x 128 x 128 tile product).
-#ifdef LQPB_PHASE_TIMERS
-__device__ long long g_piv_cycles[8];
-__device__ unsigned long long g_piv_span[64][3];     // per CTA of the last launch: globaltimer at entry / exit, SM id
-__device__ __forceinline__ unsigned long long piv_gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-#endif
-constexpr int kPivMmaThreads = 512 + 32;
-constexpr int kA0Pitch = kTB + 1;                                  // odd pitch: "lane = row" accesses are conflict-free
-constexpr int kPivOpBytes = kTB * 128;                             // one operand part: 128 rows x 128 B (k < 8 used)
-constexpr int kPivMmaSmem = 4 * kPivOpBytes + kTB * kA0Pitch * 4 + 1024;
-
-__global__ void __launch_bounds__(kPivMmaThreads, 1) tc_pivot_mma_kernel(TcArgs a) {
-  extern __shared__ unsigned char pm_smem_raw[];
-  __shared__ __align__(16) float rbuf[8][kTB];       // R: current rows S
-  __shared__ __align__(16) float ubuf[8][kTB];       // U = P R
-  __shared__ __align__(16) float pbuf[2][8][8];      // P of the current / next step
-  __shared__ __align__(16) float dbuf[8][8];         // current value of the next diagonal block
-  __shared__ __align__(16) float dg[kTB / 8][8][8];  // exact diagonal blocks of the result
-  __shared__ __align__(8) uint64_t mma_bar;
-  __shared__ uint32_t tmem_slot;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool pivot_warp = warp == 16;
-#ifdef LQPB_PHASE_TIMERS
-  long long pt0 = clock64();
-  if (tid == 0 && blockIdx.x < 64) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    g_piv_span[blockIdx.x][0] = piv_gtime();
-    g_piv_span[blockIdx.x][2] = smid;
-  }
-#define PIV_T(k) do { if (blockIdx.x == 0 && tid == 0) { long long n__ = clock64(); g_piv_cycles[k] += n__ - pt0; pt0 = n__; } } while (0)
-#else
-#define PIV_T(k)
-#endif
-  const int k = a.k, nb = a.nb;
-  float* tile = a.M + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(k, k);
-  const uint32_t sbase = (smem_u32(pm_smem_raw) + 1023u) & ~1023u;
-  unsigned char* sptr = pm_smem_raw + (sbase - smem_u32(pm_smem_raw));
-  unsigned char* sXh = sptr;
-  unsigned char* sXl = sptr + kPivOpBytes;
-  unsigned char* sYh = sptr + 2 * kPivOpBytes;
-  unsigned char* sYl = sptr + 3 * kPivOpBytes;
-  float* A0s = reinterpret_cast<float*>(sptr + 4 * kPivOpBytes);
-  if (pivot_warp) {
-    tmem_alloc(&tmem_slot, kTcCols);
-    if (lane == 0) {
-      mbar_init(&mma_bar, 1);
-      fence_mbar_init();
-    }
-  } else {
-    // the lower triangle of the tile is the reference copy: mirror it while loading (warp = row, lane = column)
-#pragma unroll 2
-    for (int r = warp; r < kTB; r += 16) {
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = (lane + 32 * j <= r) ? tile[(size_t)r * kTB + lane + 32 * j] : 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = lane + 32 * j;
-        if (c <= r) {
-          A0s[r * kA0Pitch + c] = v[j];
-          A0s[c * kA0Pitch + r] = v[j];
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  PIV_T(6);
-  const uint32_t tmem = tmem_slot;
-  uint32_t phase = 0u;
-  // rows S and P of step 0 come straight from A0
-  if (!pivot_warp) {
-    for (int idx = tid; idx < 8 * kTB; idx += 512) rbuf[idx >> 7][idx & 127] = A0s[(idx >> 7) * kA0Pitch + (idx & 127)];
-  } else {
-    const int i = lane >> 2, j0 = 2 * (lane & 3);
-    float e0 = A0s[i * kA0Pitch + j0], e1 = A0s[i * kA0Pitch + j0 + 1];
-    inv8x8_warp(e0, e1, lane);
-    *reinterpret_cast<float2*>(&pbuf[0][i][j0]) = make_float2(e0, e1);
-  }
-  const uint64_t dXh = umma_desc(smem_u32(sXh)), dXl = umma_desc(smem_u32(sXl));
-  const uint64_t dYh = umma_desc(smem_u32(sYh)), dYl = umma_desc(smem_u32(sYl));
-  __syncthreads();
-  PIV_T(7);
-
-#pragma unroll 1
-  for (int sb = 0; sb < kTB / 8; ++sb) {
-    const int S0 = 8 * sb;
-    const float(*Pc)[8] = pbuf[sb & 1];
-    PIV_T(0);
-    // ---- U. operands of the step.  Thread (r, q): U[2q][r], U[2q+1][r]; pairs of threads assemble the 16-byte
-    //      chunks: the even thread of a pair writes chunk q/2 of X^T row r, the odd one chunk q/2 of Y^T row r
-    if (!pivot_warp) {
-      const int r = tid >> 2, q = tid & 3, ch = q >> 1;
-      const bool inS = r >= S0 && r < S0 + 8;
-      const int j = r - S0;
-      float rv[8];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) rv[t] = rbuf[t][r];
-      float u2[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int s = 2 * q + h;
-        const float4 p0 = *reinterpret_cast<const float4*>(&Pc[s][0]);
-        const float4 p1 = *reinterpret_cast<const float4*>(&Pc[s][4]);
-        float u = p0.x * rv[0];
-        u = fmaf(p0.y, rv[1], u); u = fmaf(p0.z, rv[2], u); u = fmaf(p0.w, rv[3], u);
-        u = fmaf(p1.x, rv[4], u); u = fmaf(p1.y, rv[5], u); u = fmaf(p1.z, rv[6], u); u = fmaf(p1.w, rv[7], u);
-        ubuf[s][r] = u;
-        u2[h] = inS ? ((s == j ? 1.f : 0.f) - Pc[j][s]) : u;         // X[s][r]
-      }
-      // partner exchange inside the pair (q ^ 1): the even thread collects X values 4 ch .. 4 ch + 3
-      const float o0 = __shfl_xor_sync(0xffffffffu, u2[0], 1), o1 = __shfl_xor_sync(0xffffffffu, u2[1], 1);
-      float4 val;
-      if ((q & 1) == 0) {
-        val = make_float4(u2[0], u2[1], o0, o1);
-      } else {
-        const int s4 = 4 * ch;
-        val = make_float4(rv[s4], rv[s4 + 1], rv[s4 + 2], rv[s4 + 3]);   // Y[s][r] = R[s][r] - delta
-        if (inS && (j >> 2) == ch) {
-          const int jj = j & 3;
-          if (jj == 0) val.x -= 1.f; else if (jj == 1) val.y -= 1.f; else if (jj == 2) val.z -= 1.f; else val.w -= 1.f;
-        }
-      }
-      float4 hi, lo;
-      split4(val, hi, lo);
-      const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
-      *reinterpret_cast<float4*>(((q & 1) ? sYh : sXh) + off) = hi;
-      *reinterpret_cast<float4*>(((q & 1) ? sYl : sXl) + off) = lo;
-    }
-    fence_proxy_async();
-    __syncthreads();
-    PIV_T(1);
-    if (tid == 0) {
-      tc_fence_after();
-      umma_tf32(tmem + 128u, dXl, dYh, kIdescTf32, sb ? 1u : 0u);
-      umma_tf32(tmem + 128u, dXh, dYl, kIdescTf32, 1u);
-      umma_tf32(tmem, dXh, dYh, kIdescTf32, sb ? 1u : 0u);
-      umma_commit(&mma_bar);
-    }
-    // ---- while the MMAs run: look-ahead inverse (pivot warp), exact diagonal blocks (work warps)
-    if (pivot_warp) {
-      if (sb + 1 < kTB / 8) {
-        const int i = lane >> 2, j0 = 2 * (lane & 3), c0 = S0 + 8;
-        // sb == 0: the next diagonal block is still the original one; later it was read back in phase R below
-        float e0 = sb ? dbuf[i][j0] : A0s[(c0 + i) * kA0Pitch + c0 + j0];
-        float e1 = sb ? dbuf[i][j0 + 1] : A0s[(c0 + i) * kA0Pitch + c0 + j0 + 1];
-#pragma unroll
-        for (int s = 0; s < 8; ++s) {
-          const float ui = ubuf[s][c0 + i];
-          e0 = fmaf(-ui, rbuf[s][c0 + j0], e0);
-          e1 = fmaf(-ui, rbuf[s][c0 + j0 + 1], e1);
-        }
-        inv8x8_warp(e0, e1, lane);
-        *reinterpret_cast<float2*>(&pbuf[(sb + 1) & 1][i][j0]) = make_float2(e0, e1);
-      }
-    } else {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int e = tid + 512 * h, blk = e >> 6, i = (e >> 3) & 7, jc = e & 7;
-        if (blk < sb) {
-          float d = dg[blk][i][jc];
-#pragma unroll
-          for (int s = 0; s < 8; ++s) d = fmaf(-ubuf[s][8 * blk + i], rbuf[s][8 * blk + jc], d);
-          dg[blk][i][jc] = d;
-        } else if (blk == sb) {
-          dg[blk][i][jc] = -Pc[i][jc];
-        }
-      }
-    }
-    PIV_T(2);
-    if (sb + 1 == kTB / 8) break;
-    __syncthreads();                 // rbuf / ubuf are rewritten below; P' is published
-    // ---- R. rows S' of the current matrix (and, for the step after, its diagonal block S'' x S''): A0 - Sigma
-    mbar_wait(&mma_bar, phase);
-    phase ^= 1u;
-    tc_fence_after();
-    PIV_T(3);
-    {
-      // warps of the lane quarter of S' read its 8 rows (32 columns each); warp 5 (n1 / 32) -- lane quarter AND column
-      // group of the diagonal block S'' x S'' of the step after -- also picks that block out of its 32 x 32 window
-      const int n0 = S0 + 8, n1 = S0 + 16;
-      const bool rows_w = (warp & 3) == (n0 >> 5);
-      const bool diag_w = n1 < kTB && warp == 5 * (n1 >> 5);
-      if (!pivot_warp && (rows_w || diag_w)) {
-        const uint32_t trow = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-        const int c0 = (warp >> 2) * 32;
-        uint32_t vm0[16], vc0[16], vm1[16], vc1[16];
-        tmem_ld16(trow + (uint32_t)c0, vm0);
-        tmem_ld16(trow + 128u + (uint32_t)c0, vc0);
-        tmem_ld16(trow + (uint32_t)c0 + 16u, vm1);
-        tmem_ld16(trow + 128u + (uint32_t)c0 + 16u, vc1);
-        tmem_ld_wait(vm0); tmem_ld_wait(vc0); tmem_ld_wait(vm1); tmem_ld_wait(vc1);
-        if (rows_w && (lane >> 3) == ((n0 >> 3) & 3)) {
-          const int sr = lane & 7;
-          const float* a0 = A0s + (n0 + sr) * kA0Pitch + c0;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            rbuf[sr][c0 + e] = a0[e] - __uint_as_float(vm0[e]) - __uint_as_float(vc0[e]);
-            rbuf[sr][c0 + 16 + e] = a0[16 + e] - __uint_as_float(vm1[e]) - __uint_as_float(vc1[e]);
-          }
-        }
-        if (diag_w && (lane >> 3) == ((n1 >> 3) & 3)) {
-          const int sr = lane & 7;
-          const float* a0 = A0s + (n1 + sr) * kA0Pitch + n1;
-          const int o = n1 & 31;                 // 0, 8, 16 or 24: position of the block inside the window
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const uint32_t m = o == 0 ? vm0[e] : o == 8 ? vm0[8 + e] : o == 16 ? vm1[e] : vm1[8 + e];
-            const uint32_t c = o == 0 ? vc0[e] : o == 8 ? vc0[8 + e] : o == 16 ? vc1[e] : vc1[8 + e];
-            dbuf[sr][e] = a0[e] - __uint_as_float(m) - __uint_as_float(c);
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    __syncthreads();
-    PIV_T(4);
-  }
-  // (the loop's last step left through `break`: all 17 warps reach this point)
-  __syncthreads();
-  // ---- epilogue: A = A0 - Sigma, diagonal blocks from the exact side buffer, staged in the shared copy
-  mbar_wait(&mma_bar, phase);
-  tc_fence_after();
-  if (!pivot_warp) {
-    const int row = 32 * (warp & 3) + lane;
-    const uint32_t trow = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    const int c0 = (warp >> 2) * 32;
-    uint32_t vm0[16], vc0[16], vm1[16], vc1[16];
-    tmem_ld16(trow + (uint32_t)c0, vm0);
-    tmem_ld16(trow + 128u + (uint32_t)c0, vc0);
-    tmem_ld16(trow + (uint32_t)c0 + 16u, vm1);
-    tmem_ld16(trow + 128u + (uint32_t)c0 + 16u, vc1);
-    tmem_ld_wait(vm0); tmem_ld_wait(vc0); tmem_ld_wait(vm1); tmem_ld_wait(vc1);
-    float* a0 = A0s + row * kA0Pitch + c0;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      a0[e] = a0[e] - __uint_as_float(vm0[e]) - __uint_as_float(vc0[e]);
-      a0[16 + e] = a0[16 + e] - __uint_as_float(vm1[e]) - __uint_as_float(vc1[e]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (!pivot_warp) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int e = tid + 512 * h, blk = e >> 6, i = (e >> 3) & 7, jc = e & 7;
-      A0s[(8 * blk + i) * kA0Pitch + 8 * blk + jc] = dg[blk][i][jc];
-    }
-  }
-  __syncthreads();
-  if (!pivot_warp) {
-    float* P = a.Pbuf + ((size_t)b * nb + k) * kTBE;
-#pragma unroll 2
-    for (int r = warp; r < kTB; r += 16) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float v = A0s[r * kA0Pitch + lane + 32 * j];
-        tile[(size_t)r * kTB + lane + 32 * j] = v;
-        P[(size_t)r * kTB + lane + 32 * j] = -v;
-      }
-    }
-  }
-  PIV_T(5);
-  __syncthreads();
-  if (pivot_warp) tmem_dealloc(tmem, kTcCols);
-#ifdef LQPB_PHASE_TIMERS
-  __syncthreads();
-  PIV_T(7);
-  if (tid == 0 && blockIdx.x < 64) g_piv_span[blockIdx.x][1] = piv_gtime();
-#endif
-}
+// (A tensor-core variant of the pivot-block inverse was built and measured in round 1 -- the 16 rank-8 updates as
+// tcgen05.mma M = N = 128, K = 8 instructions accumulating in TMEM, rows read back with tcgen05.ld, exact 8 x 8
+// diagonal blocks in a side buffer, look-ahead inverse on a 17th warp; git history, "LQPB_TC_PIVOT=m".  Its inverse
+// was as accurate as this one (8.9e-7 against fp64), but a sequential chain of 16 steps pays the fixed latencies of
+// the asynchronous path 16 times -- fence.proxy.async + tcgen05.commit / mbarrier + tcgen05.ld round trips, 2.6 us
+// per step measured -- and the launch took 52.7 us against 41 us for the FP32-pipe kernel above.  Rejected.)
 
 // ------------------------------------------------------------------ assemble the KKT matrix (block-lower tiles)
 // Same embedding as the prologue of gj_inverse_kernel: H masked / shifted, the m equality rows right below it,
@@ -1192,10 +907,6 @@ static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemTrail);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tc_pivot_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPivMmaSmem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tc_pivot8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPivMmaSmem);
-    if (e != cudaSuccess) return e;
     attr_done = true;
   }
   TcArgs a0 = base;
@@ -1229,11 +940,8 @@ static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st
       a.Vbuf = a0.Vbuf + (size_t)b0 * nb * kTBE;
       a.Pbuf = a0.Pbuf + (size_t)b0 * nb * kTBE;
       a.k = k;
-      // developer switch (A/B): 1 = rank-1 FP32 sweep, 8 = rank-8 FP32 sweep, m = rank-8 updates on the tensor cores
-      static const char piv_mode = [] { const char* e = getenv("LQPB_TC_PIVOT"); return e && e[0] ? e[0] : '8'; }();
-      if (piv_mode == '1') tc_pivot_kernel<<<bc, kPivThreads, 0, s>>>(a);
-      else if (piv_mode == 'm') tc_pivot_mma_kernel<<<bc, kPivMmaThreads, kPivMmaSmem, s>>>(a);
-      else if (piv_mode == '9') tc_pivot8_kernel<<<bc, kPiv8Threads, kPivMmaSmem, s>>>(a);   // timing probe: carve-out switch
+      static const bool piv_v1 = [] { const char* e = getenv("LQPB_TC_PIVOT"); return e && e[0] == '1'; }();
+      if (piv_v1) tc_pivot_kernel<<<bc, kPivThreads, 0, s>>>(a);      // developer switch: rank-1 sweep (A/B)
       else tc_pivot8_kernel<<<bc, kPiv8Threads, 0, s>>>(a);
       ++*launches;
       const int span = ldl ? nb - 1 - k : nb - 1;
@@ -1337,19 +1045,6 @@ extern "C" void lqpb_debug_tc_cycles(long long* out, int reset) {
   if (reset) {
     long long z[16] = {0};
     cudaMemcpyToSymbol(lqpb::g_tc_cycles, z, sizeof(z));
-  }
-}
-// phases of tc_pivot_mma_kernel (CTA 0): [loop top, MMA wait, row read-back, 8x8 inverse, operands, issue, epilogue]
-extern "C" void lqpb_debug_piv_span(unsigned long long* out) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, lqpb::g_piv_span, sizeof(unsigned long long) * 64 * 3);
-}
-extern "C" void lqpb_debug_piv_cycles(long long* out, int reset) {
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out, lqpb::g_piv_cycles, sizeof(long long) * 8);
-  if (reset) {
-    long long z[8] = {0};
-    cudaMemcpyToSymbol(lqpb::g_piv_cycles, z, sizeof(z));
   }
 }
 #endif

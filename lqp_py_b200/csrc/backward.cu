@@ -129,10 +129,30 @@ bwd_grads_kernel(BwdWs<T> w, const T* __restrict__ dl_dz, const T* __restrict__ 
       }
     }
   } else if (dlb || dub) {
+    using V4 = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    const bool vec_ok = (n % VN) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15) == 0;   // rows start on 16-byte boundaries
     for (int i = r0 + wid; i < r1; i += kGradThreads / 32) {
       const T* Qi = Q + ((size_t)b * n + i) * n;
       T acc = T(0);
-      for (int j = lane; j < n; j += 32) acc += Qi[j] * dvs[j];
+      if (vec_ok) {
+        T a4[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) a4[e] = T(0);
+#pragma unroll 4
+        for (int j = lane * VN; j < n; j += 32 * VN) {
+          const V4 q4 = __ldcs(reinterpret_cast<const V4*>(Qi + j));      // streamed once: do not keep it in L1 / L2
+          const V4 d4 = *reinterpret_cast<const V4*>(dvs + j);
+          const T* qp = reinterpret_cast<const T*>(&q4);
+          const T* dp4 = reinterpret_cast<const T*>(&d4);
+#pragma unroll
+          for (int e = 0; e < VN; ++e) a4[e] += qp[e] * dp4[e];
+        }
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc += a4[e];
+      } else {
+        for (int j = lane; j < n; j += 32) acc += Qi[j] * dvs[j];
+      }
       acc = warp_sum(acc);
       if (lane == 0) {
         const size_t o = (size_t)b * n + i;
@@ -152,11 +172,36 @@ bwd_grads_kernel(BwdWs<T> w, const T* __restrict__ dl_dz, const T* __restrict__ 
   }
   if (dp)
     for (int i = r0 + tid; i < r1; i += kGradThreads) dp[(size_t)b * n + i] = dvs[i];   // :400
-  if (dQ) {
-    for (int i = r0; i < r1; ++i) {                                                     // :403-404
-      const T hdi = T(0.5) * dvs[i], xi = xsh[i];
-      T* row = dQ + ((size_t)b * n + i) * n;
-      for (int j = tid; j < n; j += kGradThreads) row[j] = hdi * xsh[j] + (T(0.5) * dvs[j]) * xi;
+  if (dQ) {                                                                              // :403-404
+    using V4 = typename Vec<T>::type;
+    constexpr int VN = Vec<T>::N;
+    if ((n % VN) == 0 && (reinterpret_cast<uintptr_t>(dQ) & 15) == 0) {
+      // every thread keeps its columns' x_j and dv_j / 2 in registers and writes them for all rows of the chunk:
+      // 16-byte streaming stores, no shared-memory traffic in the row loop
+      for (int j = tid * VN; j < n; j += kGradThreads * VN) {
+        const V4 x4 = *reinterpret_cast<const V4*>(xsh + j);
+        const V4 d4 = *reinterpret_cast<const V4*>(dvs + j);
+        const T* xp = reinterpret_cast<const T*>(&x4);
+        const T* dp4 = reinterpret_cast<const T*>(&d4);
+        T xj[VN], hj[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) { xj[e] = xp[e]; hj[e] = T(0.5) * dp4[e]; }
+#pragma unroll 4
+        for (int i = r0; i < r1; ++i) {
+          const T hdi = T(0.5) * dvs[i], xi = xsh[i];
+          V4 o4;
+          T* op = reinterpret_cast<T*>(&o4);
+#pragma unroll
+          for (int e = 0; e < VN; ++e) op[e] = hdi * xj[e] + hj[e] * xi;
+          __stcs(reinterpret_cast<V4*>(dQ + ((size_t)b * n + i) * n + j), o4);
+        }
+      }
+    } else {
+      for (int i = r0; i < r1; ++i) {
+        const T hdi = T(0.5) * dvs[i], xi = xsh[i];
+        T* row = dQ + ((size_t)b * n + i) * n;
+        for (int j = tid; j < n; j += kGradThreads) row[j] = hdi * xsh[j] + (T(0.5) * dvs[j]) * xi;
+      }
     }
   }
   if (m > 0 && blockIdx.x == 0) {

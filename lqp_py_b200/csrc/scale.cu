@@ -269,7 +269,7 @@ scale_pack_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q) {
     T* tp = Qpb + (size_t)t * P::TILE;
     const int j = Jc * P::TC + c;
     const T dj = j < n ? Ds[j] : T(0);
-#pragma unroll 4
+#pragma unroll 16
     for (int l0 = 0; l0 < kPackRows; l0 += P::R) {
       const int l = l0 + lane / P::TC, i = I * kPackRows + l;
       T v = T(0);

@@ -323,6 +323,42 @@ cudaError_t launch_bound_flags(const FwdWs<T>& w, const T* lb, const T* ub, cuda
   return cudaGetLastError();
 }
 
+// Host-buffer forward (abi.cu): only the block-lower part of every (symmetric) Q crosses PCIe; this fills the strict
+// upper triangle of the device copy from the lower one (32 x 32 tiles transposed through shared memory), so that
+// every later reader -- the Q dv rows of the backward included -- sees the full matrix.  grid = (tile pairs, B).
+template <typename T>
+__global__ void __launch_bounds__(256) mirror_upper_kernel(T* __restrict__ Q, int n) {
+  __shared__ T tile[32][33];
+  const int nt = (n + 31) / 32;
+  // linear index -> tile (ti >= tj) of the lower triangle
+  int ti = (int)((sqrtf(8.f * blockIdx.x + 1.f) - 1.f) * 0.5f);
+  while ((ti + 1) * (ti + 2) / 2 <= (int)blockIdx.x) ++ti;
+  while (ti * (ti + 1) / 2 > (int)blockIdx.x) --ti;
+  const int tj = blockIdx.x - ti * (ti + 1) / 2;
+  if (ti >= nt) return;
+  T* Qb = Q + (size_t)blockIdx.y * n * n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int i = ti * 32 + r, j = tj * 32 + tx;
+    tile[r][tx] = (i < n && j < n) ? Qb[(size_t)i * n + j] : T(0);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = tj * 32 + r, j = ti * 32 + tx;          // target (i, j) = source (j, i)
+    if (i < n && j < n && j > i) Qb[(size_t)i * n + j] = tile[tx][r];
+  }
+}
+
+template <typename T>
+cudaError_t launch_mirror_upper(T* Q, int B, int n, cudaStream_t st) {
+  const int nt = (n + 31) / 32;
+  dim3 grid(nt * (nt + 1) / 2, B);
+  mirror_upper_kernel<T><<<grid, 256, 0, st>>>(Q, n);
+  return cudaGetLastError();
+}
+template cudaError_t launch_mirror_upper<float>(float*, int, int, cudaStream_t);
+template cudaError_t launch_mirror_upper<double>(double*, int, int, cudaStream_t);
+
 template <typename T>
 cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, const T* p, const T* A, const T* b,
                          const T* lb, const T* ub, cudaStream_t st) {

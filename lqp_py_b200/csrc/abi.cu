@@ -298,33 +298,27 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
     }
     CK(cudaEventRecord(g_pipe.vec, cs), "vec event");
     // Q is symmetric (the reference's contract: "Q: A (n_batch,n_x,n_x) SPD tensor", :113; every kernel here reads its
-    // lower triangle only), so only the block-lower part crosses PCIe: row block r (kRowBlock rows) is sent up to the
-    // end of its diagonal block with one strided 3-D copy per chunk -- 56 % of the bytes at n = 500 -- and
-    // mirror_upper_kernel completes the device copy.  LQPB_HOST_FULL_Q=1 sends the full matrices instead.
+    // lower triangle only).  A page-locked host buffer is therefore pulled by a kernel that reads only the lower
+    // triangle over PCIe and writes the full symmetric device copy (pull_lower_kernel); pageable buffers, small
+    // problems and LQPB_HOST_FULL_Q=1 take the plain full copy.
     static const bool full_q = [] { const char* e = getenv("LQPB_HOST_FULL_Q"); return e && e[0] == '1'; }();
-    constexpr int kRowBlock = 64;
-    const bool lower_only = !full_q && n >= 2 * kRowBlock;
+    bool pull = !full_q && n >= 64;
+    if (pull) {
+      cudaPointerAttributes at{};
+      pull = cudaPointerGetAttributes(&at, host->Q) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+      if (pull) pull = at.devicePointer == (void*)host->Q;       // UVA: same address on the device
+      cudaGetLastError();                                         // a pageable pointer is not an error here
+    }
     for (int c = 0; c < C; ++c) {
       const int b0 = chunk_lo(B, C, c), bc = chunk_lo(B, C, c + 1) - b0;
-      if (!lower_only) {
+      if (pull)
+        CK(launch_pull_lower<T>(host->Q + (size_t)b0 * n * n, const_cast<T*>(Q) + (size_t)b0 * n * n, bc, n, cs), "pull Q");
+      else
         CK(cudaMemcpyAsync((void*)(Q + (size_t)b0 * n * n), host->Q + (size_t)b0 * n * n, (size_t)bc * n * n * sizeof(T),
                            cudaMemcpyHostToDevice, cs), "H2D Q");
-      } else {
-        for (int r0 = 0; r0 < n; r0 += kRowBlock) {
-          const int rows = n - r0 < kRowBlock ? n - r0 : kRowBlock;
-          const int cols = r0 + kRowBlock < n ? r0 + kRowBlock : n;
-          cudaMemcpy3DParms pm{};
-          pm.srcPtr = make_cudaPitchedPtr((void*)(host->Q + (size_t)b0 * n * n), (size_t)n * sizeof(T), (size_t)n * sizeof(T), (size_t)n);
-          pm.dstPtr = make_cudaPitchedPtr((void*)(Q + (size_t)b0 * n * n), (size_t)n * sizeof(T), (size_t)n * sizeof(T), (size_t)n);
-          pm.srcPos = make_cudaPos(0, (size_t)r0, 0);
-          pm.dstPos = make_cudaPos(0, (size_t)r0, 0);
-          pm.extent = make_cudaExtent((size_t)cols * sizeof(T), (size_t)rows, (size_t)bc);
-          pm.kind = cudaMemcpyHostToDevice;
-          CK(cudaMemcpy3DAsync(&pm, cs), "H2D Q (block-lower)");
-        }
-      }
       CK(cudaEventRecord(g_pipe.ev[c], cs), "chunk event");
     }
+    if (pull) g_prof.launches += C;
     CK(cudaStreamWaitEvent(st, g_pipe.vec, 0), "vec wait");
     CK(launch_bound_flags<T>(w, lb, ub, st), "bound_flags");
     if (prof) cudaEventRecord(g_prof.ev[1], st);
@@ -333,10 +327,6 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
       const int b0 = chunk_lo(B, C, c), bc = chunk_lo(B, C, c + 1) - b0;
       const FwdWs<T> wc = slice_fwd(w, b0, bc);
       CK(cudaStreamWaitEvent(st, g_pipe.ev[c], 0), "chunk wait");
-      if (lower_only) {
-        CK(launch_mirror_upper<T>(const_cast<T*>(Q) + (size_t)b0 * n * n, bc, n, st), "mirror_upper");
-        g_prof.launches += 1;
-      }
       CK(launch_scale<T>(*cfg, wc, Q + (size_t)b0 * n * n, p + (size_t)b0 * n, off(A, (size_t)b0 * m * n),
                          off(b, (size_t)b0 * m), lb + (size_t)b0 * n, ub + (size_t)b0 * n, st), "scale");
       CK(launch_select_rho<T>(*cfg, wc, st), "select_rho");

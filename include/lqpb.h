@@ -151,11 +151,7 @@ int lqpb_backward_kkt_f64(int B, int n, int m, const double* dl_dz, const double
  * for the backward, like ctx.save_for_backward in :48) and x, z, u, lams, nus, rho_out with the results;
  * hx (may be NULL) receives x.  backward_host uploads h_dl_dz into dl_dz, leaves every requested gradient
  * in its device buffer and copies it to the matching h* pointer (NULL = not wanted on the host); kkt != 0
- * selects the KKT backward (u, rho_dev unused).  Q is symmetric (the reference's contract, :113 "SPD tensor"; the
- * kernels read its lower triangle only): when hQ is page-locked, forward_host pulls only the lower triangle of every
- * hQ over PCIe (a kernel reading host memory directly, 51 % of the bytes at n = 500) and writes the full, exactly
- * symmetric device copy Q; pageable hQ, n < 64 or LQPB_HOST_FULL_Q=1 in the environment copy the full matrices.
- * The batch is cut into `chunks` (0 = choose) slices of
+ * selects the KKT backward (u, rho_dev unused).  The batch is cut into `chunks` (0 = choose) slices of
  * whole problems: a copy stream uploads Q slice c + 1 while slice c is scaled and factorised, and returns
  * the dQ rows of slice c while slice c + 1 is differentiated.  Both calls return after `stream` and the
  * copy stream have drained (the host buffers are valid on return). */

@@ -297,28 +297,15 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
       CK(cudaMemcpyAsync((void*)b, host->b, (size_t)B * m * sizeof(T), cudaMemcpyHostToDevice, cs), "H2D b");
     }
     CK(cudaEventRecord(g_pipe.vec, cs), "vec event");
-    // Q is symmetric (the reference's contract: "Q: A (n_batch,n_x,n_x) SPD tensor", :113; every kernel here reads its
-    // lower triangle only).  A page-locked host buffer is therefore pulled by a kernel that reads only the lower
-    // triangle over PCIe and writes the full symmetric device copy (pull_lower_kernel); pageable buffers, small
-    // problems and LQPB_HOST_FULL_Q=1 take the plain full copy.
-    static const bool full_q = [] { const char* e = getenv("LQPB_HOST_FULL_Q"); return e && e[0] == '1'; }();
-    bool pull = !full_q && n >= 64;
-    if (pull) {
-      cudaPointerAttributes at{};
-      pull = cudaPointerGetAttributes(&at, host->Q) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
-      if (pull) pull = at.devicePointer == (void*)host->Q;       // UVA: same address on the device
-      cudaGetLastError();                                         // a pageable pointer is not an error here
-    }
+    // (Sending only the lower triangle of the symmetric Q was measured twice and lost both times: strided 3-D DMA
+    // copies of the block-lower part -- 56 % of the bytes -- take as long as the full contiguous copy, and a kernel
+    // pulling the triangle from page-locked host memory with 16-byte loads is slower still)
     for (int c = 0; c < C; ++c) {
       const int b0 = chunk_lo(B, C, c), bc = chunk_lo(B, C, c + 1) - b0;
-      if (pull)
-        CK(launch_pull_lower<T>(host->Q + (size_t)b0 * n * n, const_cast<T*>(Q) + (size_t)b0 * n * n, bc, n, cs), "pull Q");
-      else
-        CK(cudaMemcpyAsync((void*)(Q + (size_t)b0 * n * n), host->Q + (size_t)b0 * n * n, (size_t)bc * n * n * sizeof(T),
-                           cudaMemcpyHostToDevice, cs), "H2D Q");
+      CK(cudaMemcpyAsync((void*)(Q + (size_t)b0 * n * n), host->Q + (size_t)b0 * n * n, (size_t)bc * n * n * sizeof(T),
+                         cudaMemcpyHostToDevice, cs), "H2D Q");
       CK(cudaEventRecord(g_pipe.ev[c], cs), "chunk event");
     }
-    if (pull) g_prof.launches += C;
     CK(cudaStreamWaitEvent(st, g_pipe.vec, 0), "vec wait");
     CK(launch_bound_flags<T>(w, lb, ub, st), "bound_flags");
     if (prof) cudaEventRecord(g_prof.ev[1], st);

@@ -191,8 +191,6 @@ cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, 
 
 template <typename T>
 cudaError_t launch_bound_flags(const FwdWs<T>& w, const T* lb, const T* ub, cudaStream_t st);
-template <typename T>
-cudaError_t launch_pull_lower(const T* hQ, T* Q, int B, int n, cudaStream_t st);
 
 // factor.cu -- K2: inverse of the KKT matrix [[H, A^T], [A, a_diag I]] by tiled symmetric Gauss-Jordan
 template <typename T>

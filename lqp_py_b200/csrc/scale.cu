@@ -323,78 +323,6 @@ cudaError_t launch_bound_flags(const FwdWs<T>& w, const T* lb, const T* ub, cuda
   return cudaGetLastError();
 }
 
-// Host-buffer forward (abi.cu): Q is symmetric, so only its lower triangle has to cross PCIe.  When the caller's
-// buffer is page-locked (device-accessible under UVA) this kernel PULLS it: persistent CTAs walk the 32 x 32 tiles of
-// the lower triangle of every problem, read them straight from host memory (128-byte row segments, thousands of
-// requests in flight -- a strided DMA copy of the same bytes runs at half the PCIe rate, measured) and write both
-// the tile and its transpose into the device copy, which every later reader -- the Q dv rows of the backward
-// included -- then sees as a full, exactly symmetric matrix.  51 % of the bytes of a full copy at n = 500.
-template <typename T>
-__global__ void __launch_bounds__(256) pull_lower_kernel(const T* __restrict__ hQ, T* __restrict__ Q, int n, int B) {
-  // work item = 32 rows x W columns (W = 32 16-byte vectors per row: 128 floats / 64 doubles), lower-triangle items only
-  using V4 = typename Vec<T>::type;
-  constexpr int VN = Vec<T>::N, W = 32 * VN;
-  __shared__ T tile[32][W + 1];
-  const int nrb = (n + 31) / 32, ncb = (n + W - 1) / W;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  // items of one problem: for row block rb, column blocks 0 .. (32 rb + 31) / W
-  int per = 0;
-  for (int rb = 0; rb < nrb; ++rb) per += min((32 * rb + 31) / W + 1, ncb);
-  const long long total = (long long)B * per;
-  for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-    const int b = (int)(w / per);
-    int t = (int)(w % per), rb = 0;
-    for (;; ++rb) {
-      const int cnt = min((32 * rb + 31) / W + 1, ncb);
-      if (t < cnt) break;
-      t -= cnt;
-    }
-    const int cb = t;
-    const T* src = hQ + (size_t)b * n * n;
-    T* dst = Q + (size_t)b * n * n;
-    V4 v[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int i = rb * 32 + ty + 8 * q, j = cb * W + tx * VN;
-      V4 z{};
-      v[q] = (i < n && j + VN <= n) ? *reinterpret_cast<const V4*>(src + (size_t)i * n + j) : z;
-      if (i < n && j < n && j + VN > n) {           // ragged row end (n not a multiple of the vector width)
-        T* vp = reinterpret_cast<T*>(&v[q]);
-        for (int e = 0; e < VN; ++e) vp[e] = j + e < n ? src[(size_t)i * n + j + e] : T(0);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const T* vp = reinterpret_cast<const T*>(&v[q]);
-#pragma unroll
-      for (int e = 0; e < VN; ++e) tile[ty + 8 * q][tx * VN + e] = vp[e];
-    }
-    __syncthreads();
-    // lower part: rows of the item as read; entries above the diagonal come from the transposed pass of other items
-    for (int q = 0; q < 4; ++q) {
-      const int r = ty + 8 * q, i = rb * 32 + r;
-      for (int c = tx; c < W; c += 32) {
-        const int j = cb * W + c;
-        if (i < n && j < n && j <= i) dst[(size_t)i * n + j] = tile[r][c];
-      }
-    }
-    // transposed part: dst[j][i] = src[i][j] for j < i; target row j, 32 consecutive columns i per warp access
-    for (int c = ty; c < W; c += 8) {
-      const int j = cb * W + c, i = rb * 32 + tx;
-      if (i < n && j < n && j < i) dst[(size_t)j * n + i] = tile[tx][c];
-    }
-    __syncthreads();
-  }
-}
-
-template <typename T>
-cudaError_t launch_pull_lower(const T* hQ, T* Q, int B, int n, cudaStream_t st) {
-  pull_lower_kernel<T><<<296, 256, 0, st>>>(hQ, Q, n, B);    // 2 small CTAs per SM: the kernel waits on PCIe, not on the SMs
-  return cudaGetLastError();
-}
-template cudaError_t launch_pull_lower<float>(const float*, float*, int, int, cudaStream_t);
-template cudaError_t launch_pull_lower<double>(const double*, double*, int, int, cudaStream_t);
-
 template <typename T>
 cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, const T* p, const T* A, const T* b,
                          const T* lb, const T* ub, cudaStream_t st) {

@@ -53,6 +53,11 @@ class SolveBoxQPLayer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Q, p, A, b, lb, ub, control):
         out_device = p.device
+        # gradient buffers and the backward workspace are taken from the allocator NOW, while the GPU still works on
+        # whatever preceded this call: the backward then starts launching as soon as autograd reaches it
+        ctx.pre = None
+        if p.is_cuda and any(ctx.needs_input_grad[:6]):
+            ctx.pre = _prealloc_backward(Q, p, A, ctx.needs_input_grad[:6])
         sol = _solve_device(Q, p, A, b, lb, ub, control, host_keys=("x",))
         # reference :33-38 -- with no finite bound the caller's dict is switched to rho = 0
         if not (sol["_any_lb"] or sol["_any_ub"]):
@@ -76,10 +81,11 @@ class SolveBoxQPLayer(torch.autograd.Function):
         if dl_dz.device.type == "cpu" and _all_on_host_devices(ctx.input_devices):
             # the caller lives on the host: gradients stream back chunk by chunk while the next chunk is differentiated
             return (*_grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need, kkt, ctx.any_bounds), None)
+        pre, ctx.pre = ctx.pre, None                 # one use: a second backward through a retained graph allocates afresh
         if kkt:
-            grads = _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, ctx.any_bounds)
+            grads = _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, ctx.any_bounds, pre=pre)
         else:
-            grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need)
+            grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need, pre=pre)
         return (*_to_devices(grads, ctx.input_devices), None)
 
 
@@ -532,7 +538,23 @@ class _UnrolledSegment(torch.autograd.Function):
         return (*outs, None, None, None, None)
 
 
-def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need):
+def _prealloc_backward(Q, p, A, need):
+    """Output buffers (only the gradients asked for) and the workspace of one backward call on ``p``'s device."""
+    L = _abi.lib()
+    dev, dt = p.device, p.dtype
+    B, n = Q.shape[0], p.shape[1]
+    m = get_ncon(A, dim=1)
+    nQ, np_, nA, nb, nlb, nub = need
+    with torch.cuda.device(dev):
+        new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+        ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{_abi.suffix(dt)}")(B, n, m)
+        return dict(dQ=new(B, n, n) if nQ else None, dp=new(B, n, 1) if np_ else None,
+                    dA=new(B, m, n) if (nA and m > 0) else None, db=new(B, m, 1) if (nb and m > 0) else None,
+                    dlb=new(B, n, 1) if nlb else None, dub=new(B, n, 1) if nub else None,
+                    ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev), key=(dev, dt, B, n, m, tuple(need)))
+
+
+def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, pre=None):
     """All tensor arguments already on one CUDA device (except dl_dz, which is staged here)."""
     L = _abi.lib()
     dev, dt = x.device, x.dtype
@@ -555,17 +577,11 @@ def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need):
             rho_dev = rho_dev.expand(B).contiguous()
     else:
         rho_scalar = float(rho)
-    nQ, np_, nA, nb, nlb, nub = need
+    if pre is None or pre["key"] != (dev, dt, B, n, m, tuple(need)):
+        pre = _prealloc_backward(Q, x, A, need)
+    dQ, dp, dA, db, dlb, dub, ws = (pre[k] for k in ("dQ", "dp", "dA", "db", "dlb", "dub", "ws"))
+    ws_bytes = ws.numel()
     with torch.cuda.device(dev):
-        new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
-        dQ = new(B, n, n) if nQ else None
-        dp = new(B, n, 1) if np_ else None
-        dA = new(B, m, n) if (nA and m > 0) else None
-        db = new(B, m, 1) if (nb and m > 0) else None
-        dlb = new(B, n, 1) if nlb else None
-        dub = new(B, n, 1) if nub else None
-        ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{sfx}")(B, n, m)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = getattr(L, f"lqpb_backward_{sfx}")(
             B, n, m, _abi.ptr(g), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A),
@@ -575,7 +591,7 @@ def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need):
     return dQ, dp, dA, db, dlb, dub
 
 
-def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds):
+def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds, pre=None):
     """KKT backward on one CUDA device.  ``any_bounds`` = ``(any_lb, any_ub)`` when the caller already knows the
     flags (the layer does, from the forward solve: the call stays asynchronous) or ``None`` to have them
     evaluated on the device (one stream synchronisation)."""
@@ -592,16 +608,13 @@ def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds):
     g = g.contiguous()
     nQ, np_, nA, nb, nlb, nub = need
     flags = (C.c_int32 * 2)()
+    if pre is None or pre["key"] != (dev, dt, B, n, m, tuple(need)):
+        pre = _prealloc_backward(Q, x, A, need)
+    dQ, dp, dA, db, ws = (pre[k] for k in ("dQ", "dp", "dA", "db", "ws"))
+    dlb = pre["dlb"] if (any_bounds is None or any_bounds[0]) else None
+    dub = pre["dub"] if (any_bounds is None or any_bounds[1]) else None
+    ws_bytes = ws.numel()
     with torch.cuda.device(dev):
-        new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
-        dQ = new(B, n, n) if nQ else None
-        dp = new(B, n, 1) if np_ else None
-        dA = new(B, m, n) if (nA and m > 0) else None
-        db = new(B, m, 1) if (nb and m > 0) else None
-        dlb = new(B, n, 1) if (nlb and (any_bounds is None or any_bounds[0])) else None
-        dub = new(B, n, 1) if (nub and (any_bounds is None or any_bounds[1])) else None
-        ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{sfx}")(B, n, m)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = getattr(L, f"lqpb_backward_kkt_{sfx}")(
             B, n, m, _abi.ptr(g), _abi.ptr(x), _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A), _abi.ptr(lb),

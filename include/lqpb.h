@@ -143,6 +143,36 @@ int lqpb_backward_kkt_f64(int B, int n, int m, const double* dl_dz, const double
                           double* dlb, double* dub, int32_t* any_bounds, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* ---- forward solve that also prepares the backward.  The adjoint system of either backward mode depends on the
+ * solution only, not on the upstream gradient: forward_prep queues its mask / KKT diagonal, assembly and block LDL^T
+ * into `bwd_workspace` (lqpb_backward_workspace_bytes_*) right behind the solve and returns as soon as the SOLVE has
+ * finished, so the GPU keeps working while the caller travels from .forward() to .backward() (reference :26-67: the
+ * same Function, same saved tensors).  *prepared = 1 when that was done (tensor-core factorisation path: fp32,
+ * n + m > 128), 0 otherwise (call lqpb_backward_* / lqpb_backward_kkt_* as usual).  backward_finish then runs only the
+ * substitution with dl_dz and the gradient assembly on the prepared workspace; arguments as lqpb_backward_*, kkt != 0
+ * for the KKT mode (u, rho_dev unused).  x, u, lams, nus, Q, A, lb, ub must be the buffers of the forward_prep call,
+ * unchanged, and no other call may have used bwd_workspace in between. */
+int lqpb_forward_prep_f32(const lqpb_config* cfg, int B, int n, int m, const float* Q, const float* p,
+                          const float* A, const float* b, const float* lb, const float* ub, float* x, float* z,
+                          float* u, float* lams, float* nus, float* rho_out, lqpb_info* info, void* workspace,
+                          size_t workspace_bytes, void* bwd_workspace, size_t bwd_workspace_bytes, int kkt,
+                          int32_t* prepared, void* stream);
+int lqpb_forward_prep_f64(const lqpb_config* cfg, int B, int n, int m, const double* Q, const double* p,
+                          const double* A, const double* b, const double* lb, const double* ub, double* x,
+                          double* z, double* u, double* lams, double* nus, double* rho_out, lqpb_info* info,
+                          void* workspace, size_t workspace_bytes, void* bwd_workspace,
+                          size_t bwd_workspace_bytes, int kkt, int32_t* prepared, void* stream);
+int lqpb_backward_finish_f32(int B, int n, int m, int kkt, const float* dl_dz, const float* x, const float* u,
+                             const float* lams, const float* nus, const float* Q, const float* A,
+                             const float* lb, const float* ub, const float* rho_dev, double rho_scalar, float* dQ,
+                             float* dp, float* dA, float* db, float* dlb, float* dub, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int lqpb_backward_finish_f64(int B, int n, int m, int kkt, const double* dl_dz, const double* x, const double* u,
+                             const double* lams, const double* nus, const double* Q, const double* A,
+                             const double* lb, const double* ub, const double* rho_dev, double rho_scalar,
+                             double* dQ, double* dp, double* dA, double* db, double* dlb, double* dub,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- host-buffer forms of the two calls above: what a caller of the reference holds are CPU tensors
  * (experiments/experiment_1.py:58-77 builds Q, p, ... on the host, calls .forward and .backward and reads
  * x and the .grad fields on the host).  h* pointers are HOST memory (page-locked memory keeps the copies

@@ -19,6 +19,7 @@ EXPORTS = (
     "lqpb_forward_f32", "lqpb_forward_f64",
     "lqpb_backward_workspace_bytes_f32", "lqpb_backward_workspace_bytes_f64",
     "lqpb_backward_f32", "lqpb_backward_f64", "lqpb_backward_kkt_f32", "lqpb_backward_kkt_f64",
+    "lqpb_forward_prep_f32", "lqpb_forward_prep_f64", "lqpb_backward_finish_f32", "lqpb_backward_finish_f64",
     "lqpb_forward_host_f32", "lqpb_forward_host_f64", "lqpb_backward_host_f32", "lqpb_backward_host_f64",
     "lqpb_unroll_snapshot_bytes_f32", "lqpb_unroll_snapshot_bytes_f64",
     "lqpb_unroll_record_f32", "lqpb_unroll_record_f64", "lqpb_unroll_forward_f32", "lqpb_unroll_forward_f64",
@@ -96,6 +97,13 @@ def lib():
         f.restype = i32
         f = getattr(L, f"lqpb_backward_kkt_{sfx}")
         f.argtypes = [i32, i32, i32] + [vp] * 8 + [vp] * 6 + [C.POINTER(C.c_int32), vp, sz, vp]
+        f.restype = i32
+        f = getattr(L, f"lqpb_forward_prep_{sfx}")
+        f.argtypes = ([C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 6 + [C.POINTER(Info), vp, sz, vp, sz, i32,
+                      C.POINTER(C.c_int32), vp])
+        f.restype = i32
+        f = getattr(L, f"lqpb_backward_finish_{sfx}")
+        f.argtypes = [i32, i32, i32, i32] + [vp] * 9 + [vp, dbl] + [vp] * 6 + [vp, sz, vp]
         f.restype = i32
         f = getattr(L, f"lqpb_forward_host_{sfx}")
         f.argtypes = ([C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 6 + [vp] * 6 + [vp]

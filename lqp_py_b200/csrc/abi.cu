@@ -32,6 +32,7 @@ struct ProfState {
   int n_fac = 0, n_it = 0;
   bool fwd_valid = false, bwd_valid = false;
   int launches = 0, it_launches = 0, fac_launches = 0;
+  int prep_launches = 0;     // kernels a forward call enqueued for the backward (stage 1)
   cudaEvent_t fac0[kMaxSeg], fac1[kMaxSeg], it0[kMaxSeg], it1[kMaxSeg];
 };
 ProfState g_prof;
@@ -78,6 +79,7 @@ int check_device() {
 
 struct HostCtrl {
   Ctrl* pinned = nullptr;
+  cudaEvent_t seg_done = nullptr;
   ~HostCtrl() {}
 };
 thread_local HostCtrl g_hctrl;
@@ -221,6 +223,19 @@ struct UnrollRec {        // recording run of a forward solve (lqpb_unroll_forwa
   int32_t* wants;         // device, (max_seg - 1, B): do_rho_update flags applied by each adaptive-rho update
 };
 
+// forward call that also enqueues the dl_dz-independent part of the backward (stage 1 of backward_impl)
+template <typename T>
+struct BwdPrep {
+  void* ws;
+  size_t ws_bytes;
+  int kkt;
+};
+template <typename T>
+int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
+                  const T* Q, const T* A, const T* lb, const T* ub, const T* rho_dev, double rho_scalar, T* dQ,
+                  T* dp, T* dA, T* db, T* dlb, T* dub, void* ws, size_t ws_bytes, void* stream, bool kkt = false,
+                  int32_t* any_bounds = nullptr, const HostBwd<T>* host = nullptr, int stage = 0);
+
 template <typename T>
 int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
   GjArgs<T> a{};
@@ -251,7 +266,8 @@ int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
 template <typename T>
 int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A, const T* b,
                  const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, lqpb_info* info, void* ws,
-                 size_t ws_bytes, void* stream, const HostFwd<T>* host = nullptr, const UnrollRec<T>* rec = nullptr) {
+                 size_t ws_bytes, void* stream, const HostFwd<T>* host = nullptr, const UnrollRec<T>* rec = nullptr,
+                 const BwdPrep<T>* prep = nullptr) {
   if (host && (!host->Q || !host->p || !host->lb || !host->ub || (m > 0 && (!host->A || !host->b))))
     return fail(LQPB_E_ARG, "null host pointer argument");
   if (!cfg || !Q || !p || !lb || !ub || !x || !z || !u || !lams || !rho_out || !info || !ws)
@@ -361,7 +377,22 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
     CK(cudaMemcpyAsync(hc, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st), "copy ctrl");
     if (host && host->x)     // wasted (and overwritten later) only in the rare segment that ends in a refactorisation
       CK(cudaMemcpyAsync(host->x, x, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToHost, st), "D2H x");
-    CK(cudaStreamSynchronize(st), "synchronize (segment end)");
+    if (prep) {
+      // the mask, the assembly and the block LDL^T of the adjoint system depend on the solution only, not on dl_dz:
+      // they are queued behind the solve NOW, and the host waits for the solve alone -- the GPU then works through
+      // them while the caller is back in Python on its way to .backward() (wasted only if this segment ends in a
+      // refactorisation, or if no backward follows)
+      if (!g_hctrl.seg_done) CK(cudaEventCreateWithFlags(&g_hctrl.seg_done, cudaEventDisableTiming), "event");
+      CK(cudaEventRecord(g_hctrl.seg_done, st), "record (segment end)");
+      const int fwd_launches = g_prof.launches;
+      rc = backward_impl<T>(B, n, m, nullptr, x, u, lams, nus, Q, A, lb, ub, nullptr, 0.0, nullptr, nullptr, nullptr,
+                            nullptr, nullptr, nullptr, prep->ws, prep->ws_bytes, stream, prep->kkt != 0, nullptr, nullptr, 1);
+      g_prof.launches = fwd_launches;
+      if (rc) return rc;
+      CK(cudaEventSynchronize(g_hctrl.seg_done), "synchronize (segment end)");
+    } else {
+      CK(cudaStreamSynchronize(st), "synchronize (segment end)");
+    }
     if (hc->status == 3) {
       i0 = hc->next_i;
       skip = 1;
@@ -398,10 +429,14 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
 template <typename T>
 int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, const T* lams, const T* nus,
                   const T* Q, const T* A, const T* lb, const T* ub, const T* rho_dev, double rho_scalar, T* dQ,
-                  T* dp, T* dA, T* db, T* dlb, T* dub, void* ws, size_t ws_bytes, void* stream, bool kkt = false,
-                  int32_t* any_bounds = nullptr, const HostBwd<T>* host = nullptr) {
+                  T* dp, T* dA, T* db, T* dlb, T* dub, void* ws, size_t ws_bytes, void* stream, bool kkt,
+                  int32_t* any_bounds, const HostBwd<T>* host, int stage) {
+  // stage 0: the whole backward.  stage 1 ("prepare", enqueued by the forward call): mask / KKT diagonal, assembly and
+  // block LDL^T of the adjoint system -- everything that does not depend on dl_dz.  stage 2 ("finish"): substitution
+  // with dl_dz and the gradients, on a workspace stage 1 left prepared.  Stages exist for the tensor-core path only.
   if (host && !host->dl_dz) return fail(LQPB_E_ARG, "null host pointer argument");
-  if (!dl_dz || !x || (!u && !kkt) || !lams || !Q || !lb || !ub || !ws) return fail(LQPB_E_ARG, "null pointer argument");
+  if ((!dl_dz && stage != 1) || !x || (!u && !kkt) || !lams || !Q || !lb || !ub || !ws)
+    return fail(LQPB_E_ARG, "null pointer argument");
   if (B <= 0 || n <= 0 || m < 0) return fail(LQPB_E_ARG, "bad dimensions");
   if (m > 0 && (!A || !nus)) return fail(LQPB_E_ARG, "A and nus are required when m > 0");
   if (m > kMaxM) return fail(LQPB_E_ARG, "more than 64 equality rows are not supported");
@@ -409,14 +444,17 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   if (rc) return rc;
   BwdWs<T> w = carve_bwd<T>(ws, B, n, m);
   if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
+  if (stage != 0 && (!w.tc || host)) return fail(LQPB_E_ARG, "staged backward needs the tensor-core path and device buffers");
   cudaStream_t st = (cudaStream_t)stream;
   const bool prof = g_prof_on;
   if (prof) prof_init();
-  g_prof.bwd_valid = false;
-  g_prof.launches = 0;
   int bwd_fac_launches = 0;
-  if (prof) cudaEventRecord(g_prof.ev[4], st);
-  if (kkt) CK(cudaMemsetAsync(w.flags, 0, 4 * sizeof(int), st), "memset flags");
+  if (stage != 2) {
+    g_prof.bwd_valid = false;
+    if (stage == 0) g_prof.launches = 0;
+    if (prof) cudaEventRecord(g_prof.ev[4], st);
+    if (kkt) CK(cudaMemsetAsync(w.flags, 0, 4 * sizeof(int), st), "memset flags");
+  }
   // device-buffer call: one chunk = the whole batch.  Host-buffer call: the adjoint chain of chunk c runs on the
   // compute stream while the copy stream returns the dQ rows of chunk c - 1 to the host.
   const int C = (host && w.tc) ? pick_chunks(host->chunks, B) : 1;
@@ -432,8 +470,10 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
     const BwdWs<T> wc = C > 1 ? slice_bwd(w, b0, bc) : w;
     const T *xc = x + o * n, *uc = off(u, o * n), *lamc = lams + o * 2 * n, *nuc = off(nus, o * m);
     const T *Qc = Q + o * n * n, *Ac = off(A, o * m * n), *lbc = lb + o * n, *ubc = ub + o * n, *gc = dl_dz + o * n;
-    if (kkt) CK(launch_bwd_kkt_prep<T>(wc, xc, lamc, lbc, ubc, st), "bwd_kkt_prep");
-    else CK(launch_bwd_mask<T>(wc, xc, uc, lbc, ubc, st), "bwd_mask");
+    if (stage != 2) {
+      if (kkt) CK(launch_bwd_kkt_prep<T>(wc, xc, lamc, lbc, ubc, st), "bwd_kkt_prep");
+      else CK(launch_bwd_mask<T>(wc, xc, uc, lbc, ubc, st), "bwd_mask");
+    }
     {
       GjArgs<T> a{};
       a.n = n; a.m = m; a.np = wc.np;
@@ -450,7 +490,7 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
       if constexpr (std::is_same<T, float>::value) {
         if (wc.tc) {
           int l = 0;
-          CK(launch_tc_ldl_solve(bc, a, wc.Pb, wc.nb, st, &l), "tensor-core LDL solve (backward)");
+          CK(launch_tc_ldl_solve(bc, a, wc.Pb, wc.nb, st, &l, stage), "tensor-core LDL solve (backward)");
           bwd_fac_launches += l;
           done = true;
         }
@@ -460,7 +500,12 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
         bwd_fac_launches += 1;
       }
     }
-    if (prof && c == C - 1) cudaEventRecord(g_prof.ev[5], st);
+    if (stage == 1) {
+      if (prof) cudaEventRecord(g_prof.ev[5], st);
+      g_prof.prep_launches = 1 + bwd_fac_launches;
+      return LQPB_OK;
+    }
+    if (prof && c == C - 1 && stage == 0) cudaEventRecord(g_prof.ev[5], st);
     if (prof && c == C - 1) cudaEventRecord(g_prof.ev[6], st);
     CK(launch_bwd_grads<T>(wc, gc, xc, uc, lamc, nuc, Qc, Ac, off(rho_dev, o), rho_scalar, off(dQ, o * n * n),
                            off(dp, o * n), off(dA, o * m * n), off(db, o * m), off(dlb, o * n), off(dub, o * n), st,
@@ -474,7 +519,7 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
     }
   }
   if (prof) cudaEventRecord(g_prof.ev[7], st);
-  g_prof.launches = 2 * C + bwd_fac_launches;
+  g_prof.launches = (stage == 2 ? 1 + g_prof.prep_launches : 2 * C) + bwd_fac_launches;
   g_prof.bwd_valid = prof;
   if (host) {
     // the small gradients follow the last chunk on the compute stream; then wait for both streams
@@ -643,6 +688,27 @@ int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x,
   return backward_impl<double>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db,
                                dlb, dub, workspace, workspace_bytes, stream);
 }
+
+#define PREP_ENTRY(SFX, T)                                                                                         \
+  int lqpb_forward_prep_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A,     \
+                              const T* b, const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, \
+                              lqpb_info* info, void* workspace, size_t workspace_bytes, void* bwd_workspace,       \
+                              size_t bwd_workspace_bytes, int kkt, int32_t* prepared, void* stream) {              \
+    const bool can = bwd_workspace != nullptr && B > 0 && n > 0 && m >= 0 && tc_factor_enabled<T>(n, m);           \
+    if (prepared) *prepared = can ? 1 : 0;                                                                         \
+    BwdPrep<T> pr{bwd_workspace, bwd_workspace_bytes, kkt};                                                        \
+    return forward_impl<T>(cfg, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, workspace,         \
+                           workspace_bytes, stream, nullptr, nullptr, can ? &pr : nullptr);                        \
+  }                                                                                                                \
+  int lqpb_backward_finish_##SFX(int B, int n, int m, int kkt, const T* dl_dz, const T* x, const T* u,            \
+                                 const T* lams, const T* nus, const T* Q, const T* A, const T* lb, const T* ub,   \
+                                 const T* rho_dev, double rho_scalar, T* dQ, T* dp, T* dA, T* db, T* dlb, T* dub, \
+                                 void* workspace, size_t workspace_bytes, void* stream) {                          \
+    return backward_impl<T>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db,   \
+                            dlb, dub, workspace, workspace_bytes, stream, kkt != 0, nullptr, nullptr, 2);          \
+  }
+PREP_ENTRY(f32, float)
+PREP_ENTRY(f64, double)
 
 #define HOST_ENTRY(SFX, T)                                                                                         \
   int lqpb_forward_host_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* hQ, const T* hp, const T* hA,  \

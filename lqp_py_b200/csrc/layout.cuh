@@ -225,7 +225,8 @@ cudaError_t launch_select_rho(const lqpb_config& cfg, const FwdWs<T>& w, cudaStr
 // scale_pack_kernel); only the shift, the equality rows and the padding are added before the sweep
 cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb, bool prebuilt, cudaStream_t st,
                               int* launches);
-cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches);
+cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches,
+                                int stage = 0);
 cudaError_t launch_tc_dev_inverse(int B, int N, const float* A, float* Ainv, float* work, cudaStream_t st);
 
 // Tape of the unrolled mode: per problem and ADMM iteration k the scaled iterate x~_k, z_k, u_k ((B, n_iter, n),

@@ -982,16 +982,22 @@ cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb
 }
 
 // backward: block LDL^T + solve, outputs as launch_ldl_solve
-cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches) {
-  dim3 ga(nb * (nb + 1) / 2, B);
-  tc_assemble_kernel<<<ga, 256, 0, st>>>(a, a.W, nb);
-  ++*launches;
-  TcArgs t{a.W, a.Wg, a.Vg, Pbuf, nb, 0, 1, 1};
-  cudaError_t e = tc_sweep(B, t, true, st, launches);
-  if (e != cudaSuccess) return e;
-  const size_t smem = ((size_t)2 * nb * kTB + 4 * kTB) * sizeof(float);
-  tc_ldl_solve_kernel<<<B, 512, smem, st>>>(a, a.W, Pbuf, nb);
-  ++*launches;
+// stage 0: everything; 1: assemble + block LDL^T only (independent of the right-hand side); 2: substitution only
+cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches,
+                                int stage) {
+  if (stage != 2) {
+    dim3 ga(nb * (nb + 1) / 2, B);
+    tc_assemble_kernel<<<ga, 256, 0, st>>>(a, a.W, nb);
+    ++*launches;
+    TcArgs t{a.W, a.Wg, a.Vg, Pbuf, nb, 0, 1, 1};
+    cudaError_t e = tc_sweep(B, t, true, st, launches);
+    if (e != cudaSuccess) return e;
+  }
+  if (stage != 1) {
+    const size_t smem = ((size_t)2 * nb * kTB + 4 * kTB) * sizeof(float);
+    tc_ldl_solve_kernel<<<B, 512, smem, st>>>(a, a.W, Pbuf, nb);
+    ++*launches;
+  }
   return cudaGetLastError();
 }
 

@@ -56,9 +56,15 @@ class SolveBoxQPLayer(torch.autograd.Function):
         # gradient buffers and the backward workspace are taken from the allocator NOW, while the GPU still works on
         # whatever preceded this call: the backward then starts launching as soon as autograd reaches it
         ctx.pre = None
+        prep = None
         if p.is_cuda and any(ctx.needs_input_grad[:6]):
             ctx.pre = _prealloc_backward(Q, p, A, ctx.needs_input_grad[:6])
-        sol = _solve_device(Q, p, A, b, lb, ub, control, host_keys=("x",))
+            # ... and the part of the backward that does not depend on dl_dz (mask, assembly, block LDL^T of the adjoint
+            # system) is queued right behind the solve by the same C call (lqpb_forward_prep_*): the GPU works through
+            # it while Python travels from here to .backward()
+            prep = dict(ws=ctx.pre["ws"], kkt=control.get('backward', 'fixed_point') == 'kkt')
+        sol = _solve_device(Q, p, A, b, lb, ub, control, host_keys=("x",), prep=prep)
+        ctx.prepared = bool(sol.get("_prepared", False))
         # reference :33-38 -- with no finite bound the caller's dict is switched to rho = 0
         if not (sol["_any_lb"] or sol["_any_ub"]):
             control['rho'] = 0
@@ -82,10 +88,12 @@ class SolveBoxQPLayer(torch.autograd.Function):
             # the caller lives on the host: gradients stream back chunk by chunk while the next chunk is differentiated
             return (*_grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need, kkt, ctx.any_bounds), None)
         pre, ctx.pre = ctx.pre, None                 # one use: a second backward through a retained graph allocates afresh
+        finish = ctx.prepared and pre is not None    # the workspace holds the factorised adjoint system of THIS solve
+        ctx.prepared = False
         if kkt:
-            grads = _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, ctx.any_bounds, pre=pre)
+            grads = _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, ctx.any_bounds, pre=pre, finish=finish)
         else:
-            grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need, pre=pre)
+            grads = _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need, pre=pre, finish=finish)
         return (*_to_devices(grads, ctx.input_devices), None)
 
 
@@ -258,11 +266,12 @@ def _host_view(t):
     return None if t is None else t.detach().contiguous()
 
 
-def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
+def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None):
     L = _abi.lib()
     out_device = p.device
     host_mode = _all_on_host((Q, p, A, b, lb, ub))
     hx = None
+    prepared = False
     if host_mode:
         # CPU tensors in (the reference's callers): lqpb_forward_host_* uploads Q in chunks on a copy stream and
         # overlaps the per-problem setup with the transfer; the device copies it fills are kept for the backward
@@ -300,6 +309,15 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
                 _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(rho_t), _abi.ptr(hx), C.byref(info), _abi.ptr(ws), ws_bytes,
                 C.c_void_p(stream), 0)
             _abi.check(rc, "lqpb_forward_host")
+        elif prep is not None:
+            flag = C.c_int32(0)
+            rc = getattr(L, f"lqpb_forward_prep_{sfx}")(
+                C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
+                _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u), _abi.ptr(lams),
+                _abi.ptr(nus), _abi.ptr(rho_t), C.byref(info), _abi.ptr(ws), ws_bytes, _abi.ptr(prep["ws"]),
+                prep["ws"].numel(), 1 if prep["kkt"] else 0, C.byref(flag), C.c_void_p(stream))
+            _abi.check(rc, "lqpb_forward_prep")
+            prepared = bool(flag.value)
         else:
             rc = getattr(L, f"lqpb_forward_{sfx}")(
                 C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
@@ -331,7 +349,7 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None):
     return {"x": hx, "z": hz, "u": hu, "lams": hlams, "nus": hnus, "rho": rho_out,
             "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor),
             "_any_lb": bool(info.any_lb), "_any_ub": bool(info.any_ub), "_dev": dv,
-            "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus, "_ws": ws, "_cfg": cfg,
+            "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus, "_ws": ws, "_cfg": cfg, "_prepared": prepared,
             "rho_dev": rho if torch.is_tensor(rho) else None}
 
 
@@ -554,7 +572,7 @@ def _prealloc_backward(Q, p, A, need):
                     ws=torch.empty(ws_bytes, dtype=torch.uint8, device=dev), key=(dev, dt, B, n, m, tuple(need)))
 
 
-def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, pre=None):
+def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, pre=None, finish=False):
     """All tensor arguments already on one CUDA device (except dl_dz, which is staged here)."""
     L = _abi.lib()
     dev, dt = x.device, x.dtype
@@ -583,6 +601,13 @@ def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, pre=None):
     ws_bytes = ws.numel()
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if finish:                          # the forward call left the factorised adjoint system in pre["ws"]
+            rc = getattr(L, f"lqpb_backward_finish_{sfx}")(
+                B, n, m, 0, _abi.ptr(g), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A),
+                _abi.ptr(lb), _abi.ptr(ub), _abi.ptr(rho_dev), rho_scalar, _abi.ptr(dQ), _abi.ptr(dp), _abi.ptr(dA),
+                _abi.ptr(db), _abi.ptr(dlb), _abi.ptr(dub), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
+            _abi.check(rc, "lqpb_backward_finish")
+            return dQ, dp, dA, db, dlb, dub
         rc = getattr(L, f"lqpb_backward_{sfx}")(
             B, n, m, _abi.ptr(g), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A),
             _abi.ptr(lb), _abi.ptr(ub), _abi.ptr(rho_dev), rho_scalar, _abi.ptr(dQ), _abi.ptr(dp), _abi.ptr(dA),
@@ -591,7 +616,7 @@ def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, pre=None):
     return dQ, dp, dA, db, dlb, dub
 
 
-def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds, pre=None):
+def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds, pre=None, finish=False):
     """KKT backward on one CUDA device.  ``any_bounds`` = ``(any_lb, any_ub)`` when the caller already knows the
     flags (the layer does, from the forward solve: the call stays asynchronous) or ``None`` to have them
     evaluated on the device (one stream synchronisation)."""
@@ -616,6 +641,13 @@ def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds, pre=No
     ws_bytes = ws.numel()
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
+        if finish and any_bounds is not None:
+            rc = getattr(L, f"lqpb_backward_finish_{sfx}")(
+                B, n, m, 1, _abi.ptr(g), _abi.ptr(x), None, _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A),
+                _abi.ptr(lb), _abi.ptr(ub), None, 0.0, _abi.ptr(dQ), _abi.ptr(dp), _abi.ptr(dA), _abi.ptr(db),
+                _abi.ptr(dlb), _abi.ptr(dub), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
+            _abi.check(rc, "lqpb_backward_finish")
+            return dQ, dp, dA, db, dlb, dub
         rc = getattr(L, f"lqpb_backward_kkt_{sfx}")(
             B, n, m, _abi.ptr(g), _abi.ptr(x), _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A), _abi.ptr(lb),
             _abi.ptr(ub), _abi.ptr(dQ), _abi.ptr(dp), _abi.ptr(dA), _abi.ptr(db), _abi.ptr(dlb), _abi.ptr(dub),

@@ -184,32 +184,37 @@ int lqpb_backward_finish_f64(int B, int n, int m, int kkt, const double* dl_dz, 
  * selects the KKT backward (u, rho_dev unused).  The batch is cut into `chunks` (0 = choose) slices of
  * whole problems: a copy stream uploads Q slice c + 1 while slice c is scaled and factorised, and returns
  * the dQ rows of slice c while slice c + 1 is differentiated.  Both calls return after `stream` and the
- * copy stream have drained (the host buffers are valid on return). */
+ * copy stream have drained (the host buffers are valid on return).  forward_host can prepare the backward like
+ * lqpb_forward_prep_* (bwd_workspace may be NULL: no preparation; *prepared tells whether it happened), and
+ * backward_host with prepared != 0 then runs only the substitution and the gradient assembly per chunk on that
+ * workspace, so the first dQ rows start their trip to the host without waiting for a factorisation. */
 int lqpb_forward_host_f32(const lqpb_config* cfg, int B, int n, int m, const float* hQ, const float* hp,
                           const float* hA, const float* hb, const float* hlb, const float* hub, float* Q,
                           float* p, float* A, float* b, float* lb, float* ub, float* x, float* z, float* u,
                           float* lams, float* nus, float* rho_out, float* hx, lqpb_info* info,
-                          void* workspace, size_t workspace_bytes, void* stream, int chunks);
+                          void* workspace, size_t workspace_bytes, void* stream, int chunks, void* bwd_workspace,
+                          size_t bwd_workspace_bytes, int bwd_kkt, int32_t* prepared);
 int lqpb_forward_host_f64(const lqpb_config* cfg, int B, int n, int m, const double* hQ, const double* hp,
                           const double* hA, const double* hb, const double* hlb, const double* hub,
                           double* Q, double* p, double* A, double* b, double* lb, double* ub, double* x,
                           double* z, double* u, double* lams, double* nus, double* rho_out, double* hx,
                           lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream,
-                          int chunks);
+                          int chunks, void* bwd_workspace, size_t bwd_workspace_bytes, int bwd_kkt,
+                          int32_t* prepared);
 int lqpb_backward_host_f32(int B, int n, int m, int kkt, const float* h_dl_dz, float* dl_dz, const float* x,
                            const float* u, const float* lams, const float* nus, const float* Q,
                            const float* A, const float* lb, const float* ub, const float* rho_dev,
                            double rho_scalar, float* dQ, float* dp, float* dA, float* db, float* dlb,
                            float* dub, float* hdQ, float* hdp, float* hdA, float* hdb, float* hdlb,
                            float* hdub, int32_t* any_bounds, void* workspace, size_t workspace_bytes,
-                           void* stream, int chunks);
+                           void* stream, int chunks, int prepared);
 int lqpb_backward_host_f64(int B, int n, int m, int kkt, const double* h_dl_dz, double* dl_dz,
                            const double* x, const double* u, const double* lams, const double* nus,
                            const double* Q, const double* A, const double* lb, const double* ub,
                            const double* rho_dev, double rho_scalar, double* dQ, double* dp, double* dA,
                            double* db, double* dlb, double* dub, double* hdQ, double* hdp, double* hdA,
                            double* hdb, double* hdlb, double* hdub, int32_t* any_bounds, void* workspace,
-                           size_t workspace_bytes, void* stream, int chunks);
+                           size_t workspace_bytes, void* stream, int chunks, int prepared);
 
 /* ---- unrolled mode: control['unroll'] = True (solve_box_qp_admm_torch.py:13-15) lets autograd differentiate
  * every ADMM iteration (:259-282), each KKT solve through TorchLULayer (lu_layer.py:18-58: dx = M^-1 (-g),

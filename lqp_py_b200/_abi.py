@@ -107,11 +107,11 @@ def lib():
         f.restype = i32
         f = getattr(L, f"lqpb_forward_host_{sfx}")
         f.argtypes = ([C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 6 + [vp] * 6 + [vp]
-                      + [C.POINTER(Info), vp, sz, vp, i32])
+                      + [C.POINTER(Info), vp, sz, vp, i32, vp, sz, i32, C.POINTER(C.c_int32)])
         f.restype = i32
         f = getattr(L, f"lqpb_backward_host_{sfx}")
         f.argtypes = ([i32, i32, i32, i32] + [vp] * 2 + [vp] * 8 + [vp, dbl] + [vp] * 6 + [vp] * 6
-                      + [C.POINTER(C.c_int32), vp, sz, vp, i32])
+                      + [C.POINTER(C.c_int32), vp, sz, vp, i32, i32])
         f.restype = i32
         f = getattr(L, f"lqpb_unroll_record_{sfx}")
         f.argtypes, f.restype = [C.POINTER(Config), i32, i32, i32, i32, vp, sz] + [vp] * 4 + [vp], i32

@@ -444,7 +444,8 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   if (rc) return rc;
   BwdWs<T> w = carve_bwd<T>(ws, B, n, m);
   if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
-  if (stage != 0 && (!w.tc || host)) return fail(LQPB_E_ARG, "staged backward needs the tensor-core path and device buffers");
+  if (stage != 0 && (!w.tc || (host && stage == 1)))
+    return fail(LQPB_E_ARG, "staged backward needs the tensor-core path (and device buffers for the prepare stage)");
   cudaStream_t st = (cudaStream_t)stream;
   const bool prof = g_prof_on;
   if (prof) prof_init();
@@ -714,19 +715,24 @@ PREP_ENTRY(f64, double)
   int lqpb_forward_host_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* hQ, const T* hp, const T* hA,  \
                               const T* hb, const T* hlb, const T* hub, T* Q, T* p, T* A, T* b, T* lb, T* ub, T* x, \
                               T* z, T* u, T* lams, T* nus, T* rho_out, T* hx, lqpb_info* info, void* workspace,    \
-                              size_t workspace_bytes, void* stream, int chunks) {                                  \
+                              size_t workspace_bytes, void* stream, int chunks, void* bwd_workspace,               \
+                              size_t bwd_workspace_bytes, int bwd_kkt, int32_t* prepared) {                        \
     HostFwd<T> h{hQ, hp, hA, hb, hlb, hub, hx, chunks};                                                            \
+    const bool can = bwd_workspace != nullptr && B > 0 && n > 0 && m >= 0 && tc_factor_enabled<T>(n, m);           \
+    if (prepared) *prepared = can ? 1 : 0;                                                                         \
+    BwdPrep<T> pr{bwd_workspace, bwd_workspace_bytes, bwd_kkt};                                                    \
     return forward_impl<T>(cfg, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, workspace,         \
-                           workspace_bytes, stream, &h);                                                           \
+                           workspace_bytes, stream, &h, nullptr, can ? &pr : nullptr);                             \
   }                                                                                                                \
   int lqpb_backward_host_##SFX(int B, int n, int m, int kkt, const T* h_dl_dz, T* dl_dz, const T* x, const T* u,  \
                                const T* lams, const T* nus, const T* Q, const T* A, const T* lb, const T* ub,     \
                                const T* rho_dev, double rho_scalar, T* dQ, T* dp, T* dA, T* db, T* dlb, T* dub,   \
                                T* hdQ, T* hdp, T* hdA, T* hdb, T* hdlb, T* hdub, int32_t* any_bounds,             \
-                               void* workspace, size_t workspace_bytes, void* stream, int chunks) {               \
+                               void* workspace, size_t workspace_bytes, void* stream, int chunks, int prepared) { \
     HostBwd<T> h{h_dl_dz, hdQ, hdp, hdA, hdb, hdlb, hdub, chunks};                                                 \
     return backward_impl<T>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db,   \
-                            dlb, dub, workspace, workspace_bytes, stream, kkt != 0, any_bounds, &h);               \
+                            dlb, dub, workspace, workspace_bytes, stream, kkt != 0, any_bounds, &h,                \
+                            prepared ? 2 : 0);                                                                     \
   }
 HOST_ENTRY(f32, float)
 HOST_ENTRY(f64, double)

@@ -57,6 +57,13 @@ class SolveBoxQPLayer(torch.autograd.Function):
         # whatever preceded this call: the backward then starts launching as soon as autograd reaches it
         ctx.pre = None
         prep = None
+        if not p.is_cuda and any(ctx.needs_input_grad[:6]) and _all_on_host((Q, p, A, b, lb, ub)) and torch.cuda.is_available():
+            # host callers: only the workspace is needed here (their gradient buffers are pinned host memory)
+            L = _abi.lib()
+            dev = _cuda_device(p)
+            nb_ws = getattr(L, f"lqpb_backward_workspace_bytes_{_abi.suffix(p.dtype)}")(Q.shape[0], p.shape[1], get_ncon(A, dim=1))
+            ctx.pre = dict(ws=torch.empty(nb_ws, dtype=torch.uint8, device=dev), key=None)
+            prep = dict(ws=ctx.pre["ws"], kkt=control.get('backward', 'fixed_point') == 'kkt')
         if p.is_cuda and any(ctx.needs_input_grad[:6]):
             ctx.pre = _prealloc_backward(Q, p, A, ctx.needs_input_grad[:6])
             # ... and the part of the backward that does not depend on dl_dz (mask, assembly, block LDL^T of the adjoint
@@ -86,7 +93,10 @@ class SolveBoxQPLayer(torch.autograd.Function):
         kkt = ctx.backward_method == 'kkt'       # reference :63-64
         if dl_dz.device.type == "cpu" and _all_on_host_devices(ctx.input_devices):
             # the caller lives on the host: gradients stream back chunk by chunk while the next chunk is differentiated
-            return (*_grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need, kkt, ctx.any_bounds), None)
+            pre, ctx.pre = ctx.pre, None
+            ws = pre["ws"] if (ctx.prepared and pre is not None) else None
+            ctx.prepared = False
+            return (*_grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, ctx.rho, need, kkt, ctx.any_bounds, prepared_ws=ws), None)
         pre, ctx.pre = ctx.pre, None                 # one use: a second backward through a retained graph allocates afresh
         finish = ctx.prepared and pre is not None    # the workspace holds the factorised adjoint system of THIS solve
         ctx.prepared = False
@@ -300,6 +310,7 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         info = _abi.Info()
         stream = torch.cuda.current_stream(dev).cuda_stream
+        flag = C.c_int32(0)
         if host_mode:
             hx = torch.empty((B, n, 1), dtype=dt, pin_memory=True)
             rc = getattr(L, f"lqpb_forward_host_{sfx}")(
@@ -307,10 +318,11 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None):
                 _abi.ptr(hv["lb"]), _abi.ptr(hv["ub"]), _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]),
                 _abi.ptr(dv["b"]), _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u),
                 _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(rho_t), _abi.ptr(hx), C.byref(info), _abi.ptr(ws), ws_bytes,
-                C.c_void_p(stream), 0)
+                C.c_void_p(stream), 0, _abi.ptr(prep["ws"]) if prep else None, prep["ws"].numel() if prep else 0,
+                1 if (prep and prep["kkt"]) else 0, C.byref(flag))
             _abi.check(rc, "lqpb_forward_host")
+            prepared = bool(flag.value)
         elif prep is not None:
-            flag = C.c_int32(0)
             rc = getattr(L, f"lqpb_forward_prep_{sfx}")(
                 C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
                 _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u), _abi.ptr(lams),
@@ -661,7 +673,7 @@ def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds, pre=No
     return dQ, dp, dA, db, dlb, dub
 
 
-def _grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, kkt, any_bounds):
+def _grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, kkt, any_bounds, prepared_ws=None):
     """Backward for host callers: saved tensors are the device copies of the forward, ``dl_dz`` is a CPU tensor and
     the gradients are returned as (pinned) CPU tensors through ``lqpb_backward_host_*``.  ``any_bounds`` is the
     (any_lb, any_ub) pair of the forward solve (KKT mode: dlb / dub are None without such bounds, :572-579)."""
@@ -695,12 +707,12 @@ def _grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, kkt, any_bounds)
         hbuf = [None if s is None else torch.empty(s, dtype=dt, pin_memory=True) for s in shapes]
         g_dev = torch.empty((B, n, 1), dtype=dt, device=dev)
         ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{sfx}")(B, n, m)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = prepared_ws if prepared_ws is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = getattr(L, f"lqpb_backward_host_{sfx}")(
             B, n, m, 1 if kkt else 0, _abi.ptr(g), _abi.ptr(g_dev), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams),
             _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A), _abi.ptr(lb), _abi.ptr(ub), _abi.ptr(rho_dev), rho_scalar,
             *[_abi.ptr(t) for t in dbuf], *[_abi.ptr(t) for t in hbuf], None, _abi.ptr(ws), ws_bytes,
-            C.c_void_p(stream), 0)
+            C.c_void_p(stream), 0, 1 if prepared_ws is not None else 0)
         _abi.check(rc, "lqpb_backward_host")
     return tuple(hbuf)

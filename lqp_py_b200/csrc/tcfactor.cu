@@ -817,22 +817,41 @@ __global__ void __launch_bounds__(512) tc_ldl_solve_kernel(GjArgs<float> a, cons
   __syncthreads();
   for (int k = 0; k + 1 < nb; ++k) {
     const float4 yk = *reinterpret_cast<const float4*>(y + k * kTB + 4 * lane);
-    for (int rr = warp; rr < (nb - 1 - k) * kTB; rr += NW) {
-      const int i = k + 1 + rr / kTB, r = rr % kTB;
-      const float4 l4 = *reinterpret_cast<const float4*>(Mb + bl_tile(i, k) + (size_t)r * kTB + 4 * lane);
-      float acc = l4.x * yk.x + l4.y * yk.y + l4.z * yk.z + l4.w * yk.w;
-      acc = warp_sum(acc);
-      if (lane == 0) y[i * kTB + r] -= acc;
+    // a warp takes 8 consecutive rows per turn (kTB is a multiple of 8, so they share the tile): 8 row loads in flight
+    for (int r8 = 8 * warp; r8 < (nb - 1 - k) * kTB; r8 += 8 * NW) {
+      const int i = k + 1 + r8 / kTB, r = r8 % kTB;
+      const float* Lr = Mb + bl_tile(i, k) + (size_t)r * kTB + 4 * lane;
+      float4 l4[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) l4[q] = *reinterpret_cast<const float4*>(Lr + (size_t)q * kTB);
+      float acc[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = l4[q].x * yk.x + l4[q].y * yk.y + l4[q].z * yk.z + l4[q].w * yk.w;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = warp_sum(acc[q]);
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) y[i * kTB + r + q] -= acc[q];
+      }
     }
     __syncthreads();
   }
-  for (int rr = warp; rr < np; rr += NW) {
-    const int k = rr / kTB, r = rr % kTB;
+  for (int r8 = 8 * warp; r8 < np; r8 += 8 * NW) {
+    const int k = r8 / kTB, r = r8 % kTB;
     const float4 yk = *reinterpret_cast<const float4*>(y + k * kTB + 4 * lane);
-    const float4 p4 = *reinterpret_cast<const float4*>(Pb + (size_t)k * kTBE + (size_t)r * kTB + 4 * lane);
-    float acc = p4.x * yk.x + p4.y * yk.y + p4.z * yk.z + p4.w * yk.w;
-    acc = warp_sum(acc);
-    if (lane == 0) z[rr] = acc;
+    const float* Pr = Pb + (size_t)k * kTBE + (size_t)r * kTB + 4 * lane;
+    float4 p4[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) p4[q] = *reinterpret_cast<const float4*>(Pr + (size_t)q * kTB);
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = p4[q].x * yk.x + p4[q].y * yk.y + p4[q].z * yk.z + p4[q].w * yk.w;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) z[r8 + q] = acc[q];
+    }
   }
   __syncthreads();
   const int c = tid & 127, chunk = tid >> 7;        // 4 row chunks of 32
@@ -840,7 +859,7 @@ __global__ void __launch_bounds__(512) tc_ldl_solve_kernel(GjArgs<float> a, cons
     float acc = 0.f;
     for (int i = k + 1; i < nb; ++i) {
       const float* L = Mb + bl_tile(i, k);
-#pragma unroll 8
+#pragma unroll 16
       for (int r = chunk * 32; r < chunk * 32 + 32; ++r) acc += L[(size_t)r * kTB + c] * z[i * kTB + r];
     }
     red[chunk * kTB + c] = acc;

@@ -697,6 +697,36 @@ __global__ void __launch_bounds__(256) tc_assemble_kernel(GjArgs<float> a, float
   const float shift = (a.diag_shift ? a.diag_shift[b] : 0.f) + a.diag_const;
   const float* dvecb = a.diag_vec ? a.diag_vec + (size_t)b * a.ldm : nullptr;
   float* dst = Mout + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(I, J);
+  // fast path for tiles that lie entirely inside the H block of a dense row-major source (the backward's Q): 16-byte
+  // loads, four of them in flight per thread; rows / columns that cross n, the equality rows and the padding take
+  // the element-wise path below.  Entries above the diagonal of a diagonal tile are written too (never read).
+  if (!packed_src && (I + 1) * kTB <= n && (a.lds & 3) == 0 && (reinterpret_cast<uintptr_t>(srcb) & 15) == 0) {
+#pragma unroll 4
+    for (int e4 = tid; e4 < kTBE / 4; e4 += 256) {
+      const int r = e4 >> 5, c = (e4 & 31) << 2;
+      const int i = I * kTB + r, j = J * kTB + c;
+      float4 v = *reinterpret_cast<const float4*>(srcb + (size_t)i * a.lds + j);
+      if (maskb) {
+        const float fi = maskb[i];
+        const float4 fj = *reinterpret_cast<const float4*>(maskb + j);
+        v.x = (fi != 0.f && fj.x != 0.f) ? v.x : 0.f;
+        v.y = (fi != 0.f && fj.y != 0.f) ? v.y : 0.f;
+        v.z = (fi != 0.f && fj.z != 0.f) ? v.z : 0.f;
+        v.w = (fi != 0.f && fj.w != 0.f) ? v.w : 0.f;
+      }
+      if (I == J && i >= j && i < j + 4) {       // the diagonal entry of row i is one of these four
+        const bool keep = !maskb || maskb[i] != 0.f;
+        const float add = shift + (dvecb ? dvecb[i] : 0.f);
+        const int d = i - j;
+        if (d == 0) v.x = keep ? v.x + add : 1.f;
+        else if (d == 1) v.y = keep ? v.y + add : 1.f;
+        else if (d == 2) v.z = keep ? v.z + add : 1.f;
+        else v.w = keep ? v.w + add : 1.f;
+      }
+      *reinterpret_cast<float4*>(dst + (size_t)r * kTB + c) = v;
+    }
+    return;
+  }
   for (int e = tid; e < kTBE; e += 256) {
     const int r = e >> 7, c = e & 127;
     const int i = I * kTB + r, j = J * kTB + c;

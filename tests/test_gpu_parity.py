@@ -570,3 +570,35 @@ def test_experiment2_learning_loop_matches_oracle_layer(dev):
     assert rel_err(np.array(h_gpu), np.array(h_ref)) <= 1e-7
     for a, r in zip(m_gpu.parameters(), m_ref.parameters()):
         assert rel_err(a.detach().cpu().numpy(), r.detach().numpy()) <= 1e-7
+
+
+@pytest.mark.parametrize("backward", ["fixed_point", "kkt"])
+def test_prepared_backward_equals_plain_backward(backward, dev):
+    """The forward call queues the dl_dz-independent part of the backward (lqpb_forward_prep_*), .backward() then only
+    substitutes and assembles (lqpb_backward_finish_*).  A second backward through the retained graph takes the
+    plain, unprepared path: both must give bit-identical gradients.  Two graphs alive at once keep separate
+    workspaces; a forward whose backward never runs leaves nothing behind."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    Q, p, A, b, lb, ub = orc.make_exp1_data(200, 24, seed=4, dtype=torch.float32)
+    QP = SolveBoxQP(control=box_qp_control(eps_abs=1e-5, eps_rel=1e-5, backward=backward))
+    g1 = torch.randn(p.shape, generator=torch.Generator().manual_seed(1)).to(dev)
+    g2 = torch.randn(p.shape, generator=torch.Generator().manual_seed(2)).to(dev)
+    ins_a = [t.to(dev).requires_grad_(True) for t in (Q, p, A, b, lb, ub)]
+    ins_b = [t.to(dev).requires_grad_(True) for t in (Q, 2 * p, A, b, lb, ub)]
+    xa = QP.forward(*ins_a)
+    xb = QP.forward(*ins_b)                      # second graph before the first backward
+    QP.forward(*[t.to(dev).requires_grad_(True) for t in (Q, 3 * p, A, b, lb, ub)])   # never differentiated
+    xa.backward(g1, retain_graph=True)           # prepared path
+    first = [t.grad.clone() for t in ins_a]
+    for t in ins_a:
+        t.grad = None
+    xa.backward(g1)                              # plain path on the same graph
+    for name, u, v in zip(("dQ", "dp", "dA", "db", "dlb", "dub"), first, [t.grad for t in ins_a]):
+        assert torch.equal(u, v), name
+    xb.backward(g2)
+    ins_c = [t.to(dev).requires_grad_(True) for t in (Q, 2 * p, A, b, lb, ub)]
+    xc = QP.forward(*ins_c)
+    xc.backward(g2)
+    for u, v in zip(ins_b, ins_c):
+        assert torch.equal(u.grad, v.grad)

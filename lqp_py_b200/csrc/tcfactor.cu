@@ -785,19 +785,20 @@ __global__ void __launch_bounds__(256) tc_fixup_kernel(GjArgs<float> a, float* _
 __global__ void __launch_bounds__(512) tc_extract_kernel(GjArgs<float> a, const float* __restrict__ Min, int nb) {
   using P = Pack<float>;
   constexpr int NW = 512 / 32;
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // grid = (tile chunks, B): one packed tile per warp, 16 per CTA; the CTA of chunk 0 also writes K21, K22 and c
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m;
   const float* Mb = Min + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE;
   float* dstb = a.dst + (size_t)b * P::elems(n);
   const int ntv = P::nt(n), ntl = P::ntiles(n);
   const int c = lane % P::TC, kc = c / P::VN, ec = c % P::VN;
-  for (int t = warp; t < ntl; t += NW) {
+  for (int t = blockIdx.x * NW + warp; t < ntl; t += gridDim.x * NW) {
     int Jc = 0, rem = t;
     while (rem >= ntv - Jc / P::R) { rem -= ntv - Jc / P::R; ++Jc; }
     const int I = Jc / P::R + rem;
     float* tp = dstb + (size_t)t * P::TILE;
     const int j = Jc * P::TC + c;
-#pragma unroll 4
+#pragma unroll 16
     for (int l0 = 0; l0 < kPackRows; l0 += P::R) {
       const int l = l0 + lane / P::TC, i = I * kPackRows + l;
       float v = 0.f;
@@ -808,6 +809,7 @@ __global__ void __launch_bounds__(512) tc_extract_kernel(GjArgs<float> a, const 
       tp[l * P::TC + ((kc + l) & 7) * P::VN + ec] = v;
     }
   }
+  if (blockIdx.x != 0) return;
   float* g21 = (m > 0) ? a.G21 + (size_t)b * m * a.ldd : nullptr;
   float* k22 = (m > 0) ? a.K22 + (size_t)b * m * m : nullptr;
   const int ldd = a.ldd;
@@ -1025,7 +1027,11 @@ cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb
   TcArgs t{a.W, a.Wg, a.Vg, Pbuf, nb, 0, 0, 1};
   cudaError_t e = tc_sweep(B, t, false, st, launches);
   if (e != cudaSuccess) return e;
-  tc_extract_kernel<<<B, 512, 0, st>>>(a, a.W, nb);
+  {
+    const int ntl = Pack<float>::ntiles(a.n);
+    dim3 ge((ntl + 15) / 16, B);
+    tc_extract_kernel<<<ge, 512, 0, st>>>(a, a.W, nb);
+  }
   ++*launches;
   return cudaGetLastError();
 }

@@ -226,7 +226,8 @@ def test_cpu_tensors_drop_in(dev):
 
 
 @pytest.mark.parametrize("n,B,dtype,backward", [(40, 70, torch.float64, "fixed_point"), (200, 64, torch.float32, "fixed_point"),
-                                                (40, 70, torch.float64, "kkt"), (500, 128, torch.float32, "fixed_point")])
+                                                (40, 70, torch.float64, "kkt"), (500, 128, torch.float32, "fixed_point"),
+                                                (200, 64, torch.float32, "kkt")])
 def test_host_buffer_pipeline_equals_device_path(n, B, dtype, backward, dev):
     """CPU tensors go through lqpb_forward_host_* / lqpb_backward_host_* (Q uploaded and dQ returned in chunks that
     overlap the per-problem setup / adjoint chains).  Problems are independent and every kernel is deterministic

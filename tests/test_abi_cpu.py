@@ -40,6 +40,22 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.lqpb_abi_version() == 1
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/lqpb.h is the C ABI: it must compile as C (no C++ in the boundary) and the struct sizes the ctypes
+    binding assumes must be the compiler's."""
+    import subprocess
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "lqpb.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%zu %zu %zu\\n", sizeof(lqpb_config), sizeof(lqpb_info), sizeof(lqpb_profile));'
+                   ' return 0; }\n')
+    exe = tmp_path / "abi_check"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    from lqp_py_b200 import _abi
+    assert sizes == [ctypes.sizeof(_abi.Config), ctypes.sizeof(_abi.Info), ctypes.sizeof(_abi.Profile)]
+
+
 def test_struct_layouts_match_header(lib):
     from lqp_py_b200 import _abi
     assert ctypes.sizeof(_abi.Config) == 10 * 4 + 9 * 8

@@ -276,6 +276,18 @@ int lqpb_unroll_backward_f64(int B, int n, int m, int n_iter, int k_lo, int k_hi
                              double* gQ, double* gp, double* gA, double* gb, double* glb, double* gub, double* grho,
                              double* gz_in, double* gu_in, void* stream);
 
+/* unroll_scale_grad: adjoint of the two O(n^2) steps that lead from the caller's Q to the scaled problem,
+ * Q~ = D Q D (:176) and rho = clamp(||Q~||_F / sqrt(n)) (:200-203), in one pass.  In: G (B,n,n) = adjoint of Q~ (gQ of
+ * unroll_backward), Q (B,n,n), D (B,n) or NULL when the solve ran without scaling, coef (B) = grho / (n rho) (zero where
+ * rho was clamped; NULL when rho was given by the caller).  Out: G overwritten with the adjoint of Q for fixed D,
+ * gD (B,n) the adjoint of D through Q~ and rho (NULL iff D is NULL).  scratch: *_scratch_elems(B, n) elements. */
+size_t lqpb_unroll_scale_grad_scratch_elems_f32(int B, int n);
+size_t lqpb_unroll_scale_grad_scratch_elems_f64(int B, int n);
+int lqpb_unroll_scale_grad_f32(int B, int n, float* G, const float* Q, const float* D, const float* coef, float* gD,
+                               float* scratch, void* stream);
+int lqpb_unroll_scale_grad_f64(int B, int n, double* G, const double* Q, const double* D, const double* coef,
+                               double* gD, double* scratch, void* stream);
+
 /* ---- lu_layer: replaces TorchLU / TorchLULayer (lu_layer.py:5-58) -------------------------
  * lu_factor: partial-pivoting LU of B general N x N matrices (torch.linalg.lu_factor, :10,:30);
  *            LU (B,N,N) packed L\U, piv (B,N) 1-based row swaps like LAPACK getrf.

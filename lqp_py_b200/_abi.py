@@ -24,6 +24,8 @@ EXPORTS = (
     "lqpb_unroll_snapshot_bytes_f32", "lqpb_unroll_snapshot_bytes_f64",
     "lqpb_unroll_record_f32", "lqpb_unroll_record_f64", "lqpb_unroll_forward_f32", "lqpb_unroll_forward_f64",
     "lqpb_unroll_backward_f32", "lqpb_unroll_backward_f64",
+    "lqpb_unroll_scale_grad_scratch_elems_f32", "lqpb_unroll_scale_grad_scratch_elems_f64",
+    "lqpb_unroll_scale_grad_f32", "lqpb_unroll_scale_grad_f64",
     "lqpb_lu_factor_f32", "lqpb_lu_factor_f64", "lqpb_lu_solve_f32", "lqpb_lu_solve_f64",
     "lqpb_outer_f32", "lqpb_outer_f64",
     "lqpb_dev_tc_inverse_work_bytes", "lqpb_dev_tc_inverse_f32",
@@ -124,6 +126,10 @@ def lib():
         f = getattr(L, f"lqpb_unroll_backward_{sfx}")
         f.argtypes = [i32] * 6 + [vp, sz, vp] + [vp] * 4 + [vp] * 4 + [vp] * 2 + [vp] * 7 + [vp] * 2 + [vp]
         f.restype = i32
+        f = getattr(L, f"lqpb_unroll_scale_grad_scratch_elems_{sfx}")
+        f.argtypes, f.restype = [i32, i32], sz
+        f = getattr(L, f"lqpb_unroll_scale_grad_{sfx}")
+        f.argtypes, f.restype = [i32, i32] + [vp] * 6 + [vp], i32
         f = getattr(L, f"lqpb_lu_factor_{sfx}")
         f.argtypes, f.restype = [i32, i32, vp, vp, vp, vp], i32
         f = getattr(L, f"lqpb_lu_solve_{sfx}")

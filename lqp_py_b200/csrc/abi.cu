@@ -780,6 +780,20 @@ int lqpb_backward_kkt_f64(int B, int n, int m, const double* dl_dz, const double
 UNROLL_ENTRY(f32, float)
 UNROLL_ENTRY(f64, double)
 
+#define SCALE_GRAD_ENTRY(SFX, T)                                                                                   \
+  size_t lqpb_unroll_scale_grad_scratch_elems_##SFX(int B, int n) { return (size_t)B * ((n + 31) / 32 + 1) * n; }  \
+  int lqpb_unroll_scale_grad_##SFX(int B, int n, T* G, const T* Q, const T* D, const T* coef, T* gD, T* scratch,   \
+                                   void* stream) {                                                                 \
+    if (!G || !Q || !scratch || B <= 0 || n <= 0 || (D != nullptr) != (gD != nullptr))                             \
+      return fail(LQPB_E_ARG, "bad argument");                                                                     \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    CK(launch_scale_grad<T>(B, n, G, Q, D, coef, gD, scratch, (cudaStream_t)stream), "scale_grad");                \
+    return LQPB_OK;                                                                                                \
+  }
+SCALE_GRAD_ENTRY(f32, float)
+SCALE_GRAD_ENTRY(f64, double)
+
 #define LU_ENTRY(SFX, T)                                                                                          \
   int lqpb_lu_factor_##SFX(int B, int N, const T* A, T* LU, int32_t* piv, void* stream) {                          \
     if (!A || !LU || !piv || B <= 0 || N <= 0) return fail(LQPB_E_ARG, "bad argument");                           \

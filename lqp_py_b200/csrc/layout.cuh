@@ -255,6 +255,9 @@ struct UnrollGrads {
 template <typename T>
 cudaError_t launch_unroll_reverse(const FwdWs<T>& w, const Tape<T>& tape, const UnrollGrads<T>& g, int* launches,
                                   cudaStream_t st);
+// adjoint of Q~ = D Q D and rho = ||Q~||_F / sqrt(n): G (B,n,n) in/out, gD (B,n) out, part = (B, ceil(n/32) + 1, n) scratch
+template <typename T>
+cudaError_t launch_scale_grad(int B, int n, T* G, const T* Q, const T* D, const T* coef, T* gD, T* part, cudaStream_t st);
 template <typename T>
 cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho_out, cudaStream_t st);
 

@@ -290,6 +290,84 @@ tape_outer_kernel(const T* __restrict__ U, int su, const T* __restrict__ V, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Adjoint of the scaling of Q and of the rho selection (reference :176, :200-203), fused:  with G the adjoint of
+// Q~ = D Q D delivered by the sweep and  c = grho / (n rho)  (zero where rho was clamped),
+//     Gt = G + c Q~,     gQ_ij = D_i Gt_ij D_j   (written over G),     gD_j = sum_i Gt_ij Q_ij D_i + sum_i Gt_ji Q_ji D_i.
+// grid = (row blocks of 32, B); a warp owns 4 rows: the row sums (second term, index j = row) are warp reductions,
+// the column sums (first term) go through per-warp slices of shared memory and leave as one partial row per CTA;
+// scale_grad_reduce_kernel adds the partials in a fixed order (deterministic).  D == nullptr: no scaling (D = 1).
+constexpr int kSgThreads = 256, kSgRows = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(kSgThreads)
+scale_grad_kernel(T* __restrict__ G, const T* __restrict__ Q, const T* __restrict__ D, const T* __restrict__ coef,
+                  T* __restrict__ part, int n, int nblk) {
+  extern __shared__ __align__(16) unsigned char sg_smem[];
+  T* colacc = reinterpret_cast<T*>(sg_smem);            // [8 warps][n]
+  const int b = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* Db = D ? D + (size_t)b * n : nullptr;
+  const T c = coef ? coef[b] : T(0);
+  T* Gb = G + (size_t)b * n * n;
+  const T* Qb = Q + (size_t)b * n * n;
+  T* ca = colacc + (size_t)warp * n;
+  for (int j = lane; j < n; j += 32) ca[j] = T(0);
+  T* rowpart = part + ((size_t)b * (nblk + 1) + nblk) * n;       // last partial row: the row sums
+  for (int r = 0; r < kSgRows / 8; ++r) {
+    const int i = blk * kSgRows + warp * (kSgRows / 8) + r;
+    if (i >= n) break;
+    const T di = Db ? Db[i] : T(1);
+    T racc = T(0);
+    for (int j = lane; j < n; j += 32) {
+      const size_t o = (size_t)i * n + j;
+      const T q = Qb[o], dj = Db ? Db[j] : T(1);
+      const T gt = Gb[o] + c * (di * q * dj);
+      Gb[o] = di * gt * dj;
+      const T t = gt * q;
+      ca[j] += t * di;
+      racc += t * dj;
+    }
+    racc = warp_sum(racc);
+    if (lane == 0) rowpart[i] = racc;
+  }
+  __syncthreads();
+  T* cp = part + ((size_t)b * (nblk + 1) + blk) * n;
+  for (int j = tid; j < n; j += kSgThreads) {
+    T s = T(0);
+#pragma unroll
+    for (int w8 = 0; w8 < kSgThreads / 32; ++w8) s += colacc[(size_t)w8 * n + j];
+    cp[j] = s;
+  }
+}
+
+template <typename T>
+__global__ void scale_grad_reduce_kernel(const T* __restrict__ part, T* __restrict__ gD, int n, int nblk) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const T* pb = part + (size_t)b * (nblk + 1) * n;
+  T s = pb[(size_t)nblk * n + j];
+  for (int k = 0; k < nblk; ++k) s += pb[(size_t)k * n + j];
+  gD[(size_t)b * n + j] = s;
+}
+
+template <typename T>
+cudaError_t launch_scale_grad(int B, int n, T* G, const T* Q, const T* D, const T* coef, T* gD, T* part, cudaStream_t st) {
+  const int nblk = (n + kSgRows - 1) / kSgRows;
+  const size_t smem = (size_t)(kSgThreads / 32) * n * sizeof(T);
+  cudaError_t e = cudaFuncSetAttribute(scale_grad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid(nblk, B);
+  scale_grad_kernel<T><<<grid, kSgThreads, smem, st>>>(G, Q, D, coef, part, n, nblk);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (gD) {
+    dim3 g2((n + 127) / 128, B);
+    scale_grad_reduce_kernel<T><<<g2, 128, 0, st>>>(part, gD, n, nblk);
+  }
+  return cudaGetLastError();
+}
+template cudaError_t launch_scale_grad<float>(int, int, float*, const float*, const float*, const float*, float*, float*, cudaStream_t);
+template cudaError_t launch_scale_grad<double>(int, int, double*, const double*, const double*, const double*, double*, double*, cudaStream_t);
+
 template <typename T>
 cudaError_t launch_unroll_reverse(const FwdWs<T>& w, const Tape<T>& tape, const UnrollGrads<T>& g, int* launches,
                                   cudaStream_t st) {

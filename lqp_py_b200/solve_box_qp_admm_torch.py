@@ -432,7 +432,10 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
             state.update(snaps=snaps, snap_each=each)
     state["tape"] = (*tape, tape_nu)
 
-    Qt, pt, At, bt, lbt, ubt, D, rho = _scaled_problem(Qd, pd, Ad, bd, lbd, ubd, control, any_lb, any_ub)
+    # without an adaptive-rho update nothing downstream reads the VALUES of Q~ (the kernels hold their own copy): the
+    # two O(n^2) glue steps Q~ = D Q D and rho = ||Q~||_F / sqrt(n) then exist only as one fused adjoint kernel
+    Qt, pt, At, bt, lbt, ubt, D, rho = _scaled_problem(Qd, pd, Ad, bd, lbd, ubd, control, any_lb, any_ub,
+                                                       fused_rho=sol["rho_dev"] if S == 1 else None, fused=S == 1)
     check = cfg.check_solved
     z_in = u_in = x_l = None
     for s_idx in range(S):
@@ -474,7 +477,7 @@ def _adapted_rho(rho, at_check, wants, Qt, p, D, cfg, control):
     return torch.clamp(rho, min=control.get('rho_min', 1e-6), max=control.get('rho_max', 1e6))
 
 
-def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub):
+def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub, fused=False, fused_rho=None):
     """Scaling and rho selection of the reference (:156-203) as differentiable torch expressions of the device
     copies.  Returns ``(Q~, p~, A~, b~, lb~, ub~, D, rho)``; ``D`` is ``(B,n,1)`` (or 1.0 without scaling) and ``rho``
     a ``(B,1,1)`` tensor when it is selected from ``||Q~||_F``, otherwise the caller's number."""
@@ -482,6 +485,7 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub):
     any_ineq = any_lb or any_ub
     rho = control.get('rho', None) if any_ineq else 0                   # :157-158
     D = 1.0
+    Dv = None
     if control.get('scale', False):
         colmax = torch.linalg.norm(Q, ord=_INF, dim=1)                   # :163
         bad = colmax <= 0.0
@@ -494,7 +498,9 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub):
             q = torch.quantile(D, torch.tensor([0.10, 0.90], dtype=D.dtype, device=D.device), dim=1)
             beta = (1 - q[0] / q[1]).unsqueeze(1)
         D = (1 - beta) * D + beta * D.mean(dim=1, keepdim=True)          # :175
-        Q = D.unsqueeze(2) * Q * D.unsqueeze(1)                          # :176
+        Dv = D
+        if not fused:
+            Q = D.unsqueeze(2) * Q * D.unsqueeze(1)                      # :176
         p = D.unsqueeze(2) * p                                           # :177
         if A is not None:
             A = A * D.unsqueeze(1)                                       # :180
@@ -508,10 +514,64 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub):
         D = D.unsqueeze(2)
         if any_ineq:
             lb, ub = lb / D, ub / D                                      # :193-194
+    if fused:
+        auto = rho is None
+        if Q.requires_grad and (Dv is not None or auto):
+            Q, rho_t = _ScaledQAndRho.apply(Q, Dv, fused_rho if auto else None, control.get('rho_min', 1e-6),
+                                            control.get('rho_max', 1e6))
+            if auto:
+                rho = rho_t
+        elif auto:
+            rho = fused_rho                                              # no gradient can reach Q: plain values
+        return Q, p, A, b, lb, ub, D, rho
     if rho is None:                                                      # :200-203
         rho = torch.linalg.matrix_norm(Q, keepdim=True) / n ** 0.5
         rho = torch.clamp(rho, min=control.get('rho_min', 1e-6), max=control.get('rho_max', 1e6))
     return Q, p, A, b, lb, ub, D, rho
+
+
+class _ScaledQAndRho(torch.autograd.Function):
+    """``Q~ = D Q D`` (:176) and ``rho = clamp(||Q~||_F / sqrt(n))`` (:200-203) as one autograd node without a forward
+    computation: the solver kernels scaled Q and selected rho themselves (``rho_vals`` is their rho), and no consumer
+    reads the values of Q~, so the forward returns a zero-stride placeholder of the right shape.  The backward is one
+    fused kernel (``lqpb_unroll_scale_grad_*``) over the adjoint of Q~ that the reverse sweep delivers."""
+
+    @staticmethod
+    def forward(ctx, Q, Dv, rho_vals, rho_min, rho_max):
+        ctx.save_for_backward(Q, Dv, rho_vals)
+        ctx.clamp = (rho_min, rho_max)
+        token = torch.zeros((), dtype=Q.dtype, device=Q.device).expand(Q.shape)
+        rho = rho_vals.detach().clone() if rho_vals is not None else torch.zeros((), dtype=Q.dtype, device=Q.device)
+        if rho_vals is None:
+            ctx.mark_non_differentiable(rho)
+        ctx.set_materialize_grads(False)
+        return token, rho
+
+    @staticmethod
+    def backward(ctx, gQt, grho):
+        L = _abi.lib()
+        Q, Dv, rho_vals = ctx.saved_tensors
+        B, n = Q.shape[0], Q.shape[1]
+        dev, dt = Q.device, Q.dtype
+        sfx = _abi.suffix(dt)
+        with torch.cuda.device(dev):
+            # the adjoint of Q~ has one producer (the loop node) and one consumer (this node): overwritten in place
+            G = gQt.contiguous() if gQt is not None else torch.zeros((B, n, n), dtype=dt, device=dev)
+            coef = None
+            if grho is not None and rho_vals is not None:
+                r = rho_vals.reshape(B)
+                inside = (r > ctx.clamp[0]) & (r < ctx.clamp[1])
+                coef = torch.where(inside, grho.reshape(B) / (n * r), torch.zeros_like(r)).contiguous()
+            gD = torch.empty((B, n), dtype=dt, device=dev) if Dv is not None else None
+            nscr = getattr(L, f"lqpb_unroll_scale_grad_scratch_elems_{sfx}")(B, n)
+            scratch = torch.empty(nscr, dtype=dt, device=dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            Dc = Dv.detach().contiguous() if Dv is not None else None
+            rc = getattr(L, f"lqpb_unroll_scale_grad_{sfx}")(
+                B, n, _abi.ptr(G), _abi.ptr(Q.detach().contiguous()), _abi.ptr(Dc), _abi.ptr(coef), _abi.ptr(gD),
+                _abi.ptr(scratch), C.c_void_p(stream))
+            _abi.check(rc, "lqpb_unroll_scale_grad")
+        return G, gD, None, None, None
 
 
 class _UnrolledSegment(torch.autograd.Function):

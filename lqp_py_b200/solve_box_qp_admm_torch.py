@@ -487,7 +487,7 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub, fused=False, fu
     D = 1.0
     Dv = None
     if control.get('scale', False):
-        colmax = torch.linalg.norm(Q, ord=_INF, dim=1)                   # :163
+        colmax = _ColumnMax.apply(Q) if (fused and Q.requires_grad) else torch.linalg.norm(Q, ord=_INF, dim=1)   # :163
         bad = colmax <= 0.0
         if bool(bad.any()):                                              # :164-168
             floor = colmax.mean(dim=1).clamp(min=1e-6).unsqueeze(1)
@@ -528,6 +528,26 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub, fused=False, fu
         rho = torch.linalg.matrix_norm(Q, keepdim=True) / n ** 0.5
         rho = torch.clamp(rho, min=control.get('rho_min', 1e-6), max=control.get('rho_max', 1e6))
     return Q, p, A, b, lb, ub, D, rho
+
+
+class _ColumnMax(torch.autograd.Function):
+    """``norm(Q, inf, dim=1)`` (:163) with a sparse adjoint: one entry per column (the first maximiser; torch's own
+    backward splits the gradient among exact ties, which only zero columns produce -- and those carry no gradient)."""
+
+    @staticmethod
+    def forward(ctx, Q):
+        colmax, idx = Q.abs().max(dim=1)
+        sign = torch.sign(torch.gather(Q, 1, idx.unsqueeze(1)).squeeze(1))
+        ctx.save_for_backward(idx, sign)
+        ctx.shape = Q.shape
+        return colmax
+
+    @staticmethod
+    def backward(ctx, g):
+        idx, sign = ctx.saved_tensors
+        out = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
+        out.scatter_(1, idx.unsqueeze(1), (sign * g).unsqueeze(1))
+        return out
 
 
 class _ScaledQAndRho(torch.autograd.Function):

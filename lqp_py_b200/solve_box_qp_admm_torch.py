@@ -15,8 +15,9 @@ but none of the arithmetic happens in torch: the functions flatten the settings 
 struct and call the hand-written sm_100a kernels through the C ABI of ``include/lqpb.h``
 (scaling + Gauss-Jordan operator setup, the persistent TMA-streamed ADMM kernel, the
 masked-inverse backward).  PyTorch only owns device memory and the CUDA stream.  The one exception
-is ``unroll=True``: its iterations run in the same kernels (recorded, then swept backwards), but the
-T-independent scaling / rho-update expressions around them are torch operators on the CUDA copies so
+is ``unroll=True``: its iterations run in the same kernels (recorded, then swept backwards) and the
+O(n^2) part of the scaling adjoint is a kernel too, but the O(n) vector expressions around them (D from
+the column norms, the scaled vectors, the rho-update ratio) are torch operators on the CUDA copies so
 that autograd reproduces the reference's subgradient conventions (see ``_solve_unrolled``).
 
 Tensors may live on the GPU (zero copy) or on the CPU like in the reference's experiments;

@@ -35,7 +35,8 @@ enum {
   LQPB_E_ARG = 1,        /* bad argument (shape, null pointer, unsupported size) */
   LQPB_E_WORKSPACE = 2,  /* workspace too small */
   LQPB_E_CUDA = 3,       /* CUDA runtime error, see lqpb_last_error() */
-  LQPB_E_NOT_BLACKWELL = 4 /* device is not sm_100 */
+  LQPB_E_NOT_BLACKWELL = 4, /* device is not sm_100 */
+  LQPB_E_TAPE = 5           /* lqpb_unroll_forward_* in first-pass mode: the solve does not fit the tape (see there) */
 };
 
 /* status written to lqpb_info.status */
@@ -232,6 +233,11 @@ int lqpb_backward_host_f64(int B, int n, int m, int kkt, const double* h_dl_dz, 
  *                  into the HOST array seg_start[n_seg + 1], and the do_rho_update flags (:310-311) each update
  *                  applied into the DEVICE array wants (n_seg - 1, B).
  *                  Both recording calls synchronise the stream (they verify the run ended at iteration n_iter - 1).
+ *                  First-pass mode (snapshots == NULL, n_seg == 1): unroll_forward IS the solve -- n_iter is then only
+ *                  the capacity of the tapes (their row stride); the call succeeds when the solve converges (or hits
+ *                  cfg->max_iters) within n_iter iterations without an adaptive-rho refactorisation, info->iter + 1
+ *                  rows are valid and the reverse sweep reads the operators from `workspace`; otherwise it returns
+ *                  LQPB_E_TAPE and the caller falls back to a plain solve followed by a recording call.
  * unroll_backward: reverse sweep over the iterations k_hi .. k_lo (inclusive) of ONE operator segment: operators from
  *                  `snapshot` (one snapshot of unroll_forward) or, when NULL, from `workspace`.  In: adjoints of
  *                  x~_{k_hi}, z_{k_hi}, u_{k_hi}, z_{k_hi - 1} (g_x, g_z, g_u, g_zprev, (B, n) each, NULL = zero).

@@ -11,6 +11,7 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "_lqpb.so")
 LOG_CAP = 64
+E_TAPE = 5          # LQPB_E_TAPE
 
 #: every symbol include/lqpb.h declares (checked by tests/test_abi_cpu.py)
 EXPORTS = (

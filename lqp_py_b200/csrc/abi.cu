@@ -221,6 +221,7 @@ struct UnrollRec {        // recording run of a forward solve (lqpb_unroll_forwa
   int max_seg;
   int32_t* seg_start;     // host, max_seg + 1 entries: first iteration of every operator segment, then n_iter
   int32_t* wants;         // device, (max_seg - 1, B): do_rho_update flags applied by each adaptive-rho update
+  int true_max_iters;     // first-pass mode (snap == nullptr): cfg->max_iters before it was cut to the tape capacity
 };
 
 // forward call that also enqueues the dl_dz-independent part of the backward (stage 1 of backward_impl)
@@ -356,14 +357,17 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
       if (prof && g_prof.n_fac < kMaxSeg) cudaEventRecord(g_prof.fac1[g_prof.n_fac++], st);
     }
     if (rec) {      // keep the operators of this segment for its reverse sweep
-      if (n_factor >= rec->max_seg) return fail(LQPB_E_ARG, "recording run needs more operator segments than announced");
-      const Snap<T> sn = carve_snap<T>((char*)rec->snap + (size_t)n_factor * carve_snap<T>(nullptr, B, n, m).bytes, B, n, m);
-      const size_t mm = m > 0 ? m : 1, sz = sizeof(T);
-      CK(cudaMemcpyAsync(sn.Kp, w.Kp, (size_t)B * Pack<T>::elems(n) * sz, cudaMemcpyDeviceToDevice, st), "snapshot K11");
-      CK(cudaMemcpyAsync(sn.Gt, w.Gt, (size_t)B * mm * w.ld * sz, cudaMemcpyDeviceToDevice, st), "snapshot K21");
-      CK(cudaMemcpyAsync(sn.Sinv, w.Sinv, (size_t)B * mm * mm * sz, cudaMemcpyDeviceToDevice, st), "snapshot K22");
-      CK(cudaMemcpyAsync(sn.c, w.c, (size_t)B * w.ld * sz, cudaMemcpyDeviceToDevice, st), "snapshot c");
-      CK(cudaMemcpyAsync(sn.rho, w.rho, (size_t)B * sz, cudaMemcpyDeviceToDevice, st), "snapshot rho");
+      if (n_factor >= rec->max_seg)
+        return fail(rec->snap ? LQPB_E_ARG : LQPB_E_TAPE, "recording run needs more operator segments than announced");
+      if (rec->snap) {
+        const Snap<T> sn = carve_snap<T>((char*)rec->snap + (size_t)n_factor * carve_snap<T>(nullptr, B, n, m).bytes, B, n, m);
+        const size_t mm = m > 0 ? m : 1, sz = sizeof(T);
+        CK(cudaMemcpyAsync(sn.Kp, w.Kp, (size_t)B * Pack<T>::elems(n) * sz, cudaMemcpyDeviceToDevice, st), "snapshot K11");
+        CK(cudaMemcpyAsync(sn.Gt, w.Gt, (size_t)B * mm * w.ld * sz, cudaMemcpyDeviceToDevice, st), "snapshot K21");
+        CK(cudaMemcpyAsync(sn.Sinv, w.Sinv, (size_t)B * mm * mm * sz, cudaMemcpyDeviceToDevice, st), "snapshot K22");
+        CK(cudaMemcpyAsync(sn.c, w.c, (size_t)B * w.ld * sz, cudaMemcpyDeviceToDevice, st), "snapshot c");
+        CK(cudaMemcpyAsync(sn.rho, w.rho, (size_t)B * sz, cudaMemcpyDeviceToDevice, st), "snapshot rho");
+      }
       rec->seg_start[n_factor] = i0;
     }
     ++n_factor;
@@ -406,7 +410,11 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
   }
   if (hc->status != LQPB_STATUS_CONVERGED && hc->status != LQPB_STATUS_MAX_ITERS)
     return fail(LQPB_E_CUDA, "iteration kernel ended without a status");
-  if (rec) {
+  if (rec && !rec->snap) {          // first-pass mode: the tape only has to be long enough
+    if (hc->status == LQPB_STATUS_MAX_ITERS && rec->true_max_iters > rec->tape.n_iter)
+      return fail(LQPB_E_TAPE, "the solve did not converge within the tape capacity");
+    rec->seg_start[n_factor] = hc->iter + 1;
+  } else if (rec) {
     if (n_factor != rec->max_seg || hc->iter != rec->tape.n_iter - 1)
       return fail(LQPB_E_CUDA, "recording run did not reproduce the forward solve");
     rec->seg_start[n_factor] = rec->tape.n_iter;
@@ -584,15 +592,15 @@ int unroll_forward_impl(const lqpb_config* cfg, int B, int n, int m, int n_iter,
                         const T* A, const T* b, const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out,
                         T* tx, T* tz, T* tu, T* tnu, void* snap, size_t snap_bytes, int32_t* seg_start, int32_t* wants,
                         lqpb_info* info, void* ws, size_t ws_bytes, void* stream) {
-  if (!cfg || !tx || !tz || !tu || (m > 0 && !tnu) || !snap || !seg_start || (n_seg > 1 && !wants))
+  if (!cfg || !tx || !tz || !tu || (m > 0 && !tnu) || !seg_start || (n_seg > 1 && (!wants || !snap)))
     return fail(LQPB_E_ARG, "null pointer argument");
   if (n_iter < 1 || n_seg < 1) return fail(LQPB_E_ARG, "bad dimensions");
-  if (B > 0 && n > 0 && m >= 0 && carve_snap<T>(nullptr, B, n, m).bytes * (size_t)n_seg > snap_bytes)
+  if (snap && B > 0 && n > 0 && m >= 0 && carve_snap<T>(nullptr, B, n, m).bytes * (size_t)n_seg > snap_bytes)
     return fail(LQPB_E_WORKSPACE, "snapshot buffer too small");
   lqpb_config c = *cfg;
   if (c.max_iters > n_iter) c.max_iters = n_iter;      // the tape has n_iter rows: the run can never write past them
-  c.verbose = 0;
-  UnrollRec<T> rec{Tape<T>{n_iter, tx, tz, tu, tnu}, snap, n_seg, seg_start, wants};
+  if (snap) c.verbose = 0;                             // a second pass stays silent; a first pass is the solve itself
+  UnrollRec<T> rec{Tape<T>{n_iter, tx, tz, tu, tnu}, snap, n_seg, seg_start, wants, cfg->max_iters};
   return forward_impl<T>(&c, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, ws, ws_bytes, stream, nullptr,
                          &rec);
 }

@@ -277,12 +277,13 @@ def _host_view(t):
     return None if t is None else t.detach().contiguous()
 
 
-def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None):
+def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_cap=None):
     L = _abi.lib()
     out_device = p.device
     host_mode = _all_on_host((Q, p, A, b, lb, ub))
     hx = None
     prepared = False
+    tape_info = None
     if host_mode:
         # CPU tensors in (the reference's callers): lqpb_forward_host_* uploads Q in chunks on a copy stream and
         # overlaps the per-problem setup with the transfer; the device copies it fills are kept for the backward
@@ -323,6 +324,21 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None):
                 1 if (prep and prep["kkt"]) else 0, C.byref(flag))
             _abi.check(rc, "lqpb_forward_host")
             prepared = bool(flag.value)
+        elif tape_cap is not None:
+            # unrolled mode, first-pass recording: the solve itself writes the tape (capacity tape_cap iterations)
+            cap = int(min(tape_cap, cfg.max_iters))
+            tape = [torch.empty((B, cap, n), dtype=dt, device=dev) for _ in range(3)]
+            tape.append(torch.empty((B, cap, m), dtype=dt, device=dev) if m > 0 else None)
+            segs = (C.c_int32 * 2)()
+            rc = getattr(L, f"lqpb_unroll_forward_{sfx}")(
+                C.byref(cfg), B, n, m, cap, 1, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
+                _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u), _abi.ptr(lams),
+                _abi.ptr(nus), _abi.ptr(rho_t), *[_abi.ptr(t) for t in tape], None, 0, segs, None, C.byref(info),
+                _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
+            if rc == _abi.E_TAPE:
+                return None                       # does not fit (refactorisation / more iterations): caller falls back
+            _abi.check(rc, "lqpb_unroll_forward")
+            tape_info = (tuple(tape), cap)
         elif prep is not None:
             rc = getattr(L, f"lqpb_forward_prep_{sfx}")(
                 C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
@@ -362,7 +378,7 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None):
     return {"x": hx, "z": hz, "u": hu, "lams": hlams, "nus": hnus, "rho": rho_out,
             "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor),
             "_any_lb": bool(info.any_lb), "_any_ub": bool(info.any_ub), "_dev": dv,
-            "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus, "_ws": ws, "_cfg": cfg, "_prepared": prepared,
+            "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus, "_ws": ws, "_cfg": cfg, "_prepared": prepared, "_tape": tape_info,
             "rho_dev": rho if torch.is_tensor(rho) else None}
 
 
@@ -394,7 +410,12 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
     Qd, pd, Ad, bd, lbd, ubd = (None if t is None else t.to(dev).contiguous() for t in (Q, p, A, b, lb, ub))
     plain = dict(control)
     plain['unroll'] = False
-    sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=())
+    # first try: the solve records itself (tape capacity 256 iterations); a solve that needs an adaptive-rho
+    # refactorisation or more iterations falls back to a plain solve followed by a recording pass
+    sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=(), tape_cap=256)
+    first_pass = sol is not None
+    if not first_pass:
+        sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=())
     any_lb, any_ub = sol["_any_lb"], sol["_any_ub"]
     B, n, dt = Qd.shape[0], pd.shape[1], pd.dtype
     m = get_ncon(Ad, dim=1)
@@ -402,12 +423,17 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
     K, S = sol["iter"] + 1, sol["n_factor"]
     cfg, ws = sol["_cfg"], sol["_ws"]
     state = dict(ws=ws, B=B, n=n, m=m, n_iter=K, snaps=None, snap_each=0)
+    wants = None
+    if first_pass:
+        (*tape, tape_nu), state["n_iter"] = sol["_tape"]       # rows beyond K are unused; n_iter is the row stride
+        seg_start = [0, K]
     with torch.cuda.device(dev):
-        tape = [torch.empty((B, K, n), dtype=dt, device=dev) for _ in range(3)]
-        tape_nu = torch.empty((B, K, m), dtype=dt, device=dev) if m > 0 else None
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        wants = None
-        if S == 1:
+        if first_pass:
+            pass
+        elif S == 1:
+            tape = [torch.empty((B, K, n), dtype=dt, device=dev) for _ in range(3)]
+            tape_nu = torch.empty((B, K, m), dtype=dt, device=dev) if m > 0 else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
             rc = getattr(L, f"lqpb_unroll_record_{sfx}")(
                 C.byref(cfg), B, n, m, K, _abi.ptr(ws), ws.numel(), _abi.ptr(tape[0]), _abi.ptr(tape[1]),
                 _abi.ptr(tape[2]), _abi.ptr(tape_nu), C.c_void_p(stream))
@@ -415,6 +441,9 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
             seg_start = [0, K]
         else:
             # adaptive-rho updates: a full recording solve that also keeps the operators of every segment
+            tape = [torch.empty((B, K, n), dtype=dt, device=dev) for _ in range(3)]
+            tape_nu = torch.empty((B, K, m), dtype=dt, device=dev) if m > 0 else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
             d = sol["_dev"]
             each = getattr(L, f"lqpb_unroll_snapshot_bytes_{sfx}")(B, n, m)
             snaps = torch.empty(S * each, dtype=torch.uint8, device=dev)

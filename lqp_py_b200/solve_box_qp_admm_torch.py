@@ -33,6 +33,7 @@ from . import _abi
 from .utils import get_ncon
 
 _INF = float("inf")
+_UNROLL_TAPE_CAP = 256      # iterations a first-pass tape of the unrolled mode can hold (longer solves: solve, then record)
 
 
 class SolveBoxQP(nn.Module):
@@ -410,9 +411,9 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
     Qd, pd, Ad, bd, lbd, ubd = (None if t is None else t.to(dev).contiguous() for t in (Q, p, A, b, lb, ub))
     plain = dict(control)
     plain['unroll'] = False
-    # first try: the solve records itself (tape capacity 256 iterations); a solve that needs an adaptive-rho
+    # first try: the solve records itself (tape capacity _UNROLL_TAPE_CAP iterations); a solve that needs an adaptive-rho
     # refactorisation or more iterations falls back to a plain solve followed by a recording pass
-    sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=(), tape_cap=256)
+    sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=(), tape_cap=_UNROLL_TAPE_CAP)
     first_pass = sol is not None
     if not first_pass:
         sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=())

@@ -603,3 +603,20 @@ def test_prepared_backward_equals_plain_backward(backward, dev):
     xc.backward(g2)
     for u, v in zip(ins_b, ins_c):
         assert torch.equal(u.grad, v.grad)
+
+
+def test_unrolled_first_pass_tape_and_its_fallback_agree(dev, monkeypatch):
+    """The unrolled solve records itself when it fits the first-pass tape; with a tape too short for the solve it
+    falls back to solve + recording pass.  Same kernels, same arithmetic: x and every gradient bit-identical."""
+    import lqp_py_b200.solve_box_qp_admm_torch as mod
+    case = UnrollCase("exp1_n50_b4_f64")
+    outs = []
+    for cap in (256, 8):
+        monkeypatch.setattr(mod, "_UNROLL_TAPE_CAP", cap)
+        leaves = [None if t is None else t.to(dev).requires_grad_(True) for t in case.inputs()]
+        x = mod.SolveBoxQP(control=dict(case.control)).forward(*leaves)
+        x.backward(torch.from_numpy(case.z["dl_dz"]).to(dev))
+        outs.append((x.detach(), [t.grad for t in leaves]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)

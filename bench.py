@@ -50,62 +50,105 @@ def workload_name(a):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampler (B200_PROFILING.md clocks line) running during the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region.  Primary source: NVML polled every
+    2 ms from a thread of this process (the main thread sits in ctypes calls that release the GIL), so even a 30 ms
+    region holds a dozen samples; fallback: the nvidia-smi query line of B200_PROFILING.md on a 25 ms loop."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
-        self.lines = []          # (host time of arrival, csv line)
+        self.samples = []        # (host time, sm MHz, max MHz, set of reasons)
         self.proc = None
+        self.nvml = None
+        self.stop_flag = False
+        self.source = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[self.index])
+                except Exception:
+                    phys = self.index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "25", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.th = threading.Thread(target=self._read_smi, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv = self.nvml
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((time.perf_counter(), mhz, self.max_mhz, {n for n, b in names if bits & b}))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _read_smi(self):
         for ln in self.proc.stdout:
-            self.lines.append((time.perf_counter(), ln.strip()))
-
-    def count(self, t_lo):
-        return sum(1 for t, _ in self.lines if t >= t_lo)
-
-    def stop(self, t_lo=0.0, t_hi=float("inf"), t_timed_hi=None):
-        """Statistics over the samples that arrived in [t_lo, t_hi] (host clock): the timed region plus, when
-        that region is shorter than a few nvidia-smi periods, the identical steps run right after it."""
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        in_timed = 0
-        for t, ln in self.lines:
-            if t < t_lo or t > t_hi:
-                continue
             f = [s.strip() for s in ln.split(",")]
             if len(f) < 9:
                 continue
-            if t_timed_hi is not None and t <= t_timed_hi:
-                in_timed += 1
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "samples_in_timed_region": in_timed, "reasons": sorted(reasons)}
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.samples.append((time.perf_counter(), sm, mx, {n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")}))
+
+    @property
+    def alive(self):
+        return self.nvml is not None or self.proc is not None
+
+    def count(self, t_lo):
+        return sum(1 for s in self.samples if s[0] >= t_lo)
+
+    def stop(self, t_lo=0.0, t_hi=float("inf"), t_timed_hi=None):
+        """Statistics over the samples taken in [t_lo, t_hi] (host clock): the timed region plus, when that region is
+        too short to hold 8 samples, the identical steps run right after it."""
+        if not self.alive:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (NVML, nvidia-smi) available"]}
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sel = [s for s in self.samples if t_lo <= s[0] <= t_hi]
+        sm = sorted(s[1] for s in sel)
+        reasons = set()
+        for s in sel:
+            reasons |= s[3]
+        in_timed = sum(1 for s in sel if t_timed_hi is not None and s[0] <= t_timed_hi)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((s[2] for s in sel), default=None),
+                "samples": len(sm), "samples_in_timed_region": in_timed, "reasons": sorted(reasons), "source": self.source}
 
 
 def log(msg):
@@ -364,7 +407,7 @@ def run_b200(a):
         # K steps last tens of ms, a handful of nvidia-smi periods at best: keep the GPU under the SAME load (the
         # same steps, untimed) until at least 8 samples have been taken since the timed region began
         k, t_end = 0, time.perf_counter() + 3.0
-        while sampler.proc and sampler.count(t_host0) < 8 and time.perf_counter() < t_end:
+        while sampler.alive and sampler.count(t_host0) < 8 and time.perf_counter() < t_end:
             step(W + K + k, False)
             k += 1
             if k % 8 == 0:

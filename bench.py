@@ -374,7 +374,11 @@ def run_b200(a):
     log(f"rank {rank}: data on {dev}, {W} warm-up + {K} timed steps")
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()          # started before the warm-up: nvidia-smi needs ~0.2 s to deliver its first line
+        try:
+            sampler.start()      # started before the warm-up: an nvidia-smi loop needs ~0.2 s to deliver its first line
+        except Exception as exc:                     # the clocks object is evidence, never a reason to lose the run
+            log(f"clock sampler failed to start: {exc!r}")
+            sampler = None
     for k in range(W):
         step(k, False)
     sync_all()
@@ -415,7 +419,10 @@ def run_b200(a):
                 add_prof(BWD)                      # backward phases: read after a drain, outside the timed region
                 n_prof[1] += 1                     # (the next forward call re-records the prepare-stage events)
         torch.cuda.synchronize(dev)
-        clocks = sampler.stop(t_host0, time.perf_counter(), t_host1)
+        try:
+            clocks = sampler.stop(t_host0, time.perf_counter(), t_host1)
+        except Exception as exc:
+            clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"clock sampler failed: {exc!r}"]}
         clocks["extra_load_steps"] = k
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

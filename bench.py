@@ -51,8 +51,8 @@ def workload_name(a):
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled DURING the timed region.  Primary source: NVML polled every
-    2 ms from a thread of this process (the main thread sits in ctypes calls that release the GIL), so even a 30 ms
-    region holds a dozen samples; fallback: the nvidia-smi query line of B200_PROFILING.md on a 25 ms loop."""
+    4 ms from a thread of this process (the main thread sits in ctypes calls that release the GIL), so even a 30 ms
+    region holds half a dozen samples; fallback: the nvidia-smi query line of B200_PROFILING.md on a 25 ms loop."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -108,7 +108,7 @@ class ClockSampler:
                 self.samples.append((time.perf_counter(), mhz, self.max_mhz, {n for n, b in names if bits & b}))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.004)
 
     def _read_smi(self):
         for ln in self.proc.stdout:

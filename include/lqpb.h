@@ -315,6 +315,10 @@ int lqpb_outer_f64(int B, int N, int M, const double* a, const double* b, double
  * tools/tc_check.py and the GPU tests measure the tcgen05 3xTF32 path in isolation. */
 size_t lqpb_dev_tc_inverse_work_bytes(int B, int N);
 int lqpb_dev_tc_inverse_f32(int B, int N, const float* A, float* Ainv, void* work, void* stream);
+/* Streaming read of `bytes` bytes of device memory, `reps` passes, 16-byte loads that bypass L1: bench.py times it on a
+ * buffer smaller than the L2 (and on one far larger) to measure the read-bandwidth ceilings the iteration kernel's
+ * roofline is quoted against.  sink: 4 bytes of device memory (never written for real data). */
+int lqpb_dev_stream_read(const void* buf, size_t bytes, int reps, void* sink, void* stream);
 
 #ifdef __cplusplus
 }

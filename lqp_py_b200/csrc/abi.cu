@@ -22,7 +22,8 @@ using namespace lqpb;
 namespace {
 
 thread_local std::string g_err;
-bool g_prof_on = false;   // process-wide: autograd runs the backward on its own thread
+bool g_prof_on = false;   // process-wide switch: autograd runs the backward on its own thread
+constexpr int kMaxDev = 64;
 
 constexpr int kMaxSeg = 16;
 struct ProfState {
@@ -35,9 +36,20 @@ struct ProfState {
   int prep_launches = 0;     // kernels a forward call enqueued for the backward (stage 1)
   cudaEvent_t fac0[kMaxSeg], fac1[kMaxSeg], it0[kMaxSeg], it1[kMaxSeg];
 };
-ProfState g_prof;
+// Profiling state (only touched while lqpb_profile_enable(1) is in force): one record per DEVICE, because CUDA events
+// belong to the device they were created on; calls made with profiling off write to a per-thread scratch record, so
+// the solver itself keeps no process-global state.
+ProfState g_prof_tab[kMaxDev];
+thread_local ProfState g_prof_scratch;
 
-void prof_init() {
+int cur_dev() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDev) d = 0;
+  return d;
+}
+ProfState& prof_state() { return g_prof_on ? g_prof_tab[cur_dev()] : g_prof_scratch; }
+
+void prof_init(ProfState& g_prof) {
   if (g_prof.have_events) return;
   for (auto& e : g_prof.ev) cudaEventCreate(&e);
   for (int i = 0; i < kMaxSeg; ++i) {
@@ -78,8 +90,8 @@ int check_device() {
 }
 
 struct HostCtrl {
-  Ctrl* pinned = nullptr;
-  cudaEvent_t seg_done = nullptr;
+  Ctrl* pinned = nullptr;                     // page-locked host memory: usable from every device (UVA)
+  cudaEvent_t seg_done[kMaxDev] = {};         // events belong to a device: one per device, created on first use
   ~HostCtrl() {}
 };
 thread_local HostCtrl g_hctrl;
@@ -93,7 +105,8 @@ struct HostPipe {
   cudaStream_t cs;
   cudaEvent_t fork, vec, done, ev[kMaxChunks];
 };
-thread_local HostPipe g_pipe;
+thread_local HostPipe g_pipe_tab[kMaxDev];      // streams and events belong to a device: one set per device ordinal
+#define g_pipe (g_pipe_tab[cur_dev()])
 
 cudaError_t pipe_init() {
   int dev = 0;
@@ -248,6 +261,7 @@ int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
   a.W = w.W; a.Vg = w.Vg; a.Wg = w.Wg;
   a.dst = w.Kp; a.ldd = w.ld; a.G21 = w.Gt; a.K22 = w.Sinv;
   a.bt = w.bt; a.c_out = w.m > 0 ? w.c : nullptr;
+  ProfState& g_prof = prof_state();
   if constexpr (std::is_same<T, float>::value) {
     if (w.tc) {
       int l = 0;
@@ -287,7 +301,8 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
   Ctrl* hc = g_hctrl.pinned;
 
   const bool prof = g_prof_on;
-  if (prof) prof_init();
+  ProfState& g_prof = prof_state();
+  if (prof) prof_init(g_prof);
   g_prof.launches = g_prof.it_launches = g_prof.fac_launches = 0;
   g_prof.n_fac = g_prof.n_it = 0;
   g_prof.fwd_valid = false;
@@ -386,14 +401,15 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
       // they are queued behind the solve NOW, and the host waits for the solve alone -- the GPU then works through
       // them while the caller is back in Python on its way to .backward() (wasted only if this segment ends in a
       // refactorisation, or if no backward follows)
-      if (!g_hctrl.seg_done) CK(cudaEventCreateWithFlags(&g_hctrl.seg_done, cudaEventDisableTiming), "event");
-      CK(cudaEventRecord(g_hctrl.seg_done, st), "record (segment end)");
+      cudaEvent_t& seg_done = g_hctrl.seg_done[cur_dev()];
+      if (!seg_done) CK(cudaEventCreateWithFlags(&seg_done, cudaEventDisableTiming), "event");
+      CK(cudaEventRecord(seg_done, st), "record (segment end)");
       const int fwd_launches = g_prof.launches;
       rc = backward_impl<T>(B, n, m, nullptr, x, u, lams, nus, Q, A, lb, ub, nullptr, 0.0, nullptr, nullptr, nullptr,
                             nullptr, nullptr, nullptr, prep->ws, prep->ws_bytes, stream, prep->kkt != 0, nullptr, nullptr, 1);
       g_prof.launches = fwd_launches;
       if (rc) return rc;
-      CK(cudaEventSynchronize(g_hctrl.seg_done), "synchronize (segment end)");
+      CK(cudaEventSynchronize(seg_done), "synchronize (segment end)");
     } else {
       CK(cudaStreamSynchronize(st), "synchronize (segment end)");
     }
@@ -456,7 +472,8 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
     return fail(LQPB_E_ARG, "staged backward needs the tensor-core path (and device buffers for the prepare stage)");
   cudaStream_t st = (cudaStream_t)stream;
   const bool prof = g_prof_on;
-  if (prof) prof_init();
+  ProfState& g_prof = prof_state();
+  if (prof) prof_init(g_prof);
   int bwd_fac_launches = 0;
   if (stage != 2) {
     g_prof.bwd_valid = false;
@@ -626,7 +643,7 @@ int unroll_backward_impl(int B, int n, int m, int n_iter, int k_lo, int k_hi, vo
   UnrollGrads<T> g{k_lo, k_hi, gx, gz_last, gu_last, gzprev_last, gz_in, gu_in, tw, twnu, gQ, gp, gA, gb, glb, gub, grho};
   int l = 0;
   CK(launch_unroll_reverse<T>(w, tape, g, &l, (cudaStream_t)stream), "unroll reverse sweep");
-  g_prof.launches = l;
+  prof_state().launches = l;
   return LQPB_OK;
 }
 
@@ -641,6 +658,7 @@ void lqpb_profile_enable(int on) { g_prof_on = on != 0; }
 void lqpb_profile_get(lqpb_profile* out) {
   if (!out) return;
   memset(out, 0, sizeof(*out));
+  ProfState& g_prof = prof_state();
   auto el = [](cudaEvent_t a, cudaEvent_t b) {
     float ms = 0.f;
     cudaEventSynchronize(b);

@@ -24,6 +24,7 @@
 // row-major and contiguous; diagonal tiles hold both triangles.  Operands are staged in shared memory by the
 // CTA's threads in the canonical K-major SWIZZLE_128B layout (8-row x 128-byte atoms, 16-byte chunk index
 // XOR row % 8), 32 k-columns (one 16 KB slab per operand part) at a time, while the previous slab's MMAs run.
+#include <atomic>
 #include "layout.cuh"
 
 namespace lqpb {
@@ -915,7 +916,13 @@ struct TcStreams {
   cudaStream_t aux[kTcMaxGroups - 1];
   cudaEvent_t fork, join[kTcMaxGroups - 1];
 };
-static thread_local TcStreams g_tcs;
+static thread_local TcStreams g_tcs_tab[64];     // streams and events belong to a device: one set per device ordinal
+#define g_tcs (g_tcs_tab[tc_dev_slot()])
+static int tc_dev_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
 
 static cudaError_t tc_streams_init() {
   int dev = 0;
@@ -935,30 +942,34 @@ static cudaError_t tc_streams_init() {
 }
 
 static int tc_groups(int B) {
-  static int cfg = -1;
-  if (cfg < 0) {
+  static const int cfg = [] {
     const char* e = getenv("LQPB_TC_GROUPS");     // developer switch; default chosen from measurements
-    cfg = e ? atoi(e) : 2;   // measured at dz=500, B=128: forward sweep 0.644 (1) / 0.593 (2) / 0.602 (3) / 0.608 ms (4)
-    if (cfg < 1) cfg = 1;
-    if (cfg > kTcMaxGroups) cfg = kTcMaxGroups;
-  }
+    int c = e ? atoi(e) : 2;   // measured at dz=500, B=128: forward sweep 0.644 (1) / 0.593 (2) / 0.602 (3) / 0.608 ms (4)
+    if (c < 1) c = 1;
+    if (c > kTcMaxGroups) c = kTcMaxGroups;
+    return c;
+  }();
   int g = cfg;
   while (g > 1 && B / g < 16) --g;                // slices of fewer than 16 problems no longer fill the tile grids
   return g;
 }
 
 static cudaError_t tc_sweep(int B, const TcArgs& base, bool ldl, cudaStream_t st, int* launches) {
-  static bool attr_done = false;
-  static int n_sm = 148;
-  if (!attr_done) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+  // function attributes and the SM count are PER DEVICE (a process may drive several GPUs, and autograd calls in from
+  // its own thread): one slot per device ordinal, published with release / acquire
+  static std::atomic<int> sm_of_dev[64];
+  int dev = 0;
+  cudaError_t e0 = cudaGetDevice(&dev);
+  if (e0 != cudaSuccess) return e0;
+  const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+  int n_sm = (dev >= 0 && dev < 64) ? sm_of_dev[slot].load(std::memory_order_acquire) : 0;
+  if (n_sm == 0) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaFuncSetAttribute(tc_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemTrail);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) sm_of_dev[slot].store(n_sm, std::memory_order_release);
   }
   TcArgs a0 = base;
   a0.ldl = ldl ? 1 : 0;

@@ -215,6 +215,8 @@ def iterate(w: dict, st: Settings):
             tol_p = st.eps_abs + st.eps_rel * scale_p
             tol_d = st.eps_abs + st.eps_rel * scale_d
             done = (res_p < tol_p) & (res_d < tol_d)
+            if w.get("trace") is not None:      # test aid: how far the slowest problem is from the stop threshold
+                w["trace"].append((i, float((res_p / tol_p).max()), float((res_d / tol_d).max())))
             wants_update = (res_p > torch.maximum(tol_p, floor)) | (res_d > torch.maximum(tol_d, floor))
             if bool(done.all()):
                 break
@@ -232,12 +234,14 @@ def conclude(w: dict, x, z, u, sol, i):
     return {"x": x, "z": z, "u": u, "lams": lams, "nus": nus, "rho": rho, "iter": i}
 
 
-def solve(Q, p, A, b, lb, ub, control: dict) -> dict:
+def solve(Q, p, A, b, lb, ub, control: dict, trace=None) -> dict:
     """Forward solve; same dict as the reference's ``torch_solve_box_qp`` (:331)
-    plus ``'factorisations'`` (number of LU factorisations, 1 + rho updates)."""
+    plus ``'factorisations'`` (number of LU factorisations, 1 + rho updates).  ``trace`` (a list, test aid)
+    receives ``(i, max_b primal/tol_primal, max_b dual/tol_dual)`` of every stop check (:301-309)."""
     with torch.no_grad():
         st = derive_settings(control, p.shape[1])
         w = prepare(Q, p, A, b, lb, ub, st)
+        w["trace"] = trace
         x, z, u, sol, i, nfac = iterate(w, st)
         out = conclude(w, x, z, u, sol, i)
     out["factorisations"] = nfac

@@ -19,9 +19,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "QP/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # oracle/_ref (the unmodified reference, pip-installed by __graft_entry__.build()) when present, else the port
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     assert d["e2e"] == {"value": d["value"], "unit": "QP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    # the SAME config object as the GPU arm prints (one builder function): the driver's same_config check
+    assert set(d["config"]) == {"workload", "global_batch", "dz", "n_eq", "admm_iter", "parallelism", "l2"}
+    assert d["config"]["dz"] == 24 and d["config"]["global_batch"] == 16
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(NT) gj_inverse_kernel(GjArgs<T> a) {
           v = -Wb[(size_t)i * np + j];
           if (i == j) v *= T(0.5);
         }
-        tp[l * P::TC + ((kc + l) & 7) * P::VN + ec] = v;
+        tp[P::in_tile(l, kc, ec)] = v;
       }
     }
   }

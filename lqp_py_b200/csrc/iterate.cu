@@ -130,10 +130,10 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
     bool dirty = false;
     for (int r = 0; r < run_len; ++r) {
       mbar_wait(&full_w[c_slot], c_phase);
-      const T* tp = ring_w + (size_t)c_slot * TILE + lane * TC;
+      const T* tp = ring_w + (size_t)c_slot * TILE;
       V4 kv[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) kv[k] = *reinterpret_cast<const V4*>(tp + ((k + lane) & 7) * VN);
+      for (int k = 0; k < 8; ++k) kv[k] = *reinterpret_cast<const V4*>(tp + P::in_tile(lane, k));
       const T vI = vec[I * kPackRows + lane];
       xp[I * kPackRows + lane] += sa.apply(kv, vI);
       __syncwarp();                       // every lane has consumed the slot: it can be re-armed
@@ -377,6 +377,15 @@ __global__ void finalize_kernel(FwdWs<T> w, T* x, T* z, T* u, T* lams, T* rho_ou
 template <typename T>
 cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
                            int* launches, cudaStream_t st, const Tape<T>* tape) {
+  // regime dispatch: operators that fit in shared memory stay there for the whole solve
+  // (iterate_res.cu); everything else -- and the recording pass of the unrolled mode -- streams them (this file)
+  if (!tape) {
+    bool taken = false;
+    cudaError_t er = launch_iterate_rows<T>(cfg, w, i0, skip_rho_check, nus_out, launches, st, &taken);
+    if (er != cudaSuccess || taken) return er;
+    er = launch_iterate_resident<T>(cfg, w, i0, skip_rho_check, nus_out, launches, st, &taken);
+    if (er != cudaSuccess || taken) return er;
+  }
   int dev = 0, max_smem = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;

@@ -1,0 +1,488 @@
+// K3, small-problem regime -- the ADMM iteration kernel for problems whose operators fit in shared memory as FULL
+// matrices (dz <= ~150 in fp32, ~105 in fp64: the dz = 10, 50, 100 configurations of the reference's Experiment 1).
+//
+// Same loop as iterate.cu (reference lqp_py/solve_box_qp_admm_torch.py:235-313, :327) with the same global semantics
+// (all problems advance in lock step, stop together, adaptive-rho trigger from the previous check).  SURVEY App. C:
+// at these sizes an iteration is bound by instruction latency and synchronisation, not by bytes, so the kernel is
+// organised to have as few dependent steps per iteration as possible:
+//   * the packed K11 (and Q~) of every problem a CTA owns are expanded ONCE into dense row-major matrices in shared
+//     memory; an x-update is then a plain row-times-vector product -- `lpr` lanes share a row, each reads 16-byte
+//     chunks of the row and of the broadcast rhs, a log2(lpr)-step shuffle completes the dot product -- with no
+//     partial sums across warps and no column accumulators;
+//   * the lane that owns row r finishes the iteration for that coordinate in registers (clamp, dual update, next
+//     rhs into the OTHER rhs buffer, residual maxima): ONE group barrier per iteration;
+//   * a group of `gw` warps owns whole problems, groups run independently (dz = 10: one problem per warp, the
+//     barrier is a __syncwarp); the CTA meets only at the stop checks;
+//   * a stop check publishes the CTA's three flags AND its barrier arrival with ONE 64-bit reduction
+//     (arrivals | wants << 16 | ratio_out << 32 | not_optimal << 48); the word that completes the count carries the
+//     global decision, so the grid barrier costs one L2 round trip.  When the batch fits <= 8 CTAs the grid is one
+//     thread-block cluster and the wait is the hardware cluster barrier (0.26 us measured against 1.3 us);
+//   * nus (:327) is formed once, after the loop, from the rhs of the last solve (still intact in its buffer).
+#include <cstring>
+#include "itergeom.cuh"
+
+namespace lqpb {
+
+constexpr int kRowWarps = 16;
+constexpr int kRowThreads = kRowWarps * 32;
+constexpr int kRowVecs = 10;         // v0, v1, z, u, p~, lb~, ub~, c, D, x~ per resident problem
+
+struct RowGeom {
+  int G, ppc, gw, ngroups, cluster;
+  int lpr;        // lanes per row (power of two)
+  int ldk;        // row stride of the dense matrices (elements); chosen so that the lanes of a quarter warp hit
+                  // distinct banks
+  int nch;        // 16-byte chunks per row that hold data
+  int ldv;        // padded vector length (covers nch chunks)
+  size_t prob_elems, group_elems;
+};
+
+__device__ __forceinline__ void row_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void row_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_release_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRowThreads, 1)
+iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, RowGeom geo) {
+  using P = Pack<T>;
+  constexpr int VN = P::VN;
+  using V4 = typename Vec<T>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ unsigned long long s_word;
+  __shared__ int s_flags[4];
+  const int n = w.n, m = w.m, ld = w.ld;
+  const int gw = geo.gw, ngroups = geo.ngroups, lpr = geo.lpr, ldk = geo.ldk, nch = geo.nch, ldv = geo.ldv;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int grp = wid / gw, wg = wid % gw;
+  const int gtid = wg * 32 + lane, gthreads = gw * 32;
+  const int sub = gtid & (lpr - 1), rslot = gtid / lpr, rpp = gthreads / lpr;   // my chunk phase, my row slot, rows per pass
+  const int nprob = (w.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  Ctrl* ctrl = w.ctrl;
+
+  T* base = reinterpret_cast<T*>(smem_raw);
+  auto prob_K = [&](int q) { return base + (size_t)q * geo.prob_elems; };
+  auto prob_Q = [&](int q) { return prob_K(q) + (size_t)n * ldk; };
+  auto prob_vec = [&](int q, int k) { return prob_K(q) + 2 * (size_t)n * ldk + (size_t)k * ldv; };
+  T* red = base + (size_t)geo.ppc * geo.prob_elems + (size_t)grp * geo.group_elems;     // [6][16]
+  T* pscal = base + (size_t)geo.ppc * geo.prob_elems + (size_t)ngroups * geo.group_elems;   // [ppc][2]: rho, pnorm
+
+  // ---- one-time load: zero the problem blocks, expand the packed lower triangles into dense symmetric matrices
+  for (size_t t = tid; t < (size_t)nprob * geo.prob_elems; t += kRowThreads) base[t] = T(0);
+  if (tid == 0) s_flags[0] = s_flags[1] = s_flags[2] = 0;
+  __syncthreads();
+  {
+    const int ntv = P::nt(n), ntiles = P::ntiles(n);
+    const size_t per = (size_t)ntiles * P::TILE;
+    for (size_t t = tid; t < (size_t)nprob * per; t += kRowThreads) {
+      const int q = (int)(t / per);
+      const size_t o = t % per;
+      const int tile = (int)(o / P::TILE), in = (int)(o % P::TILE);
+      // inverse of Pack::in_tile (chunk-major): in = (k * 32 + l) * VN + e
+      const int e = in % VN, l = (in / VN) % kPackRows, k = in / (VN * kPackRows);
+      int Jc = 0, rem = tile;
+      while (rem >= ntv - Jc / P::R) { rem -= ntv - Jc / P::R; ++Jc; }
+      const int I = Jc / P::R + rem;
+      const int i = I * kPackRows + l, j = Jc * P::TC + k * VN + e;
+      if (i < n && j <= i) {
+        const int b = blockIdx.x + q * gridDim.x;
+        const size_t go = (size_t)b * per + o;
+        T kv = w.Kp[go], qv = w.Qp[go];
+        if (i == j) { kv += kv; qv += qv; }          // the packed layout stores the diagonal halved
+        prob_K(q)[(size_t)i * ldk + j] = kv;
+        prob_K(q)[(size_t)j * ldk + i] = kv;
+        prob_Q(q)[(size_t)i * ldk + j] = qv;
+        prob_Q(q)[(size_t)j * ldk + i] = qv;
+      }
+    }
+  }
+  for (int t = tid; t < nprob * n; t += kRowThreads) {
+    const int q = t / n, e = t % n;
+    const int b = blockIdx.x + q * gridDim.x;
+    const size_t vo = (size_t)b * ld + e;
+    const T rho = w.rho[b], z = w.z[vo], u = w.u[vo], pt = w.pt[vo];
+    prob_vec(q, 0)[e] = -pt + rho * (z - u);       // rhs of the first iteration (:259-262)
+    prob_vec(q, 2)[e] = z;
+    prob_vec(q, 3)[e] = u;
+    prob_vec(q, 4)[e] = pt;
+    prob_vec(q, 5)[e] = w.lbt[vo];
+    prob_vec(q, 6)[e] = w.ubt[vo];
+    prob_vec(q, 7)[e] = w.c[vo];
+    prob_vec(q, 8)[e] = w.D[vo];
+  }
+  for (int q = tid; q < nprob; q += kRowThreads) {
+    const int b = blockIdx.x + q * gridDim.x;
+    pscal[2 * q] = w.rho[b];
+    pscal[2 * q + 1] = w.pnorm[b];
+  }
+  __syncthreads();
+
+  const bool any_lb = ctrl->any_lb != 0, any_ub = ctrl->any_ub != 0;
+  int last_wants = ctrl->last_wants, last_rout = ctrl->last_ratio_out;
+  const int check = cfg.check_solved;
+  const T eps_abs = (T)cfg.eps_abs, eps_rel = (T)cfg.eps_rel, zc = (T)cfg.zero_clamp;
+  const T thr = (T)cfg.adaptive_rho_threshold, ar_tol = (T)cfg.adaptive_rho_tol, ar_tol_inv = (T)(1.0 / cfg.adaptive_rho_tol);
+  auto group_sync = [&]() {
+    if (gw == 1) __syncwarp();
+    else bar_sync(1 + grp, gthreads);
+  };
+  // dot product of row r of a dense matrix with a vector: the lpr lanes of the row take the chunks sub, sub + lpr, ...
+  auto row_dot = [&](const T* M, const T* vec, int r) -> T {
+    T a0 = T(0), a1 = T(0);
+    if (r < n) {
+      const T* row = M + (size_t)r * ldk;
+      for (int c = sub; c < nch; c += lpr) {
+        const V4 mv = *reinterpret_cast<const V4*>(row + c * VN);
+        const V4 vv = *reinterpret_cast<const V4*>(vec + c * VN);
+        const T* mp = reinterpret_cast<const T*>(&mv);
+        const T* vp = reinterpret_cast<const T*>(&vv);
+#pragma unroll
+        for (int e = 0; e < VN; e += 2) {
+          a0 += mp[e] * vp[e];
+          a1 += mp[e + 1] * vp[e + 1];
+        }
+      }
+    }
+    T a = a0 + a1;
+    for (int o = lpr >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    return a;
+  };
+
+  int i = i0, cur = 0;       // cur: which rhs buffer holds the rhs of iteration i
+  int status = 0;
+
+  while (true) {
+    // ---------------- adaptive rho (:237-256): decided from the previous check, applied before iteration i
+    if (cfg.adaptive_rho && i > 0 && i < cfg.adaptive_rho_max_iter && (i % cfg.adaptive_rho_iter) == 0 &&
+        !(i == i0 && skip_rho_check)) {
+      if (last_wants && last_rout) {
+        for (int k = tid; k < nprob; k += kRowThreads) {
+          const int b = blockIdx.x + k * gridDim.x;
+          if (w.wants[b]) {
+            T r = w.rho[b] * w.ratio[b];
+            r = t_min(t_max(r, (T)cfg.rho_min), (T)cfg.rho_max);
+            w.rho[b] = r;
+          }
+        }
+        status = 3;
+        break;
+      }
+    }
+    const bool is_check = (i % check) == 0;
+    const bool is_last = i == cfg.max_iters - 1;
+
+    for (int q = grp; q < nprob; q += ngroups) {
+      const int b = blockIdx.x + q * gridDim.x;
+      const T* v = prob_vec(q, cur);
+      T* vn = prob_vec(q, cur ^ 1);
+      T* zs = prob_vec(q, 2);
+      T* us = prob_vec(q, 3);
+      const T* pts = prob_vec(q, 4);
+      const T* lbs = prob_vec(q, 5);
+      const T* ubs = prob_vec(q, 6);
+      const T* cs = prob_vec(q, 7);
+      const T* Ds = prob_vec(q, 8);
+      T* xs = prob_vec(q, 9);
+      const T rho = pscal[2 * q];
+      // ---- x~ = K11 v + c, then the element-wise ADMM update (:271-282) by the lane that owns the row
+      T mx_p = T(0), mx_d = T(0), mx_x = T(0), mx_z = T(0), mx_y = T(0);
+      for (int r0 = 0; r0 < n; r0 += rpp) {
+        const int r = r0 + rslot;
+        const T dot = row_dot(prob_K(q), v, r);
+        if (sub == 0 && r < n) {
+          const T x = dot + cs[r];
+          const T z_prev = zs[r], u_prev = us[r];
+          T zn = x + u_prev;
+          if (any_lb) zn = t_max(zn, lbs[r]);
+          if (any_ub) zn = t_min(zn, ubs[r]);
+          const T res = x - zn;
+          const T sres = rho * (zn - z_prev);
+          const T un = u_prev + res;
+          zs[r] = zn;
+          us[r] = un;
+          vn[r] = -pts[r] + rho * (zn - un);        // rhs of the next iteration (:259-262)
+          xs[r] = x;
+          if (is_check) {
+            const T d = Ds[r];
+            mx_p = t_max(mx_p, t_abs(d * res));
+            mx_d = t_max(mx_d, t_abs(d * sres));
+            mx_x = t_max(mx_x, t_abs(d * x));
+            mx_z = t_max(mx_z, t_abs(d * zn));
+            mx_y = t_max(mx_y, t_abs(rho * d * un));
+          }
+        }
+      }
+      group_sync();
+      if (is_check) {
+        // ---- ||Q~ x~ / D||_inf (:299)
+        T mx_q = T(0);
+        for (int r0 = 0; r0 < n; r0 += rpp) {
+          const int r = r0 + rslot;
+          const T dot = row_dot(prob_Q(q), xs, r);
+          if (sub == 0 && r < n) mx_q = t_max(mx_q, t_abs(dot / Ds[r]));
+        }
+        mx_p = warp_max(mx_p); mx_d = warp_max(mx_d); mx_x = warp_max(mx_x);
+        mx_z = warp_max(mx_z); mx_y = warp_max(mx_y); mx_q = warp_max(mx_q);
+        if (gw > 1) {
+          if (lane == 0) {
+            red[0 * 16 + wg] = mx_p; red[1 * 16 + wg] = mx_d; red[2 * 16 + wg] = mx_x;
+            red[3 * 16 + wg] = mx_z; red[4 * 16 + wg] = mx_y; red[5 * 16 + wg] = mx_q;
+          }
+          group_sync();
+        }
+        if (gtid == 0) {
+          T mm[6] = {mx_p, mx_d, mx_x, mx_z, mx_y, mx_q};
+          if (gw > 1) {
+            for (int a = 0; a < 6; ++a) {
+              T r = red[a * 16];
+              for (int ww = 1; ww < gw; ++ww) r = t_max(r, red[a * 16 + ww]);
+              mm[a] = r;
+            }
+          }
+          const T primal = mm[0], dual = mm[1];
+          const T tol_p_rel = t_max(t_max(mm[2], mm[3]), zc);                      // :301
+          const T tol_p = eps_abs + eps_rel * tol_p_rel;                           // :302
+          const T tol_d_rel = t_max(t_max(t_max(mm[4], mm[5]), pscal[2 * q + 1]), zc);   // :303
+          const T tol_d = eps_abs + eps_rel * tol_d_rel;                           // :304
+          const bool optimal = (primal < tol_p) && (dual < tol_d);                // :307-309
+          const bool wants = (primal > t_max(tol_p, thr)) || (dual > t_max(tol_d, thr));   // :310-311
+          const T num = t_max(primal / tol_p_rel, zc), den = t_max(dual / tol_d_rel, zc);  // :239-242
+          const T ratio = t_sqrt(num / den);                                       // :243
+          w.chk[4 * b + 0] = primal; w.chk[4 * b + 1] = dual;
+          w.chk[4 * b + 2] = tol_p_rel; w.chk[4 * b + 3] = tol_d_rel;
+          w.wants[b] = wants ? 1 : 0;
+          w.ratio[b] = ratio;
+          if (!optimal) atomicOr(&s_flags[0], 1);
+          if (wants) atomicOr(&s_flags[1], 1);
+          if (ratio > ar_tol || ratio < ar_tol_inv) atomicOr(&s_flags[2], 1);     // :244-245
+          if (cfg.verbose) {
+            const int ci = i / check;
+            if (ci < LQPB_LOG_CAP) {
+              atomic_max_nonneg(&ctrl->log_primal[ci], (double)primal);
+              atomic_max_nonneg(&ctrl->log_dual[ci], (double)dual);
+              ctrl->log_iter[ci] = i;
+            }
+          }
+        }
+        if (gw > 1) group_sync();   // red[] reusable
+      }
+    }
+    // ---- the global decision (:312 torch.all): one packed word per check carries arrivals and flags
+    if (is_check) {
+      __syncthreads();
+      unsigned long long* word = reinterpret_cast<unsigned long long*>(&ctrl->slot[(i / check) & 3][0]);
+      if (tid == 0) {
+        const unsigned long long mine = 1ull | (s_flags[1] ? (1ull << 16) : 0ull) | (s_flags[2] ? (1ull << 32) : 0ull) |
+                                        (s_flags[0] ? (1ull << 48) : 0ull);
+        s_flags[0] = s_flags[1] = s_flags[2] = 0;
+        red_release_add_u64(word, mine);
+      }
+      if (geo.cluster) {
+        if (gridDim.x > 1) {
+          row_cluster_arrive();
+          row_cluster_wait();
+        }
+        if (tid == 0) s_word = ld_acquire_u64(word);
+      } else if (tid == 0) {
+        unsigned long long v;
+        do {
+          v = ld_acquire_u64(word);
+        } while ((unsigned)(v & 0xffffull) < gridDim.x);
+        s_word = v;
+      }
+      if (tid == 0 && blockIdx.x == 0) {
+        // slot of the check after next: every CTA has read it (it passed the previous barrier); the store is ordered
+        // before this CTA's next arrival, which every other CTA acquires before it can reach that check
+        unsigned long long* nxt = reinterpret_cast<unsigned long long*>(&ctrl->slot[((i / check) + 2) & 3][0]);
+        *nxt = 0ull;
+        const unsigned long long v = s_word;
+        ctrl->last_wants = (int)((v >> 16) & 0xffffull) != 0;
+        ctrl->last_ratio_out = (int)((v >> 32) & 0xffffull) != 0;
+        if (cfg.verbose) ctrl->n_log = min(i / check + 1, LQPB_LOG_CAP);
+      }
+      __syncthreads();
+      const unsigned long long v = s_word;
+      last_wants = ((v >> 16) & 0xffffull) != 0;
+      last_rout = ((v >> 32) & 0xffffull) != 0;
+      const bool all_optimal = ((v >> 48) & 0xffffull) == 0;
+      __syncthreads();
+      if (all_optimal) { status = 1; break; }
+    }
+    if (is_last) { status = 2; break; }
+    ++i;
+    cur ^= 1;
+  }
+  // ---- epilogue: nus of the LAST solve (:327) from its rhs, which is still intact in buffer `cur` (status 1 / 2:
+  //      the loop left before flipping; status 3 left before iteration i ran: nothing to report yet), and the state
+  __syncthreads();
+  if (status != 3 && m > 0) {
+    for (int q = grp; q < nprob; q += ngroups) {
+      const int b = blockIdx.x + q * gridDim.x;
+      const T* v = prob_vec(q, cur);
+      const T* Gt = w.Gt + (size_t)b * m * ld;
+      const T* K22 = w.Sinv + (size_t)b * m * m;
+      for (int l = wg; l < m; l += gw) {
+        T d = T(0);
+        for (int e = lane; e < n; e += 32) d += Gt[(size_t)l * ld + e] * v[e];
+        d = warp_sum(d);
+        if (lane == 0) {
+          T a = d;
+          for (int l2 = 0; l2 < m; ++l2) a += K22[l * m + l2] * w.bt[(size_t)b * m + l2];
+          nus_out[(size_t)b * m + l] = a * w.E[(size_t)b * m + l];
+        }
+      }
+    }
+  }
+  for (int t = tid; t < nprob * n; t += kRowThreads) {
+    const int q = t / n, e = t % n;
+    const int b = blockIdx.x + q * gridDim.x;
+    const size_t vo = (size_t)b * ld + e;
+    w.z[vo] = prob_vec(q, 2)[e];
+    w.u[vo] = prob_vec(q, 3)[e];
+    w.xs[vo] = prob_vec(q, 9)[e];
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    ctrl->status = status;
+    if (status == 3) ctrl->next_i = i;
+    else ctrl->iter = i;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static bool plan_rows(const FwdWs<T>& w, const lqpb_config& cfg, int max_smem, int n_sm, RowGeom* out, size_t* smem_bytes) {
+  constexpr int VN = Vec<T>::N;
+  const int n = w.n;
+  RowGeom g{};
+  g.nch = (n + VN - 1) / VN;
+  g.ldv = g.nch * VN;
+  const size_t budget = (size_t)max_smem / sizeof(T);
+  auto geom = [&](int ppc, int gw, RowGeom* gg, size_t* total) {
+    const int gthreads = gw * 32;
+    // lanes per row: the cheapest of the powers of two (passes over the rows x chunk steps per lane)
+    int best_lpr = 1;
+    long best_cost = -1;
+    for (int lpr = 1; lpr <= 32; lpr *= 2) {
+      const int rpp = gthreads / lpr;
+      const long passes = (n + rpp - 1) / rpp;
+      const long steps = (g.nch + lpr - 1) / lpr;
+      int lg = 0;
+      while ((1 << lg) < lpr) ++lg;
+      const long cost = passes * (steps * (2 + VN) + 2 * lg + 24);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_lpr = lpr; }
+    }
+    gg->lpr = best_lpr;
+    // row stride: a multiple of the 16-byte chunk with (stride in 4-byte banks) = 4 lpr mod 32 for lpr <= 8, so that
+    // the 8 / lpr rows a quarter warp touches per LDS.128 phase fall into disjoint bank groups
+    const int chunk_banks = 4;                         // 16 bytes
+    int ldk_banks = g.nch * chunk_banks;
+    if (best_lpr < 8) {
+      const int want = (chunk_banks * best_lpr) % 32;
+      while (ldk_banks % 32 != want) ldk_banks += chunk_banks;
+    }
+    gg->ldk = ldk_banks * 4 / (int)sizeof(T);
+    gg->prob_elems = 2 * (size_t)n * gg->ldk + (size_t)kRowVecs * g.ldv;
+    gg->prob_elems = (gg->prob_elems + VN - 1) / VN * VN;
+    gg->group_elems = 6 * 16;
+    const int ng = kRowWarps / gw;
+    *total = (size_t)ppc * gg->prob_elems + (size_t)ng * gg->group_elems + 2 * (size_t)ppc + 64;
+    return *total <= budget;
+  };
+  // warps per problem: enough lanes for ~one pass with 4 lanes per row, at most the whole CTA
+  int gw = 1;
+  while (gw < kRowWarps && gw * 32 < 2 * n) gw *= 2;
+  const bool chatty = cfg.check_solved <= 2;
+  int grids[2], ngr = 0;
+  if (chatty) {
+    // one cluster of <= 8 CTAs: the smallest grid in which every group owns at most one problem, else the largest
+    // that fits
+    int pick = 0;
+    for (int G = 1; G <= 8; G *= 2) {
+      RowGeom t = g;
+      size_t tot;
+      const int ppc = (w.B + G - 1) / G;
+      if (!geom(ppc, gw, &t, &tot)) continue;
+      pick = G;
+      if (ppc <= kRowWarps / gw) break;
+    }
+    if (pick) grids[ngr++] = pick;
+  }
+  grids[ngr++] = w.B < n_sm ? w.B : n_sm;
+  for (int c = 0; c < ngr; ++c) {
+    const int G = grids[c];
+    const int ppc = (w.B + G - 1) / G;
+    int gwx = gw;
+    while (gwx < kRowWarps && kRowWarps / gwx > ppc) gwx *= 2;      // no idle groups: fewer, wider groups
+    RowGeom t = g;
+    size_t tot;
+    if (!geom(ppc, gwx, &t, &tot)) continue;
+    t.G = G; t.ppc = ppc; t.gw = gwx; t.ngroups = kRowWarps / gwx;
+    t.cluster = (G <= 8) ? 1 : 0;
+    *smem_bytes = tot * sizeof(T);
+    *out = t;
+    return true;
+  }
+  return false;
+}
+
+template <typename T>
+cudaError_t launch_iterate_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
+                                int* launches, cudaStream_t st, bool* taken) {
+  *taken = false;
+  {
+    const char* e = getenv("LQPB_ITER");          // developer switch (A/B measurements): auto | rows | packed | stream
+    if (e && (!strcmp(e, "stream") || !strcmp(e, "packed"))) return cudaSuccess;
+  }
+  int dev = 0, max_smem = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  RowGeom geo{};
+  size_t smem = 0;
+  if (!plan_rows(w, cfg, max_smem - 2048, sms, &geo, &smem)) return cudaSuccess;
+  e = cudaMemsetAsync(&w.ctrl->barrier, 0, sizeof(unsigned), st);
+  if (e != cudaSuccess) return e;
+  void* kern = (void*)iterate_row_kernel<T>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lqpb_config c = cfg;
+  FwdWs<T> ww = w;
+  if (geo.cluster) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(geo.G);
+    lc.blockDim = dim3(kRowThreads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = geo.G;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    e = cudaLaunchKernelEx(&lc, iterate_row_kernel<T>, c, ww, i0, skip_rho_check, nus_out, geo);
+  } else {
+    void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo};
+    e = cudaLaunchCooperativeKernel(kern, dim3(geo.G), dim3(kRowThreads), args, smem, st);
+  }
+  if (e != cudaSuccess) return e;
+  if (launches) ++*launches;
+  *taken = true;
+  return cudaSuccess;
+}
+
+#define INST(T)                                                                                                      \
+  template cudaError_t launch_iterate_rows<T>(const lqpb_config&, const FwdWs<T>&, int, int, T*, int*, cudaStream_t, \
+                                              bool*);
+INST(float)
+INST(double)
+#undef INST
+
+}  // namespace lqpb

@@ -30,11 +30,14 @@ template <> inline bool tc_factor_enabled<float>(int n, int m) {
 // symmetric, so only the lower triangle is stored and streamed: half the bytes per ADMM iteration.
 // Layout: tiles of 32 rows x TC columns (TC = 32 floats / 16 doubles: 4 KB either way), ordered by
 // block column Jc and, inside a column, by block row I >= Jc / R (R = 32 / TC) -- a contiguous tile
-// sequence that is cut into per-warp runs and fetched with 1-D bulk TMA.  Inside a tile, row l holds its
-// 8 16-byte chunks rotated by l (chunk k at position (k + l) & 7), so that "lane l reads chunk k of row l"
-// is a bank-conflict-free shared-memory access.  Entries above the diagonal (inside diagonal tiles) and in
-// the padding rows/columns are zero and the diagonal is stored HALVED: every tile can then be applied
-// symmetrically ( x_I += T v_J  and  x_J += T^T v_I ) without a special case for diagonal tiles.
+// sequence that is cut into per-warp runs.  Inside a tile the data is CHUNK-MAJOR: the 16-byte chunk k (columns
+// k VN .. k VN + VN - 1) of all 32 rows is one contiguous 512-byte segment, row l at offset 16 l inside it.  The
+// access every consumer makes -- "lane l reads chunk k of row l" -- is then one fully coalesced 512-byte request
+// when the tile is read straight from global memory / L2 (streaming iteration kernel) and a bank-conflict-free
+// LDS.128 when the tile sits in shared memory (resident kernels, TMA-staged reverse sweep).  Entries above the
+// diagonal (inside diagonal tiles) and in the padding rows/columns are zero and the diagonal is stored HALVED: every
+// tile can then be applied symmetrically ( x_I += T v_J  and  x_J += T^T v_I ) without a special case for diagonal
+// tiles.  in_tile() is the ONE place that encodes the order inside a tile.
 constexpr int kPackRows = 32;
 template <typename T>
 struct Pack {
@@ -42,6 +45,8 @@ struct Pack {
   static constexpr int TC = 8 * VN;             // tile columns
   static constexpr int R = kPackRows / TC;      // block columns per block row (1 or 2)
   static constexpr int TILE = kPackRows * TC;   // elements per tile (4096 bytes)
+  // position of (row l, 16-byte chunk k, element e of the chunk) inside a tile
+  __host__ __device__ static int in_tile(int l, int k, int e = 0) { return (k * kPackRows + l) * VN + e; }
   __host__ __device__ static int nt(int n) { return (n + kPackRows - 1) / kPackRows; }
   __host__ __device__ static int nbc(int n) { return nt(n) * R; }
   __host__ __device__ static int col_start(int Jc, int ntv) {     // tiles in the block columns before Jc
@@ -53,7 +58,7 @@ struct Pack {
   // offset of element (i, j), j <= i
   __host__ __device__ static size_t offset(int i, int j, int ntv) {
     const int Jc = j / TC, I = i / kPackRows, l = i % kPackRows, c = j % TC, k = c / VN, e = c % VN;
-    return (size_t)(col_start(Jc, ntv) + I - Jc / R) * TILE + l * TC + ((k + l) & 7) * VN + e;
+    return (size_t)(col_start(Jc, ntv) + I - Jc / R) * TILE + in_tile(l, k, e);
   }
 };
 
@@ -241,6 +246,17 @@ struct Tape {
 template <typename T>
 cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
                            int* launches, cudaStream_t st, const Tape<T>* tape = nullptr);
+
+// iterate_res.cu -- K3, resident regime: the same loop with the operators held in shared memory for the whole solve
+// (problems whose packed K11 fits the shared memory of the SMs the batch can use).  *taken = false: does not apply.
+template <typename T>
+cudaError_t launch_iterate_resident(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
+                                    int* launches, cudaStream_t st, bool* taken);
+
+// iterate_row.cu -- K3, small-problem regime: dense operators in shared memory, one row per lane group
+template <typename T>
+cudaError_t launch_iterate_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
+                                int* launches, cudaStream_t st, bool* taken);
 
 // unroll.cu -- reverse sweep of the unrolled mode and the rank-n_iter products that form dQ~ and dA~
 template <typename T>

@@ -283,7 +283,7 @@ scale_pack_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ Q) {
         }
         if (i == j) v *= T(0.5);
       }
-      tp[l * P::TC + ((k + l) & 7) * P::VN + e] = v;
+      tp[P::in_tile(l, k, e)] = v;
     }
   }
   fro = warp_sum(fro);

@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(512) tc_extract_kernel(GjArgs<float> a, const 
         v = -Mb[bl_off(i, j)];
         if (i == j) v *= 0.5f;
       }
-      tp[l * P::TC + ((kc + l) & 7) * P::VN + ec] = v;
+      tp[P::in_tile(l, kc, ec)] = v;
     }
   }
   if (blockIdx.x != 0) return;

@@ -108,10 +108,10 @@ unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) 
     bool dirty = false;
     for (int r = 0; r < run_len; ++r) {
       mbar_wait(&full_w[c_slot], c_phase);
-      const T* tp = ring_w + (size_t)c_slot * TILE + lane * TC;
+      const T* tp = ring_w + (size_t)c_slot * TILE;
       V4 kv[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) kv[k] = *reinterpret_cast<const V4*>(tp + ((k + lane) & 7) * VN);
+      for (int k = 0; k < 8; ++k) kv[k] = *reinterpret_cast<const V4*>(tp + P::in_tile(lane, k));
       const T vI = vec[I * kPackRows + lane];
       xp[I * kPackRows + lane] += sa.apply(kv, vI);
       __syncwarp();

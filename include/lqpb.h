@@ -39,8 +39,9 @@ enum {
   LQPB_E_TAPE = 5           /* lqpb_unroll_forward_* in first-pass mode: the solve does not fit the tape (see there) */
 };
 
-/* status written to lqpb_info.status */
-enum { LQPB_STATUS_CONVERGED = 1, LQPB_STATUS_MAX_ITERS = 2 };
+/* status written to lqpb_info.status.  BREAKDOWN: an iterate became NaN / inf (singular or indefinite KKT system,
+ * non-finite input) -- the loop stops at the stop check that sees it instead of running on to max_iters. */
+enum { LQPB_STATUS_CONVERGED = 1, LQPB_STATUS_MAX_ITERS = 2, LQPB_STATUS_BREAKDOWN = 4 };
 
 /* Derived settings of solve_box_qp_admm_torch.py:134-154 (the keys the solver *reads*),
  * flattened by the Python adapter (lqp_py_b200/solve_box_qp_admm_torch.py). */
@@ -107,6 +108,28 @@ int lqpb_forward_f64(const lqpb_config* cfg, int B, int n, int m, const double* 
                      const double* A, const double* b, const double* lb, const double* ub,
                      double* x, double* z, double* u, double* lams, double* nus, double* rho_out,
                      lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- additions to the reference's behaviour (the reference always starts from x = z = u = 0,
+ * solve_box_qp_admm_torch.py:221-223, and keeps no record of how a solve ended, :235, :331) ---------------
+ * forward_warm:     lqpb_forward_* started from the caller's z0, u0 (B,n): the UNSCALED z and u an earlier solve of a
+ *                   nearby problem returned (both or neither; NULL, NULL = lqpb_forward_*).
+ * solution_status:  per-problem record of the LAST stop check of the solve whose workspace is passed (call it right
+ *                   after lqpb_forward_* on the same stream): residuals (B,4) = [primal residual, dual residual,
+ *                   primal tolerance, dual tolerance] (:286-304) and converged (B) = that problem's own stop test
+ *                   (:307-309).  The global stop needs ALL problems converged (:312); after LQPB_STATUS_MAX_ITERS
+ *                   this tells which ones were not. */
+int lqpb_forward_warm_f32(const lqpb_config* cfg, int B, int n, int m, const float* Q, const float* p,
+                          const float* A, const float* b, const float* lb, const float* ub, const float* z0,
+                          const float* u0, float* x, float* z, float* u, float* lams, float* nus, float* rho_out,
+                          lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream);
+int lqpb_forward_warm_f64(const lqpb_config* cfg, int B, int n, int m, const double* Q, const double* p,
+                          const double* A, const double* b, const double* lb, const double* ub, const double* z0,
+                          const double* u0, double* x, double* z, double* u, double* lams, double* nus,
+                          double* rho_out, lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream);
+int lqpb_solution_status_f32(const lqpb_config* cfg, int B, int n, int m, void* workspace, size_t workspace_bytes,
+                             float* residuals, int32_t* converged, void* stream);
+int lqpb_solution_status_f64(const lqpb_config* cfg, int B, int n, int m, void* workspace, size_t workspace_bytes,
+                             double* residuals, int32_t* converged, void* stream);
 
 /* ---- backward: replaces torch_solve_box_qp_grad (solve_box_qp_admm_torch.py:349-432) ------
  * rho_dev: per-problem rho (B) or NULL, in which case rho_scalar is used (:356-357, :379-382).

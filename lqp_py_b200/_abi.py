@@ -17,7 +17,8 @@ E_TAPE = 5          # LQPB_E_TAPE
 EXPORTS = (
     "lqpb_abi_version", "lqpb_last_error", "lqpb_profile_enable", "lqpb_profile_get",
     "lqpb_forward_workspace_bytes_f32", "lqpb_forward_workspace_bytes_f64",
-    "lqpb_forward_f32", "lqpb_forward_f64",
+    "lqpb_forward_f32", "lqpb_forward_f64", "lqpb_forward_warm_f32", "lqpb_forward_warm_f64",
+    "lqpb_solution_status_f32", "lqpb_solution_status_f64",
     "lqpb_backward_workspace_bytes_f32", "lqpb_backward_workspace_bytes_f64",
     "lqpb_backward_f32", "lqpb_backward_f64", "lqpb_backward_kkt_f32", "lqpb_backward_kkt_f64",
     "lqpb_forward_prep_f32", "lqpb_forward_prep_f64", "lqpb_backward_finish_f32", "lqpb_backward_finish_f64",
@@ -95,6 +96,11 @@ def lib():
         f = getattr(L, f"lqpb_forward_{sfx}")
         f.argtypes = [C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 6 + [C.POINTER(Info), vp, sz, vp]
         f.restype = i32
+        f = getattr(L, f"lqpb_forward_warm_{sfx}")
+        f.argtypes = [C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 2 + [vp] * 6 + [C.POINTER(Info), vp, sz, vp]
+        f.restype = i32
+        f = getattr(L, f"lqpb_solution_status_{sfx}")
+        f.argtypes, f.restype = [C.POINTER(Config), i32, i32, i32, vp, sz, vp, vp, vp], i32
         f = getattr(L, f"lqpb_backward_{sfx}")
         f.argtypes = [i32, i32, i32] + [vp] * 9 + [vp, dbl] + [vp] * 6 + [vp, sz, vp]
         f.restype = i32

@@ -176,6 +176,8 @@ FwdWs<T> slice_fwd(const FwdWs<T>& w, int b0, int bc) {
   s.fro_part += o * w.n_fro;
   s.chk += 4 * o;
   s.wants += o;
+  if (w.z0) s.z0 += o * w.n;
+  if (w.u0) s.u0 += o * w.n;
   return s;
 }
 template <typename T>
@@ -282,20 +284,23 @@ template <typename T>
 int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A, const T* b,
                  const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, lqpb_info* info, void* ws,
                  size_t ws_bytes, void* stream, const HostFwd<T>* host = nullptr, const UnrollRec<T>* rec = nullptr,
-                 const BwdPrep<T>* prep = nullptr) {
+                 const BwdPrep<T>* prep = nullptr, const T* z0 = nullptr, const T* u0 = nullptr) {
   if (host && (!host->Q || !host->p || !host->lb || !host->ub || (m > 0 && (!host->A || !host->b))))
     return fail(LQPB_E_ARG, "null host pointer argument");
   if (!cfg || !Q || !p || !lb || !ub || !x || !z || !u || !lams || !rho_out || !info || !ws)
     return fail(LQPB_E_ARG, "null pointer argument");
   if (B <= 0 || n <= 0 || m < 0) return fail(LQPB_E_ARG, "bad dimensions");
   if (m > 0 && (!A || !b || !nus)) return fail(LQPB_E_ARG, "A, b and nus are required when m > 0");
-  if (m > kMaxM) return fail(LQPB_E_ARG, "more than 64 equality rows are not supported");
+  if (m > kMaxM) return fail(LQPB_E_ARG, "more than 256 equality rows are not supported");
+  if ((z0 == nullptr) != (u0 == nullptr)) return fail(LQPB_E_ARG, "a warm start needs both z0 and u0");
   if (cfg->max_iters < 1 || cfg->check_solved < 1 || cfg->adaptive_rho_iter < 1)
     return fail(LQPB_E_ARG, "max_iters, check_solved and adaptive_rho_iter must be >= 1");
   int rc = check_device();
   if (rc) return rc;
   FwdWs<T> w = carve_fwd<T>(ws, B, n, m);
   if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
+  w.z0 = z0;
+  w.u0 = u0;
   cudaStream_t st = (cudaStream_t)stream;
   if (!g_hctrl.pinned) CK(cudaMallocHost(&g_hctrl.pinned, sizeof(Ctrl)), "cudaMallocHost");
   Ctrl* hc = g_hctrl.pinned;
@@ -424,7 +429,7 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
     }
     break;
   }
-  if (hc->status != LQPB_STATUS_CONVERGED && hc->status != LQPB_STATUS_MAX_ITERS)
+  if (hc->status != LQPB_STATUS_CONVERGED && hc->status != LQPB_STATUS_MAX_ITERS && hc->status != LQPB_STATUS_BREAKDOWN)
     return fail(LQPB_E_CUDA, "iteration kernel ended without a status");
   if (rec && !rec->snap) {          // first-pass mode: the tape only has to be long enough
     if (hc->status == LQPB_STATUS_MAX_ITERS && rec->true_max_iters > rec->tape.n_iter)
@@ -463,7 +468,7 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
     return fail(LQPB_E_ARG, "null pointer argument");
   if (B <= 0 || n <= 0 || m < 0) return fail(LQPB_E_ARG, "bad dimensions");
   if (m > 0 && (!A || !nus)) return fail(LQPB_E_ARG, "A and nus are required when m > 0");
-  if (m > kMaxM) return fail(LQPB_E_ARG, "more than 64 equality rows are not supported");
+  if (m > kMaxM) return fail(LQPB_E_ARG, "more than 256 equality rows are not supported");
   int rc = check_device();
   if (rc) return rc;
   BwdWs<T> w = carve_bwd<T>(ws, B, n, m);
@@ -715,6 +720,28 @@ int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x,
   return backward_impl<double>(B, n, m, dl_dz, x, u, lams, nus, Q, A, lb, ub, rho_dev, rho_scalar, dQ, dp, dA, db,
                                dlb, dub, workspace, workspace_bytes, stream);
 }
+
+#define WARM_ENTRY(SFX, T)                                                                                          \
+  int lqpb_forward_warm_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A,     \
+                              const T* b, const T* lb, const T* ub, const T* z0, const T* u0, T* x, T* z, T* u,    \
+                              T* lams, T* nus, T* rho_out, lqpb_info* info, void* workspace, size_t workspace_bytes, \
+                              void* stream) {                                                                      \
+    return forward_impl<T>(cfg, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, workspace,         \
+                           workspace_bytes, stream, nullptr, nullptr, nullptr, z0, u0);                            \
+  }                                                                                                                \
+  int lqpb_solution_status_##SFX(const lqpb_config* cfg, int B, int n, int m, void* workspace,                     \
+                                 size_t workspace_bytes, T* residuals, int32_t* converged, void* stream) {         \
+    if (!cfg || !workspace || !residuals || !converged || B <= 0 || n <= 0 || m < 0)                               \
+      return fail(LQPB_E_ARG, "bad argument");                                                                     \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    FwdWs<T> w = carve_fwd<T>(workspace, B, n, m);                                                                 \
+    if (w.bytes > workspace_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");                           \
+    CK(launch_status<T>(*cfg, w, residuals, converged, (cudaStream_t)stream), "status");                           \
+    return LQPB_OK;                                                                                                \
+  }
+WARM_ENTRY(f32, float)
+WARM_ENTRY(f64, double)
 
 #define PREP_ENTRY(SFX, T)                                                                                         \
   int lqpb_forward_prep_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A,     \

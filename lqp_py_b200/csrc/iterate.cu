@@ -37,7 +37,7 @@ template <typename T, bool TAPE>
 __global__ void __launch_bounds__(kIterMaxThreads, 1)
 iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, IterGeom geo, Tape<T> tape) {
   using P = Pack<T>;
-  constexpr int VN = P::VN, TC = P::TC, TILE = P::TILE;
+  constexpr int TC = P::TC, TILE = P::TILE;
   using V4 = typename Vec<T>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = w.n, m = w.m, ld = w.ld, np = geo.np;
@@ -178,7 +178,7 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
     const bool is_last = i == cfg.max_iters - 1;
     const bool maybe_final = TAPE || is_check || is_last;
 
-    int cta_notopt = 0, cta_wants = 0, cta_rout = 0;
+    int cta_notopt = 0, cta_wants = 0, cta_rout = 0, cta_bad = 0;
     for (int k = 0; k < nprob; ++k) {
       const int b = blockIdx.x + k * gridDim.x;
       const size_t vo = (size_t)b * ld;
@@ -231,6 +231,7 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
           tape.u[to] = un;
         }
         if (is_check) {
+          if (!(t_abs(x) < t_inf<T>())) cta_bad = 1;       // NaN / inf iterate: numerical breakdown
           const T d = w.D[vo + e];
           Ds[e] = d;
           mx_p = t_max(mx_p, t_abs(d * r));
@@ -307,11 +308,13 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
     }
     // ---- publish this CTA's flags and make the decision global (:312 torch.all)
     if (is_check) {
+      cta_bad = __syncthreads_or(cta_bad);
       if (tid == 0) {
         int* slot = ctrl->slot[(i / check) & 3];
         if (cta_notopt) atomicAdd(&slot[0], cta_notopt);
         if (cta_wants) atomicOr(&slot[1], 1);
         if (cta_rout) atomicOr(&slot[2], 1);
+        if (cta_bad) atomicOr(&slot[3], 1);
         __threadfence();
         atomicAdd(&ctrl->barrier, 1u);
         const unsigned target = (barrier_epoch + 1) * gridDim.x;
@@ -321,9 +324,10 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
         s_dec[0] = *(volatile int*)&slot[0];
         s_dec[1] = *(volatile int*)&slot[1];
         s_dec[2] = *(volatile int*)&slot[2];
+        s_dec[3] = *(volatile int*)&slot[3];
         if (blockIdx.x == 0) {
           int* nxt = ctrl->slot[((i / check) + 2) & 3];
-          nxt[0] = 0; nxt[1] = 0; nxt[2] = 0;
+          nxt[0] = 0; nxt[1] = 0; nxt[2] = 0; nxt[3] = 0;
           ctrl->last_wants = s_dec[1];
           ctrl->last_ratio_out = s_dec[2];
           if (cfg.verbose) ctrl->n_log = min(i / check + 1, LQPB_LOG_CAP);
@@ -335,7 +339,9 @@ iterate_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_o
       const int notopt = s_dec[0];
       last_wants = s_dec[1];
       last_rout = s_dec[2];
+      const int broken = s_dec[3];
       __syncthreads();
+      if (broken) { status = 4; break; }           // LQPB_STATUS_BREAKDOWN: some iterate is NaN / inf
       if (notopt == 0) { status = 1; break; }
     }
     if (is_last) { status = 2; break; }
@@ -409,6 +415,29 @@ cudaError_t launch_iterate(const lqpb_config& cfg, const FwdWs<T>& w, int i0, in
   return e;
 }
 
+// Per-problem record of the LAST stop check (reference :286-311 evaluates these and throws them away; a solve that
+// runs out of iterations is silent there): residual norms, the relative scales of their tolerances, and whether the
+// problem satisfied its own stop test.  out: (B, 4) = [primal, dual, tol_primal, tol_dual], converged: (B) int.
+template <typename T>
+__global__ void status_kernel(lqpb_config cfg, FwdWs<T> w, T* out, int* converged) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= w.B) return;
+  const T primal = w.chk[4 * b + 0], dual = w.chk[4 * b + 1];
+  const T tol_p = (T)cfg.eps_abs + (T)cfg.eps_rel * w.chk[4 * b + 2];
+  const T tol_d = (T)cfg.eps_abs + (T)cfg.eps_rel * w.chk[4 * b + 3];
+  out[4 * b + 0] = primal;
+  out[4 * b + 1] = dual;
+  out[4 * b + 2] = tol_p;
+  out[4 * b + 3] = tol_d;
+  converged[b] = (primal < tol_p && dual < tol_d) ? 1 : 0;
+}
+
+template <typename T>
+cudaError_t launch_status(const lqpb_config& cfg, const FwdWs<T>& w, T* out, int* converged, cudaStream_t st) {
+  status_kernel<T><<<(w.B + 127) / 128, 128, 0, st>>>(cfg, w, out, converged);
+  return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho_out, cudaStream_t st) {
   dim3 grid((w.n + 127) / 128, w.B);
@@ -419,7 +448,8 @@ cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho
 #define INST(T)                                                                                            \
   template cudaError_t launch_iterate<T>(const lqpb_config&, const FwdWs<T>&, int, int, T*, int*, cudaStream_t, \
                                          const Tape<T>*);                                                  \
-  template cudaError_t launch_finalize<T>(const FwdWs<T>&, T*, T*, T*, T*, T*, cudaStream_t);
+  template cudaError_t launch_finalize<T>(const FwdWs<T>&, T*, T*, T*, T*, T*, cudaStream_t);                \
+  template cudaError_t launch_status<T>(const lqpb_config&, const FwdWs<T>&, T*, int*, cudaStream_t);
 INST(float)
 INST(double)
 #undef INST

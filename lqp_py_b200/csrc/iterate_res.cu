@@ -64,7 +64,7 @@ template <typename T>
 __global__ void __launch_bounds__(kResThreads, 1)
 iterate_res_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, ResGeom geo) {
   using P = Pack<T>;
-  constexpr int VN = P::VN, TC = P::TC, TILE = P::TILE;
+  constexpr int TC = P::TC, TILE = P::TILE;
   using V4 = typename Vec<T>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t load_bar;
@@ -92,7 +92,7 @@ iterate_res_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
   if (tid == 0) {
     mbar_init(&load_bar, 1);
     fence_mbar_init();
-    s_flags[0] = s_flags[1] = s_flags[2] = 0;
+    s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
   }
   __syncthreads();
   if (tid == 0) {
@@ -272,6 +272,7 @@ iterate_res_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
         v[e] = -pts[e] + rho * (zn - un);
         xs[e] = x;
         if (is_check) {
+          if (!(t_abs(x) < t_inf<T>())) s_flags[3] = 1;    // NaN / inf iterate: numerical breakdown (benign race: all write 1)
           const T d = Ds[e];
           mx_p = t_max(mx_p, t_abs(d * r));
           mx_d = t_max(mx_d, t_abs(d * sres));
@@ -358,7 +359,8 @@ iterate_res_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
         if (s_flags[0]) atomicAdd(&slot[0], s_flags[0]);
         if (s_flags[1]) atomicOr(&slot[1], 1);
         if (s_flags[2]) atomicOr(&slot[2], 1);
-        s_flags[0] = s_flags[1] = s_flags[2] = 0;
+        if (s_flags[3]) atomicOr(&slot[3], 1);
+        s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
         __threadfence();
       }
       if (geo.cluster) {
@@ -377,9 +379,10 @@ iterate_res_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
         s_dec[0] = ld_acquire_s32(&slot[0]);
         s_dec[1] = ld_acquire_s32(&slot[1]);
         s_dec[2] = ld_acquire_s32(&slot[2]);
+        s_dec[3] = ld_acquire_s32(&slot[3]);
         if (blockIdx.x == 0) {
           int* nxt = ctrl->slot[((i / check) + 2) & 3];
-          nxt[0] = 0; nxt[1] = 0; nxt[2] = 0;
+          nxt[0] = 0; nxt[1] = 0; nxt[2] = 0; nxt[3] = 0;
           ctrl->last_wants = s_dec[1];
           ctrl->last_ratio_out = s_dec[2];
           if (cfg.verbose) ctrl->n_log = min(i / check + 1, LQPB_LOG_CAP);
@@ -392,7 +395,9 @@ iterate_res_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
       const int notopt = s_dec[0];
       last_wants = s_dec[1];
       last_rout = s_dec[2];
+      const int broken = s_dec[3];
       __syncthreads();
+      if (broken) { status = 4; break; }           // LQPB_STATUS_BREAKDOWN
       if (notopt == 0) { status = 1; break; }
     }
     if (is_last) { status = 2; break; }

@@ -14,7 +14,7 @@
 //   * a group of `gw` warps owns whole problems, groups run independently (dz = 10: one problem per warp, the
 //     barrier is a __syncwarp); the CTA meets only at the stop checks;
 //   * a stop check publishes the CTA's three flags AND its barrier arrival with ONE 64-bit reduction
-//     (arrivals | wants << 16 | ratio_out << 32 | not_optimal << 48); the word that completes the count carries the
+//     (arrivals | wants << 16 | ratio_out << 28 | not_optimal << 40 | breakdown << 52); the word that completes the count carries the
 //     global decision, so the grid barrier costs one L2 round trip.  When the batch fits <= 8 CTAs the grid is one
 //     thread-block cluster and the wait is the hardware cluster barrier (0.26 us measured against 1.3 us);
 //   * nus (:327) is formed once, after the loop, from the rhs of the last solve (still intact in its buffer).
@@ -75,7 +75,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
 
   // ---- one-time load: zero the problem blocks, expand the packed lower triangles into dense symmetric matrices
   for (size_t t = tid; t < (size_t)nprob * geo.prob_elems; t += kRowThreads) base[t] = T(0);
-  if (tid == 0) s_flags[0] = s_flags[1] = s_flags[2] = 0;
+  if (tid == 0) s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
   __syncthreads();
   {
     const int ntv = P::nt(n), ntiles = P::ntiles(n);
@@ -209,6 +209,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
           vn[r] = -pts[r] + rho * (zn - un);        // rhs of the next iteration (:259-262)
           xs[r] = x;
           if (is_check) {
+            if (!(t_abs(x) < t_inf<T>())) s_flags[3] = 1;  // NaN / inf iterate: numerical breakdown (benign race)
             const T d = Ds[r];
             mx_p = t_max(mx_p, t_abs(d * res));
             mx_d = t_max(mx_d, t_abs(d * sres));
@@ -278,9 +279,9 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
       __syncthreads();
       unsigned long long* word = reinterpret_cast<unsigned long long*>(&ctrl->slot[(i / check) & 3][0]);
       if (tid == 0) {
-        const unsigned long long mine = 1ull | (s_flags[1] ? (1ull << 16) : 0ull) | (s_flags[2] ? (1ull << 32) : 0ull) |
-                                        (s_flags[0] ? (1ull << 48) : 0ull);
-        s_flags[0] = s_flags[1] = s_flags[2] = 0;
+        const unsigned long long mine = 1ull | (s_flags[1] ? (1ull << 16) : 0ull) | (s_flags[2] ? (1ull << 28) : 0ull) |
+                                        (s_flags[0] ? (1ull << 40) : 0ull) | (s_flags[3] ? (1ull << 52) : 0ull);
+        s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
         red_release_add_u64(word, mine);
       }
       if (geo.cluster) {
@@ -302,16 +303,18 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
         unsigned long long* nxt = reinterpret_cast<unsigned long long*>(&ctrl->slot[((i / check) + 2) & 3][0]);
         *nxt = 0ull;
         const unsigned long long v = s_word;
-        ctrl->last_wants = (int)((v >> 16) & 0xffffull) != 0;
-        ctrl->last_ratio_out = (int)((v >> 32) & 0xffffull) != 0;
+        ctrl->last_wants = ((v >> 16) & 0xfffull) != 0;
+        ctrl->last_ratio_out = ((v >> 28) & 0xfffull) != 0;
         if (cfg.verbose) ctrl->n_log = min(i / check + 1, LQPB_LOG_CAP);
       }
       __syncthreads();
       const unsigned long long v = s_word;
-      last_wants = ((v >> 16) & 0xffffull) != 0;
-      last_rout = ((v >> 32) & 0xffffull) != 0;
-      const bool all_optimal = ((v >> 48) & 0xffffull) == 0;
+      last_wants = ((v >> 16) & 0xfffull) != 0;
+      last_rout = ((v >> 28) & 0xfffull) != 0;
+      const bool all_optimal = ((v >> 40) & 0xfffull) == 0;
+      const bool broken = (v >> 52) != 0;
       __syncthreads();
+      if (broken) { status = 4; break; }           // LQPB_STATUS_BREAKDOWN: some iterate is NaN / inf
       if (all_optimal) { status = 1; break; }
     }
     if (is_last) { status = 2; break; }
@@ -321,7 +324,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
   // ---- epilogue: nus of the LAST solve (:327) from its rhs, which is still intact in buffer `cur` (status 1 / 2:
   //      the loop left before flipping; status 3 left before iteration i ran: nothing to report yet), and the state
   __syncthreads();
-  if (status != 3 && m > 0) {
+  if (status != 3 && m > 0) {      // (after a breakdown the values are NaN like everything else)
     for (int q = grp; q < nprob; q += ngroups) {
       const int b = blockIdx.x + q * gridDim.x;
       const T* v = prob_vec(q, cur);

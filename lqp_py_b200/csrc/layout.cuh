@@ -12,7 +12,7 @@ namespace lqpb {
 
 constexpr int kTile = 32;      // Gauss-Jordan tile edge
 constexpr int kMacro = 64;     // macro tile edge of the trailing update (np is a multiple of it)
-constexpr int kMaxM = 64;      // max equality rows handled by the Schur-complement path
+constexpr int kMaxM = 256;     // max equality rows (they live in the padding of the factorisation; per-CTA scratch is sized by it)
 constexpr int kTcBlock = 128;  // block edge of the tensor-core factorisation (tcfactor.cu)
 
 // fp32 problems with n + m > 128 are factorised on the tensor cores (tcfactor.cu: blocked sweep with
@@ -83,6 +83,7 @@ struct FwdWs {
   T* chk;       // B*4  [primal, dual, tol_primal_rel, tol_dual_rel] of the last check
   int* wants;   // B    do_rho_update of the last check
   Ctrl* ctrl;
+  const T *z0, *u0;   // optional warm start (caller's UNSCALED z, u of an earlier solve, (B, n)); null = zero start (:221-223)
   size_t bytes;
 };
 
@@ -90,6 +91,7 @@ template <typename T>
 inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
   FwdWs<T> w;
   w.B = B; w.n = n; w.m = m;
+  w.z0 = w.u0 = nullptr;
   w.ld = round_up(n, Vec<T>::N);
   w.np = round_up(n + m, kMacro);
   char* p = static_cast<char*>(base);
@@ -276,6 +278,9 @@ template <typename T>
 cudaError_t launch_scale_grad(int B, int n, T* G, const T* Q, const T* D, const T* coef, T* gD, T* part, cudaStream_t st);
 template <typename T>
 cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho_out, cudaStream_t st);
+
+template <typename T>
+cudaError_t launch_status(const lqpb_config& cfg, const FwdWs<T>& w, T* out, int* converged, cudaStream_t st);
 
 // backward.cu -- K5/K6
 template <typename T>

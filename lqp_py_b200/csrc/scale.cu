@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(kColmaxThreads) colmax_kernel(FwdWs<T> w, cons
 template <typename T>
 __global__ void __launch_bounds__(kScaleThreads)
 scale_vec_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ p, const T* __restrict__ A,
-                 const T* __restrict__ bvec, const T* __restrict__ lb, const T* __restrict__ ub, int P2) {
+                 const T* __restrict__ bvec, const T* __restrict__ lb, const T* __restrict__ ub, int P2, int SB) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Ds = reinterpret_cast<T*>(smem_raw);           // [ld]   column norms, then D
-  T* sortbuf = Ds + w.ld;                           // [P2]
-  T* scratch = sortbuf + P2;                        // [32]
+  T* sortbuf = Ds + w.ld;                           // [SB = max(P2, m)]: sort buffer of P2 entries, later the m row norms
+  T* scratch = sortbuf + SB;                        // [32]
   double* dscratch = reinterpret_cast<double*>(scratch + 32);  // [32]
   __shared__ T s_beta, s_mean;
 
@@ -173,8 +173,10 @@ scale_vec_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ p, const T* 
     w.pt[vo + j] = pv;
     w.lbt[vo + j] = l;
     w.ubt[vo + j] = uu;
-    w.z[vo + j] = T(0);
-    w.u[vo + j] = T(0);
+    // ADMM state: zero (reference :221-223), or a warm start from the caller's unscaled z, u of an earlier solve
+    // (z = D z~, u = u~ / D, :316-318)
+    w.z[vo + j] = (w.z0 && j < n) ? w.z0[(size_t)b * n + j] / d : T(0);
+    w.u[vo + j] = (w.u0 && j < n) ? w.u0[(size_t)b * n + j] * d : T(0);
     w.c[vo + j] = T(0);
     w.xs[vo + j] = T(0);
   }
@@ -192,7 +194,7 @@ scale_vec_kernel(lqpb_config cfg, FwdWs<T> w, const T* __restrict__ p, const T* 
 
   // ---- equality rows: A~ = E (A D), b~ = E b (:179-190)
   if (m > 0) {
-    T* rown = sortbuf;  // reuse: [m] row norms (m <= kMaxM <= P2)
+    T* rown = sortbuf;  // reuse: [m] row norms (m <= SB)
     for (int l = 0; l < m; ++l) {
       const T* Al = A + ((size_t)b * m + l) * n;
       T mx = T(0);
@@ -335,10 +337,11 @@ cudaError_t launch_scale(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, 
   }
   int P2 = 64;
   while (P2 < w.n) P2 <<= 1;
-  const size_t smem = (size_t)(w.ld + P2 + 32) * sizeof(T) + 32 * sizeof(double) + 16;
+  const int SB = P2 > w.m ? P2 : round_up(w.m, 4);
+  const size_t smem = (size_t)(w.ld + SB + 32) * sizeof(T) + 32 * sizeof(double) + 16;
   e = cudaFuncSetAttribute(scale_vec_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  scale_vec_kernel<T><<<w.B, kScaleThreads, smem, st>>>(cfg, w, p, A, b, lb, ub, P2);
+  scale_vec_kernel<T><<<w.B, kScaleThreads, smem, st>>>(cfg, w, p, A, b, lb, ub, P2, SB);
   dim3 gp(w.n_fro, w.B);
   scale_pack_kernel<T><<<gp, kPackThreads, 0, st>>>(cfg, w, Q);
   return cudaGetLastError();

@@ -27,7 +27,7 @@ template <typename T>
 __global__ void __launch_bounds__(kIterMaxThreads, 1)
 unroll_reverse_kernel(FwdWs<T> w, Tape<T> tape, UnrollGrads<T> g, IterGeom geo) {
   using P = Pack<T>;
-  constexpr int VN = P::VN, TC = P::TC, TILE = P::TILE;
+  constexpr int TC = P::TC, TILE = P::TILE;
   using V4 = typename Vec<T>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int n = w.n, m = w.m, ld = w.ld, np = geo.np, K = tape.n_iter;     // K: rows of the tape per problem

@@ -63,7 +63,7 @@ class SolveBoxQPLayer(torch.autograd.Function):
             # host callers: only the workspace is needed here (their gradient buffers are pinned host memory)
             L = _abi.lib()
             dev = _cuda_device(p)
-            nb_ws = getattr(L, f"lqpb_backward_workspace_bytes_{_abi.suffix(p.dtype)}")(Q.shape[0], p.shape[1], get_ncon(A, dim=1))
+            nb_ws = _ws_bytes("backward", _abi.suffix(p.dtype), Q.shape[0], p.shape[1], get_ncon(A, dim=1))
             ctx.pre = dict(ws=torch.empty(nb_ws, dtype=torch.uint8, device=dev), key=None)
             prep = dict(ws=ctx.pre["ws"], kkt=control.get('backward', 'fixed_point') == 'kkt')
         if p.is_cuda and any(ctx.needs_input_grad[:6]):
@@ -120,8 +120,15 @@ class BoxQPTH:
         self.control = control
         self.sol = {}
 
-    def solve(self):
-        sol = torch_solve_box_qp(Q=self.Q, p=self.p, A=self.A, b=self.b, lb=self.lb, ub=self.ub, control=self.control)
+    def solve(self, warm_start=False):
+        """``warm_start=True`` (an addition: the reference always starts from zero, :221-223) starts the ADMM loop from
+        the ``z`` / ``u`` of the previous ``solve()`` of this holder -- the natural mode when only ``p`` changed a
+        little between two solves, as in a learning loop."""
+        z0 = u0 = None
+        if warm_start and self.sol.get('z') is not None and self.sol.get('u') is not None:
+            z0, u0 = self.sol['z'], self.sol['u']
+        sol = torch_solve_box_qp(Q=self.Q, p=self.p, A=self.A, b=self.b, lb=self.lb, ub=self.ub, control=self.control,
+                                 z0=z0, u0=u0)
         self.sol = sol
         return sol.get('x')
 
@@ -139,14 +146,42 @@ class BoxQPTH:
 # ------------------------------------------------------------------------------------------
 # functional API
 # ------------------------------------------------------------------------------------------
-def torch_solve_box_qp(Q, p, A, b, lb, ub, control):
-    """Forward solve (reference :108-333).  Returns the same dict
+STATUS_CONVERGED, STATUS_MAX_ITERS, STATUS_BREAKDOWN = 1, 2, 4      # lqpb_info.status
+
+
+def torch_solve_box_qp(Q, p, A, b, lb, ub, control, z0=None, u0=None):
+    """Forward solve (reference :108-333).  Returns the reference's dict
     ``{"x","z","u","lams","nus","rho","iter"}``; ``rho`` is a ``(B,1,1)`` tensor when it was
-    selected automatically or adapted and the caller's scalar otherwise, ``iter`` a Python int."""
+    selected automatically or adapted and the caller's scalar otherwise, ``iter`` a Python int.
+
+    Additions (the reference has neither): ``z0`` / ``u0`` -- the ``z`` / ``u`` of an earlier solve --
+    warm-start the loop (the reference always starts from zero, :221-223); and the dict also says HOW the solve ended,
+    which the reference drops (:235, :331): ``status`` (1 converged, 2 max_iters reached, 4 numerical breakdown: an
+    iterate became NaN / inf) and, per problem, ``converged`` (B,) bool = its own stop test at the last check
+    (:307-309), ``primal_residual`` / ``dual_residual`` / ``primal_tolerance`` / ``dual_tolerance`` (B,1,1)
+    (:286-304).  ``control['validate'] = True`` checks the documented preconditions (finite inputs, symmetric Q) first
+    and raises ``ValueError`` instead of returning a silently different answer."""
+    if control.get('validate', False):
+        _validate_inputs(Q, p, A, b, lb, ub)
     if control.get('unroll', False):
         return _solve_unrolled(Q, p, A, b, lb, ub, control)           # :328-329 -- a bare x, connected to autograd
-    sol = _solve_device(Q, p, A, b, lb, ub, control)
-    return {k: sol[k] for k in ("x", "z", "u", "lams", "nus", "rho", "iter")}
+    sol = _solve_device(Q, p, A, b, lb, ub, control, z0=z0, u0=u0, want_status=True)
+    return {k: sol[k] for k in ("x", "z", "u", "lams", "nus", "rho", "iter", "status", "converged", "primal_residual",
+                                "dual_residual", "primal_tolerance", "dual_tolerance")}
+
+
+def _validate_inputs(Q, p, A, b, lb, ub):
+    """Preconditions of the path (reference docstring :109-121: Q an SPD tensor): the factorisations read the lower
+    triangle of Q and do not pivot, so a non-symmetric Q would give a different answer than the reference's pivoted LU."""
+    for name, t in (("Q", Q), ("p", p), ("A", A), ("b", b)):
+        if t is not None and not bool(torch.isfinite(t).all()):
+            raise ValueError(f"{name} contains non-finite entries")
+    if bool(torch.isnan(lb).any()) or bool(torch.isnan(ub).any()):
+        raise ValueError("lb / ub contain NaN")
+    asym = float((Q - Q.transpose(1, 2)).abs().max())
+    scale = float(Q.abs().max())
+    if asym > 1e-6 * max(scale, 1e-300) * (1.0 if Q.dtype == torch.float32 else 1e-6):
+        raise ValueError(f"Q is not symmetric (max |Q - Q^T| = {asym:.3e}); the solver reads its lower triangle")
 
 
 def torch_solve_box_qp_grad(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho):
@@ -224,10 +259,53 @@ def _to_device_of(t, device):
     return _to_devices([t], [device])[0]
 
 
+_DTYPE_VALUE_CACHE = {}
+
+
 def _default_dtype_value(v):
     """The reference builds some constants with ``torch.ones(1) * v`` in the *default* dtype
-    (:150, :230); reproduce the rounding."""
-    return float((torch.ones(1) * v).item())
+    (:150, :230); reproduce the rounding (cached per default dtype: the tensor round trip costs ~10 us)."""
+    key = (torch.get_default_dtype(), v)
+    r = _DTYPE_VALUE_CACHE.get(key)
+    if r is None:
+        r = _DTYPE_VALUE_CACHE[key] = float((torch.ones(1) * v).item())
+    return r
+
+
+def _raw_stream(dev):
+    """cudaStream_t of torch's current stream on ``dev`` (the raw-handle accessor skips building a Stream object)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device())
+    except Exception:
+        return _raw_stream(dev)
+
+
+class _on_device:
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already the current device (the context manager costs ~5 us)."""
+
+    def __init__(self, dev):
+        self.ctx = None if (dev.index is None or dev.index == torch.cuda.current_device()) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
+
+
+_WS_BYTES_CACHE = {}
+
+
+def _ws_bytes(kind, sfx, B, n, m):
+    """lqpb_{forward,backward}_workspace_bytes_* (pure functions of the shape), cached."""
+    key = (kind, sfx, B, n, m)
+    r = _WS_BYTES_CACHE.get(key)
+    if r is None:
+        r = _WS_BYTES_CACHE[key] = getattr(_abi.lib(), f"lqpb_{kind}_workspace_bytes_{sfx}")(B, n, m)
+    return r
 
 
 def _derive_config(control, n_x):
@@ -278,7 +356,8 @@ def _host_view(t):
     return None if t is None else t.detach().contiguous()
 
 
-def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_cap=None):
+def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_cap=None, z0=None, u0=None,
+                  want_status=False):
     L = _abi.lib()
     out_device = p.device
     host_mode = _all_on_host((Q, p, A, b, lb, ub))
@@ -303,16 +382,16 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
     B, n = Qd.shape[0], pd.shape[1]
     m = get_ncon(dv["A"], dim=1)
     cfg = _derive_config(control, n)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
         x, z, u = new(B, n, 1), new(B, n, 1), new(B, n, 1)
         lams = new(B, 2 * n, 1)
         nus = new(B, m, 1) if m > 0 else None
         rho_t = new(B, 1, 1)
-        ws_bytes = getattr(L, f"lqpb_forward_workspace_bytes_{sfx}")(B, n, m)
+        ws_bytes = _ws_bytes("forward", sfx, B, n, m)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         info = _abi.Info()
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _raw_stream(dev)
         flag = C.c_int32(0)
         if host_mode:
             hx = torch.empty((B, n, 1), dtype=dt, pin_memory=True)
@@ -348,12 +427,33 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
                 prep["ws"].numel(), 1 if prep["kkt"] else 0, C.byref(flag), C.c_void_p(stream))
             _abi.check(rc, "lqpb_forward_prep")
             prepared = bool(flag.value)
+        elif z0 is not None or u0 is not None:
+            if z0 is None or u0 is None:
+                raise ValueError("a warm start needs both z0 and u0")
+            wz, wu = (t.detach().to(device=dev, dtype=dt).reshape(B, n).contiguous() for t in (z0, u0))
+            rc = getattr(L, f"lqpb_forward_warm_{sfx}")(
+                C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
+                _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(wz), _abi.ptr(wu), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u),
+                _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(rho_t), C.byref(info), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
+            _abi.check(rc, "lqpb_forward_warm")
         else:
             rc = getattr(L, f"lqpb_forward_{sfx}")(
                 C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
                 _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u), _abi.ptr(lams),
                 _abi.ptr(nus), _abi.ptr(rho_t), C.byref(info), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
             _abi.check(rc, "lqpb_forward")
+        extra = {}
+        if want_status:
+            resid = torch.empty((B, 4), dtype=dt, device=dev)
+            conv = torch.empty((B,), dtype=torch.int32, device=dev)
+            rc = getattr(L, f"lqpb_solution_status_{sfx}")(C.byref(cfg), B, n, m, _abi.ptr(ws), ws_bytes, _abi.ptr(resid),
+                                                          _abi.ptr(conv), C.c_void_p(stream))
+            _abi.check(rc, "lqpb_solution_status")
+            if out_device.type == "cpu":
+                resid, conv = resid.cpu(), conv.cpu()
+            extra = {"converged": conv != 0, "primal_residual": resid[:, 0].reshape(B, 1, 1),
+                     "dual_residual": resid[:, 1].reshape(B, 1, 1), "primal_tolerance": resid[:, 2].reshape(B, 1, 1),
+                     "dual_tolerance": resid[:, 3].reshape(B, 1, 1)}
     if cfg.verbose:
         for k in range(info.n_log):          # same text as the reference prints (:289-294)
             print(f'iteration = {info.log_iter[k]}')
@@ -376,7 +476,7 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
     x_out, hz, hu, hlams, hnus, hrho = _to_devices(vals, want)
     hx = hx if hx is not None else x_out
     rho_out = hrho if torch.is_tensor(rho) else rho
-    return {"x": hx, "z": hz, "u": hu, "lams": hlams, "nus": hnus, "rho": rho_out,
+    return {**extra, "x": hx, "z": hz, "u": hu, "lams": hlams, "nus": hnus, "rho": rho_out,
             "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor),
             "_any_lb": bool(info.any_lb), "_any_ub": bool(info.any_ub), "_dev": dv,
             "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus, "_ws": ws, "_cfg": cfg, "_prepared": prepared, "_tape": tape_info,
@@ -428,13 +528,13 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
     if first_pass:
         (*tape, tape_nu), state["n_iter"] = sol["_tape"]       # rows beyond K are unused; n_iter is the row stride
         seg_start = [0, K]
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         if first_pass:
             pass
         elif S == 1:
             tape = [torch.empty((B, K, n), dtype=dt, device=dev) for _ in range(3)]
             tape_nu = torch.empty((B, K, m), dtype=dt, device=dev) if m > 0 else None
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            stream = _raw_stream(dev)
             rc = getattr(L, f"lqpb_unroll_record_{sfx}")(
                 C.byref(cfg), B, n, m, K, _abi.ptr(ws), ws.numel(), _abi.ptr(tape[0]), _abi.ptr(tape[1]),
                 _abi.ptr(tape[2]), _abi.ptr(tape_nu), C.c_void_p(stream))
@@ -444,7 +544,7 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
             # adaptive-rho updates: a full recording solve that also keeps the operators of every segment
             tape = [torch.empty((B, K, n), dtype=dt, device=dev) for _ in range(3)]
             tape_nu = torch.empty((B, K, m), dtype=dt, device=dev) if m > 0 else None
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            stream = _raw_stream(dev)
             d = sol["_dev"]
             each = getattr(L, f"lqpb_unroll_snapshot_bytes_{sfx}")(B, n, m)
             snaps = torch.empty(S * each, dtype=torch.uint8, device=dev)
@@ -605,7 +705,7 @@ class _ScaledQAndRho(torch.autograd.Function):
         B, n = Q.shape[0], Q.shape[1]
         dev, dt = Q.device, Q.dtype
         sfx = _abi.suffix(dt)
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             # the adjoint of Q~ has one producer (the loop node) and one consumer (this node): overwritten in place
             G = gQt.contiguous() if gQt is not None else torch.zeros((B, n, n), dtype=dt, device=dev)
             coef = None
@@ -616,7 +716,7 @@ class _ScaledQAndRho(torch.autograd.Function):
             gD = torch.empty((B, n), dtype=dt, device=dev) if Dv is not None else None
             nscr = getattr(L, f"lqpb_unroll_scale_grad_scratch_elems_{sfx}")(B, n)
             scratch = torch.empty(nscr, dtype=dt, device=dev)
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            stream = _raw_stream(dev)
             Dc = Dv.detach().contiguous() if Dv is not None else None
             rc = getattr(L, f"lqpb_unroll_scale_grad_{sfx}")(
                 B, n, _abi.ptr(G), _abi.ptr(Q.detach().contiguous()), _abi.ptr(Dc), _abi.ptr(coef), _abi.ptr(gD),
@@ -656,7 +756,7 @@ class _UnrolledSegment(torch.autograd.Function):
         snap = None
         if st["snaps"] is not None:
             snap = C.c_void_p(st["snaps"].data_ptr() + ctx.seg * st["snap_each"])
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
             if "tw" not in st:                        # scratch for the adjoint solves, shared by all segments
                 st["tw"] = new(B, K, n)
@@ -667,7 +767,7 @@ class _UnrolledSegment(torch.autograd.Function):
             gb = new(B, m, 1) if m > 0 else None
             gz_in = new(B, n, 1) if need[7] else None
             gu_in = new(B, n, 1) if need[8] else None
-            stream = torch.cuda.current_stream(dev).cuda_stream
+            stream = _raw_stream(dev)
             rc = getattr(L, f"lqpb_unroll_backward_{sfx}")(
                 B, n, m, K, k_lo, k_hi, _abi.ptr(ws), ws.numel(), snap, _abi.ptr(gx), _abi.ptr(gz), _abi.ptr(gu),
                 _abi.ptr(gzp), _abi.ptr(tx), _abi.ptr(tz), _abi.ptr(tu), _abi.ptr(tnu), _abi.ptr(st["tw"]),
@@ -686,9 +786,9 @@ def _prealloc_backward(Q, p, A, need):
     B, n = Q.shape[0], p.shape[1]
     m = get_ncon(A, dim=1)
     nQ, np_, nA, nb, nlb, nub = need
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
-        ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{_abi.suffix(dt)}")(B, n, m)
+        ws_bytes = _ws_bytes("backward", _abi.suffix(dt), B, n, m)
         return dict(dQ=new(B, n, n) if nQ else None, dp=new(B, n, 1) if np_ else None,
                     dA=new(B, m, n) if (nA and m > 0) else None, db=new(B, m, 1) if (nb and m > 0) else None,
                     dlb=new(B, n, 1) if nlb else None, dub=new(B, n, 1) if nub else None,
@@ -722,8 +822,8 @@ def _grad_device(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, pre=None, fini
         pre = _prealloc_backward(Q, x, A, need)
     dQ, dp, dA, db, dlb, dub, ws = (pre[k] for k in ("dQ", "dp", "dA", "db", "dlb", "dub", "ws"))
     ws_bytes = ws.numel()
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
+    with _on_device(dev):
+        stream = _raw_stream(dev)
         if finish:                          # the forward call left the factorised adjoint system in pre["ws"]
             rc = getattr(L, f"lqpb_backward_finish_{sfx}")(
                 B, n, m, 0, _abi.ptr(g), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A),
@@ -762,8 +862,8 @@ def _grad_kkt_device(dl_dz, x, lams, nus, Q, A, lb, ub, need, any_bounds, pre=No
     dlb = pre["dlb"] if (any_bounds is None or any_bounds[0]) else None
     dub = pre["dub"] if (any_bounds is None or any_bounds[1]) else None
     ws_bytes = ws.numel()
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
+    with _on_device(dev):
+        stream = _raw_stream(dev)
         if finish and any_bounds is not None:
             rc = getattr(L, f"lqpb_backward_finish_{sfx}")(
                 B, n, m, 1, _abi.ptr(g), _abi.ptr(x), None, _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A),
@@ -813,13 +913,13 @@ def _grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, kkt, any_bounds,
         nub = nub and any_bounds[1]
     shapes = [(B, n, n) if nQ else None, (B, n, 1) if np_ else None, (B, m, n) if (nA and m > 0) else None,
               (B, m, 1) if (nb and m > 0) else None, (B, n, 1) if nlb else None, (B, n, 1) if nub else None]
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         dbuf = [None if s is None else torch.empty(s, dtype=dt, device=dev) for s in shapes]
         hbuf = [None if s is None else torch.empty(s, dtype=dt, pin_memory=True) for s in shapes]
         g_dev = torch.empty((B, n, 1), dtype=dt, device=dev)
-        ws_bytes = getattr(L, f"lqpb_backward_workspace_bytes_{sfx}")(B, n, m)
+        ws_bytes = _ws_bytes("backward", sfx, B, n, m)
         ws = prepared_ws if prepared_ws is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        stream = torch.cuda.current_stream(dev).cuda_stream
+        stream = _raw_stream(dev)
         rc = getattr(L, f"lqpb_backward_host_{sfx}")(
             B, n, m, 1 if kkt else 0, _abi.ptr(g), _abi.ptr(g_dev), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams),
             _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A), _abi.ptr(lb), _abi.ptr(ub), _abi.ptr(rho_dev), rho_scalar,

@@ -569,38 +569,38 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
                                                        fused_rho=sol["rho_dev"] if S == 1 else None, fused=S == 1)
     check = cfg.check_solved
     z_in = u_in = x_l = None
+    at_check = rho_at_check = None
     for s_idx in range(S):
         lo, hi = seg_start[s_idx], seg_start[s_idx + 1] - 1
-        pieces = [(lo, hi)]
-        if s_idx < S - 1:                       # the update at hi + 1 reads the last check before it, iteration c (:239-243)
-            c = (hi // check) * check
-            if c < lo:
-                raise NotImplementedError("unroll=True with adaptive_rho_iter < check_solved: an adaptive-rho update "
-                                          "would read a check made before the previous update")
-            pieces = [(lo, c)] + ([(c + 1, hi)] if c < hi else [])
+        # every segment is cut after the last check iteration it contains: an adaptive-rho update reads the residual
+        # norms of the most recent check (:239-243), which may lie in THIS segment or -- when adaptive_rho_iter is
+        # shorter than check_solved -- in an earlier one, whose state (and the rho then in force) is kept
+        c = (hi // check) * check
+        pieces = [(lo, hi)] if (s_idx == S - 1 or c < lo) else [(lo, c)] + ([(c + 1, hi)] if c < hi else [])
         for (k_lo, k_hi) in pieces:
             x_l, z_l, u_l, zp_l = _UnrolledSegment.apply(
                 Qt, pt, At, bt, lbt if any_lb else None, ubt if any_ub else None, rho if torch.is_tensor(rho) else None,
                 z_in, u_in, state, k_lo, k_hi, s_idx)
             z_in, u_in = z_l, u_l
-            if s_idx < S - 1 and k_hi == pieces[0][1]:
-                at_check = (x_l, z_l, u_l, zp_l)
+            if s_idx < S - 1 and c >= lo and k_hi == c:
+                at_check, rho_at_check = (x_l, z_l, u_l, zp_l), rho
         if s_idx < S - 1:
-            rho = _adapted_rho(rho, at_check, wants[s_idx].view(B, 1, 1) != 0, Qt, pd, D, cfg, control)
+            rho = _adapted_rho(rho, rho_at_check, at_check, wants[s_idx].view(B, 1, 1) != 0, Qt, pd, D, cfg, control)
     x = D * x_l                                                          # :316
     return x if x.device == out_device else x.to(out_device)
 
 
-def _adapted_rho(rho, at_check, wants, Qt, p, D, cfg, control):
+def _adapted_rho(rho, rho_chk, at_check, wants, Qt, p, D, cfg, control):
     """rho after an adaptive update (reference :239-250) as a differentiable function of the state recorded at the
-    last check (:286-304).  ``wants`` is the kernel's do_rho_update mask (:310-311), a decision, not differentiated."""
+    last check (:286-304) and of ``rho_chk``, the rho in force at that check (it differs from ``rho`` when several
+    updates follow one check).  ``wants`` is the kernel's do_rho_update mask (:310-311), a decision, not differentiated."""
     x, z, u, z_prev = at_check
     ninf = lambda t: torch.linalg.norm(t, ord=_INF, dim=1, keepdim=True)
     tiny = torch.full((1,), cfg.zero_clamp, dtype=x.dtype, device=x.device)                    # :229-230
-    r, s = x - z, rho * (z - z_prev)                                                          # :279-280
+    r, s = x - z, rho_chk * (z - z_prev)                                                      # :279-280
     primal, dual = ninf(D * r), ninf(D * s)                                                  # :286-287
     scale_p = torch.maximum(torch.maximum(ninf(D * x), ninf(D * z)), tiny)                   # :296-301
-    scale_d = torch.maximum(torch.maximum(torch.maximum(ninf(rho * D * u), ninf(torch.matmul(Qt, x) / D)), ninf(p)), tiny)
+    scale_d = torch.maximum(torch.maximum(torch.maximum(ninf(rho_chk * D * u), ninf(torch.matmul(Qt, x) / D)), ninf(p)), tiny)
     num = torch.clamp(primal / scale_p, min=cfg.zero_clamp)                                  # :239-242
     den = torch.clamp(dual / scale_d, min=cfg.zero_clamp)
     ratio = (num / den) ** 0.5                                                               # :243
@@ -662,19 +662,30 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub, fused=False, fu
 
 
 class _ColumnMax(torch.autograd.Function):
-    """``norm(Q, inf, dim=1)`` (:163) with a sparse adjoint: one entry per column (the first maximiser; torch's own
-    backward splits the gradient among exact ties, which only zero columns produce -- and those carry no gradient)."""
+    """``norm(Q, inf, dim=1)`` (:163) with a sparse adjoint: one entry per column when the maximiser is unique.  torch's
+    own backward of the inf-norm splits the gradient evenly among EXACT ties (constant blocks, equicorrelation
+    matrices, |Q_ij| == Q_jj); columns with ties take that dense rule here too, so dQ matches the reference's."""
 
     @staticmethod
     def forward(ctx, Q):
-        colmax, idx = Q.abs().max(dim=1)
+        aQ = Q.abs()
+        colmax, idx = aQ.max(dim=1)
+        ties = (aQ == colmax.unsqueeze(1)).sum(dim=1)              # maximisers per column
         sign = torch.sign(torch.gather(Q, 1, idx.unsqueeze(1)).squeeze(1))
-        ctx.save_for_backward(idx, sign)
+        ctx.tied = bool((ties > 1).any())
+        if ctx.tied:
+            ctx.save_for_backward(idx, sign, Q, colmax, ties)
+        else:
+            ctx.save_for_backward(idx, sign)
         ctx.shape = Q.shape
         return colmax
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.tied:
+            idx, sign, Q, colmax, ties = ctx.saved_tensors
+            mask = Q.abs() == colmax.unsqueeze(1)
+            return mask * torch.sign(Q) * (g / ties).unsqueeze(1)
         idx, sign = ctx.saved_tensors
         out = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
         out.scatter_(1, idx.unsqueeze(1), (sign * g).unsqueeze(1))

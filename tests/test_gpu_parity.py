@@ -742,3 +742,33 @@ def test_experiment2_nccl_two_gpus():
     out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert out["world"] == 2 and out["ranks_hold_identical_weights"]
     assert out["loss_curve_rel_err_vs_single_process"] < 1e-6 and out["weights_rel_err_vs_single_process"] < 1e-6
+
+
+def test_unrolled_adaptive_rho_iter_shorter_than_check(dev):
+    """unroll=True with adaptive_rho_iter rounding below check_solved (reference :145-147 turns 4 into 1 at n = 30):
+    every iteration may update rho from the residuals of a check made several updates ago (:237-250).  Round 1 refused
+    this configuration; the stale check's state and the rho then in force are now kept across segments.  Compared with
+    autograd through the oracle's loop (the rho recursion is unstable by construction, so the run is cut at 25
+    iterations like any max_iters exit)."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP
+    dtype = torch.float64
+    Q, p, A, b, lb, ub = orc.make_exp1_data(30, 4, seed=3, dtype=dtype)
+    g = torch.randn(p.shape, generator=torch.Generator().manual_seed(5), dtype=dtype)
+    control = box_qp_control(eps_abs=1e-6, eps_rel=1e-6, rho=100.0, adaptive_rho_iter=4, max_iters=25, unroll=True)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        leaves = [t.clone().requires_grad_(True) for t in (Q, p, A, b, lb, ub)]
+        xr = orc.solve_unrolled(*leaves, dict(control))
+        xr.backward(g)
+        plain = orc.solve(Q, p, A, b, lb, ub, dict(control, unroll=False))
+    finally:
+        torch.set_default_dtype(prev)
+    assert plain["factorisations"] > 3                     # several updates between two checks
+    ins = [t.to(dev).requires_grad_(True) for t in (Q, p, A, b, lb, ub)]
+    x = SolveBoxQP(control=control).forward(*ins)
+    x.backward(g.to(dev))
+    assert rel_err(x.detach().cpu().numpy(), xr.detach().numpy()) <= 1e-8
+    for a, r, nm in zip(ins, leaves, ("dQ", "dp", "dA", "db", "dlb", "dub")):
+        assert rel_err(a.grad.cpu().numpy(), r.grad.numpy()) <= 1e-7, nm

@@ -673,6 +673,11 @@ __global__ void __launch_bounds__(kPiv8Threads, 1) tc_pivot8_kernel(TcArgs a) {
   }
 }
 
+// (Round 2 measured the same sweep with 16 pivots per step -- 8 rank-16 updates, rows S in two warps, the look-ahead warp
+// forming and inverting a 16 x 16 block by a ping-pong sweep in shared memory; git history, "tc_pivot16_kernel".  Correct
+// (all parity tests), but the look-ahead chain -- 16 serial shared-memory sweep steps behind a 16-step D' update on ONE
+// warp -- became the critical path: 84 us per launch against 39 us here.  Rejected; the 8 x 8 inverse in registers with
+// shuffles is what keeps the look-ahead off the critical path.)
 // (A tensor-core variant of the pivot-block inverse was built and measured in round 1 -- the 16 rank-8 updates as
 // tcgen05.mma M = N = 128, K = 8 instructions accumulating in TMEM, rows read back with tcgen05.ld, exact 8 x 8
 // diagonal blocks in a side buffer, look-ahead inverse on a 17th warp; git history, "LQPB_TC_PIVOT=m".  Its inverse

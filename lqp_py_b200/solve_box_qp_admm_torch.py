@@ -25,6 +25,7 @@ CPU tensors are staged to the current CUDA device and the results are returned o
 There is no CPU compute path: without a CUDA device (or without ``_lqpb.so``) the calls raise.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -301,7 +302,7 @@ _WS_BYTES_CACHE = {}
 
 def _ws_bytes(kind, sfx, B, n, m):
     """lqpb_{forward,backward}_workspace_bytes_* (pure functions of the shape), cached."""
-    key = (kind, sfx, B, n, m)
+    key = (kind, sfx, B, n, m, os.environ.get("LQPB_FACTOR"))      # (the developer switch changes the layout)
     r = _WS_BYTES_CACHE.get(key)
     if r is None:
         r = _WS_BYTES_CACHE[key] = getattr(_abi.lib(), f"lqpb_{kind}_workspace_bytes_{sfx}")(B, n, m)

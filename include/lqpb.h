@@ -55,7 +55,8 @@ typedef struct lqpb_config {
   int32_t rho_auto;              /* 1 when control['rho'] is None (:200) */
   int32_t beta_auto;             /* 1 when control['beta'] is None (:171) */
   int32_t verbose;               /* :151 -- per-check residual log is returned in lqpb_info */
-  int32_t reserved;
+  int32_t keep_operators;        /* 1: leave K11 / K21 / K22 / Q~ of the solve in the workspace (the recording pass of the
+                                    unrolled mode re-reads them); 0 lets small problems take the one-launch forward */
   double eps_abs;                /* :135-136 clamped to >= 1e-12 */
   double eps_rel;                /* :137-138 */
   double rho;                    /* user rho when rho_auto == 0 */
@@ -126,6 +127,25 @@ int lqpb_forward_warm_f64(const lqpb_config* cfg, int B, int n, int m, const dou
                           const double* A, const double* b, const double* lb, const double* ub, const double* z0,
                           const double* u0, double* x, double* z, double* u, double* lams, double* nus,
                           double* rho_out, lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream);
+/* forward_async: lqpb_forward_warm_* without the end-of-solve synchronisation, for callers that only need x (the autograd
+ * layer, :26-53).  When the one-launch forward applies (small problems; adaptive-rho refactorisations happen on the device
+ * there, so nothing about the solve needs the host) the call returns as soon as the bound flags are known: info->any_lb /
+ * any_ub are valid, *deferred = 1, and everything else is written into `pinned_ctrl` (lqpb_ctrl_bytes() bytes of
+ * page-locked host memory, owned by the caller) when the stream reaches the end of the solve; lqpb_forward_collect decodes
+ * it into info after the caller has synchronised the stream.  Otherwise (*deferred = 0) the call behaved exactly like
+ * lqpb_forward_warm_* and info is complete. */
+size_t lqpb_ctrl_bytes(void);
+int lqpb_forward_async_f32(const lqpb_config* cfg, int B, int n, int m, const float* Q, const float* p,
+                           const float* A, const float* b, const float* lb, const float* ub, const float* z0,
+                           const float* u0, float* x, float* z, float* u, float* lams, float* nus, float* rho_out,
+                           void* pinned_ctrl, lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream,
+                           int32_t* deferred);
+int lqpb_forward_async_f64(const lqpb_config* cfg, int B, int n, int m, const double* Q, const double* p,
+                           const double* A, const double* b, const double* lb, const double* ub, const double* z0,
+                           const double* u0, double* x, double* z, double* u, double* lams, double* nus,
+                           double* rho_out, void* pinned_ctrl, lqpb_info* info, void* workspace,
+                           size_t workspace_bytes, void* stream, int32_t* deferred);
+int lqpb_forward_collect(const void* pinned_ctrl, const lqpb_config* cfg, lqpb_info* info);
 int lqpb_solution_status_f32(const lqpb_config* cfg, int B, int n, int m, void* workspace, size_t workspace_bytes,
                              float* residuals, int32_t* converged, void* stream);
 int lqpb_solution_status_f64(const lqpb_config* cfg, int B, int n, int m, void* workspace, size_t workspace_bytes,

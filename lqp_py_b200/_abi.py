@@ -18,7 +18,8 @@ EXPORTS = (
     "lqpb_abi_version", "lqpb_last_error", "lqpb_profile_enable", "lqpb_profile_get",
     "lqpb_forward_workspace_bytes_f32", "lqpb_forward_workspace_bytes_f64",
     "lqpb_forward_f32", "lqpb_forward_f64", "lqpb_forward_warm_f32", "lqpb_forward_warm_f64",
-    "lqpb_solution_status_f32", "lqpb_solution_status_f64",
+    "lqpb_solution_status_f32", "lqpb_solution_status_f64", "lqpb_forward_async_f32", "lqpb_forward_async_f64",
+    "lqpb_ctrl_bytes", "lqpb_forward_collect",
     "lqpb_backward_workspace_bytes_f32", "lqpb_backward_workspace_bytes_f64",
     "lqpb_backward_f32", "lqpb_backward_f64", "lqpb_backward_kkt_f32", "lqpb_backward_kkt_f64",
     "lqpb_forward_prep_f32", "lqpb_forward_prep_f64", "lqpb_backward_finish_f32", "lqpb_backward_finish_f64",
@@ -39,7 +40,7 @@ class Config(C.Structure):
     _fields_ = [
         ("max_iters", C.c_int32), ("check_solved", C.c_int32), ("adaptive_rho", C.c_int32),
         ("adaptive_rho_iter", C.c_int32), ("adaptive_rho_max_iter", C.c_int32), ("scale", C.c_int32),
-        ("rho_auto", C.c_int32), ("beta_auto", C.c_int32), ("verbose", C.c_int32), ("reserved", C.c_int32),
+        ("rho_auto", C.c_int32), ("beta_auto", C.c_int32), ("verbose", C.c_int32), ("keep_operators", C.c_int32),
         ("eps_abs", C.c_double), ("eps_rel", C.c_double), ("rho", C.c_double), ("rho_min", C.c_double),
         ("rho_max", C.c_double), ("adaptive_rho_tol", C.c_double), ("adaptive_rho_threshold", C.c_double),
         ("beta", C.c_double), ("zero_clamp", C.c_double),
@@ -99,6 +100,10 @@ def lib():
         f = getattr(L, f"lqpb_forward_warm_{sfx}")
         f.argtypes = [C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 2 + [vp] * 6 + [C.POINTER(Info), vp, sz, vp]
         f.restype = i32
+        f = getattr(L, f"lqpb_forward_async_{sfx}")
+        f.argtypes = ([C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 2 + [vp] * 6 + [vp, C.POINTER(Info), vp, sz, vp,
+                      C.POINTER(C.c_int32)])
+        f.restype = i32
         f = getattr(L, f"lqpb_solution_status_{sfx}")
         f.argtypes, f.restype = [C.POINTER(Config), i32, i32, i32, vp, sz, vp, vp, vp], i32
         f = getattr(L, f"lqpb_backward_{sfx}")
@@ -143,6 +148,8 @@ def lib():
         f.argtypes, f.restype = [i32, i32, i32, vp, vp, vp, vp, i32, vp], i32
         f = getattr(L, f"lqpb_outer_{sfx}")
         f.argtypes, f.restype = [i32, i32, i32, vp, vp, vp, vp], i32
+    L.lqpb_ctrl_bytes.argtypes, L.lqpb_ctrl_bytes.restype = [], sz
+    L.lqpb_forward_collect.argtypes, L.lqpb_forward_collect.restype = [vp, C.POINTER(Config), C.POINTER(Info)], i32
     L.lqpb_dev_tc_inverse_work_bytes.argtypes, L.lqpb_dev_tc_inverse_work_bytes.restype = [i32, i32], sz
     L.lqpb_dev_tc_inverse_f32.argtypes, L.lqpb_dev_tc_inverse_f32.restype = [i32, i32, vp, vp, vp, vp], i32
     L.lqpb_dev_stream_read.argtypes, L.lqpb_dev_stream_read.restype = [vp, sz, i32, vp, vp], i32

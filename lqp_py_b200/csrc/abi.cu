@@ -284,7 +284,8 @@ template <typename T>
 int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A, const T* b,
                  const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, lqpb_info* info, void* ws,
                  size_t ws_bytes, void* stream, const HostFwd<T>* host = nullptr, const UnrollRec<T>* rec = nullptr,
-                 const BwdPrep<T>* prep = nullptr, const T* z0 = nullptr, const T* u0 = nullptr) {
+                 const BwdPrep<T>* prep = nullptr, const T* z0 = nullptr, const T* u0 = nullptr,
+                 void* async_ctrl = nullptr, int32_t* deferred = nullptr) {
   if (host && (!host->Q || !host->p || !host->lb || !host->ub || (m > 0 && (!host->A || !host->b))))
     return fail(LQPB_E_ARG, "null host pointer argument");
   if (!cfg || !Q || !p || !lb || !ub || !x || !z || !u || !lams || !rho_out || !info || !ws)
@@ -314,6 +315,80 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
 
   CK(cudaMemsetAsync(w.ctrl, 0, sizeof(Ctrl), st), "memset ctrl");
   if (prof) cudaEventRecord(g_prof.ev[0], st);
+  // ---- small problems: scaling, factorisation, the ADMM loop (adaptive-rho refactorisations included, on the device)
+  //      and the finalisation are ONE launch (iterate_row.cu, FUSED) -- unless the caller needs the operators to stay
+  //      in the workspace afterwards (recording pass of the unrolled mode)
+  if (!rec && !prep && cfg->keep_operators == 0 && forward_fused_applies<T>(*cfg, w)) {
+    if (host) {
+      const size_t sv = (size_t)B * n * sizeof(T);
+      CK(cudaMemcpyAsync((void*)p, host->p, sv, cudaMemcpyHostToDevice, st), "H2D p");
+      CK(cudaMemcpyAsync((void*)lb, host->lb, sv, cudaMemcpyHostToDevice, st), "H2D lb");
+      CK(cudaMemcpyAsync((void*)ub, host->ub, sv, cudaMemcpyHostToDevice, st), "H2D ub");
+      if (m > 0) {
+        CK(cudaMemcpyAsync((void*)A, host->A, (size_t)B * m * n * sizeof(T), cudaMemcpyHostToDevice, st), "H2D A");
+        CK(cudaMemcpyAsync((void*)b, host->b, (size_t)B * m * sizeof(T), cudaMemcpyHostToDevice, st), "H2D b");
+      }
+      CK(cudaMemcpyAsync((void*)Q, host->Q, (size_t)B * n * n * sizeof(T), cudaMemcpyHostToDevice, st), "H2D Q");
+    }
+    CK(launch_bound_flags<T>(w, lb, ub, st), "bound_flags");
+    // asynchronous form (lqpb_forward_async_*): the host waits for the bound flags alone -- the one thing the caller's
+    // Python needs before it can return (reference :33-38) -- and collects iter / status whenever it wants them.
+    // Stream order: flags kernel, copy of the control block (flags valid), event, solve, copy of the control block.
+    const bool go_async = async_ctrl != nullptr && !host && !cfg->verbose;
+    cudaEvent_t flags_done = nullptr;
+    if (go_async) {
+      cudaEvent_t& ev = g_hctrl.seg_done[cur_dev()];
+      if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event");
+      flags_done = ev;
+      CK(cudaMemcpyAsync(async_ctrl, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st), "copy ctrl (flags)");
+      CK(cudaEventRecord(flags_done, st), "record (flags)");
+    }
+    if (prof) cudaEventRecord(g_prof.ev[1], st);
+    if (prof) cudaEventRecord(g_prof.it0[0], st);
+    bool taken = false;
+    CK(launch_forward_fused<T>(*cfg, w, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, &g_prof.it_launches, st, &taken),
+       "fused forward");
+    if (!taken) return fail(LQPB_E_CUDA, "fused forward kernel did not launch");
+    if (prof) {
+      cudaEventRecord(g_prof.it1[0], st);
+      cudaEventRecord(g_prof.ev[2], st);
+      cudaEventRecord(g_prof.ev[3], st);
+    }
+    g_prof.n_it = 1;
+    g_prof.launches += 2;
+    if (go_async) {
+      CK(cudaEventSynchronize(flags_done), "synchronize (bound flags)");
+      const Ctrl* ac = static_cast<const Ctrl*>(async_ctrl);
+      info->iter = -1;                 // pending: lqpb_forward_collect fills these once the stream has drained
+      info->status = 0;
+      info->n_factor = 0;
+      info->any_lb = ac->any_lb;
+      info->any_ub = ac->any_ub;
+      info->n_log = 0;
+      CK(cudaMemcpyAsync(async_ctrl, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st), "copy ctrl (result)");
+      if (deferred) *deferred = 1;
+      g_prof.fwd_valid = prof;
+      return LQPB_OK;
+    }
+    CK(cudaMemcpyAsync(hc, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st), "copy ctrl");
+    if (host && host->x) CK(cudaMemcpyAsync(host->x, x, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToHost, st), "D2H x");
+    CK(cudaStreamSynchronize(st), "synchronize (fused forward)");
+    if (hc->status != LQPB_STATUS_CONVERGED && hc->status != LQPB_STATUS_MAX_ITERS && hc->status != LQPB_STATUS_BREAKDOWN)
+      return fail(LQPB_E_CUDA, "fused forward kernel ended without a status");
+    info->iter = hc->iter;
+    info->status = hc->status;
+    info->n_factor = 1 + hc->pad0;
+    info->any_lb = hc->any_lb;
+    info->any_ub = hc->any_ub;
+    info->n_log = cfg->verbose ? hc->n_log : 0;
+    if (cfg->verbose) {
+      memcpy(info->log_iter, hc->log_iter, sizeof(info->log_iter));
+      memcpy(info->log_primal, hc->log_primal, sizeof(info->log_primal));
+      memcpy(info->log_dual, hc->log_dual, sizeof(info->log_dual));
+    }
+    g_prof.fwd_valid = prof;
+    return LQPB_OK;
+  }
   bool factored = false;
   if (host) {
     // ---- inputs on the host: the vectors first (they decide any_lb / any_ub for the whole batch), then Q chunk
@@ -742,6 +817,35 @@ int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x,
   }
 WARM_ENTRY(f32, float)
 WARM_ENTRY(f64, double)
+
+#define ASYNC_ENTRY(SFX, T)                                                                                         \
+  int lqpb_forward_async_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A,    \
+                               const T* b, const T* lb, const T* ub, const T* z0, const T* u0, T* x, T* z, T* u,   \
+                               T* lams, T* nus, T* rho_out, void* pinned_ctrl, lqpb_info* info, void* workspace,   \
+                               size_t workspace_bytes, void* stream, int32_t* deferred) {                          \
+    if (!pinned_ctrl || !deferred) return fail(LQPB_E_ARG, "null pointer argument");                               \
+    *deferred = 0;                                                                                                 \
+    return forward_impl<T>(cfg, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, workspace,         \
+                           workspace_bytes, stream, nullptr, nullptr, nullptr, z0, u0, pinned_ctrl, deferred);     \
+  }
+ASYNC_ENTRY(f32, float)
+ASYNC_ENTRY(f64, double)
+
+size_t lqpb_ctrl_bytes(void) { return sizeof(Ctrl); }
+
+int lqpb_forward_collect(const void* pinned_ctrl, const lqpb_config* cfg, lqpb_info* info) {
+  if (!pinned_ctrl || !cfg || !info) return fail(LQPB_E_ARG, "null pointer argument");
+  const Ctrl* hc = static_cast<const Ctrl*>(pinned_ctrl);
+  if (hc->status != LQPB_STATUS_CONVERGED && hc->status != LQPB_STATUS_MAX_ITERS && hc->status != LQPB_STATUS_BREAKDOWN)
+    return fail(LQPB_E_CUDA, "the solve has not finished (synchronise the stream first) or ended without a status");
+  info->iter = hc->iter;
+  info->status = hc->status;
+  info->n_factor = 1 + hc->pad0;
+  info->any_lb = hc->any_lb;
+  info->any_ub = hc->any_ub;
+  info->n_log = 0;
+  return LQPB_OK;
+}
 
 #define PREP_ENTRY(SFX, T)                                                                                         \
   int lqpb_forward_prep_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A,     \

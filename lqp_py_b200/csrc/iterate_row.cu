@@ -18,6 +18,15 @@
 //     global decision, so the grid barrier costs one L2 round trip.  When the batch fits <= 8 CTAs the grid is one
 //     thread-block cluster and the wait is the hardware cluster barrier (0.26 us measured against 1.3 us);
 //   * nus (:327) is formed once, after the loop, from the rhs of the last solve (still intact in its buffer).
+//
+// FUSED = true is the whole forward solve of such a problem in ONE launch (lqpb_forward_* takes it when the recording
+// pass of the unrolled mode is not involved): the group first builds everything else in shared memory too -- the
+// scaling of :161-197 (column norms, zero guard, the q10 / q90 quantiles of D by a bitonic sort, blend, Q~ = D Q D,
+// p~, A~, E, b~, lb~, ub~), rho of :200-203, the KKT matrix of :206-212 and its inverse by an in-place symmetric
+// Gauss-Jordan sweep (H pivots first, equality rows last; replaces lu_factor, :215) -- then runs the loop above and
+// finishes with :315-327 (un-scaling, split duals, nus) straight into the caller's tensors.  The adaptive-rho update of
+// :237-256 happens ON THE DEVICE here: the flagged problems rebuild and re-sweep their KKT matrix in place and the
+// loop carries on -- no status 3, no host round trip -- so the host never has to look at the solve before it ends.
 #include <cstring>
 #include "itergeom.cuh"
 
@@ -26,6 +35,8 @@ namespace lqpb {
 constexpr int kRowWarps = 16;
 constexpr int kRowThreads = kRowWarps * 32;
 constexpr int kRowVecs = 10;         // v0, v1, z, u, p~, lb~, ub~, c, D, x~ per resident problem
+constexpr int kPS = 8;               // per-problem scalars in shared memory: rho, ||p||_inf, and the record of the last
+                                     // stop check [primal, dual, tol_primal_rel, tol_dual_rel, ratio, wants]
 
 struct RowGeom {
   int G, ppc, gw, ngroups, cluster;
@@ -34,7 +45,16 @@ struct RowGeom {
                   // distinct banks
   int nch;        // 16-byte chunks per row that hold data
   int ldv;        // padded vector length (covers nch chunks)
+  int fused;      // 1: FUSED kernel (K block is the (n + m) x (n + m) KKT matrix, A~ rows resident, sort / sweep scratch)
+  int P2;         // FUSED: power of two >= n (bitonic sort of D)
   size_t prob_elems, group_elems;
+};
+
+// raw problem data and outputs of the FUSED kernel (the caller's tensors, reference layouts)
+template <typename T>
+struct FusedIO {
+  const T *Q, *p, *A, *b, *lb, *ub;
+  T *x, *z, *u, *lams, *rho_out;
 };
 
 __device__ __forceinline__ void row_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
@@ -48,14 +68,15 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   return v;
 }
 
-template <typename T>
+template <typename T, bool FUSED>
 __global__ void __launch_bounds__(kRowThreads, 1)
-iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, RowGeom geo) {
+iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, RowGeom geo, FusedIO<T> io) {
   using P = Pack<T>;
   constexpr int VN = P::VN;
   using V4 = typename Vec<T>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ unsigned long long s_word;
+  __shared__ unsigned long long s_slots[2][8];      // cluster mode: the packed check words of the CTAs of the cluster
   __shared__ int s_flags[4];
   const int n = w.n, m = w.m, ld = w.ld;
   const int gw = geo.gw, ngroups = geo.ngroups, lpr = geo.lpr, ldk = geo.ldk, nch = geo.nch, ldv = geo.ldv;
@@ -67,17 +88,25 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
   Ctrl* ctrl = w.ctrl;
 
   T* base = reinterpret_cast<T*>(smem_raw);
+  const int N = n + m;                                      // FUSED: order of the KKT matrix held in the K block
+  const int krows = FUSED ? N : n;
   auto prob_K = [&](int q) { return base + (size_t)q * geo.prob_elems; };
-  auto prob_Q = [&](int q) { return prob_K(q) + (size_t)n * ldk; };
-  auto prob_vec = [&](int q, int k) { return prob_K(q) + 2 * (size_t)n * ldk + (size_t)k * ldv; };
-  T* red = base + (size_t)geo.ppc * geo.prob_elems + (size_t)grp * geo.group_elems;     // [6][16]
-  T* pscal = base + (size_t)geo.ppc * geo.prob_elems + (size_t)ngroups * geo.group_elems;   // [ppc][2]: rho, pnorm
+  auto prob_Q = [&](int q) { return prob_K(q) + (size_t)krows * ldk; };
+  auto prob_At = [&](int q) { return prob_Q(q) + (size_t)n * ldk; };            // FUSED: A~ rows [m][ldk]
+  auto prob_vec = [&](int q, int k) { return prob_Q(q) + (size_t)(n + (FUSED ? m : 0)) * ldk + (size_t)k * ldv; };
+  T* gscr = base + (size_t)geo.ppc * geo.prob_elems + (size_t)grp * geo.group_elems;
+  T* red = gscr;                                            // [6][16]
+  double* dred = reinterpret_cast<double*>(gscr + 96);      // [16]   (FUSED)
+  T* sortbuf = gscr + 96 + 16 * (int)(sizeof(double) / sizeof(T));   // [P2]  (FUSED)
+  T* csv = sortbuf + geo.P2;                                // [ldk]  (FUSED) pivot column of a sweep step
+  T* pscal = base + (size_t)geo.ppc * geo.prob_elems + (size_t)ngroups * geo.group_elems;   // [ppc][kPS]
 
-  // ---- one-time load: zero the problem blocks, expand the packed lower triangles into dense symmetric matrices
+  // ---- one-time load: zero the problem blocks, then either expand the packed lower triangles a factorisation left in
+  //      the workspace into dense symmetric matrices, or (FUSED) leave the set-up to the groups below
   for (size_t t = tid; t < (size_t)nprob * geo.prob_elems; t += kRowThreads) base[t] = T(0);
   if (tid == 0) s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
   __syncthreads();
-  {
+  if constexpr (!FUSED) {
     const int ntv = P::nt(n), ntiles = P::ntiles(n);
     const size_t per = (size_t)ntiles * P::TILE;
     for (size_t t = tid; t < (size_t)nprob * per; t += kRowThreads) {
@@ -101,27 +130,30 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
         prob_Q(q)[(size_t)j * ldk + i] = qv;
       }
     }
+    for (int t = tid; t < nprob * n; t += kRowThreads) {
+      const int q = t / n, e = t % n;
+      const int b = blockIdx.x + q * gridDim.x;
+      const size_t vo = (size_t)b * ld + e;
+      const T rho = w.rho[b], z = w.z[vo], u = w.u[vo], pt = w.pt[vo];
+      prob_vec(q, 0)[e] = -pt + rho * (z - u);       // rhs of the first iteration (:259-262)
+      prob_vec(q, 2)[e] = z;
+      prob_vec(q, 3)[e] = u;
+      prob_vec(q, 4)[e] = pt;
+      prob_vec(q, 5)[e] = w.lbt[vo];
+      prob_vec(q, 6)[e] = w.ubt[vo];
+      prob_vec(q, 7)[e] = w.c[vo];
+      prob_vec(q, 8)[e] = w.D[vo];
+    }
+    for (int q = tid; q < nprob; q += kRowThreads) {
+      const int b = blockIdx.x + q * gridDim.x;
+      pscal[kPS * q] = w.rho[b];
+      pscal[kPS * q + 1] = w.pnorm[b];
+      for (int k = 0; k < 4; ++k) pscal[kPS * q + 2 + k] = w.chk[4 * b + k];
+      pscal[kPS * q + 6] = w.ratio[b];
+      pscal[kPS * q + 7] = (T)w.wants[b];
+    }
+    __syncthreads();
   }
-  for (int t = tid; t < nprob * n; t += kRowThreads) {
-    const int q = t / n, e = t % n;
-    const int b = blockIdx.x + q * gridDim.x;
-    const size_t vo = (size_t)b * ld + e;
-    const T rho = w.rho[b], z = w.z[vo], u = w.u[vo], pt = w.pt[vo];
-    prob_vec(q, 0)[e] = -pt + rho * (z - u);       // rhs of the first iteration (:259-262)
-    prob_vec(q, 2)[e] = z;
-    prob_vec(q, 3)[e] = u;
-    prob_vec(q, 4)[e] = pt;
-    prob_vec(q, 5)[e] = w.lbt[vo];
-    prob_vec(q, 6)[e] = w.ubt[vo];
-    prob_vec(q, 7)[e] = w.c[vo];
-    prob_vec(q, 8)[e] = w.D[vo];
-  }
-  for (int q = tid; q < nprob; q += kRowThreads) {
-    const int b = blockIdx.x + q * gridDim.x;
-    pscal[2 * q] = w.rho[b];
-    pscal[2 * q + 1] = w.pnorm[b];
-  }
-  __syncthreads();
 
   const bool any_lb = ctrl->any_lb != 0, any_ub = ctrl->any_ub != 0;
   int last_wants = ctrl->last_wants, last_rout = ctrl->last_ratio_out;
@@ -154,24 +186,265 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
     return a;
   };
 
+  // ---- FUSED: group-level reductions, the KKT build + sweep, and the set-up of every problem of this group
+  auto gsum_d = [&](double v) -> double {
+    v = warp_sum(v);
+    if (gw == 1) return v;
+    if (lane == 0) dred[wg] = v;
+    group_sync();
+    double r = 0.0;
+    for (int ww = 0; ww < gw; ++ww) r += dred[ww];
+    group_sync();
+    return r;
+  };
+  auto gmax = [&](T v) -> T {
+    v = warp_max(v);
+    if (gw == 1) return v;
+    if (lane == 0) red[wg] = v;
+    group_sync();
+    T r = red[0];
+    for (int ww = 1; ww < gw; ++ww) r = t_max(r, red[ww]);
+    group_sync();
+    return r;
+  };
+  // K block <- inverse of the KKT matrix [[Q~ + rho I, A~^T], [A~, 0]] (:206-215): build, in-place symmetric
+  // Gauss-Jordan sweep without pivoting (H pivots are positive, the equality rows are swept last, when their pivot
+  // block has become -(A~ H^-1 A~^T)), negate; then c = K21^T b~
+  auto build_and_sweep = [&](int q, int b, T rho) {
+    T* M = prob_K(q);
+    const T* Qm = prob_Q(q);
+    const T* At = prob_At(q);
+    for (int t = gtid; t < N * ldk; t += gthreads) {
+      const int i = t / ldk, j = t % ldk;
+      T v = T(0);
+      if (j < N) {
+        if (i < n && j < n) v = Qm[(size_t)i * ldk + j] + (i == j ? rho : T(0));
+        else if (i >= n && j < n) v = At[(size_t)(i - n) * ldk + j];
+        else if (i < n && j >= n) v = At[(size_t)(j - n) * ldk + i];
+      }
+      M[t] = v;
+    }
+    group_sync();
+    const int nchN = (N + VN - 1) / VN;
+    for (int s = 0; s < N; ++s) {
+      for (int j = gtid; j < nchN * VN; j += gthreads) csv[j] = j < N ? M[(size_t)s * ldk + j] : T(0);   // row s == column s
+      group_sync();
+      const T piv = T(1) / csv[s];
+      const int cs = s / VN, es = s % VN;
+      // 16-byte chunks, the lane mapping of row_dot: conflict-free LDS.128 / STS.128 under the padded row stride
+      for (int r0 = 0; r0 < N; r0 += rpp) {
+        const int i = r0 + rslot;
+        if (i < N) {
+          T* row = M + (size_t)i * ldk;
+          const T ci = csv[i] * piv;
+          for (int c = sub; c < nchN; c += lpr) {
+            const V4 cv = *reinterpret_cast<const V4*>(csv + c * VN);
+            V4 rv = *reinterpret_cast<const V4*>(row + c * VN);
+            const T* cp = reinterpret_cast<const T*>(&cv);
+            T* rp = reinterpret_cast<T*>(&rv);
+            if (i == s) {
+#pragma unroll
+              for (int e = 0; e < VN; ++e) rp[e] = (c == cs && e == es) ? -piv : cp[e] * piv;
+            } else {
+#pragma unroll
+              for (int e = 0; e < VN; ++e) rp[e] = (c == cs && e == es) ? ci : rp[e] - ci * cp[e];
+            }
+            *reinterpret_cast<V4*>(row + c * VN) = rv;
+          }
+        }
+      }
+      group_sync();
+    }
+    for (int t = gtid; t < N * ldk; t += gthreads) M[t] = -M[t];
+    group_sync();
+    T* cvec = prob_vec(q, 7);
+    for (int i = gtid; i < n; i += gthreads) {
+      T a = T(0);
+      for (int l = 0; l < m; ++l) a += M[(size_t)(n + l) * ldk + i] * w.bt[(size_t)b * m + l];
+      cvec[i] = a;
+    }
+    group_sync();
+  };
+  if constexpr (FUSED) {
+    const bool boxed = ctrl->any_lb != 0 || ctrl->any_ub != 0;       // bound_flags_kernel ran before this launch
+    for (int q = grp; q < nprob; q += ngroups) {
+      const int b = blockIdx.x + q * gridDim.x;
+      T* Qm = prob_Q(q);
+      T* At = prob_At(q);
+      T* Dv = prob_vec(q, 8);
+      const T* Qb = io.Q + (size_t)b * n * n;
+      for (int t = gtid; t < n * n; t += gthreads) Qm[(size_t)(t / n) * ldk + (t % n)] = Qb[t];
+      group_sync();
+      if (cfg.scale) {
+        // column inf-norms (:163), zero guard (:164-168), D = sqrt(1 / norm) (:170)
+        for (int j = gtid; j < n; j += gthreads) {
+          T mx = T(0);
+          for (int i = 0; i < n; ++i) mx = t_max(mx, t_abs(Qm[(size_t)i * ldk + j]));
+          Dv[j] = mx;
+        }
+        group_sync();
+        double part = 0.0;
+        for (int j = gtid; j < n; j += gthreads) part += (double)Dv[j];
+        const double tot = gsum_d(part);
+        const T floor_v = t_max((T)(tot / n), T(1e-6));
+        for (int j = gtid; j < n; j += gthreads) {
+          T qn = Dv[j];
+          if (qn <= T(0)) qn = t_max(qn, floor_v);
+          Dv[j] = t_sqrt(T(1) / qn);
+        }
+        group_sync();
+        // beta = 1 - q10(D) / q90(D) (:171-174): bitonic sort + torch.quantile's linear interpolation
+        T beta = (T)cfg.beta;
+        if (cfg.beta_auto) {
+          const int P2 = geo.P2;
+          for (int j = gtid; j < P2; j += gthreads) sortbuf[j] = j < n ? Dv[j] : t_inf<T>();
+          group_sync();
+          for (int k = 2; k <= P2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+              for (int ii = gtid; ii < P2; ii += gthreads) {
+                const int ixj = ii ^ j;
+                if (ixj > ii) {
+                  const T a = sortbuf[ii], c = sortbuf[ixj];
+                  const bool asc = (ii & k) == 0;
+                  if ((a > c) == asc) { sortbuf[ii] = c; sortbuf[ixj] = a; }
+                }
+              }
+              group_sync();
+            }
+          }
+          T qv[2];
+          const T qs[2] = {T(0.10), T(0.90)};
+          for (int k = 0; k < 2; ++k) {
+            const T rank = qs[k] * T(n - 1);
+            const T lo = floor(rank), hi = ceil(rank);
+            const T a = sortbuf[(int)lo], c = sortbuf[(int)hi], wgt = rank - lo;
+            qv[k] = wgt < T(0.5) ? a + wgt * (c - a) : c - (c - a) * (T(1) - wgt);      // torch's lerp
+          }
+          beta = T(1) - qv[0] / qv[1];
+          group_sync();
+        }
+        // D <- (1 - beta) D + beta mean(D) (:175)
+        part = 0.0;
+        for (int j = gtid; j < n; j += gthreads) part += (double)Dv[j];
+        const T mean = (T)(gsum_d(part) / n);
+        for (int j = gtid; j < n; j += gthreads) Dv[j] = (T(1) - beta) * Dv[j] + beta * mean;
+      } else {
+        for (int j = gtid; j < n; j += gthreads) Dv[j] = T(1);
+      }
+      group_sync();
+      // vectors (:127, :177, :192-194, :221-223 or the warm start)
+      T pmax = T(0);
+      for (int j = gtid; j < n; j += gthreads) {
+        const T d = Dv[j];
+        T pv = io.p[(size_t)b * n + j], l = io.lb[(size_t)b * n + j], uu = io.ub[(size_t)b * n + j];
+        pmax = t_max(pmax, t_abs(pv));
+        if (cfg.scale) { pv = d * pv; l = l / d; uu = uu / d; }
+        prob_vec(q, 4)[j] = pv;
+        prob_vec(q, 5)[j] = l;
+        prob_vec(q, 6)[j] = uu;
+        prob_vec(q, 2)[j] = w.z0 ? w.z0[(size_t)b * n + j] / d : T(0);
+        prob_vec(q, 3)[j] = w.u0 ? w.u0[(size_t)b * n + j] * d : T(0);
+      }
+      pmax = gmax(pmax);
+      // Q~ = (D_i Q_ij) D_j (:176) in place, ||Q~||_F^2 in double (:201), rho (:156-158, :200-203)
+      double fro = 0.0;
+      for (int t = gtid; t < n * n; t += gthreads) {
+        const int i = t / n, j = t % n;
+        T v = Qm[(size_t)i * ldk + j];
+        if (cfg.scale) v = (Dv[i] * v) * Dv[j];
+        Qm[(size_t)i * ldk + j] = v;
+        fro += (double)v * (double)v;
+      }
+      fro = gsum_d(fro);
+      T rc = (T)sqrt(fro) / (T)sqrt((double)n);
+      rc = t_min(t_max(rc, (T)cfg.rho_min), (T)cfg.rho_max);
+      T rho = cfg.rho_auto ? rc : (T)cfg.rho;
+      if (!boxed) rho = T(0);
+      // equality rows: A~ = E (A D), b~ = E b (:179-190)
+      for (int l = 0; l < m; ++l) {
+        const T* Al = io.A + ((size_t)b * m + l) * n;
+        T mx = T(0);
+        for (int j = gtid; j < n; j += gthreads) {
+          const T v = Al[j] * Dv[j];
+          At[(size_t)l * ldk + j] = cfg.scale ? v : Al[j];
+          mx = t_max(mx, t_abs(v));
+        }
+        mx = gmax(mx);
+        if (gtid == 0) sortbuf[l % geo.P2] = mx;      // m <= P2 is guaranteed by the plan
+        group_sync();
+      }
+      if (m > 0) {
+        if (gtid == 0) {
+          double sden = 0.0;
+          for (int l = 0; l < m; ++l) sden += (double)sortbuf[l];
+          const T fl = t_max((T)(sden / m), T(1e-6));
+          for (int l = 0; l < m; ++l) {
+            T r = sortbuf[l];
+            if (r <= T(0)) r = t_max(r, fl);
+            const T e = cfg.scale ? T(1) / r : T(1);
+            sortbuf[l] = e;
+            w.E[(size_t)b * m + l] = e;
+            w.bt[(size_t)b * m + l] = cfg.scale ? e * io.b[(size_t)b * m + l] : io.b[(size_t)b * m + l];
+          }
+        }
+        group_sync();
+        if (cfg.scale)
+          for (int t = gtid; t < m * n; t += gthreads) At[(size_t)(t / n) * ldk + (t % n)] *= sortbuf[t / n];
+        group_sync();
+      }
+      if (gtid == 0) {
+        pscal[kPS * q] = rho;
+        pscal[kPS * q + 1] = pmax;
+        pscal[kPS * q + 2] = pscal[kPS * q + 3] = pscal[kPS * q + 4] = pscal[kPS * q + 5] = T(0);
+        pscal[kPS * q + 6] = T(1);
+        pscal[kPS * q + 7] = T(0);
+      }
+      build_and_sweep(q, b, rho);
+      for (int j = gtid; j < n; j += gthreads)
+        prob_vec(q, 0)[j] = -prob_vec(q, 4)[j] + rho * (prob_vec(q, 2)[j] - prob_vec(q, 3)[j]);   // :259-262
+      group_sync();
+    }
+    __syncthreads();
+  }
+
   int i = i0, cur = 0;       // cur: which rhs buffer holds the rhs of iteration i
   int status = 0;
+  int last_check = -1;       // iteration of the most recent stop check of THIS launch
 
   while (true) {
     // ---------------- adaptive rho (:237-256): decided from the previous check, applied before iteration i
     if (cfg.adaptive_rho && i > 0 && i < cfg.adaptive_rho_max_iter && (i % cfg.adaptive_rho_iter) == 0 &&
         !(i == i0 && skip_rho_check)) {
       if (last_wants && last_rout) {
-        for (int k = tid; k < nprob; k += kRowThreads) {
-          const int b = blockIdx.x + k * gridDim.x;
-          if (w.wants[b]) {
-            T r = w.rho[b] * w.ratio[b];
-            r = t_min(t_max(r, (T)cfg.rho_min), (T)cfg.rho_max);
-            w.rho[b] = r;
+        if constexpr (FUSED) {
+          // on the device: every flagged problem of this group updates rho, rebuilds and re-sweeps its KKT matrix in
+          // place and re-forms the rhs of THIS iteration with the new rho (u is not rescaled, like the reference)
+          for (int q = grp; q < nprob; q += ngroups) {
+            const int b = blockIdx.x + q * gridDim.x;
+            if (pscal[kPS * q + 7] != T(0)) {
+              T r = pscal[kPS * q] * pscal[kPS * q + 6];
+              r = t_min(t_max(r, (T)cfg.rho_min), (T)cfg.rho_max);
+              group_sync();
+              if (gtid == 0) pscal[kPS * q] = r;
+              build_and_sweep(q, b, r);
+              T* v = prob_vec(q, cur);
+              for (int j = gtid; j < n; j += gthreads) v[j] = -prob_vec(q, 4)[j] + r * (prob_vec(q, 2)[j] - prob_vec(q, 3)[j]);
+              group_sync();
+            }
           }
+          if (blockIdx.x == 0 && tid == 0) ctrl->pad0 += 1;        // refactorisations done on the device
+        } else {
+          for (int k = tid; k < nprob; k += kRowThreads) {
+            const int b = blockIdx.x + k * gridDim.x;
+            if (pscal[kPS * k + 7] != T(0)) {
+              T r = pscal[kPS * k] * pscal[kPS * k + 6];
+              r = t_min(t_max(r, (T)cfg.rho_min), (T)cfg.rho_max);
+              w.rho[b] = r;
+            }
+          }
+          status = 3;
+          break;
         }
-        status = 3;
-        break;
       }
     }
     const bool is_check = (i % check) == 0;
@@ -179,6 +452,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
 
     for (int q = grp; q < nprob; q += ngroups) {
       const int b = blockIdx.x + q * gridDim.x;
+      (void)b;
       const T* v = prob_vec(q, cur);
       T* vn = prob_vec(q, cur ^ 1);
       T* zs = prob_vec(q, 2);
@@ -189,7 +463,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
       const T* cs = prob_vec(q, 7);
       const T* Ds = prob_vec(q, 8);
       T* xs = prob_vec(q, 9);
-      const T rho = pscal[2 * q];
+      const T rho = pscal[kPS * q];
       // ---- x~ = K11 v + c, then the element-wise ADMM update (:271-282) by the lane that owns the row
       T mx_p = T(0), mx_d = T(0), mx_x = T(0), mx_z = T(0), mx_y = T(0);
       for (int r0 = 0; r0 < n; r0 += rpp) {
@@ -249,16 +523,17 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
           const T primal = mm[0], dual = mm[1];
           const T tol_p_rel = t_max(t_max(mm[2], mm[3]), zc);                      // :301
           const T tol_p = eps_abs + eps_rel * tol_p_rel;                           // :302
-          const T tol_d_rel = t_max(t_max(t_max(mm[4], mm[5]), pscal[2 * q + 1]), zc);   // :303
+          const T tol_d_rel = t_max(t_max(t_max(mm[4], mm[5]), pscal[kPS * q + 1]), zc);   // :303
           const T tol_d = eps_abs + eps_rel * tol_d_rel;                           // :304
           const bool optimal = (primal < tol_p) && (dual < tol_d);                // :307-309
           const bool wants = (primal > t_max(tol_p, thr)) || (dual > t_max(tol_d, thr));   // :310-311
           const T num = t_max(primal / tol_p_rel, zc), den = t_max(dual / tol_d_rel, zc);  // :239-242
           const T ratio = t_sqrt(num / den);                                       // :243
-          w.chk[4 * b + 0] = primal; w.chk[4 * b + 1] = dual;
-          w.chk[4 * b + 2] = tol_p_rel; w.chk[4 * b + 3] = tol_d_rel;
-          w.wants[b] = wants ? 1 : 0;
-          w.ratio[b] = ratio;
+          // the record of this check stays in shared memory (the adaptive-rho update and the exit read it there)
+          pscal[kPS * q + 2] = primal; pscal[kPS * q + 3] = dual;
+          pscal[kPS * q + 4] = tol_p_rel; pscal[kPS * q + 5] = tol_d_rel;
+          pscal[kPS * q + 6] = ratio;
+          pscal[kPS * q + 7] = wants ? T(1) : T(0);
           if (!optimal) atomicOr(&s_flags[0], 1);
           if (wants) atomicOr(&s_flags[1], 1);
           if (ratio > ar_tol || ratio < ar_tol_inv) atomicOr(&s_flags[2], 1);     // :244-245
@@ -274,38 +549,53 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
         if (gw > 1) group_sync();   // red[] reusable
       }
     }
-    // ---- the global decision (:312 torch.all): one packed word per check carries arrivals and flags
+    // ---- the global decision (:312 torch.all): one packed word per CTA and check carries its arrival and its flags
     if (is_check) {
       __syncthreads();
-      unsigned long long* word = reinterpret_cast<unsigned long long*>(&ctrl->slot[(i / check) & 3][0]);
-      if (tid == 0) {
-        const unsigned long long mine = 1ull | (s_flags[1] ? (1ull << 16) : 0ull) | (s_flags[2] ? (1ull << 28) : 0ull) |
-                                        (s_flags[0] ? (1ull << 40) : 0ull) | (s_flags[3] ? (1ull << 52) : 0ull);
-        s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
-        red_release_add_u64(word, mine);
-      }
+      const unsigned long long mine = 1ull | (s_flags[1] ? (1ull << 16) : 0ull) | (s_flags[2] ? (1ull << 28) : 0ull) |
+                                      (s_flags[0] ? (1ull << 40) : 0ull) | (s_flags[3] ? (1ull << 52) : 0ull);
       if (geo.cluster) {
+        // the grid is ONE cluster: every CTA drops its word into slot [parity][its rank] of every CTA's shared memory
+        // (DSMEM stores), the hardware cluster barrier orders them, and each CTA adds up its own copy -- no global
+        // memory traffic at all at a check (a single-CTA grid needs nothing)
+        const int par = (i / check) & 1;
         if (gridDim.x > 1) {
+          if (tid < (int)gridDim.x) {
+            const uint32_t laddr = smem_u32(&s_slots[par][blockIdx.x]);
+            uint32_t raddr;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(tid));
+            asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(raddr), "l"(mine) : "memory");
+          }
           row_cluster_arrive();
           row_cluster_wait();
         }
-        if (tid == 0) s_word = ld_acquire_u64(word);
-      } else if (tid == 0) {
-        unsigned long long v;
-        do {
-          v = ld_acquire_u64(word);
-        } while ((unsigned)(v & 0xffffull) < gridDim.x);
-        s_word = v;
-      }
-      if (tid == 0 && blockIdx.x == 0) {
-        // slot of the check after next: every CTA has read it (it passed the previous barrier); the store is ordered
-        // before this CTA's next arrival, which every other CTA acquires before it can reach that check
-        unsigned long long* nxt = reinterpret_cast<unsigned long long*>(&ctrl->slot[((i / check) + 2) & 3][0]);
-        *nxt = 0ull;
-        const unsigned long long v = s_word;
-        ctrl->last_wants = ((v >> 16) & 0xfffull) != 0;
-        ctrl->last_ratio_out = ((v >> 28) & 0xfffull) != 0;
-        if (cfg.verbose) ctrl->n_log = min(i / check + 1, LQPB_LOG_CAP);
+        if (tid == 0) {
+          unsigned long long v = mine;
+          if (gridDim.x > 1) {
+            v = 0ull;
+            for (int r = 0; r < (int)gridDim.x; ++r) v += s_slots[par][r];
+          }
+          s_word = v;
+          s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
+        }
+      } else {
+        unsigned long long* word = reinterpret_cast<unsigned long long*>(&ctrl->slot[(i / check) & 3][0]);
+        __syncthreads();          // every thread has read s_flags
+        if (tid == 0) {
+          s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
+          red_release_add_u64(word, mine);
+          unsigned long long v;
+          do {
+            v = ld_acquire_u64(word);
+          } while ((unsigned)(v & 0xffffull) < gridDim.x);
+          s_word = v;
+          if (blockIdx.x == 0) {
+            // slot of the check after next: every CTA has read it (it passed the previous barrier); the store is
+            // ordered before this CTA's next arrival, which every other CTA acquires before it can reach that check
+            unsigned long long* nxt = reinterpret_cast<unsigned long long*>(&ctrl->slot[((i / check) + 2) & 3][0]);
+            *nxt = 0ull;
+          }
+        }
       }
       __syncthreads();
       const unsigned long long v = s_word;
@@ -313,6 +603,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
       last_rout = ((v >> 28) & 0xfffull) != 0;
       const bool all_optimal = ((v >> 40) & 0xfffull) == 0;
       const bool broken = (v >> 52) != 0;
+      last_check = i;
       __syncthreads();
       if (broken) { status = 4; break; }           // LQPB_STATUS_BREAKDOWN: some iterate is NaN / inf
       if (all_optimal) { status = 1; break; }
@@ -321,23 +612,34 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
     ++i;
     cur ^= 1;
   }
-  // ---- epilogue: nus of the LAST solve (:327) from its rhs, which is still intact in buffer `cur` (status 1 / 2:
+  // ---- epilogue: nus of the LAST solve (:327) from its rhs, which is still intact in buffer `cur` (status 1 / 2 / 4:
   //      the loop left before flipping; status 3 left before iteration i ran: nothing to report yet), and the state
   __syncthreads();
   if (status != 3 && m > 0) {      // (after a breakdown the values are NaN like everything else)
     for (int q = grp; q < nprob; q += ngroups) {
       const int b = blockIdx.x + q * gridDim.x;
       const T* v = prob_vec(q, cur);
-      const T* Gt = w.Gt + (size_t)b * m * ld;
-      const T* K22 = w.Sinv + (size_t)b * m * m;
       for (int l = wg; l < m; l += gw) {
         T d = T(0);
-        for (int e = lane; e < n; e += 32) d += Gt[(size_t)l * ld + e] * v[e];
-        d = warp_sum(d);
-        if (lane == 0) {
-          T a = d;
-          for (int l2 = 0; l2 < m; ++l2) a += K22[l * m + l2] * w.bt[(size_t)b * m + l2];
-          nus_out[(size_t)b * m + l] = a * w.E[(size_t)b * m + l];
+        if constexpr (FUSED) {
+          const T* Kl = prob_K(q) + (size_t)(n + l) * ldk;        // K21 row l | K22 row l
+          for (int e = lane; e < n; e += 32) d += Kl[e] * v[e];
+          d = warp_sum(d);
+          if (lane == 0) {
+            T a = d;
+            for (int l2 = 0; l2 < m; ++l2) a += Kl[n + l2] * w.bt[(size_t)b * m + l2];
+            nus_out[(size_t)b * m + l] = a * w.E[(size_t)b * m + l];
+          }
+        } else {
+          const T* Gt = w.Gt + (size_t)b * m * ld;
+          const T* K22 = w.Sinv + (size_t)b * m * m;
+          for (int e = lane; e < n; e += 32) d += Gt[(size_t)l * ld + e] * v[e];
+          d = warp_sum(d);
+          if (lane == 0) {
+            T a = d;
+            for (int l2 = 0; l2 < m; ++l2) a += K22[l * m + l2] * w.bt[(size_t)b * m + l2];
+            nus_out[(size_t)b * m + l] = a * w.E[(size_t)b * m + l];
+          }
         }
       }
     }
@@ -345,12 +647,36 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
   for (int t = tid; t < nprob * n; t += kRowThreads) {
     const int q = t / n, e = t % n;
     const int b = blockIdx.x + q * gridDim.x;
-    const size_t vo = (size_t)b * ld + e;
-    w.z[vo] = prob_vec(q, 2)[e];
-    w.u[vo] = prob_vec(q, 3)[e];
-    w.xs[vo] = prob_vec(q, 9)[e];
+    if constexpr (FUSED) {
+      // :315-323 undo the scaling, split the duals -- straight into the caller's tensors
+      const size_t o = (size_t)b * n + e;
+      const T d = prob_vec(q, 8)[e], rho = pscal[kPS * q];
+      io.x[o] = d * prob_vec(q, 9)[e];
+      io.z[o] = d * prob_vec(q, 2)[e];
+      const T uu = prob_vec(q, 3)[e] / d;
+      io.u[o] = uu;
+      const T y = uu * rho;
+      io.lams[(size_t)b * 2 * n + e] = (-y > T(0)) ? -y : T(0);
+      io.lams[(size_t)b * 2 * n + n + e] = (y > T(0)) ? y : T(0);
+      if (e == 0) io.rho_out[b] = rho;
+    } else {
+      const size_t vo = (size_t)b * ld + e;
+      w.z[vo] = prob_vec(q, 2)[e];
+      w.u[vo] = prob_vec(q, 3)[e];
+      w.xs[vo] = prob_vec(q, 9)[e];
+    }
+  }
+  for (int q = tid; q < nprob; q += kRowThreads) {      // record of the last check, rho (status kernel, relaunch, warm restarts)
+    const int b = blockIdx.x + q * gridDim.x;
+    for (int k = 0; k < 4; ++k) w.chk[4 * b + k] = pscal[kPS * q + 2 + k];
+    w.ratio[b] = pscal[kPS * q + 6];
+    w.wants[b] = pscal[kPS * q + 7] != T(0) ? 1 : 0;
+    if (FUSED) w.rho[b] = pscal[kPS * q];
   }
   if (blockIdx.x == 0 && tid == 0) {
+    ctrl->last_wants = last_wants;                 // flags of the most recent check (a relaunch after status 3 reads them)
+    ctrl->last_ratio_out = last_rout;
+    if (cfg.verbose && last_check >= 0) ctrl->n_log = min(last_check / check + 1, LQPB_LOG_CAP);
     ctrl->status = status;
     if (status == 3) ctrl->next_i = i;
     else ctrl->iter = i;
@@ -359,12 +685,16 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
 
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-static bool plan_rows(const FwdWs<T>& w, const lqpb_config& cfg, int max_smem, int n_sm, RowGeom* out, size_t* smem_bytes) {
+static bool plan_rows(const FwdWs<T>& w, const lqpb_config& cfg, int max_smem, int n_sm, bool fused, RowGeom* out,
+                      size_t* smem_bytes) {
   constexpr int VN = Vec<T>::N;
-  const int n = w.n;
+  const int n = w.n, m = w.m, N = n + m;
   RowGeom g{};
+  g.fused = fused ? 1 : 0;
   g.nch = (n + VN - 1) / VN;
   g.ldv = g.nch * VN;
+  g.P2 = 32;
+  while (g.P2 < n || g.P2 < m) g.P2 <<= 1;
   const size_t budget = (size_t)max_smem / sizeof(T);
   auto geom = [&](int ppc, int gw, RowGeom* gg, size_t* total) {
     const int gthreads = gw * 32;
@@ -384,17 +714,19 @@ static bool plan_rows(const FwdWs<T>& w, const lqpb_config& cfg, int max_smem, i
     // row stride: a multiple of the 16-byte chunk with (stride in 4-byte banks) = 4 lpr mod 32 for lpr <= 8, so that
     // the 8 / lpr rows a quarter warp touches per LDS.128 phase fall into disjoint bank groups
     const int chunk_banks = 4;                         // 16 bytes
-    int ldk_banks = g.nch * chunk_banks;
+    int ldk_banks = ((fused ? N : n) + VN - 1) / VN * chunk_banks;
     if (best_lpr < 8) {
       const int want = (chunk_banks * best_lpr) % 32;
       while (ldk_banks % 32 != want) ldk_banks += chunk_banks;
     }
     gg->ldk = ldk_banks * 4 / (int)sizeof(T);
-    gg->prob_elems = 2 * (size_t)n * gg->ldk + (size_t)kRowVecs * g.ldv;
+    gg->prob_elems = (size_t)(fused ? N + n + m : 2 * n) * gg->ldk + (size_t)kRowVecs * g.ldv;
     gg->prob_elems = (gg->prob_elems + VN - 1) / VN * VN;
     gg->group_elems = 6 * 16;
+    if (fused) gg->group_elems += 16 * (sizeof(double) / sizeof(T)) + g.P2 + gg->ldk;
+    gg->group_elems = (gg->group_elems + VN - 1) / VN * VN;
     const int ng = kRowWarps / gw;
-    *total = (size_t)ppc * gg->prob_elems + (size_t)ng * gg->group_elems + 2 * (size_t)ppc + 64;
+    *total = (size_t)ppc * gg->prob_elems + (size_t)ng * gg->group_elems + kPS * (size_t)ppc + 64;
     return *total <= budget;
   };
   // warps per problem: enough lanes for ~one pass with 4 lanes per row, at most the whole CTA
@@ -434,14 +766,10 @@ static bool plan_rows(const FwdWs<T>& w, const lqpb_config& cfg, int max_smem, i
   return false;
 }
 
-template <typename T>
-cudaError_t launch_iterate_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
-                                int* launches, cudaStream_t st, bool* taken) {
+template <typename T, bool FUSED>
+static cudaError_t launch_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
+                               const FusedIO<T>& io, int* launches, cudaStream_t st, bool* taken) {
   *taken = false;
-  {
-    const char* e = getenv("LQPB_ITER");          // developer switch (A/B measurements): auto | rows | packed | stream
-    if (e && (!strcmp(e, "stream") || !strcmp(e, "packed"))) return cudaSuccess;
-  }
   int dev = 0, max_smem = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
@@ -449,14 +777,15 @@ cudaError_t launch_iterate_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   RowGeom geo{};
   size_t smem = 0;
-  if (!plan_rows(w, cfg, max_smem - 2048, sms, &geo, &smem)) return cudaSuccess;
+  if (!plan_rows(w, cfg, max_smem - 2048, sms, FUSED, &geo, &smem)) return cudaSuccess;
   e = cudaMemsetAsync(&w.ctrl->barrier, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
-  void* kern = (void*)iterate_row_kernel<T>;
+  void* kern = (void*)iterate_row_kernel<T, FUSED>;
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   lqpb_config c = cfg;
   FwdWs<T> ww = w;
+  FusedIO<T> ioc = io;
   if (geo.cluster) {
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(geo.G);
@@ -470,9 +799,9 @@ cudaError_t launch_iterate_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i
     at[0].val.clusterDim.z = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    e = cudaLaunchKernelEx(&lc, iterate_row_kernel<T>, c, ww, i0, skip_rho_check, nus_out, geo);
+    e = cudaLaunchKernelEx(&lc, iterate_row_kernel<T, FUSED>, c, ww, i0, skip_rho_check, nus_out, geo, ioc);
   } else {
-    void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo};
+    void* args[] = {&c, &ww, &i0, &skip_rho_check, &nus_out, &geo, &ioc};
     e = cudaLaunchCooperativeKernel(kern, dim3(geo.G), dim3(kRowThreads), args, smem, st);
   }
   if (e != cudaSuccess) return e;
@@ -481,9 +810,53 @@ cudaError_t launch_iterate_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i
   return cudaSuccess;
 }
 
+template <typename T>
+cudaError_t launch_iterate_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
+                                int* launches, cudaStream_t st, bool* taken) {
+  *taken = false;
+  const char* e = getenv("LQPB_ITER");          // developer switch (A/B measurements): auto | rows | packed | stream
+  if (e && (!strcmp(e, "stream") || !strcmp(e, "packed"))) return cudaSuccess;
+  return launch_rows<T, false>(cfg, w, i0, skip_rho_check, nus_out, FusedIO<T>{}, launches, st, taken);
+}
+
+// The whole forward solve of a small problem in one launch (FUSED kernel).  The caller has zeroed the control block and
+// run bound_flags_kernel (any_lb / any_ub of the whole batch) on the same stream.  *taken = false: does not apply.
+template <typename T>
+cudaError_t launch_forward_fused(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, const T* p, const T* A, const T* b,
+                                 const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, int* launches,
+                                 cudaStream_t st, bool* taken) {
+  *taken = false;
+  const char* e = getenv("LQPB_FUSED");         // developer switch (A/B measurements): 0 = separate kernels
+  if (e && e[0] == '0') return cudaSuccess;
+  const char* it = getenv("LQPB_ITER");
+  if (it && strcmp(it, "auto") && strcmp(it, "rows")) return cudaSuccess;
+  const FusedIO<T> io{Q, p, A, b, lb, ub, x, z, u, lams, rho_out};
+  return launch_rows<T, true>(cfg, w, 0, 0, nus, io, launches, st, taken);
+}
+
+template <typename T>
+bool forward_fused_applies(const lqpb_config& cfg, const FwdWs<T>& w) {
+  const char* e = getenv("LQPB_FUSED");
+  if (e && e[0] == '0') return false;
+  const char* it = getenv("LQPB_ITER");
+  if (it && strcmp(it, "auto") && strcmp(it, "rows")) return false;
+  int dev = 0, max_smem = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  RowGeom geo{};
+  size_t smem = 0;
+  return plan_rows(w, cfg, max_smem - 2048, sms, true, &geo, &smem);
+}
+template bool forward_fused_applies<float>(const lqpb_config&, const FwdWs<float>&);
+template bool forward_fused_applies<double>(const lqpb_config&, const FwdWs<double>&);
+
 #define INST(T)                                                                                                      \
   template cudaError_t launch_iterate_rows<T>(const lqpb_config&, const FwdWs<T>&, int, int, T*, int*, cudaStream_t, \
-                                              bool*);
+                                              bool*);                                                                \
+  template cudaError_t launch_forward_fused<T>(const lqpb_config&, const FwdWs<T>&, const T*, const T*, const T*,    \
+                                               const T*, const T*, const T*, T*, T*, T*, T*, T*, T*, int*,           \
+                                               cudaStream_t, bool*);
 INST(float)
 INST(double)
 #undef INST

@@ -260,6 +260,16 @@ template <typename T>
 cudaError_t launch_iterate_rows(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
                                 int* launches, cudaStream_t st, bool* taken);
 
+// iterate_row.cu, FUSED kernel: scaling + rho + KKT inverse + ADMM loop + finalisation of small problems in one launch
+// (adaptive-rho refactorisations on the device).  Needs a zeroed control block and bound_flags_kernel before it.
+template <typename T>
+cudaError_t launch_forward_fused(const lqpb_config& cfg, const FwdWs<T>& w, const T* Q, const T* p, const T* A, const T* b,
+                                 const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, int* launches,
+                                 cudaStream_t st, bool* taken);
+
+template <typename T>
+bool forward_fused_applies(const lqpb_config& cfg, const FwdWs<T>& w);
+
 // unroll.cu -- reverse sweep of the unrolled mode and the rank-n_iter products that form dQ~ and dA~
 template <typename T>
 struct UnrollGrads {

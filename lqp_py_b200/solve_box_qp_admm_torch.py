@@ -73,7 +73,7 @@ class SolveBoxQPLayer(torch.autograd.Function):
             # system) is queued right behind the solve by the same C call (lqpb_forward_prep_*): the GPU works through
             # it while Python travels from here to .backward()
             prep = dict(ws=ctx.pre["ws"], kkt=control.get('backward', 'fixed_point') == 'kkt')
-        sol = _solve_device(Q, p, A, b, lb, ub, control, host_keys=("x",), prep=prep)
+        sol = _solve_device(Q, p, A, b, lb, ub, control, host_keys=("x",), prep=prep, allow_async=True)
         ctx.prepared = bool(sol.get("_prepared", False))
         # reference :33-38 -- with no finite bound the caller's dict is switched to rho = 0
         if not (sol["_any_lb"] or sol["_any_ub"]):
@@ -297,6 +297,21 @@ class _on_device:
         return False
 
 
+_PINNED_POOL = []
+_PINNED_NEXT = [0]
+
+
+def _pinned_ctrl():
+    """A page-locked buffer for the control block of an asynchronous forward (lqpb_forward_async_*), from a small ring:
+    nobody reads a buffer unless its own call asks for ``iter`` / ``status``, so reuse 32 calls later is harmless."""
+    if not _PINNED_POOL:
+        nbytes = int(_abi.lib().lqpb_ctrl_bytes())
+        _PINNED_POOL.extend(torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(32))
+    k = _PINNED_NEXT[0]
+    _PINNED_NEXT[0] = (k + 1) % len(_PINNED_POOL)
+    return _PINNED_POOL[k]
+
+
 _WS_BYTES_CACHE = {}
 
 
@@ -358,12 +373,13 @@ def _host_view(t):
 
 
 def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_cap=None, z0=None, u0=None,
-                  want_status=False):
+                  want_status=False, keep_operators=False, allow_async=False):
     L = _abi.lib()
     out_device = p.device
     host_mode = _all_on_host((Q, p, A, b, lb, ub))
     hx = None
     prepared = False
+    deferred = False
     tape_info = None
     if host_mode:
         # CPU tensors in (the reference's callers): lqpb_forward_host_* uploads Q in chunks on a copy stream and
@@ -383,6 +399,7 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
     B, n = Qd.shape[0], pd.shape[1]
     m = get_ncon(dv["A"], dim=1)
     cfg = _derive_config(control, n)
+    cfg.keep_operators = 1 if keep_operators else 0
     with _on_device(dev):
         new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
         x, z, u = new(B, n, 1), new(B, n, 1), new(B, n, 1)
@@ -394,6 +411,10 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
         info = _abi.Info()
         stream = _raw_stream(dev)
         flag = C.c_int32(0)
+        # the tensor-core sizes (fp32, n + m > 128) queue the backward's factorisation behind the solve (prep); the
+        # others can take the asynchronous forward
+        use_async = (allow_async and not host_mode and tape_cap is None and z0 is None and u0 is None and not cfg.verbose
+                     and not (dt == torch.float32 and n + m > 128))
         if host_mode:
             hx = torch.empty((B, n, 1), dtype=dt, pin_memory=True)
             rc = getattr(L, f"lqpb_forward_host_{sfx}")(
@@ -420,6 +441,18 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
                 return None                       # does not fit (refactorisation / more iterations): caller falls back
             _abi.check(rc, "lqpb_unroll_forward")
             tape_info = (tuple(tape), cap)
+        elif use_async:
+            # the layer only hands x to autograd: small problems run as ONE launch whose adaptive-rho refactorisations
+            # happen on the device, so the call returns once the bound flags are known and the GPU keeps working while
+            # Python travels on to .backward(); iter / status stay in a pinned buffer until somebody asks
+            pinned = _pinned_ctrl()
+            rc = getattr(L, f"lqpb_forward_async_{sfx}")(
+                C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
+                _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), None, None, _abi.ptr(x), _abi.ptr(z), _abi.ptr(u),
+                _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(rho_t), _abi.ptr(pinned), C.byref(info), _abi.ptr(ws), ws_bytes,
+                C.c_void_p(stream), C.byref(flag))
+            _abi.check(rc, "lqpb_forward_async")
+            deferred = bool(flag.value)
         elif prep is not None:
             rc = getattr(L, f"lqpb_forward_prep_{sfx}")(
                 C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
@@ -464,8 +497,9 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
     user_rho = control.get('rho', None)
     if not any_ineq:
         rho = 0                                   # :157-158
-    elif user_rho is None or info.n_factor > 1:
-        rho = rho_t                               # :200-203 / :248-250
+    elif user_rho is None or info.n_factor > 1 or deferred:
+        rho = rho_t                               # :200-203 / :248-250 (deferred: the per-problem tensor always --
+                                                  # it holds the caller's scalar when rho was given and never adapted)
     else:
         rho = user_rho
     # results go back to where the caller's tensors live; the layer only hands x to autograd (host_keys)
@@ -478,7 +512,7 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
     hx = hx if hx is not None else x_out
     rho_out = hrho if torch.is_tensor(rho) else rho
     return {**extra, "x": hx, "z": hz, "u": hu, "lams": hlams, "nus": hnus, "rho": rho_out,
-            "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor),
+            "iter": int(info.iter), "status": int(info.status), "n_factor": int(info.n_factor), "_deferred": deferred,
             "_any_lb": bool(info.any_lb), "_any_ub": bool(info.any_ub), "_dev": dv,
             "_x_dev": x, "_u_dev": u, "_lams_dev": lams, "_nus_dev": nus, "_ws": ws, "_cfg": cfg, "_prepared": prepared, "_tape": tape_info,
             "rho_dev": rho if torch.is_tensor(rho) else None}
@@ -517,7 +551,7 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
     sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=(), tape_cap=_UNROLL_TAPE_CAP)
     first_pass = sol is not None
     if not first_pass:
-        sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=())
+        sol = _solve_device(Qd, pd, Ad, bd, lbd, ubd, plain, host_keys=(), keep_operators=True)
     any_lb, any_ub = sol["_any_lb"], sol["_any_ub"]
     B, n, dt = Qd.shape[0], pd.shape[1], pd.dtype
     m = get_ncon(Ad, dim=1)

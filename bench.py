@@ -452,6 +452,9 @@ def time_layer(cx, dev_sets, B, n, dtype, K, W, backward="fixed_point", sampler=
     t_host0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    # the forward phases are read back (a blocking event query) on a few steps only: on the small configurations the
+    # layer's forward is asynchronous and every read-back would serialise host and device for that step
+    prof_every = max(prof_every, K // 8)
     for k in range(K):
         step(W + k, k % prof_every == 0)
     e1.record()

@@ -77,7 +77,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ unsigned long long s_word;
   __shared__ unsigned long long s_slots[2][8];      // cluster mode: the packed check words of the CTAs of the cluster
-  __shared__ int s_flags[4];
+  __shared__ int s_flags[2][4];                     // per check parity: not_optimal, wants, ratio_out, breakdown
   const int n = w.n, m = w.m, ld = w.ld;
   const int gw = geo.gw, ngroups = geo.ngroups, lpr = geo.lpr, ldk = geo.ldk, nch = geo.nch, ldv = geo.ldv;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -104,7 +104,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
   // ---- one-time load: zero the problem blocks, then either expand the packed lower triangles a factorisation left in
   //      the workspace into dense symmetric matrices, or (FUSED) leave the set-up to the groups below
   for (size_t t = tid; t < (size_t)nprob * geo.prob_elems; t += kRowThreads) base[t] = T(0);
-  if (tid == 0) s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
+  if (tid < 8) s_flags[tid >> 2][tid & 3] = 0;
   __syncthreads();
   if constexpr (!FUSED) {
     const int ntv = P::nt(n), ntiles = P::ntiles(n);
@@ -483,7 +483,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
           vn[r] = -pts[r] + rho * (zn - un);        // rhs of the next iteration (:259-262)
           xs[r] = x;
           if (is_check) {
-            if (!(t_abs(x) < t_inf<T>())) s_flags[3] = 1;  // NaN / inf iterate: numerical breakdown (benign race)
+            if (!(t_abs(x) < t_inf<T>())) s_flags[(i / check) & 1][3] = 1;  // NaN / inf iterate: breakdown (benign race)
             const T d = Ds[r];
             mx_p = t_max(mx_p, t_abs(d * res));
             mx_d = t_max(mx_d, t_abs(d * sres));
@@ -534,9 +534,10 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
           pscal[kPS * q + 4] = tol_p_rel; pscal[kPS * q + 5] = tol_d_rel;
           pscal[kPS * q + 6] = ratio;
           pscal[kPS * q + 7] = wants ? T(1) : T(0);
-          if (!optimal) atomicOr(&s_flags[0], 1);
-          if (wants) atomicOr(&s_flags[1], 1);
-          if (ratio > ar_tol || ratio < ar_tol_inv) atomicOr(&s_flags[2], 1);     // :244-245
+          int* fl = s_flags[(i / check) & 1];
+          if (!optimal) atomicOr(&fl[0], 1);
+          if (wants) atomicOr(&fl[1], 1);
+          if (ratio > ar_tol || ratio < ar_tol_inv) atomicOr(&fl[2], 1);          // :244-245
           if (cfg.verbose) {
             const int ci = i / check;
             if (ci < LQPB_LOG_CAP) {
@@ -549,16 +550,21 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
         if (gw > 1) group_sync();   // red[] reusable
       }
     }
-    // ---- the global decision (:312 torch.all): one packed word per CTA and check carries its arrival and its flags
+    // ---- the global decision (:312 torch.all): one packed word per CTA and check carries its arrival and its flags.
+    //      The CTA flags are double-buffered by check parity (tid 0 clears a buffer after the barrier of its check; the
+    //      next writers of that buffer are two checks away, behind the next barrier), so a check costs ONE __syncthreads
+    //      plus the barrier itself.
     if (is_check) {
+      const int par = (i / check) & 1;
       __syncthreads();
-      const unsigned long long mine = 1ull | (s_flags[1] ? (1ull << 16) : 0ull) | (s_flags[2] ? (1ull << 28) : 0ull) |
-                                      (s_flags[0] ? (1ull << 40) : 0ull) | (s_flags[3] ? (1ull << 52) : 0ull);
+      const int* fl = s_flags[par];
+      const unsigned long long mine = 1ull | (fl[1] ? (1ull << 16) : 0ull) | (fl[2] ? (1ull << 28) : 0ull) |
+                                      (fl[0] ? (1ull << 40) : 0ull) | (fl[3] ? (1ull << 52) : 0ull);
+      unsigned long long v = mine;
       if (geo.cluster) {
         // the grid is ONE cluster: every CTA drops its word into slot [parity][its rank] of every CTA's shared memory
-        // (DSMEM stores), the hardware cluster barrier orders them, and each CTA adds up its own copy -- no global
-        // memory traffic at all at a check (a single-CTA grid needs nothing)
-        const int par = (i / check) & 1;
+        // (DSMEM stores), the hardware cluster barrier orders them, and every thread adds up its CTA's copy -- no
+        // global memory traffic at all at a check (a single-CTA grid needs nothing)
         if (gridDim.x > 1) {
           if (tid < (int)gridDim.x) {
             const uint32_t laddr = smem_u32(&s_slots[par][blockIdx.x]);
@@ -568,23 +574,16 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
           }
           row_cluster_arrive();
           row_cluster_wait();
+          v = 0ull;
+          for (int r = 0; r < (int)gridDim.x; ++r) v += s_slots[par][r];
+        } else {
+          __syncthreads();        // every thread has read the flags before tid 0 clears them
         }
-        if (tid == 0) {
-          unsigned long long v = mine;
-          if (gridDim.x > 1) {
-            v = 0ull;
-            for (int r = 0; r < (int)gridDim.x; ++r) v += s_slots[par][r];
-          }
-          s_word = v;
-          s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
-        }
+        if (tid == 0) s_flags[par][0] = s_flags[par][1] = s_flags[par][2] = s_flags[par][3] = 0;
       } else {
         unsigned long long* word = reinterpret_cast<unsigned long long*>(&ctrl->slot[(i / check) & 3][0]);
-        __syncthreads();          // every thread has read s_flags
         if (tid == 0) {
-          s_flags[0] = s_flags[1] = s_flags[2] = s_flags[3] = 0;
           red_release_add_u64(word, mine);
-          unsigned long long v;
           do {
             v = ld_acquire_u64(word);
           } while ((unsigned)(v & 0xffffull) < gridDim.x);
@@ -596,15 +595,15 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
             *nxt = 0ull;
           }
         }
+        __syncthreads();
+        v = s_word;
+        if (tid == 0) s_flags[par][0] = s_flags[par][1] = s_flags[par][2] = s_flags[par][3] = 0;
       }
-      __syncthreads();
-      const unsigned long long v = s_word;
       last_wants = ((v >> 16) & 0xfffull) != 0;
       last_rout = ((v >> 28) & 0xfffull) != 0;
       const bool all_optimal = ((v >> 40) & 0xfffull) == 0;
       const bool broken = (v >> 52) != 0;
       last_check = i;
-      __syncthreads();
       if (broken) { status = 4; break; }           // LQPB_STATUS_BREAKDOWN: some iterate is NaN / inf
       if (all_optimal) { status = 1; break; }
     }

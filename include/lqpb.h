@@ -113,7 +113,9 @@ int lqpb_forward_f64(const lqpb_config* cfg, int B, int n, int m, const double* 
 /* ---- additions to the reference's behaviour (the reference always starts from x = z = u = 0,
  * solve_box_qp_admm_torch.py:221-223, and keeps no record of how a solve ended, :235, :331) ---------------
  * forward_warm:     lqpb_forward_* started from the caller's z0, u0 (B,n): the UNSCALED z and u an earlier solve of a
- *                   nearby problem returned (both or neither; NULL, NULL = lqpb_forward_*).
+ *                   nearby problem returned (both or neither; NULL, NULL = lqpb_forward_*).  rho0 (B) or NULL: a
+ *                   per-problem rho given by the caller (the reference broadcasts a (B,1,1) tensor in control['rho'],
+ *                   :200, e.g. sol['rho'] fed back); used when cfg->rho_auto == 0 instead of cfg->rho.
  * solution_status:  per-problem record of the LAST stop check of the solve whose workspace is passed (call it right
  *                   after lqpb_forward_* on the same stream): residuals (B,4) = [primal residual, dual residual,
  *                   primal tolerance, dual tolerance] (:286-304) and converged (B) = that problem's own stop test
@@ -121,12 +123,13 @@ int lqpb_forward_f64(const lqpb_config* cfg, int B, int n, int m, const double* 
  *                   this tells which ones were not. */
 int lqpb_forward_warm_f32(const lqpb_config* cfg, int B, int n, int m, const float* Q, const float* p,
                           const float* A, const float* b, const float* lb, const float* ub, const float* z0,
-                          const float* u0, float* x, float* z, float* u, float* lams, float* nus, float* rho_out,
-                          lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream);
+                          const float* u0, const float* rho0, float* x, float* z, float* u, float* lams, float* nus,
+                          float* rho_out, lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream);
 int lqpb_forward_warm_f64(const lqpb_config* cfg, int B, int n, int m, const double* Q, const double* p,
                           const double* A, const double* b, const double* lb, const double* ub, const double* z0,
-                          const double* u0, double* x, double* z, double* u, double* lams, double* nus,
-                          double* rho_out, lqpb_info* info, void* workspace, size_t workspace_bytes, void* stream);
+                          const double* u0, const double* rho0, double* x, double* z, double* u, double* lams,
+                          double* nus, double* rho_out, lqpb_info* info, void* workspace, size_t workspace_bytes,
+                          void* stream);
 /* forward_async: lqpb_forward_warm_* without the end-of-solve synchronisation, for callers that only need x (the autograd
  * layer, :26-53).  When the one-launch forward applies (small problems; adaptive-rho refactorisations happen on the device
  * there, so nothing about the solve needs the host) the call returns as soon as the bound flags are known: info->any_lb /
@@ -146,6 +149,13 @@ int lqpb_forward_async_f64(const lqpb_config* cfg, int B, int n, int m, const do
                            double* rho_out, void* pinned_ctrl, lqpb_info* info, void* workspace,
                            size_t workspace_bytes, void* stream, int32_t* deferred);
 int lqpb_forward_collect(const void* pinned_ctrl, const lqpb_config* cfg, lqpb_info* info);
+
+/* Which iteration kernel a forward solve of this shape takes on the current device (SURVEY App. C regimes; needs a CUDA
+ * device): the x-update operator streamed from L2 / HBM every iteration, held in shared memory as packed tiles, held in
+ * shared memory as dense matrices, or the latter inside the one-launch forward.  -1: no sm_100 device. */
+enum { LQPB_REGIME_STREAM = 0, LQPB_REGIME_PACKED_RESIDENT = 1, LQPB_REGIME_ROWS = 2, LQPB_REGIME_FUSED_ROWS = 3 };
+int lqpb_iterate_regime_f32(const lqpb_config* cfg, int B, int n, int m);
+int lqpb_iterate_regime_f64(const lqpb_config* cfg, int B, int n, int m);
 int lqpb_solution_status_f32(const lqpb_config* cfg, int B, int n, int m, void* workspace, size_t workspace_bytes,
                              float* residuals, int32_t* converged, void* stream);
 int lqpb_solution_status_f64(const lqpb_config* cfg, int B, int n, int m, void* workspace, size_t workspace_bytes,

@@ -19,7 +19,7 @@ EXPORTS = (
     "lqpb_forward_workspace_bytes_f32", "lqpb_forward_workspace_bytes_f64",
     "lqpb_forward_f32", "lqpb_forward_f64", "lqpb_forward_warm_f32", "lqpb_forward_warm_f64",
     "lqpb_solution_status_f32", "lqpb_solution_status_f64", "lqpb_forward_async_f32", "lqpb_forward_async_f64",
-    "lqpb_ctrl_bytes", "lqpb_forward_collect",
+    "lqpb_ctrl_bytes", "lqpb_forward_collect", "lqpb_iterate_regime_f32", "lqpb_iterate_regime_f64",
     "lqpb_backward_workspace_bytes_f32", "lqpb_backward_workspace_bytes_f64",
     "lqpb_backward_f32", "lqpb_backward_f64", "lqpb_backward_kkt_f32", "lqpb_backward_kkt_f64",
     "lqpb_forward_prep_f32", "lqpb_forward_prep_f64", "lqpb_backward_finish_f32", "lqpb_backward_finish_f64",
@@ -98,12 +98,14 @@ def lib():
         f.argtypes = [C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 6 + [C.POINTER(Info), vp, sz, vp]
         f.restype = i32
         f = getattr(L, f"lqpb_forward_warm_{sfx}")
-        f.argtypes = [C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 2 + [vp] * 6 + [C.POINTER(Info), vp, sz, vp]
+        f.argtypes = [C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 3 + [vp] * 6 + [C.POINTER(Info), vp, sz, vp]
         f.restype = i32
         f = getattr(L, f"lqpb_forward_async_{sfx}")
         f.argtypes = ([C.POINTER(Config), i32, i32, i32] + [vp] * 6 + [vp] * 2 + [vp] * 6 + [vp, C.POINTER(Info), vp, sz, vp,
                       C.POINTER(C.c_int32)])
         f.restype = i32
+        f = getattr(L, f"lqpb_iterate_regime_{sfx}")
+        f.argtypes, f.restype = [C.POINTER(Config), i32, i32, i32], i32
         f = getattr(L, f"lqpb_solution_status_{sfx}")
         f.argtypes, f.restype = [C.POINTER(Config), i32, i32, i32, vp, sz, vp, vp, vp], i32
         f = getattr(L, f"lqpb_backward_{sfx}")

@@ -178,6 +178,7 @@ FwdWs<T> slice_fwd(const FwdWs<T>& w, int b0, int bc) {
   s.wants += o;
   if (w.z0) s.z0 += o * w.n;
   if (w.u0) s.u0 += o * w.n;
+  if (w.rho_in) s.rho_in += o;
   return s;
 }
 template <typename T>
@@ -285,7 +286,7 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
                  const T* lb, const T* ub, T* x, T* z, T* u, T* lams, T* nus, T* rho_out, lqpb_info* info, void* ws,
                  size_t ws_bytes, void* stream, const HostFwd<T>* host = nullptr, const UnrollRec<T>* rec = nullptr,
                  const BwdPrep<T>* prep = nullptr, const T* z0 = nullptr, const T* u0 = nullptr,
-                 void* async_ctrl = nullptr, int32_t* deferred = nullptr) {
+                 void* async_ctrl = nullptr, int32_t* deferred = nullptr, const T* rho_in = nullptr) {
   if (host && (!host->Q || !host->p || !host->lb || !host->ub || (m > 0 && (!host->A || !host->b))))
     return fail(LQPB_E_ARG, "null host pointer argument");
   if (!cfg || !Q || !p || !lb || !ub || !x || !z || !u || !lams || !rho_out || !info || !ws)
@@ -302,6 +303,7 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
   if (w.bytes > ws_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");
   w.z0 = z0;
   w.u0 = u0;
+  w.rho_in = rho_in;
   cudaStream_t st = (cudaStream_t)stream;
   if (!g_hctrl.pinned) CK(cudaMallocHost(&g_hctrl.pinned, sizeof(Ctrl)), "cudaMallocHost");
   Ctrl* hc = g_hctrl.pinned;
@@ -798,11 +800,11 @@ int lqpb_backward_f64(int B, int n, int m, const double* dl_dz, const double* x,
 
 #define WARM_ENTRY(SFX, T)                                                                                          \
   int lqpb_forward_warm_##SFX(const lqpb_config* cfg, int B, int n, int m, const T* Q, const T* p, const T* A,     \
-                              const T* b, const T* lb, const T* ub, const T* z0, const T* u0, T* x, T* z, T* u,    \
-                              T* lams, T* nus, T* rho_out, lqpb_info* info, void* workspace, size_t workspace_bytes, \
-                              void* stream) {                                                                      \
+                              const T* b, const T* lb, const T* ub, const T* z0, const T* u0, const T* rho0,      \
+                              T* x, T* z, T* u, T* lams, T* nus, T* rho_out, lqpb_info* info, void* workspace,     \
+                              size_t workspace_bytes, void* stream) {                                              \
     return forward_impl<T>(cfg, B, n, m, Q, p, A, b, lb, ub, x, z, u, lams, nus, rho_out, info, workspace,         \
-                           workspace_bytes, stream, nullptr, nullptr, nullptr, z0, u0);                            \
+                           workspace_bytes, stream, nullptr, nullptr, nullptr, z0, u0, nullptr, nullptr, rho0);    \
   }                                                                                                                \
   int lqpb_solution_status_##SFX(const lqpb_config* cfg, int B, int n, int m, void* workspace,                     \
                                  size_t workspace_bytes, T* residuals, int32_t* converged, void* stream) {         \
@@ -832,6 +834,18 @@ ASYNC_ENTRY(f32, float)
 ASYNC_ENTRY(f64, double)
 
 size_t lqpb_ctrl_bytes(void) { return sizeof(Ctrl); }
+
+#define REGIME_ENTRY(SFX, T)                                                                               \
+  int lqpb_iterate_regime_##SFX(const lqpb_config* cfg, int B, int n, int m) {                             \
+    if (!cfg || B <= 0 || n <= 0 || m < 0 || check_device()) return -1;                                    \
+    const FwdWs<T> w = carve_fwd<T>(nullptr, B, n, m);                                                     \
+    if (cfg->keep_operators == 0 && forward_fused_applies<T>(*cfg, w)) return LQPB_REGIME_FUSED_ROWS;      \
+    if (iterate_rows_applies<T>(*cfg, w)) return LQPB_REGIME_ROWS;                                         \
+    if (iterate_resident_applies<T>(*cfg, w)) return LQPB_REGIME_PACKED_RESIDENT;                          \
+    return LQPB_REGIME_STREAM;                                                                             \
+  }
+REGIME_ENTRY(f32, float)
+REGIME_ENTRY(f64, double)
 
 int lqpb_forward_collect(const void* pinned_ctrl, const lqpb_config* cfg, lqpb_info* info) {
   if (!pinned_ctrl || !cfg || !info) return fail(LQPB_E_ARG, "null pointer argument");

@@ -559,7 +559,7 @@ __global__ void select_rho_kernel(lqpb_config cfg, FwdWs<T> w) {
   T rc = (T)sqrt(tot) / (T)sqrt((double)w.n);
   rc = t_min(t_max(rc, (T)cfg.rho_min), (T)cfg.rho_max);
   w.rho_cand[b] = rc;
-  T r = cfg.rho_auto ? rc : (T)cfg.rho;
+  T r = cfg.rho_auto ? rc : (w.rho_in ? w.rho_in[b] : (T)cfg.rho);
   if (!boxed) r = T(0);
   w.rho[b] = r;
 }

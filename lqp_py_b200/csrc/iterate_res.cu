@@ -525,6 +525,21 @@ cudaError_t launch_iterate_resident(const lqpb_config& cfg, const FwdWs<T>& w, i
   return cudaSuccess;
 }
 
+template <typename T>
+bool iterate_resident_applies(const lqpb_config& cfg, const FwdWs<T>& w) {
+  const char* e = getenv("LQPB_ITER");
+  if (e && (!strcmp(e, "stream") || !strcmp(e, "rows"))) return false;
+  int dev = 0, max_smem = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ResGeom geo{};
+  size_t smem = 0;
+  return plan_resident(w, cfg, max_smem - 2048, sms, &geo, &smem);
+}
+template bool iterate_resident_applies<float>(const lqpb_config&, const FwdWs<float>&);
+template bool iterate_resident_applies<double>(const lqpb_config&, const FwdWs<double>&);
+
 #define INST(T)                                                                                                  \
   template cudaError_t launch_iterate_resident<T>(const lqpb_config&, const FwdWs<T>&, int, int, T*, int*, cudaStream_t, \
                                                   bool*);

@@ -358,7 +358,7 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
       fro = gsum_d(fro);
       T rc = (T)sqrt(fro) / (T)sqrt((double)n);
       rc = t_min(t_max(rc, (T)cfg.rho_min), (T)cfg.rho_max);
-      T rho = cfg.rho_auto ? rc : (T)cfg.rho;
+      T rho = cfg.rho_auto ? rc : (w.rho_in ? w.rho_in[b] : (T)cfg.rho);
       if (!boxed) rho = T(0);
       // equality rows: A~ = E (A D), b~ = E b (:179-190)
       for (int l = 0; l < m; ++l) {
@@ -847,6 +847,20 @@ bool forward_fused_applies(const lqpb_config& cfg, const FwdWs<T>& w) {
   size_t smem = 0;
   return plan_rows(w, cfg, max_smem - 2048, sms, true, &geo, &smem);
 }
+template <typename T>
+bool iterate_rows_applies(const lqpb_config& cfg, const FwdWs<T>& w) {
+  const char* it = getenv("LQPB_ITER");
+  if (it && (!strcmp(it, "stream") || !strcmp(it, "packed"))) return false;
+  int dev = 0, max_smem = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  RowGeom geo{};
+  size_t smem = 0;
+  return plan_rows(w, cfg, max_smem - 2048, sms, false, &geo, &smem);
+}
+template bool iterate_rows_applies<float>(const lqpb_config&, const FwdWs<float>&);
+template bool iterate_rows_applies<double>(const lqpb_config&, const FwdWs<double>&);
 template bool forward_fused_applies<float>(const lqpb_config&, const FwdWs<float>&);
 template bool forward_fused_applies<double>(const lqpb_config&, const FwdWs<double>&);
 

@@ -84,6 +84,7 @@ struct FwdWs {
   int* wants;   // B    do_rho_update of the last check
   Ctrl* ctrl;
   const T *z0, *u0;   // optional warm start (caller's UNSCALED z, u of an earlier solve, (B, n)); null = zero start (:221-223)
+  const T* rho_in;    // optional per-problem rho (B) given by the caller (a (B,1,1) tensor in control['rho']); null = cfg.rho
   size_t bytes;
 };
 
@@ -92,6 +93,7 @@ inline FwdWs<T> carve_fwd(void* base, int B, int n, int m) {
   FwdWs<T> w;
   w.B = B; w.n = n; w.m = m;
   w.z0 = w.u0 = nullptr;
+  w.rho_in = nullptr;
   w.ld = round_up(n, Vec<T>::N);
   w.np = round_up(n + m, kMacro);
   char* p = static_cast<char*>(base);
@@ -269,6 +271,10 @@ cudaError_t launch_forward_fused(const lqpb_config& cfg, const FwdWs<T>& w, cons
 
 template <typename T>
 bool forward_fused_applies(const lqpb_config& cfg, const FwdWs<T>& w);
+template <typename T>
+bool iterate_rows_applies(const lqpb_config& cfg, const FwdWs<T>& w);
+template <typename T>
+bool iterate_resident_applies(const lqpb_config& cfg, const FwdWs<T>& w);
 
 // unroll.cu -- reverse sweep of the unrolled mode and the rank-n_iter products that form dQ~ and dA~
 template <typename T>

@@ -335,7 +335,11 @@ def _derive_config(control, n_x):
     cfg.check_solved = int(check)
     rho = g('rho', None)
     cfg.rho_auto = 1 if rho is None else 0
-    cfg.rho = 0.0 if rho is None else float(rho)
+    # a tensor rho (the reference broadcasts a (B,1,1) tensor, e.g. sol['rho'] fed back) travels as a device array
+    # (lqpb_forward_warm_*'s rho0); a one-element tensor is just a number
+    if torch.is_tensor(rho) and rho.numel() == 1:
+        rho = float(rho)
+    cfg.rho = 0.0 if (rho is None or torch.is_tensor(rho)) else float(rho)
     cfg.rho_min = g('rho_min', 1e-6)
     cfg.rho_max = g('rho_max', 1e6)
     cfg.adaptive_rho = 1 if g('adaptive_rho', False) else 0
@@ -413,8 +417,17 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
         flag = C.c_int32(0)
         # the tensor-core sizes (fp32, n + m > 128) queue the backward's factorisation behind the solve (prep); the
         # others can take the asynchronous forward
+        rho_vec = None
+        user_rho_t = control.get('rho', None)
+        if torch.is_tensor(user_rho_t) and user_rho_t.numel() > 1:
+            if user_rho_t.numel() != B:
+                raise ValueError(f"control['rho'] has {user_rho_t.numel()} entries for a batch of {B}")
+            if host_mode or tape_cap is not None:
+                raise NotImplementedError("a per-problem rho tensor needs CUDA input tensors and unroll=False")
+            prep = None                # (the per-problem rho travels through lqpb_forward_warm_* only)
+            rho_vec = user_rho_t.detach().to(device=dev, dtype=dt).reshape(B).contiguous()
         use_async = (allow_async and not host_mode and tape_cap is None and z0 is None and u0 is None and not cfg.verbose
-                     and not (dt == torch.float32 and n + m > 128))
+                     and rho_vec is None and not (dt == torch.float32 and n + m > 128))
         if host_mode:
             hx = torch.empty((B, n, 1), dtype=dt, pin_memory=True)
             rc = getattr(L, f"lqpb_forward_host_{sfx}")(
@@ -461,13 +474,16 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
                 prep["ws"].numel(), 1 if prep["kkt"] else 0, C.byref(flag), C.c_void_p(stream))
             _abi.check(rc, "lqpb_forward_prep")
             prepared = bool(flag.value)
-        elif z0 is not None or u0 is not None:
-            if z0 is None or u0 is None:
+        elif z0 is not None or u0 is not None or rho_vec is not None:
+            if (z0 is None) != (u0 is None):
                 raise ValueError("a warm start needs both z0 and u0")
-            wz, wu = (t.detach().to(device=dev, dtype=dt).reshape(B, n).contiguous() for t in (z0, u0))
+            wz = wu = None
+            if z0 is not None:
+                wz, wu = (t.detach().to(device=dev, dtype=dt).reshape(B, n).contiguous() for t in (z0, u0))
             rc = getattr(L, f"lqpb_forward_warm_{sfx}")(
                 C.byref(cfg), B, n, m, _abi.ptr(Qd), _abi.ptr(pd), _abi.ptr(dv["A"]), _abi.ptr(dv["b"]),
-                _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(wz), _abi.ptr(wu), _abi.ptr(x), _abi.ptr(z), _abi.ptr(u),
+                _abi.ptr(dv["lb"]), _abi.ptr(dv["ub"]), _abi.ptr(wz), _abi.ptr(wu), _abi.ptr(rho_vec), _abi.ptr(x),
+                _abi.ptr(z), _abi.ptr(u),
                 _abi.ptr(lams), _abi.ptr(nus), _abi.ptr(rho_t), C.byref(info), _abi.ptr(ws), ws_bytes, C.c_void_p(stream))
             _abi.check(rc, "lqpb_forward_warm")
         else:

@@ -774,3 +774,22 @@ def test_unrolled_adaptive_rho_iter_shorter_than_check(dev):
     assert rel_err(x.detach().cpu().numpy(), xr.detach().numpy()) <= 1e-8
     for a, r, nm in zip(ins, leaves, ("dQ", "dp", "dA", "db", "dlb", "dub")):
         assert rel_err(a.grad.cpu().numpy(), r.grad.numpy()) <= 1e-6, nm
+
+
+@pytest.mark.parametrize("n,dtype", [(40, torch.float64), (200, torch.float32)])
+def test_per_problem_rho_tensor_in_control(n, dtype, dev):
+    """The reference broadcasts a (B,1,1) tensor in control['rho'] (:200: only None triggers the automatic choice), e.g.
+    the `rho` of an earlier solve fed back.  Feeding the automatic rho back must reproduce that solve bit for bit
+    (same kernels, same per-problem rho), through the functional API and through the layer."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP, torch_solve_box_qp
+    Q, p, A, b, lb, ub = [t.to(dev) for t in orc.make_exp1_data(n, 6, seed=9, dtype=dtype)]
+    auto = torch_solve_box_qp(Q, p, A, b, lb, ub, box_qp_control(eps_abs=1e-5, eps_rel=1e-5))
+    assert torch.is_tensor(auto["rho"]) and auto["rho"].shape == (6, 1, 1)
+    again = torch_solve_box_qp(Q, p, A, b, lb, ub, box_qp_control(eps_abs=1e-5, eps_rel=1e-5, rho=auto["rho"]))
+    assert again["iter"] == auto["iter"] and torch.equal(again["x"], auto["x"])
+    assert torch.is_tensor(again["rho"]) and torch.equal(again["rho"], auto["rho"])
+    ins = [t.clone().requires_grad_(True) for t in (Q, p, A, b, lb, ub)]
+    x = SolveBoxQP(control=box_qp_control(eps_abs=1e-5, eps_rel=1e-5, rho=auto["rho"])).forward(*ins)
+    x.backward(torch.ones_like(x))
+    assert torch.equal(x.detach(), auto["x"]) and ins[1].grad is not None

@@ -347,6 +347,29 @@ int lqpb_unroll_scale_grad_f32(int B, int n, float* G, const float* Q, const flo
 int lqpb_unroll_scale_grad_f64(int B, int n, double* G, const double* Q, const double* D, const double* coef,
                                double* gD, double* scratch, void* stream);
 
+/* The O(B n) part of the same scaling map (:161-197): (column inf-norms of Q, p, A, b, lb, ub) -> (D, p~ = D p, A~ = E (A D),
+ * b~ = E b, lb~ = lb / D, ub~ = ub / D) with D = blend(sqrt(1 / guard(norms))) (:163-175) and E = 1 / guard(||A D||_inf)
+ * (:180-188).  scaled_vectors copies the VALUES out of the workspace of the recording solve (D, pt, lbt, ubt (B,n); At (B,m,n);
+ * bt, E (B,m)); scale_vec_grad is the adjoint of the whole map in one kernel per problem, with torch's subgradient rules
+ * (inf-norms split evenly among exact ties, torch.quantile sends (1 - w, w) to the two order statistics it interpolates,
+ * guarded entries route to the mean).  g* inputs may be NULL (= zero); use_lb / use_ub = the bound vector enters the loop
+ * (any_lb / any_ub); beta_auto = control['beta'] is None. */
+int lqpb_unroll_scaled_vectors_f32(int B, int n, int m, void* workspace, size_t workspace_bytes, float* D, float* pt,
+                                   float* At, float* bt, float* lbt, float* ubt, float* E, void* stream);
+int lqpb_unroll_scaled_vectors_f64(int B, int n, int m, void* workspace, size_t workspace_bytes, double* D, double* pt,
+                                   double* At, double* bt, double* lbt, double* ubt, double* E, void* stream);
+int lqpb_unroll_scale_vec_grad_f32(int B, int n, int m, int beta_auto, double beta, int use_lb, int use_ub,
+                                   const float* colmax, const float* p, const float* A, const float* b, const float* lb,
+                                   const float* ub, const float* D, const float* E, const float* gD, const float* gpt,
+                                   const float* gAt, const float* gbt, const float* glbt, const float* gubt,
+                                   float* gcolmax, float* gp, float* gA, float* gb, float* glb, float* gub, void* stream);
+int lqpb_unroll_scale_vec_grad_f64(int B, int n, int m, int beta_auto, double beta, int use_lb, int use_ub,
+                                   const double* colmax, const double* p, const double* A, const double* b,
+                                   const double* lb, const double* ub, const double* D, const double* E, const double* gD,
+                                   const double* gpt, const double* gAt, const double* gbt, const double* glbt,
+                                   const double* gubt, double* gcolmax, double* gp, double* gA, double* gb, double* glb,
+                                   double* gub, void* stream);
+
 /* ---- lu_layer: replaces TorchLU / TorchLULayer (lu_layer.py:5-58) -------------------------
  * lu_factor: partial-pivoting LU of B general N x N matrices (torch.linalg.lu_factor, :10,:30);
  *            LU (B,N,N) packed L\U, piv (B,N) 1-based row swaps like LAPACK getrf.

@@ -965,6 +965,36 @@ UNROLL_ENTRY(f64, double)
 SCALE_GRAD_ENTRY(f32, float)
 SCALE_GRAD_ENTRY(f64, double)
 
+#define SCALE_VEC_ENTRY(SFX, T)                                                                                     \
+  int lqpb_unroll_scaled_vectors_##SFX(int B, int n, int m, void* workspace, size_t workspace_bytes, T* D, T* pt,   \
+                                       T* At, T* bt, T* lbt, T* ubt, T* E, void* stream) {                          \
+    if (!workspace || !D || !pt || !lbt || !ubt || B <= 0 || n <= 0 || m < 0 || (m > 0 && (!At || !bt || !E)))      \
+      return fail(LQPB_E_ARG, "bad argument");                                                                     \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    FwdWs<T> w = carve_fwd<T>(workspace, B, n, m);                                                                 \
+    if (w.bytes > workspace_bytes) return fail(LQPB_E_WORKSPACE, "workspace too small");                           \
+    CK(launch_scaled_vectors<T>(w, D, pt, At, bt, lbt, ubt, E, (cudaStream_t)stream), "scaled_vectors");           \
+    return LQPB_OK;                                                                                                \
+  }                                                                                                                \
+  int lqpb_unroll_scale_vec_grad_##SFX(int B, int n, int m, int beta_auto, double beta, int use_lb, int use_ub,    \
+                                       const T* colmax, const T* p, const T* A, const T* b, const T* lb,           \
+                                       const T* ub, const T* D, const T* E, const T* gD, const T* gpt,             \
+                                       const T* gAt, const T* gbt, const T* glbt, const T* gubt, T* gcolmax,       \
+                                       T* gp, T* gA, T* gb, T* glb, T* gub, void* stream) {                        \
+    if (!colmax || !p || !lb || !ub || !D || !gcolmax || !gp || !glb || !gub || B <= 0 || n <= 0 || m < 0 ||       \
+        (m > 0 && (!A || !b || !E || !gA || !gb)))                                                                 \
+      return fail(LQPB_E_ARG, "bad argument");                                                                     \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    ScaleVecGrad<T> a{n, m, beta_auto, use_lb, use_ub, (T)beta, colmax, p, A, b, lb, ub, D, E, gD, gpt, gAt, gbt,  \
+                      glbt, gubt, gcolmax, gp, gA, gb, glb, gub};                                                   \
+    CK(launch_scale_vec_grad<T>(B, a, (cudaStream_t)stream), "scale_vec_grad");                                    \
+    return LQPB_OK;                                                                                                \
+  }
+SCALE_VEC_ENTRY(f32, float)
+SCALE_VEC_ENTRY(f64, double)
+
 #define LU_ENTRY(SFX, T)                                                                                          \
   int lqpb_lu_factor_##SFX(int B, int N, const T* A, T* LU, int32_t* piv, void* stream) {                          \
     if (!A || !LU || !piv || B <= 0 || N <= 0) return fail(LQPB_E_ARG, "bad argument");                           \

@@ -292,6 +292,20 @@ cudaError_t launch_unroll_reverse(const FwdWs<T>& w, const Tape<T>& tape, const 
 // adjoint of Q~ = D Q D and rho = ||Q~||_F / sqrt(n): G (B,n,n) in/out, gD (B,n) out, part = (B, ceil(n/32) + 1, n) scratch
 template <typename T>
 cudaError_t launch_scale_grad(int B, int n, T* G, const T* Q, const T* D, const T* coef, T* gD, T* part, cudaStream_t st);
+// the O(B n) part of the scaling map (:161-197) in the unrolled mode: values out of the workspace, adjoint in one kernel
+template <typename T>
+struct ScaleVecGrad {
+  int n, m, beta_auto, use_lb, use_ub;
+  T beta;
+  const T *colmax, *p, *A, *b, *lb, *ub, *D, *E;          // forward inputs / outputs
+  const T *gD, *gpt, *gAt, *gbt, *glbt, *gubt;             // upstream adjoints (any may be null = zero)
+  T *gcolmax, *gp, *gA, *gb, *glb, *gub;                   // outputs (gA / gb null when m == 0)
+};
+
+template <typename T>
+cudaError_t launch_scaled_vectors(const FwdWs<T>& w, T* D, T* pt, T* At, T* bt, T* lbt, T* ubt, T* E, cudaStream_t st);
+template <typename T>
+cudaError_t launch_scale_vec_grad(int B, const ScaleVecGrad<T>& a, cudaStream_t st);
 template <typename T>
 cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho_out, cudaStream_t st);
 

@@ -368,6 +368,259 @@ cudaError_t launch_scale_grad(int B, int n, T* G, const T* Q, const T* D, const 
 template cudaError_t launch_scale_grad<float>(int, int, float*, const float*, const float*, const float*, float*, float*, cudaStream_t);
 template cudaError_t launch_scale_grad<double>(int, int, double*, const double*, const double*, const double*, double*, double*, cudaStream_t);
 
+// ---------------------------------------------------------------------------------------------
+// The O(B n) part of the scaling map (:161-197) for the unrolled mode: what autograd walks through between the caller's
+// (p, A, b, lb, ub, column norms of Q) and the scaled problem (D, p~, A~, b~, lb~, ub~).
+//   scaled_vectors_kernel  -- forward VALUES: copied out of the workspace of the recording solve (the kernels computed
+//                             them already; same numbers the loop used)
+//   scale_vec_grad_kernel  -- the adjoint of the whole map in one kernel per problem, with torch's (sub)gradient rules
+//                             for the operators the reference uses: inf-norms split their gradient evenly among exact
+//                             ties, torch.quantile sends (1 - w, w) to the two order statistics it interpolates,
+//                             where(bad, maximum(norm, floor), norm) routes the guarded entries to the mean
+template <typename T>
+__global__ void scaled_vectors_kernel(FwdWs<T> w, T* D, T* pt, T* At, T* bt, T* lbt, T* ubt, T* E) {
+  const int b = blockIdx.y, n = w.n, m = w.m, ld = w.ld;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const size_t vo = (size_t)b * ld + j, o = (size_t)b * n + j;
+    D[o] = w.D[vo];
+    pt[o] = w.pt[vo];
+    lbt[o] = w.lbt[vo];
+    ubt[o] = w.ubt[vo];
+    for (int l = 0; l < m; ++l) At[((size_t)b * m + l) * n + j] = w.At[((size_t)b * m + l) * ld + j];
+  }
+  if (blockIdx.x == 0)
+    for (int l = threadIdx.x; l < m; l += blockDim.x) {
+      bt[(size_t)b * m + l] = w.bt[(size_t)b * m + l];
+      E[(size_t)b * m + l] = w.E[(size_t)b * m + l];
+    }
+}
+
+constexpr int kSvThreads = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kSvThreads) scale_vec_grad_kernel(ScaleVecGrad<T> a, int P2) {
+  extern __shared__ __align__(16) unsigned char sv_raw[];
+  double* gDt = reinterpret_cast<double*>(sv_raw);             // [n] total adjoint of D, then of D0
+  double* dscr = gDt + a.n;                                    // [32]
+  T* D0 = reinterpret_cast<T*>(dscr + 32);                     // [n]
+  T* cg = D0 + a.n;                                            // [n] guarded column norms
+  T* skey = cg + a.n;                                          // [P2]
+  int* sidx = reinterpret_cast<int*>(skey + P2);               // [P2]
+  __shared__ double s_tot;
+  const int b = blockIdx.x, tid = threadIdx.x, n = a.n, m = a.m;
+  const size_t vo = (size_t)b * n;
+  auto bsum = [&](double v) -> double {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) dscr[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double r = 0.0;
+      for (int k = 0; k < kSvThreads / 32; ++k) r += dscr[k];
+      s_tot = r;
+    }
+    __syncthreads();
+    return s_tot;
+  };
+  // ---- forward quantities again: guarded norms, D0, beta, mean
+  double part = 0.0;
+  for (int j = tid; j < n; j += kSvThreads) part += (double)a.colmax[vo + j];
+  const double mean_c = bsum(part) / n;
+  const T floor_c = t_max((T)mean_c, T(1e-6));
+  for (int j = tid; j < n; j += kSvThreads) {
+    T c = a.colmax[vo + j];
+    if (c <= T(0)) c = t_max(c, floor_c);
+    cg[j] = c;
+    D0[j] = t_sqrt(T(1) / c);
+  }
+  __syncthreads();
+  T beta = a.beta, q10 = T(0), q90 = T(1);
+  int ilo[2] = {0, 0}, ihi[2] = {0, 0};
+  T wq[2] = {T(0), T(0)};
+  if (a.beta_auto) {
+    for (int j = tid; j < P2; j += kSvThreads) { skey[j] = j < n ? D0[j] : t_inf<T>(); sidx[j] = j; }
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < P2; i += kSvThreads) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const T x = skey[i], y = skey[ixj];
+            const bool asc = (i & k) == 0;
+            if ((x > y) == asc) {
+              skey[i] = y; skey[ixj] = x;
+              const int t = sidx[i]; sidx[i] = sidx[ixj]; sidx[ixj] = t;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    const T qs[2] = {T(0.10), T(0.90)};
+    T qv[2];
+    for (int k = 0; k < 2; ++k) {
+      const T rank = qs[k] * T(n - 1);
+      const T lo = floor(rank), hi = ceil(rank);
+      const T x = skey[(int)lo], y = skey[(int)hi], wgt = rank - lo;
+      qv[k] = wgt < T(0.5) ? x + wgt * (y - x) : y - (y - x) * (T(1) - wgt);
+      ilo[k] = sidx[(int)lo]; ihi[k] = sidx[(int)hi]; wq[k] = wgt;
+    }
+    q10 = qv[0]; q90 = qv[1];
+    beta = T(1) - q10 / q90;
+  }
+  part = 0.0;
+  for (int j = tid; j < n; j += kSvThreads) part += (double)D0[j];
+  const double meanD0 = bsum(part) / n;
+
+  // ---- adjoint of the vectors: everything that reaches D, and the gradients of p, lb, ub
+  for (int j = tid; j < n; j += kSvThreads) {
+    const T d = a.D[vo + j];
+    double g = a.gD ? (double)a.gD[vo + j] : 0.0;
+    if (a.gpt) {
+      g += (double)(a.gpt[vo + j] * a.p[vo + j]);
+      a.gp[vo + j] = a.gpt[vo + j] * d;
+    } else {
+      a.gp[vo + j] = T(0);
+    }
+    if (a.use_lb && a.glbt) {
+      const T gl = a.glbt[vo + j];
+      g += (double)(gl * (-a.lb[vo + j] / (d * d)));      // 0 * inf = NaN on an infinite entry, like torch's division
+      a.glb[vo + j] = gl / d;
+    } else {
+      a.glb[vo + j] = T(0);
+    }
+    if (a.use_ub && a.gubt) {
+      const T gu = a.gubt[vo + j];
+      g += (double)(gu * (-a.ub[vo + j] / (d * d)));
+      a.gub[vo + j] = gu / d;
+    } else {
+      a.gub[vo + j] = T(0);
+    }
+    gDt[j] = g;
+  }
+  __syncthreads();
+  // ---- equality rows: A~ = E (A D), b~ = E b, E = 1 / guard(||A D||_inf per row)
+  if (m > 0) {
+    // raw row norms, their mean (for the guard) -- m is small, one row at a time
+    double rsum = 0.0;
+    for (int l = 0; l < m; ++l) {
+      const T* Al = a.A + ((size_t)b * m + l) * n;
+      T mx = T(0);
+      for (int j = tid; j < n; j += kSvThreads) mx = t_max(mx, t_abs(Al[j] * a.D[vo + j]));
+      mx = warp_max(mx);
+      __syncthreads();
+      if ((tid & 31) == 0) dscr[tid >> 5] = (double)mx;
+      __syncthreads();
+      double r = dscr[0];
+      for (int k = 1; k < kSvThreads / 32; ++k) r = r > dscr[k] ? r : dscr[k];
+      skey[l % P2] = (T)r;         // (reuse: m <= P2 is guaranteed by the launcher)
+      rsum += r;
+      __syncthreads();
+    }
+    const bool mean_active = (T)(rsum / m) > T(1e-6);
+    double gfloor_r = 0.0;
+    for (int l = 0; l < m; ++l) {
+      const T* Al = a.A + ((size_t)b * m + l) * n;
+      const T e = a.E[(size_t)b * m + l], rraw = skey[l % P2];
+      // gE_l = sum_j gAt_lj A_lj D_j + gbt_l b_l
+      part = 0.0;
+      if (a.gAt)
+        for (int j = tid; j < n; j += kSvThreads) part += (double)(a.gAt[((size_t)b * m + l) * n + j] * (Al[j] * a.D[vo + j]));
+      double gE = bsum(part);
+      if (a.gbt) gE += (double)(a.gbt[(size_t)b * m + l] * a.b[(size_t)b * m + l]);
+      const double gr = -gE * (double)e * (double)e;            // E = 1 / r
+      const bool bad = rraw <= T(0);
+      if (bad) gfloor_r += gr;                                  // maximum(r, floor) picks the floor
+      // ties of the inf-norm split the gradient evenly
+      part = 0.0;
+      if (!bad)
+        for (int j = tid; j < n; j += kSvThreads) part += (t_abs(Al[j] * a.D[vo + j]) == rraw) ? 1.0 : 0.0;
+      const double cnt = bad ? 1.0 : bsum(part);
+      for (int j = tid; j < n; j += kSvThreads) {
+        const T ad = Al[j] * a.D[vo + j];
+        double gad = 0.0;                                       // adjoint of (A D)_lj
+        if (a.gAt) gad += (double)(a.gAt[((size_t)b * m + l) * n + j] * e);
+        if (!bad && t_abs(ad) == rraw) gad += gr * (ad > T(0) ? 1.0 : (ad < T(0) ? -1.0 : 0.0)) / cnt;
+        a.gA[((size_t)b * m + l) * n + j] = (T)(gad * (double)a.D[vo + j]);
+        gDt[j] += gad * (double)Al[j];
+      }
+      if (tid == 0) a.gb[(size_t)b * m + l] = a.gbt ? a.gbt[(size_t)b * m + l] * e : T(0);
+      __syncthreads();
+    }
+    // guarded rows send their gradient to the mean of the raw norms, i.e. evenly to every row's maximisers
+    if (gfloor_r != 0.0 && mean_active) {
+      for (int l = 0; l < m; ++l) {
+        const T* Al = a.A + ((size_t)b * m + l) * n;
+        const T rraw = skey[l % P2];
+        part = 0.0;
+        for (int j = tid; j < n; j += kSvThreads) part += (t_abs(Al[j] * a.D[vo + j]) == rraw) ? 1.0 : 0.0;
+        const double cnt = bsum(part);
+        for (int j = tid; j < n; j += kSvThreads) {
+          const T ad = Al[j] * a.D[vo + j];
+          if (t_abs(ad) == rraw) {
+            const double gad = (gfloor_r / m) * (ad > T(0) ? 1.0 : (ad < T(0) ? -1.0 : 0.0)) / cnt;
+            a.gA[((size_t)b * m + l) * n + j] += (T)(gad * (double)a.D[vo + j]);
+            gDt[j] += gad * (double)Al[j];
+          }
+        }
+        __syncthreads();
+      }
+    }
+  }
+  __syncthreads();
+  // ---- D = (1 - beta) D0 + beta mean(D0), beta = 1 - q10 / q90
+  part = 0.0;
+  double part2 = 0.0;
+  for (int j = tid; j < n; j += kSvThreads) {
+    part += gDt[j];
+    part2 += gDt[j] * (meanD0 - (double)D0[j]);
+  }
+  const double S = bsum(part);
+  const double gbeta = bsum(part2);
+  for (int j = tid; j < n; j += kSvThreads) gDt[j] = (1.0 - (double)beta) * gDt[j] + (double)beta * S / n;
+  __syncthreads();
+  if (a.beta_auto && tid == 0) {
+    const double gq10 = -gbeta / (double)q90, gq90 = gbeta * (double)q10 / ((double)q90 * (double)q90);
+    const double gq[2] = {gq10, gq90};
+    for (int k = 0; k < 2; ++k) {
+      gDt[ilo[k]] += gq[k] * (1.0 - (double)wq[k]);
+      gDt[ihi[k]] += gq[k] * (double)wq[k];
+    }
+  }
+  __syncthreads();
+  // ---- D0 = sqrt(1 / c'), guard
+  part = 0.0;
+  for (int j = tid; j < n; j += kSvThreads) {
+    const double gc = gDt[j] * (-0.5) * (double)D0[j] / (double)cg[j];
+    const bool bad = a.colmax[vo + j] <= T(0);
+    if (bad) part += gc;
+    gDt[j] = bad ? 0.0 : gc;
+  }
+  const double gfloor = bsum(part);
+  const double spread = ((T)mean_c > T(1e-6)) ? gfloor / n : 0.0;
+  for (int j = tid; j < n; j += kSvThreads) a.gcolmax[vo + j] = (T)(gDt[j] + spread);
+}
+
+template <typename T>
+cudaError_t launch_scaled_vectors(const FwdWs<T>& w, T* D, T* pt, T* At, T* bt, T* lbt, T* ubt, T* E, cudaStream_t st) {
+  dim3 grid((w.n + 255) / 256, w.B);
+  scaled_vectors_kernel<T><<<grid, 256, 0, st>>>(w, D, pt, At, bt, lbt, ubt, E);
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_scale_vec_grad(int B, const ScaleVecGrad<T>& a, cudaStream_t st) {
+  int P2 = 64;
+  while (P2 < a.n || P2 < a.m) P2 <<= 1;
+  const size_t smem = (size_t)(a.n + 32) * sizeof(double) + (size_t)(2 * a.n + P2) * sizeof(T) + (size_t)P2 * sizeof(int) + 64;
+  cudaError_t e = cudaFuncSetAttribute(scale_vec_grad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  scale_vec_grad_kernel<T><<<B, kSvThreads, smem, st>>>(a, P2);
+  return cudaGetLastError();
+}
+template cudaError_t launch_scaled_vectors<float>(const FwdWs<float>&, float*, float*, float*, float*, float*, float*, float*, cudaStream_t);
+template cudaError_t launch_scaled_vectors<double>(const FwdWs<double>&, double*, double*, double*, double*, double*, double*, double*, cudaStream_t);
+template cudaError_t launch_scale_vec_grad<float>(int, const ScaleVecGrad<float>&, cudaStream_t);
+template cudaError_t launch_scale_vec_grad<double>(int, const ScaleVecGrad<double>&, cudaStream_t);
+
 template <typename T>
 cudaError_t launch_unroll_reverse(const FwdWs<T>& w, const Tape<T>& tape, const UnrollGrads<T>& g, int* launches,
                                   cudaStream_t st) {

@@ -617,7 +617,8 @@ def _solve_unrolled(Q, p, A, b, lb, ub, control):
     # without an adaptive-rho update nothing downstream reads the VALUES of Q~ (the kernels hold their own copy): the
     # two O(n^2) glue steps Q~ = D Q D and rho = ||Q~||_F / sqrt(n) then exist only as one fused adjoint kernel
     Qt, pt, At, bt, lbt, ubt, D, rho = _scaled_problem(Qd, pd, Ad, bd, lbd, ubd, control, any_lb, any_ub,
-                                                       fused_rho=sol["rho_dev"] if S == 1 else None, fused=S == 1)
+                                                       fused_rho=sol["rho_dev"] if S == 1 else None, fused=S == 1,
+                                                       ws=ws if S == 1 else None)
     check = cfg.check_solved
     z_in = u_in = x_l = None
     at_check = rho_at_check = None
@@ -659,7 +660,7 @@ def _adapted_rho(rho, rho_chk, at_check, wants, Qt, p, D, cfg, control):
     return torch.clamp(rho, min=control.get('rho_min', 1e-6), max=control.get('rho_max', 1e6))
 
 
-def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub, fused=False, fused_rho=None):
+def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub, fused=False, fused_rho=None, ws=None):
     """Scaling and rho selection of the reference (:156-203) as differentiable torch expressions of the device
     copies.  Returns ``(Q~, p~, A~, b~, lb~, ub~, D, rho)``; ``D`` is ``(B,n,1)`` (or 1.0 without scaling) and ``rho``
     a ``(B,1,1)`` tensor when it is selected from ``||Q~||_F``, otherwise the caller's number."""
@@ -668,7 +669,18 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub, fused=False, fu
     rho = control.get('rho', None) if any_ineq else 0                   # :157-158
     D = 1.0
     Dv = None
-    if control.get('scale', False):
+    if control.get('scale', False) and fused and ws is not None:
+        # one kernel pair for the whole O(B n) part of the scaling map (:163-194): values out of the recording solve's
+        # workspace, adjoint with torch's subgradient rules (lqpb_unroll_scaled_vectors_* / lqpb_unroll_scale_vec_grad_*)
+        colmax = _ColumnMax.apply(Q) if Q.requires_grad else Q.abs().amax(dim=1)                                  # :163
+        Dv, p, At_, bt_, lbt_, ubt_ = _ScaledVectors.apply(colmax, p, A, b, lb, ub, ws, control.get('beta'),
+                                                           bool(any_lb), bool(any_ub))
+        if A is not None:
+            A, b = At_, bt_
+        if any_ineq:
+            lb, ub = lbt_, ubt_
+        D = Dv.unsqueeze(2)
+    elif control.get('scale', False):
         colmax = _ColumnMax.apply(Q) if (fused and Q.requires_grad) else torch.linalg.norm(Q, ord=_INF, dim=1)   # :163
         bad = colmax <= 0.0
         if bool(bad.any()):                                              # :164-168
@@ -741,6 +753,58 @@ class _ColumnMax(torch.autograd.Function):
         out = torch.zeros(ctx.shape, dtype=g.dtype, device=g.device)
         out.scatter_(1, idx.unsqueeze(1), (sign * g).unsqueeze(1))
         return out
+
+
+class _ScaledVectors(torch.autograd.Function):
+    """(column norms of Q, p, A, b, lb, ub) -> (D, p~, A~, b~, lb~, ub~): the O(B n) part of the scaling (:163-194) as one
+    autograd node.  Forward: the values the recording solve left in its workspace (the numbers the loop really used);
+    backward: one kernel per problem with torch's subgradient conventions for norm(inf), quantile, maximum / where."""
+
+    @staticmethod
+    def forward(ctx, colmax, p, A, b, lb, ub, ws, beta, any_lb, any_ub):
+        L = _abi.lib()
+        dev, dt = p.device, p.dtype
+        sfx = _abi.suffix(dt)
+        B, n = p.shape[0], p.shape[1]
+        m = get_ncon(A, dim=1)
+        with _on_device(dev):
+            new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+            D, pt, lbt, ubt = new(B, n), new(B, n, 1), new(B, n, 1), new(B, n, 1)
+            At = new(B, m, n) if m > 0 else None
+            bt = new(B, m, 1) if m > 0 else None
+            E = new(B, m) if m > 0 else None
+            rc = getattr(L, f"lqpb_unroll_scaled_vectors_{sfx}")(
+                B, n, m, _abi.ptr(ws), ws.numel(), _abi.ptr(D), _abi.ptr(pt), _abi.ptr(At), _abi.ptr(bt), _abi.ptr(lbt),
+                _abi.ptr(ubt), _abi.ptr(E), C.c_void_p(_raw_stream(dev)))
+            _abi.check(rc, "lqpb_unroll_scaled_vectors")
+        ctx.save_for_backward(colmax, p, A, b, lb, ub, D, E)
+        ctx.meta = (B, n, m, beta, any_lb, any_ub)
+        ctx.set_materialize_grads(False)
+        return D, pt, At, bt, lbt, ubt
+
+    @staticmethod
+    def backward(ctx, gD, gpt, gAt, gbt, glbt, gubt):
+        L = _abi.lib()
+        colmax, p, A, b, lb, ub, D, E = ctx.saved_tensors
+        B, n, m, beta, any_lb, any_ub = ctx.meta
+        dev, dt = p.device, p.dtype
+        sfx = _abi.suffix(dt)
+        cont = lambda t: None if t is None else t.detach().to(device=dev, dtype=dt).contiguous()
+        gD, gpt, gAt, gbt, glbt, gubt = (cont(t) for t in (gD, gpt, gAt, gbt, glbt, gubt))
+        with _on_device(dev):
+            new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+            gc, gp, glb, gub = new(B, n), new(B, n, 1), new(B, n, 1), new(B, n, 1)
+            gA = new(B, m, n) if m > 0 else None
+            gb = new(B, m, 1) if m > 0 else None
+            rc = getattr(L, f"lqpb_unroll_scale_vec_grad_{sfx}")(
+                B, n, m, 1 if beta is None else 0, 0.0 if beta is None else float(beta), 1 if any_lb else 0,
+                1 if any_ub else 0, _abi.ptr(colmax.contiguous()), _abi.ptr(p.contiguous()), _abi.ptr(cont(A)),
+                _abi.ptr(cont(b)), _abi.ptr(lb.contiguous()), _abi.ptr(ub.contiguous()), _abi.ptr(D), _abi.ptr(E),
+                _abi.ptr(gD), _abi.ptr(gpt), _abi.ptr(gAt), _abi.ptr(gbt), _abi.ptr(glbt), _abi.ptr(gubt), _abi.ptr(gc),
+                _abi.ptr(gp), _abi.ptr(gA), _abi.ptr(gb), _abi.ptr(glb), _abi.ptr(gub), C.c_void_p(_raw_stream(dev)))
+            _abi.check(rc, "lqpb_unroll_scale_vec_grad")
+        any_ineq = any_lb or any_ub
+        return (gc, gp, gA, gb, glb if any_ineq else None, gub if any_ineq else None, None, None, None, None)
 
 
 class _ScaledQAndRho(torch.autograd.Function):

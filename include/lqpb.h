@@ -360,15 +360,25 @@ int lqpb_unroll_scaled_vectors_f64(int B, int n, int m, void* workspace, size_t 
                                    double* At, double* bt, double* lbt, double* ubt, double* E, void* stream);
 int lqpb_unroll_scale_vec_grad_f32(int B, int n, int m, int beta_auto, double beta, int use_lb, int use_ub,
                                    const float* colmax, const float* p, const float* A, const float* b, const float* lb,
-                                   const float* ub, const float* D, const float* E, const float* gD, const float* gpt,
-                                   const float* gAt, const float* gbt, const float* glbt, const float* gubt,
-                                   float* gcolmax, float* gp, float* gA, float* gb, float* glb, float* gub, void* stream);
+                                   const float* ub, const float* D, const float* E, const float* gD, const float* gD2,
+                                   const float* gpt, const float* gAt, const float* gbt, const float* glbt,
+                                   const float* gubt, float* gcolmax, float* gp, float* gA, float* gb, float* glb,
+                                   float* gub, void* stream);
 int lqpb_unroll_scale_vec_grad_f64(int B, int n, int m, int beta_auto, double beta, int use_lb, int use_ub,
                                    const double* colmax, const double* p, const double* A, const double* b,
                                    const double* lb, const double* ub, const double* D, const double* E, const double* gD,
-                                   const double* gpt, const double* gAt, const double* gbt, const double* glbt,
-                                   const double* gubt, double* gcolmax, double* gp, double* gA, double* gb, double* glb,
-                                   double* gub, void* stream);
+                                   const double* gD2, const double* gpt, const double* gAt, const double* gbt,
+                                   const double* glbt, const double* gubt, double* gcolmax, double* gp, double* gA,
+                                   double* gb, double* glb, double* gub, void* stream);
+/* The column inf-norms of Q (:163: torch.linalg.norm(Q, inf, dim=1)) and their adjoint: colmax (B,n); colmax_grad adds
+ * sign(Q_ij) gcolmax_j / (number of maximisers of column j) IN PLACE to G (B,n,n) on every maximiser of every column --
+ * torch's inf-norm backward, exact ties included (gD and gD2 of scale_vec_grad are both added to the adjoint of D). */
+int lqpb_unroll_colmax_f32(int B, int n, const float* Q, float* colmax, void* stream);
+int lqpb_unroll_colmax_f64(int B, int n, const double* Q, double* colmax, void* stream);
+int lqpb_unroll_colmax_grad_f32(int B, int n, const float* Q, const float* colmax, const float* gcolmax, float* G,
+                                void* stream);
+int lqpb_unroll_colmax_grad_f64(int B, int n, const double* Q, const double* colmax, const double* gcolmax, double* G,
+                                void* stream);
 
 /* ---- lu_layer: replaces TorchLU / TorchLULayer (lu_layer.py:5-58) -------------------------
  * lu_factor: partial-pivoting LU of B general N x N matrices (torch.linalg.lu_factor, :10,:30);

@@ -31,6 +31,7 @@ EXPORTS = (
     "lqpb_unroll_scale_grad_f32", "lqpb_unroll_scale_grad_f64",
     "lqpb_unroll_scaled_vectors_f32", "lqpb_unroll_scaled_vectors_f64",
     "lqpb_unroll_scale_vec_grad_f32", "lqpb_unroll_scale_vec_grad_f64",
+    "lqpb_unroll_colmax_f32", "lqpb_unroll_colmax_f64", "lqpb_unroll_colmax_grad_f32", "lqpb_unroll_colmax_grad_f64",
     "lqpb_lu_factor_f32", "lqpb_lu_factor_f64", "lqpb_lu_solve_f32", "lqpb_lu_solve_f64",
     "lqpb_outer_f32", "lqpb_outer_f64",
     "lqpb_dev_tc_inverse_work_bytes", "lqpb_dev_tc_inverse_f32", "lqpb_dev_stream_read",
@@ -149,7 +150,11 @@ def lib():
         f = getattr(L, f"lqpb_unroll_scaled_vectors_{sfx}")
         f.argtypes, f.restype = [i32, i32, i32, vp, sz] + [vp] * 7 + [vp], i32
         f = getattr(L, f"lqpb_unroll_scale_vec_grad_{sfx}")
-        f.argtypes, f.restype = [i32, i32, i32, i32, dbl, i32, i32] + [vp] * 8 + [vp] * 6 + [vp] * 6 + [vp], i32
+        f.argtypes, f.restype = [i32, i32, i32, i32, dbl, i32, i32] + [vp] * 8 + [vp] * 7 + [vp] * 6 + [vp], i32
+        f = getattr(L, f"lqpb_unroll_colmax_{sfx}")
+        f.argtypes, f.restype = [i32, i32, vp, vp, vp], i32
+        f = getattr(L, f"lqpb_unroll_colmax_grad_{sfx}")
+        f.argtypes, f.restype = [i32, i32, vp, vp, vp, vp, vp], i32
         f = getattr(L, f"lqpb_lu_factor_{sfx}")
         f.argtypes, f.restype = [i32, i32, vp, vp, vp, vp], i32
         f = getattr(L, f"lqpb_lu_solve_{sfx}")

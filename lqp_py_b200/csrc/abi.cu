@@ -979,17 +979,31 @@ SCALE_GRAD_ENTRY(f64, double)
   }                                                                                                                \
   int lqpb_unroll_scale_vec_grad_##SFX(int B, int n, int m, int beta_auto, double beta, int use_lb, int use_ub,    \
                                        const T* colmax, const T* p, const T* A, const T* b, const T* lb,           \
-                                       const T* ub, const T* D, const T* E, const T* gD, const T* gpt,             \
-                                       const T* gAt, const T* gbt, const T* glbt, const T* gubt, T* gcolmax,       \
-                                       T* gp, T* gA, T* gb, T* glb, T* gub, void* stream) {                        \
+                                       const T* ub, const T* D, const T* E, const T* gD, const T* gD2,             \
+                                       const T* gpt, const T* gAt, const T* gbt, const T* glbt, const T* gubt,     \
+                                       T* gcolmax, T* gp, T* gA, T* gb, T* glb, T* gub, void* stream) {            \
     if (!colmax || !p || !lb || !ub || !D || !gcolmax || !gp || !glb || !gub || B <= 0 || n <= 0 || m < 0 ||       \
         (m > 0 && (!A || !b || !E || !gA || !gb)))                                                                 \
       return fail(LQPB_E_ARG, "bad argument");                                                                     \
     int rc = check_device();                                                                                       \
     if (rc) return rc;                                                                                             \
-    ScaleVecGrad<T> a{n, m, beta_auto, use_lb, use_ub, (T)beta, colmax, p, A, b, lb, ub, D, E, gD, gpt, gAt, gbt,  \
-                      glbt, gubt, gcolmax, gp, gA, gb, glb, gub};                                                   \
+    ScaleVecGrad<T> a{n, m, beta_auto, use_lb, use_ub, (T)beta, colmax, p, A, b, lb, ub, D, E, gD, gD2, gpt, gAt,  \
+                      gbt, glbt, gubt, gcolmax, gp, gA, gb, glb, gub};                                              \
     CK(launch_scale_vec_grad<T>(B, a, (cudaStream_t)stream), "scale_vec_grad");                                    \
+    return LQPB_OK;                                                                                                \
+  }                                                                                                                \
+  int lqpb_unroll_colmax_##SFX(int B, int n, const T* Q, T* colmax, void* stream) {                                \
+    if (!Q || !colmax || B <= 0 || n <= 0) return fail(LQPB_E_ARG, "bad argument");                                \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    CK(launch_colmax_plain<T>(B, n, Q, colmax, (cudaStream_t)stream), "colmax");                                   \
+    return LQPB_OK;                                                                                                \
+  }                                                                                                                \
+  int lqpb_unroll_colmax_grad_##SFX(int B, int n, const T* Q, const T* colmax, const T* gcolmax, T* G, void* stream) { \
+    if (!Q || !colmax || !gcolmax || !G || B <= 0 || n <= 0) return fail(LQPB_E_ARG, "bad argument");              \
+    int rc = check_device();                                                                                       \
+    if (rc) return rc;                                                                                             \
+    CK(launch_colmax_scatter<T>(B, n, Q, colmax, gcolmax, G, (cudaStream_t)stream), "colmax_grad");                \
     return LQPB_OK;                                                                                                \
   }
 SCALE_VEC_ENTRY(f32, float)

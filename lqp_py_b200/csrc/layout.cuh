@@ -298,7 +298,7 @@ struct ScaleVecGrad {
   int n, m, beta_auto, use_lb, use_ub;
   T beta;
   const T *colmax, *p, *A, *b, *lb, *ub, *D, *E;          // forward inputs / outputs
-  const T *gD, *gpt, *gAt, *gbt, *glbt, *gubt;             // upstream adjoints (any may be null = zero)
+  const T *gD, *gD2, *gpt, *gAt, *gbt, *glbt, *gubt;       // upstream adjoints (any may be null = zero; gD + gD2 reach D)
   T *gcolmax, *gp, *gA, *gb, *glb, *gub;                   // outputs (gA / gb null when m == 0)
 };
 
@@ -306,6 +306,10 @@ template <typename T>
 cudaError_t launch_scaled_vectors(const FwdWs<T>& w, T* D, T* pt, T* At, T* bt, T* lbt, T* ubt, T* E, cudaStream_t st);
 template <typename T>
 cudaError_t launch_scale_vec_grad(int B, const ScaleVecGrad<T>& a, cudaStream_t st);
+template <typename T>
+cudaError_t launch_colmax_plain(int B, int n, const T* Q, T* out, cudaStream_t st);
+template <typename T>
+cudaError_t launch_colmax_scatter(int B, int n, const T* Q, const T* colmax, const T* g, T* G, cudaStream_t st);
 template <typename T>
 cudaError_t launch_finalize(const FwdWs<T>& w, T* x, T* z, T* u, T* lams, T* rho_out, cudaStream_t st);
 

@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(kSvThreads) scale_vec_grad_kernel(ScaleVecGrad
   // ---- adjoint of the vectors: everything that reaches D, and the gradients of p, lb, ub
   for (int j = tid; j < n; j += kSvThreads) {
     const T d = a.D[vo + j];
-    double g = a.gD ? (double)a.gD[vo + j] : 0.0;
+    double g = (a.gD ? (double)a.gD[vo + j] : 0.0) + (a.gD2 ? (double)a.gD2[vo + j] : 0.0);
     if (a.gpt) {
       g += (double)(a.gpt[vo + j] * a.p[vo + j]);
       a.gp[vo + j] = a.gpt[vo + j] * d;
@@ -599,6 +599,52 @@ __global__ void __launch_bounds__(kSvThreads) scale_vec_grad_kernel(ScaleVecGrad
   const double spread = ((T)mean_c > T(1e-6)) ? gfloor / n : 0.0;
   for (int j = tid; j < n; j += kSvThreads) a.gcolmax[vo + j] = (T)(gDt[j] + spread);
 }
+
+// Column inf-norms of Q (:163) and their adjoint.  colmax_plain: thread = column, rows scanned in order (coalesced across
+// the warp).  colmax_scatter: G[i][j] += sign(Q_ij) g_j / (number of maximisers of column j) on every maximiser --
+// torch's inf-norm backward, exact ties included -- added IN PLACE to the dense adjoint of Q that scale_grad_kernel left in G.
+template <typename T>
+__global__ void colmax_plain_kernel(const T* __restrict__ Q, T* __restrict__ out, int n) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const T* Qb = Q + (size_t)b * n * n;
+  T mx = T(0);
+  for (int i = 0; i < n; ++i) mx = t_max(mx, t_abs(Qb[(size_t)i * n + j]));
+  out[(size_t)b * n + j] = mx;
+}
+template <typename T>
+__global__ void colmax_scatter_kernel(const T* __restrict__ Q, const T* __restrict__ colmax, const T* __restrict__ g,
+                                      T* __restrict__ G, int n) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const T gj = g[(size_t)b * n + j], mx = colmax[(size_t)b * n + j];
+  if (gj == T(0) || !(mx > T(0))) return;          // sign(0) = 0: zero columns carry no gradient
+  const T* Qb = Q + (size_t)b * n * n;
+  T* Gb = G + (size_t)b * n * n;
+  int cnt = 0;
+  for (int i = 0; i < n; ++i) cnt += (t_abs(Qb[(size_t)i * n + j]) == mx) ? 1 : 0;
+  const T share = gj / (T)cnt;
+  for (int i = 0; i < n; ++i) {
+    const T q = Qb[(size_t)i * n + j];
+    if (t_abs(q) == mx) Gb[(size_t)i * n + j] += q > T(0) ? share : -share;
+  }
+}
+template <typename T>
+cudaError_t launch_colmax_plain(int B, int n, const T* Q, T* out, cudaStream_t st) {
+  dim3 grid((n + 127) / 128, B);
+  colmax_plain_kernel<T><<<grid, 128, 0, st>>>(Q, out, n);
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_colmax_scatter(int B, int n, const T* Q, const T* colmax, const T* g, T* G, cudaStream_t st) {
+  dim3 grid((n + 127) / 128, B);
+  colmax_scatter_kernel<T><<<grid, 128, 0, st>>>(Q, colmax, g, G, n);
+  return cudaGetLastError();
+}
+template cudaError_t launch_colmax_plain<float>(int, int, const float*, float*, cudaStream_t);
+template cudaError_t launch_colmax_plain<double>(int, int, const double*, double*, cudaStream_t);
+template cudaError_t launch_colmax_scatter<float>(int, int, const float*, const float*, const float*, float*, cudaStream_t);
+template cudaError_t launch_colmax_scatter<double>(int, int, const double*, const double*, const double*, double*, cudaStream_t);
 
 template <typename T>
 cudaError_t launch_scaled_vectors(const FwdWs<T>& w, T* D, T* pt, T* At, T* bt, T* lbt, T* ubt, T* E, cudaStream_t st) {

@@ -670,16 +670,20 @@ def _scaled_problem(Q, p, A, b, lb, ub, control, any_lb, any_ub, fused=False, fu
     D = 1.0
     Dv = None
     if control.get('scale', False) and fused and ws is not None:
-        # one kernel pair for the whole O(B n) part of the scaling map (:163-194): values out of the recording solve's
-        # workspace, adjoint with torch's subgradient rules (lqpb_unroll_scaled_vectors_* / lqpb_unroll_scale_vec_grad_*)
-        colmax = _ColumnMax.apply(Q) if Q.requires_grad else Q.abs().amax(dim=1)                                  # :163
-        Dv, p, At_, bt_, lbt_, ubt_ = _ScaledVectors.apply(colmax, p, A, b, lb, ub, ws, control.get('beta'),
-                                                           bool(any_lb), bool(any_ub))
+        # the whole map from the caller's tensors to the scaled problem (:161-203) is ONE autograd node backed by
+        # kernels: values out of the recording solve's workspace, adjoint = scale_grad (Q~ = D Q D, rho), scale_vec_grad
+        # (D, p~, A~, b~, lb~, ub~ with torch's subgradient rules) and the column-max scatter, all on one dense buffer
+        auto = rho is None
+        Q, rho_t, Dv, p, At_, bt_, lbt_, ubt_ = _ScaledProblem.apply(
+            Q, p, A, b, lb, ub, ws, fused_rho if auto else None, control.get('beta'), bool(any_lb), bool(any_ub),
+            control.get('rho_min', 1e-6), control.get('rho_max', 1e6))
+        if auto:
+            rho = rho_t
         if A is not None:
             A, b = At_, bt_
         if any_ineq:
             lb, ub = lbt_, ubt_
-        D = Dv.unsqueeze(2)
+        return Q, p, A, b, lb, ub, Dv.unsqueeze(2), rho
     elif control.get('scale', False):
         colmax = _ColumnMax.apply(Q) if (fused and Q.requires_grad) else torch.linalg.norm(Q, ord=_INF, dim=1)   # :163
         bad = colmax <= 0.0
@@ -755,13 +759,20 @@ class _ColumnMax(torch.autograd.Function):
         return out
 
 
-class _ScaledVectors(torch.autograd.Function):
-    """(column norms of Q, p, A, b, lb, ub) -> (D, p~, A~, b~, lb~, ub~): the O(B n) part of the scaling (:163-194) as one
-    autograd node.  Forward: the values the recording solve left in its workspace (the numbers the loop really used);
-    backward: one kernel per problem with torch's subgradient conventions for norm(inf), quantile, maximum / where."""
+class _ScaledProblem(torch.autograd.Function):
+    """(Q, p, A, b, lb, ub) -> (Q~, rho, D, p~, A~, b~, lb~, ub~): the scaling and rho selection of :161-203 as one
+    autograd node of the unrolled mode (scale=True, no adaptive-rho update inside the loop).
+
+    Forward: no arithmetic -- the recording solve computed all of it; D and the scaled vectors are copied out of its
+    workspace (``lqpb_unroll_scaled_vectors_*``), ``rho_vals`` is its rho, and since nothing downstream reads the VALUES
+    of Q~ (the kernels hold their own packed copy) Q~ is a zero-stride placeholder.  Backward: three kernels on one dense
+    buffer -- ``lqpb_unroll_scale_grad_*`` (adjoint of Q~ = D Q D and of rho = clamp(||Q~||_F / sqrt(n)), in place),
+    ``lqpb_unroll_scale_vec_grad_*`` (adjoint of D / p~ / A~ / b~ / lb~ / ub~ with torch's subgradient conventions for
+    norm(inf), quantile, maximum / where) and ``lqpb_unroll_colmax_grad_*`` (adjoint of the column inf-norms of :163,
+    exact ties split evenly like torch's, added in place)."""
 
     @staticmethod
-    def forward(ctx, colmax, p, A, b, lb, ub, ws, beta, any_lb, any_ub):
+    def forward(ctx, Q, p, A, b, lb, ub, ws, rho_vals, beta, any_lb, any_ub, rho_min, rho_max):
         L = _abi.lib()
         dev, dt = p.device, p.dtype
         sfx = _abi.suffix(dt)
@@ -777,34 +788,62 @@ class _ScaledVectors(torch.autograd.Function):
                 B, n, m, _abi.ptr(ws), ws.numel(), _abi.ptr(D), _abi.ptr(pt), _abi.ptr(At), _abi.ptr(bt), _abi.ptr(lbt),
                 _abi.ptr(ubt), _abi.ptr(E), C.c_void_p(_raw_stream(dev)))
             _abi.check(rc, "lqpb_unroll_scaled_vectors")
-        ctx.save_for_backward(colmax, p, A, b, lb, ub, D, E)
-        ctx.meta = (B, n, m, beta, any_lb, any_ub)
+        ctx.save_for_backward(Q, p, A, b, lb, ub, D, E, rho_vals)
+        ctx.meta = (B, n, m, beta, any_lb, any_ub, rho_min, rho_max)
+        token = torch.zeros((), dtype=dt, device=dev).expand(Q.shape)
+        rho = rho_vals.detach().clone() if rho_vals is not None else torch.zeros((), dtype=dt, device=dev)
+        if rho_vals is None:
+            ctx.mark_non_differentiable(rho)
         ctx.set_materialize_grads(False)
-        return D, pt, At, bt, lbt, ubt
+        return token, rho, D, pt, At, bt, lbt, ubt
 
     @staticmethod
-    def backward(ctx, gD, gpt, gAt, gbt, glbt, gubt):
+    def backward(ctx, gQt, grho, gD, gpt, gAt, gbt, glbt, gubt):
         L = _abi.lib()
-        colmax, p, A, b, lb, ub, D, E = ctx.saved_tensors
-        B, n, m, beta, any_lb, any_ub = ctx.meta
+        Q, p, A, b, lb, ub, D, E, rho_vals = ctx.saved_tensors
+        B, n, m, beta, any_lb, any_ub, rho_min, rho_max = ctx.meta
         dev, dt = p.device, p.dtype
         sfx = _abi.suffix(dt)
+        need_Q = ctx.needs_input_grad[0]
         cont = lambda t: None if t is None else t.detach().to(device=dev, dtype=dt).contiguous()
         gD, gpt, gAt, gbt, glbt, gubt = (cont(t) for t in (gD, gpt, gAt, gbt, glbt, gubt))
+        Qc = Q.detach().contiguous()
         with _on_device(dev):
+            stream = C.c_void_p(_raw_stream(dev))
             new = lambda *shape: torch.empty(shape, dtype=dt, device=dev)
+            G = gDq = None
+            if need_Q:
+                # the adjoint of Q~ has one producer (the loop node) and one consumer (this node): overwritten in place
+                G = gQt.contiguous() if gQt is not None else torch.zeros((B, n, n), dtype=dt, device=dev)
+                coef = None
+                if grho is not None and rho_vals is not None:
+                    r = rho_vals.reshape(B)
+                    inside = (r > rho_min) & (r < rho_max)
+                    coef = torch.where(inside, grho.reshape(B) / (n * r), torch.zeros_like(r)).contiguous()
+                gDq = new(B, n)
+                nscr = getattr(L, f"lqpb_unroll_scale_grad_scratch_elems_{sfx}")(B, n)
+                scratch = torch.empty(nscr, dtype=dt, device=dev)
+                rc = getattr(L, f"lqpb_unroll_scale_grad_{sfx}")(B, n, _abi.ptr(G), _abi.ptr(Qc), _abi.ptr(D), _abi.ptr(coef),
+                                                                 _abi.ptr(gDq), _abi.ptr(scratch), stream)
+                _abi.check(rc, "lqpb_unroll_scale_grad")
+            colmax = new(B, n)
+            _abi.check(getattr(L, f"lqpb_unroll_colmax_{sfx}")(B, n, _abi.ptr(Qc), _abi.ptr(colmax), stream), "lqpb_unroll_colmax")
             gc, gp, glb, gub = new(B, n), new(B, n, 1), new(B, n, 1), new(B, n, 1)
             gA = new(B, m, n) if m > 0 else None
             gb = new(B, m, 1) if m > 0 else None
             rc = getattr(L, f"lqpb_unroll_scale_vec_grad_{sfx}")(
                 B, n, m, 1 if beta is None else 0, 0.0 if beta is None else float(beta), 1 if any_lb else 0,
-                1 if any_ub else 0, _abi.ptr(colmax.contiguous()), _abi.ptr(p.contiguous()), _abi.ptr(cont(A)),
-                _abi.ptr(cont(b)), _abi.ptr(lb.contiguous()), _abi.ptr(ub.contiguous()), _abi.ptr(D), _abi.ptr(E),
-                _abi.ptr(gD), _abi.ptr(gpt), _abi.ptr(gAt), _abi.ptr(gbt), _abi.ptr(glbt), _abi.ptr(gubt), _abi.ptr(gc),
-                _abi.ptr(gp), _abi.ptr(gA), _abi.ptr(gb), _abi.ptr(glb), _abi.ptr(gub), C.c_void_p(_raw_stream(dev)))
+                1 if any_ub else 0, _abi.ptr(colmax), _abi.ptr(p.contiguous()), _abi.ptr(cont(A)), _abi.ptr(cont(b)),
+                _abi.ptr(lb.contiguous()), _abi.ptr(ub.contiguous()), _abi.ptr(D), _abi.ptr(E), _abi.ptr(gD), _abi.ptr(gDq),
+                _abi.ptr(gpt), _abi.ptr(gAt), _abi.ptr(gbt), _abi.ptr(glbt), _abi.ptr(gubt), _abi.ptr(gc), _abi.ptr(gp),
+                _abi.ptr(gA), _abi.ptr(gb), _abi.ptr(glb), _abi.ptr(gub), stream)
             _abi.check(rc, "lqpb_unroll_scale_vec_grad")
+            if need_Q:
+                rc = getattr(L, f"lqpb_unroll_colmax_grad_{sfx}")(B, n, _abi.ptr(Qc), _abi.ptr(colmax), _abi.ptr(gc), _abi.ptr(G),
+                                                                  stream)
+                _abi.check(rc, "lqpb_unroll_colmax_grad")
         any_ineq = any_lb or any_ub
-        return (gc, gp, gA, gb, glb if any_ineq else None, gub if any_ineq else None, None, None, None, None)
+        return (G, gp, gA, gb, glb if any_ineq else None, gub if any_ineq else None) + (None,) * 7
 
 
 class _ScaledQAndRho(torch.autograd.Function):

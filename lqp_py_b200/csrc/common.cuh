@@ -113,6 +113,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// the same for a whole group of waiting warps: back off between polls, so that the pollers do not take issue slots and
+// shared-memory bandwidth from the warps that are working on the same SM
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 // 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier.
 // dst/src 16-byte aligned, bytes a multiple of 16.
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-child"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-child", "reference-cuda"])
     ap.add_argument("--threads", type=int, default=1, help="(reference-child) torch / BLAS threads")
     ap.add_argument("--nprob", type=int, default=8, help="(reference-child) problems per pass")
     ap.add_argument("--kind", default="reference", choices=["reference", "port"], help="(reference-child) which CPU code")
@@ -366,6 +366,68 @@ def run_reference(a):
            "cpu_baseline": cpu,
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
+
+
+def run_reference_cuda(a, quiet=False):
+    """Secondary baseline: the UNMODIFIED reference package (oracle/_ref) with its tensors on cuda:0, i.e.
+    torch's library path on the same B200 (batched cuSOLVER / cuBLAS LU factor + 2 triangular solves per ADMM iteration,
+    torch.linalg.solve in the backward) -- `torch.set_default_device` makes the reference's own factory calls
+    (solve_box_qp_admm_torch.py:206-223) allocate on the GPU; nothing of this repo's library is on that path.  Rank 0 only;
+    prints one JSON line with "impl": "reference-cuda" (returns it when quiet)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return None
+    if not (have_reference() and torch.cuda.is_available()):
+        out = {"impl": "reference-cuda", "unavailable": "needs oracle/_ref (built by __graft_entry__.build() where "
+               "/root/reference exists) and a CUDA device"}
+        if not quiet:
+            print(json.dumps(out), flush=True)
+        return out
+    K = a.steps if a.steps is not None else 5
+    W = a.warmup if a.warmup is not None else 3
+    dtype = torch.float32 if a.dtype == "f32" else torch.float64
+    data_cpu = gen_data(a.dz, a.batch, 0, dtype)
+    prev_dev, prev_dt = torch.get_default_device(), torch.get_default_dtype()
+    try:
+        torch.set_default_device("cuda:0")
+        torch.set_default_dtype(dtype)
+        sys.path.insert(0, REF_DIR)
+        from lqp_py.control import box_qp_control as ref_control
+        from lqp_py.solve_box_qp_admm_torch import SolveBoxQP as RefSolveBoxQP
+        from lqp_py.solve_box_qp_admm_torch import torch_solve_box_qp as ref_solve
+        control = ref_control(eps_rel=1e-5, eps_abs=1e-5, verbose=False, reduce='max')     # experiment_1.py:22
+        QP = RefSolveBoxQP(control=control)
+        data = [t.to("cuda:0") for t in data_cpu]
+        g = torch.ones(a.batch, a.dz, 1, dtype=dtype)                                      # experiment_1.py:75
+
+        def one():
+            ins = [t.detach().clone().requires_grad_(j < 2) for j, t in enumerate(data)]   # experiments/utils.py:41-50
+            x = QP.forward(Q=ins[0], p=ins[1], A=ins[2], b=ins[3], lb=ins[4], ub=ins[5])
+            x.backward(g)
+            return x.detach(), ins[0].grad
+        it = int(ref_solve(*data, control)["iter"])
+        for _ in range(W):
+            one()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(K):
+            x, dQ = one()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / K
+        ok = bool(torch.isfinite(x).all()) and bool(torch.isfinite(dQ).all())
+    finally:
+        torch.set_default_device(prev_dev)
+        torch.set_default_dtype(prev_dt)
+    val = a.batch / (ms * 1e-3)
+    out = {"impl": "reference-cuda", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype,
+           "data": "synthetic", "config": config_dict(a, 1, it), "finite": ok,
+           "how": "unmodified reference package (oracle/_ref) under torch.set_default_device('cuda:0'): torch's library "
+                  "kernels (batched LU factor / solve) on the same GPU; CUDA events around K forward+backward passes"}
+    if not quiet:
+        print(json.dumps(out), flush=True)
+    return out
 
 
 def cpu_baseline(a):
@@ -915,6 +977,21 @@ def run_b200(a):
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(a)
+    # the unmodified reference through torch's CUDA library path on this GPU (secondary baseline; its own process: it
+    # changes torch's default device)
+    library = None
+    if rank == 0 and world == 1 and not a.no_extras and have_reference():
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-cuda", "--steps", "3", "--warmup", "2",
+                   "--dz", str(a.dz), "--batch", str(a.batch), "--dtype", a.dtype]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            d = json.loads(line[-1]) if line else {"unavailable": r.stderr[-300:]}
+            library = {k: d[k] for k in ("value", "unit", "ms_per_step", "steps", "finite", "how", "unavailable") if k in d}
+            if "value" in library:
+                log(f"reference on cuda (torch library path): {library['value']:.0f} QP/s")
+        except Exception as exc:
+            library = {"unavailable": repr(exc)[:300]}
 
     if rank == 0:
         out = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -922,7 +999,8 @@ def run_b200(a):
                "dtype": a.dtype, "data": "synthetic", "config": config_dict(a, world, it),
                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": main["launches_per_step"] * K,
                "phases_ms": main["phases_ms"], "clocks": main["clocks"], "peaks": peaks, "roofline_hbm": roofline_hbm,
-               "roofline_factor": roofline_factor, "configs": configs, "sweep": sweep, "exp2": exp2}
+               "roofline_factor": roofline_factor, "configs": configs, "sweep": sweep, "exp2": exp2,
+               "library_baseline": library}
         print(json.dumps(out), flush=True)
     if world > 1:
         cx.dist.destroy_process_group()
@@ -934,5 +1012,7 @@ if __name__ == "__main__":
         reference_child(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-cuda":
+        run_reference_cuda(args)
     else:
         run_b200(args)

@@ -399,10 +399,7 @@ __global__ void __launch_bounds__(kFuThreads, 1) tc_fused_kernel(TcArgs a, int B
           for (int J = 0; J <= I; ++J) {
             const bool panel = a.ldl ? (J == k && I > k) : ((J == k) != (I == k));
             const bool trail = a.ldl ? (J > k) : (I != k && J != k);
-            if (panel || (trail && nb <= kFuPrefetchAllNb)) {
-#pragma unroll
-              for (int part = 0; part < 8; ++part) l2_prefetch_bulk(Mp + bl_tile(I, J) + part * (kTBE / 8), kTBE / 2);
-            }
+            if (panel || (trail && nb <= kFuPrefetchAllNb)) l2_prefetch_bulk(Mp + bl_tile(I, J), kTBE * 4);
           }
       }
       fu_pivot(a.M + (size_t)b * ntile * kTBE + bl_tile(k, k), a.Pbuf + ((size_t)b * nb + k) * kTBE,

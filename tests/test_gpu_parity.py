@@ -793,3 +793,17 @@ def test_per_problem_rho_tensor_in_control(n, dtype, dev):
     x = SolveBoxQP(control=box_qp_control(eps_abs=1e-5, eps_rel=1e-5, rho=auto["rho"])).forward(*ins)
     x.backward(torch.ones_like(x))
     assert torch.equal(x.detach(), auto["x"]) and ins[1].grad is not None
+
+
+def test_fused_block_sweep_equals_per_phase_kernels():
+    """The fused persistent factorisation kernel (csrc/tcfused.cu) and the per-phase kernels (csrc/tcfactor.cu) run the same
+    arithmetic in the same order: forward solution and all gradients must agree BIT FOR BIT.  The switch is read once per
+    process, so each form runs in its own child (tools/tc_fused_ab.py); shapes: 3 and 4 block rows, with equality rows."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dz, B in ((300, 8), (500, 6)):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "tc_fused_ab.py"), str(dz), str(B)], capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert "bit-identical" in r.stdout and '"finite": true' in r.stdout, r.stdout[-2000:]

@@ -600,45 +600,68 @@ __global__ void __launch_bounds__(kSvThreads) scale_vec_grad_kernel(ScaleVecGrad
   for (int j = tid; j < n; j += kSvThreads) a.gcolmax[vo + j] = (T)(gDt[j] + spread);
 }
 
-// Column inf-norms of Q (:163) and their adjoint.  colmax_plain: thread = column, rows scanned in order (coalesced across
-// the warp).  colmax_scatter: G[i][j] += sign(Q_ij) g_j / (number of maximisers of column j) on every maximiser --
-// torch's inf-norm backward, exact ties included -- added IN PLACE to the dense adjoint of Q that scale_grad_kernel left in G.
+// Column inf-norms of Q (:163) and their adjoint.  Both kernels: CTA = 32 columns of one problem, 8 warps; warp w walks rows
+// w, w + 8, ... with lane = column (one 128-byte segment of a row per warp access), the per-warp results meet in shared
+// memory.  colmax_scatter: G[i][j] += sign(Q_ij) g_j / (number of maximisers of column j) on every maximiser -- torch's
+// inf-norm backward, exact ties included -- added IN PLACE to the dense adjoint of Q that scale_grad_kernel left in G:
+// pass 1 counts the maximisers, pass 2 (same traversal, the rows are L2 hits) writes the few entries that are maximisers.
+constexpr int kCmWarps = 8;
 template <typename T>
-__global__ void colmax_plain_kernel(const T* __restrict__ Q, T* __restrict__ out, int n) {
-  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+__global__ void __launch_bounds__(32 * kCmWarps) colmax_plain_kernel(const T* __restrict__ Q, T* __restrict__ out, int n) {
+  __shared__ T part[kCmWarps][32];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = blockIdx.x * 32 + lane;
   const T* Qb = Q + (size_t)b * n * n;
   T mx = T(0);
-  for (int i = 0; i < n; ++i) mx = t_max(mx, t_abs(Qb[(size_t)i * n + j]));
-  out[(size_t)b * n + j] = mx;
+  if (j < n) {
+#pragma unroll 4
+    for (int i = warp; i < n; i += kCmWarps) mx = t_max(mx, t_abs(Qb[(size_t)i * n + j]));
+  }
+  part[warp][lane] = mx;
+  __syncthreads();
+  if (warp == 0 && j < n) {
+#pragma unroll
+    for (int w = 1; w < kCmWarps; ++w) mx = t_max(mx, part[w][lane]);
+    out[(size_t)b * n + j] = mx;
+  }
 }
 template <typename T>
-__global__ void colmax_scatter_kernel(const T* __restrict__ Q, const T* __restrict__ colmax, const T* __restrict__ g,
-                                      T* __restrict__ G, int n) {
-  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const T gj = g[(size_t)b * n + j], mx = colmax[(size_t)b * n + j];
-  if (gj == T(0) || !(mx > T(0))) return;          // sign(0) = 0: zero columns carry no gradient
+__global__ void __launch_bounds__(32 * kCmWarps) colmax_scatter_kernel(const T* __restrict__ Q, const T* __restrict__ colmax,
+                                                                      const T* __restrict__ g, T* __restrict__ G, int n) {
+  __shared__ int part[kCmWarps][32];
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = blockIdx.x * 32 + lane;
+  const bool col = j < n;
+  const T gj = col ? g[(size_t)b * n + j] : T(0), mx = col ? colmax[(size_t)b * n + j] : T(0);
+  const bool live = col && gj != T(0) && mx > T(0);          // sign(0) = 0: zero columns carry no gradient
   const T* Qb = Q + (size_t)b * n * n;
   T* Gb = G + (size_t)b * n * n;
   int cnt = 0;
-  for (int i = 0; i < n; ++i) cnt += (t_abs(Qb[(size_t)i * n + j]) == mx) ? 1 : 0;
+  if (live) {
+#pragma unroll 4
+    for (int i = warp; i < n; i += kCmWarps) cnt += (t_abs(Qb[(size_t)i * n + j]) == mx) ? 1 : 0;
+  }
+  part[warp][lane] = cnt;
+  __syncthreads();
+  cnt = 0;
+#pragma unroll
+  for (int w = 0; w < kCmWarps; ++w) cnt += part[w][lane];
+  if (!live || cnt == 0) return;
   const T share = gj / (T)cnt;
-  for (int i = 0; i < n; ++i) {
+#pragma unroll 4
+  for (int i = warp; i < n; i += kCmWarps) {
     const T q = Qb[(size_t)i * n + j];
     if (t_abs(q) == mx) Gb[(size_t)i * n + j] += q > T(0) ? share : -share;
   }
 }
 template <typename T>
 cudaError_t launch_colmax_plain(int B, int n, const T* Q, T* out, cudaStream_t st) {
-  dim3 grid((n + 127) / 128, B);
-  colmax_plain_kernel<T><<<grid, 128, 0, st>>>(Q, out, n);
+  dim3 grid((n + 31) / 32, B);
+  colmax_plain_kernel<T><<<grid, 32 * kCmWarps, 0, st>>>(Q, out, n);
   return cudaGetLastError();
 }
 template <typename T>
 cudaError_t launch_colmax_scatter(int B, int n, const T* Q, const T* colmax, const T* g, T* G, cudaStream_t st) {
-  dim3 grid((n + 127) / 128, B);
-  colmax_scatter_kernel<T><<<grid, 128, 0, st>>>(Q, colmax, g, G, n);
+  dim3 grid((n + 31) / 32, B);
+  colmax_scatter_kernel<T><<<grid, 32 * kCmWarps, 0, st>>>(Q, colmax, g, G, n);
   return cudaGetLastError();
 }
 template cudaError_t launch_colmax_plain<float>(int, int, const float*, float*, cudaStream_t);

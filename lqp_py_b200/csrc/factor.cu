@@ -35,7 +35,7 @@ __device__ long long g_phase_cycles[16];
 
 template <typename T> struct GjCfg;
 template <> struct GjCfg<float>  { static constexpr int NT = 1024; };
-template <> struct GjCfg<double> { static constexpr int NT = 512; };
+template <> struct GjCfg<double> { static constexpr int NT = 1024; };
 
 // ---------------------------------------------------------------------------------------------
 // Rank-32 update of one 64 x 64 macro tile, C -= W V^T, by a group of 256 threads with the two 32 x 64

@@ -10,6 +10,9 @@ tail -3 gpurun_out/pytest_gpu.log gpurun_out/smoke.log
 timeout 600 python bench.py > gpurun_out/bench_f32.json 2> gpurun_out/bench_f32.err
 timeout 300 python bench.py --steps 40 --warmup 3 --dtype f64 --no-extras > gpurun_out/bench_f64.json 2> gpurun_out/bench_f64.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+timeout 300 python bench.py --impl reference-cuda > gpurun_out/bench_refcuda.json 2> gpurun_out/bench_refcuda.err
+LQPB_TC_FUSED=0 timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-extras > gpurun_out/bench_f32_perphase.json 2> gpurun_out/bench_f32_perphase.err
+timeout 300 python tools/unroll_bench.py > gpurun_out/unroll_bench.jsonl 2>&1
 cat gpurun_out/bench_f32.json gpurun_out/bench_f64.json gpurun_out/bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_f32.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_launch.log 2>&1
@@ -17,9 +20,13 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ite
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_iter32.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'iterate_kernel' -s 3 -c 1 -o gpurun_out/iterate_f64 -f \
   python bench.py --steps 1 --warmup 3 --dtype f64 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_iter64.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_tile_kernel' -s 24 -c 2 -o gpurun_out/tc_tile_f32 -f \
+# the fused block-sweep kernel (default at B = 128), then the per-phase kernels it replaced there (LQPB_TC_FUSED=0: still the
+# path of B < 64, B > 148 and sweeps of more than 4 block rows)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_fused_kernel' -s 6 -c 2 -o gpurun_out/tc_fused_f32 -f \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_fused32.log 2>&1
+LQPB_TC_FUSED=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_tile_kernel' -s 24 -c 2 -o gpurun_out/tc_tile_f32 -f \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_tile32.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_pivot8' -s 12 -c 1 -o gpurun_out/tc_pivot_f32 -f \
+LQPB_TC_FUSED=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_pivot8' -s 12 -c 1 -o gpurun_out/tc_pivot_f32 -f \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_pivot32.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gj_inverse_kernel' -s 6 -c 1 -o gpurun_out/gj_f64 -f \
   python bench.py --steps 1 --warmup 3 --dtype f64 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_gj64.log 2>&1

@@ -392,18 +392,21 @@ def run_reference_cuda(a, quiet=False):
         torch.set_default_dtype(dtype)
         sys.path.insert(0, REF_DIR)
         from lqp_py.control import box_qp_control as ref_control
-        from lqp_py.solve_box_qp_admm_torch import SolveBoxQP as RefSolveBoxQP
         from lqp_py.solve_box_qp_admm_torch import torch_solve_box_qp as ref_solve
         control = ref_control(eps_rel=1e-5, eps_abs=1e-5, verbose=False, reduce='max')     # experiment_1.py:22
-        QP = RefSolveBoxQP(control=control)
         data = [t.to("cuda:0") for t in data_cpu]
         g = torch.ones(a.batch, a.dz, 1, dtype=dtype)                                      # experiment_1.py:75
 
+        from lqp_py.solve_box_qp_admm_torch import torch_solve_box_qp_grad as ref_grad
+
         def one():
-            ins = [t.detach().clone().requires_grad_(j < 2) for j, t in enumerate(data)]   # experiments/utils.py:41-50
-            x = QP.forward(Q=ins[0], p=ins[1], A=ins[2], b=ins[3], lb=ins[4], ub=ins[5])
-            x.backward(g)
-            return x.detach(), ins[0].grad
+            # forward = SolveBoxQPLayer.forward's call (:39), backward = SolveBoxQPLayer.backward's call (:63), both made
+            # from THIS thread: torch's default device is thread-local, and the reference's backward allocates with bare
+            # factory calls (:363), so inside autograd's own thread it would land on the CPU
+            sol = ref_solve(*data, control)
+            grads = ref_grad(g, x=sol["x"], u=sol["u"], lams=sol["lams"], nus=sol["nus"], Q=data[0], A=data[2], lb=data[4],
+                             ub=data[5], rho=sol["rho"])
+            return sol["x"], grads[0]
         it = int(ref_solve(*data, control)["iter"])
         for _ in range(W):
             one()
@@ -424,7 +427,7 @@ def run_reference_cuda(a, quiet=False):
            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype,
            "data": "synthetic", "config": config_dict(a, 1, it), "finite": ok,
            "how": "unmodified reference package (oracle/_ref) under torch.set_default_device('cuda:0'): torch's library "
-                  "kernels (batched LU factor / solve) on the same GPU; CUDA events around K forward+backward passes"}
+                  "kernels (batched LU factor / solve) on the same GPU, torch_solve_box_qp + torch_solve_box_qp_grad called as the layer calls them; CUDA events around K forward+backward passes"}
     if not quiet:
         print(json.dumps(out), flush=True)
     return out

@@ -265,15 +265,13 @@ int factor_forward(const FwdWs<T>& w, bool first, cudaStream_t st) {
   a.dst = w.Kp; a.ldd = w.ld; a.G21 = w.Gt; a.K22 = w.Sinv;
   a.bt = w.bt; a.c_out = w.m > 0 ? w.c : nullptr;
   ProfState& g_prof = prof_state();
-  if constexpr (std::is_same<T, float>::value) {
-    if (w.tc) {
-      int l = 0;
-      // the first factorisation of a call finds the H block already in place (scale_pack_kernel)
-      CK(launch_tc_inverse(w.B, a, w.Pb, w.nb, first, st, &l), "tensor-core inverse (forward)");
-      g_prof.launches += l;
-      g_prof.fac_launches += l;
-      return LQPB_OK;
-    }
+  if (w.tc) {
+    int l = 0;
+    // the first factorisation of a call finds the H block already in place (scale_pack_kernel)
+    CK(launch_tc_inverse(w.B, a, w.Pb, w.nb, first, st, &l), "tensor-core inverse (forward)");
+    g_prof.launches += l;
+    g_prof.fac_launches += l;
+    return LQPB_OK;
   }
   CK(launch_gj_inverse<T>(w.B, a, st), "gj_inverse (forward)");
   g_prof.launches += 1;
@@ -595,13 +593,11 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
       a.bt = nullptr; a.c_out = nullptr;
       a.rhs_g = gc; a.sol_x = wc.dv; a.sol_nu = wc.dnu;
       bool done = false;
-      if constexpr (std::is_same<T, float>::value) {
-        if (wc.tc) {
-          int l = 0;
-          CK(launch_tc_ldl_solve(bc, a, wc.Pb, wc.nb, st, &l, stage), "tensor-core LDL solve (backward)");
-          bwd_fac_launches += l;
-          done = true;
-        }
+      if (wc.tc) {
+        int l = 0;
+        CK(launch_tc_ldl_solve(bc, a, wc.Pb, wc.nb, st, &l, stage), "tensor-core LDL solve (backward)");
+        bwd_fac_launches += l;
+        done = true;
       }
       if (!done) {
         CK(launch_ldl_solve<T>(bc, a, st), "ldl_solve (backward)");

@@ -15,11 +15,10 @@ constexpr int kMacro = 64;     // macro tile edge of the trailing update (np is 
 constexpr int kMaxM = 256;     // max equality rows (they live in the padding of the factorisation; per-CTA scratch is sized by it)
 constexpr int kTcBlock = 128;  // block edge of the tensor-core factorisation (tcfactor.cu)
 
-// fp32 problems with n + m > 128 are factorised on the tensor cores (tcfactor.cu: blocked sweep with
-// tcgen05 3xTF32 tile products); everything else (fp64, small problems) uses the Gauss-Jordan kernel of
-// factor.cu.  LQPB_FACTOR=gj in the environment forces the latter (A/B measurements).
-template <typename T> inline bool tc_factor_enabled(int, int) { return false; }
-template <> inline bool tc_factor_enabled<float>(int n, int m) {
+// Problems with n + m > 128 are factorised by the blocked sweep with 128 x 128 tile products on the tensor cores: fp32 in
+// tcfactor.cu / tcfused.cu (tcgen05, 3xTF32), fp64 in f64block.cu (DMMA); small problems use the Gauss-Jordan kernel of
+// factor.cu.  LQPB_FACTOR=gj in the environment forces the latter for every size (A/B measurements).
+template <typename T> inline bool tc_factor_enabled(int n, int m) {
   const char* e = getenv("LQPB_FACTOR");
   if (e && !strcmp(e, "gj")) return false;
   return n + m > kTcBlock;
@@ -237,6 +236,11 @@ cudaError_t launch_tc_inverse(int B, const GjArgs<float>& a, float* Pbuf, int nb
 cudaError_t launch_tc_ldl_solve(int B, const GjArgs<float>& a, float* Pbuf, int nb, cudaStream_t st, int* launches,
                                 int stage = 0);
 cudaError_t launch_tc_dev_inverse(int B, int N, const float* A, float* Ainv, float* work, cudaStream_t st);
+// f64block.cu -- the same blocked sweep in fp64 (DMMA tile products); same arguments / outputs
+cudaError_t launch_tc_inverse(int B, const GjArgs<double>& a, double* Pbuf, int nb, bool prebuilt, cudaStream_t st,
+                              int* launches);
+cudaError_t launch_tc_ldl_solve(int B, const GjArgs<double>& a, double* Pbuf, int nb, cudaStream_t st, int* launches,
+                                int stage);
 
 // Tape of the unrolled mode: per problem and ADMM iteration k the scaled iterate x~_k, z_k, u_k ((B, n_iter, n),
 // unpadded rows) and the equality part nu_k of the KKT solve ((B, n_iter, m), before the E un-scaling).

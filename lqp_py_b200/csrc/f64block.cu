@@ -294,6 +294,178 @@ __global__ void __launch_bounds__(512, 1) d_pivot_kernel(DArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ pivot block inverse, blocked by 8 (DMMA)
+// The same sweep 8 pivots at a time (the scheme of pivot8_body, tcmma.cuh): with S the 8 pivot indices of a step and R the rest,
+//     P = inv(A_SS),  U = P A_S:,  A_RR -= U_R^T A_SR,  A_SR <- U,  A_RS <- U^T,  A_SS <- -P.
+// 16 work warps hold the tile as accumulator fragments of the fp64 tensor-core MMA -- warp w owns rows 8 w .. 8 w + 7 as
+// sixteen 8 x 8 blocks, lane (gid, tig) the entries [8 w + gid][8 t + 2 tig .. + 1] -- so the rank-8 update is 32
+// DMMA.8x8x4 per warp and step (A fragment = -U^T of the warp's rows, B fragments = the published pivot rows) instead of
+// 256 DFMAs per thread, the pivot rows of a step live in ONE warp and the pivot columns in ONE block index.  A 17th warp
+// inverts the next 8 x 8 diagonal block (look-ahead: D' = A_S'S' - U_S'^T A_SS', two entries per lane, shuffles) while the
+// update runs.  Two barriers per step; rows of step sb + 1 and the raw diagonal block of step sb + 2 are published at the
+// end of step sb into the other halves of double-buffered arrays.
+constexpr int kDP8Threads = 544;
+constexpr int kDPLd = 132;                 // row stride of the published rows / of U: fragment loads at the 2-wavefront minimum
+
+__device__ __forceinline__ void d_inv8x8_warp(double& e0, double& e1, int lane) {
+  const int i = lane >> 2, jq = lane & 3;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const double d_s0 = __shfl_sync(0xffffffffu, e0, s * 4 + jq);       // row s, my two columns
+    const double d_s1 = __shfl_sync(0xffffffffu, e1, s * 4 + jq);
+    const double d_isa = __shfl_sync(0xffffffffu, e0, i * 4 + (s >> 1)); // my row, column s
+    const double d_isb = __shfl_sync(0xffffffffu, e1, i * 4 + (s >> 1));
+    const double d_ssa = __shfl_sync(0xffffffffu, e0, s * 4 + (s >> 1));
+    const double d_ssb = __shfl_sync(0xffffffffu, e1, s * 4 + (s >> 1));
+    const double d_is = (s & 1) ? d_isb : d_isa;
+    const double piv = 1.0 / ((s & 1) ? d_ssb : d_ssa);
+    const double ci = d_is * piv;
+    const int j0 = 2 * jq;
+    if (i != s) {
+      e0 = (j0 == s) ? ci : fma(-ci, d_s0, e0);
+      e1 = (j0 + 1 == s) ? ci : fma(-ci, d_s1, e1);
+    } else {
+      e0 = (j0 == s) ? -piv : d_s0 * piv;
+      e1 = (j0 + 1 == s) ? -piv : d_s1 * piv;
+    }
+  }
+  e0 = -e0;
+  e1 = -e1;
+}
+
+__device__ __forceinline__ void dmma8x8x4(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kDP8Threads, 1) d_pivot8_kernel(DArgs a) {
+  __shared__ __align__(16) double rowbuf[2][8][kDPLd];   // rows S of step parity
+  __shared__ __align__(16) double ubuf[8][kDPLd];        // U = P A_S:
+  __shared__ __align__(16) double pbuf[2][8][8];         // P of step parity
+  __shared__ __align__(16) double dbuf[2][8][8];         // raw diagonal block
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gid = lane >> 2, tig = lane & 3;
+  const bool la = warp == 16;
+  const int k = a.k, nb = a.nb;
+  double* tile = a.M + ((size_t)b * ((size_t)nb * (nb + 1) / 2)) * kTBE + bl_tile(k, k);
+  double* P = a.Pbuf + ((size_t)b * nb + k) * kTBE;
+  double acc[16][2];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) acc[t][0] = acc[t][1] = 0.0;       // defined on every path (see pivot8_body)
+  const int r = 8 * warp + gid;                                     // the lane's row (work warps)
+  if (!la) {
+    // the lower triangle is the reference copy: entries above the diagonal are read transposed
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int c = 8 * t + 2 * tig;
+      if (t < warp) {
+        const double2 v = *reinterpret_cast<const double2*>(tile + (size_t)r * kTB + c);
+        acc[t][0] = v.x;
+        acc[t][1] = v.y;
+      } else {
+        acc[t][0] = r >= c ? tile[(size_t)r * kTB + c] : tile[(size_t)c * kTB + r];
+        acc[t][1] = r >= c + 1 ? tile[(size_t)r * kTB + c + 1] : tile[(size_t)(c + 1) * kTB + r];
+      }
+    }
+    if (warp == 0) {
+#pragma unroll
+      for (int t = 0; t < 16; ++t) *reinterpret_cast<double2*>(&rowbuf[0][gid][8 * t + 2 * tig]) = make_double2(acc[t][0], acc[t][1]);
+    }
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+      if (warp == t) *reinterpret_cast<double2*>(&dbuf[t][gid][2 * tig]) = make_double2(acc[t][0], acc[t][1]);
+  }
+  __syncthreads();
+  if (la) {
+    const int i = lane >> 2, j0 = 2 * (lane & 3);
+    double e0 = dbuf[0][i][j0], e1 = dbuf[0][i][j0 + 1];
+    d_inv8x8_warp(e0, e1, lane);
+    *reinterpret_cast<double2*>(&pbuf[0][i][j0]) = make_double2(e0, e1);
+  }
+  __syncthreads();
+
+#pragma unroll 1
+  for (int sb = 0; sb < kTB / 8; ++sb) {
+    const int cur = sb & 1;
+    const double(*Pc)[8] = pbuf[cur];
+    const double(*rows)[kDPLd] = rowbuf[cur];
+    // ---- B. U = P A_S: (8 x 128): thread -> column c = tid % 128, rows s = tid / 128 and tid / 128 + 4
+    if (!la) {
+      const int c = tid & 127, s0 = tid >> 7;
+      double rv[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) rv[t] = rows[t][c];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int s = s0 + 4 * hh;
+        double u = Pc[s][0] * rv[0];
+#pragma unroll
+        for (int t = 1; t < 8; ++t) u = fma(Pc[s][t], rv[t], u);
+        ubuf[s][c] = u;
+      }
+    }
+    __syncthreads();
+    if (la) {
+      // ---- C'. look-ahead: D' = A_S'S' - U_S'^T A_SS', P' = inv(D')
+      if (sb + 1 < kTB / 8) {
+        const int i = lane >> 2, j0 = 2 * (lane & 3), c0 = 8 * (sb + 1);
+        double e0 = dbuf[cur ^ 1][i][j0], e1 = dbuf[cur ^ 1][i][j0 + 1];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const double ui = ubuf[s][c0 + i];
+          e0 = fma(-ui, rows[s][c0 + j0], e0);
+          e1 = fma(-ui, rows[s][c0 + j0 + 1], e1);
+        }
+        d_inv8x8_warp(e0, e1, lane);
+        *reinterpret_cast<double2*>(&pbuf[cur ^ 1][i][j0]) = make_double2(e0, e1);
+      }
+    } else {
+      // ---- C. rank-8 update:  A_rc -= sum_s U[s][r] * A_S[s][c]  as two DMMA k-steps per 8 x 8 block
+#pragma unroll
+      for (int k4 = 0; k4 < 2; ++k4) {
+        const double af = -ubuf[4 * k4 + tig][r];                       // A[row gid][k tig] = -U[k][row]
+#pragma unroll
+        for (int t = 0; t < 16; ++t) dmma8x8x4(acc[t], af, rows[4 * k4 + tig][8 * t + gid]);   // B[k tig][col gid]
+      }
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        if (t == sb) {               // columns S of the lane's row:  A_rS <- U^T
+          acc[t][0] = ubuf[2 * tig][r];
+          acc[t][1] = ubuf[2 * tig + 1][r];
+        }
+      }
+      if (warp == sb) {              // rows S:  A_Sc <- U, and A_SS <- -P
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const double2 u = *reinterpret_cast<const double2*>(&ubuf[gid][8 * t + 2 * tig]);
+          const double2 p = *reinterpret_cast<const double2*>(&Pc[gid][2 * tig]);
+          acc[t][0] = t == sb ? -p.x : u.x;
+          acc[t][1] = t == sb ? -p.y : u.y;
+        }
+      }
+      // ---- publish for the next steps (the other halves of the double buffers; last read one step ago)
+      if (warp == sb + 1) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          *reinterpret_cast<double2*>(&rowbuf[cur ^ 1][gid][8 * t + 2 * tig]) = make_double2(acc[t][0], acc[t][1]);
+      }
+      if (warp == sb + 2) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (t == sb + 2) *reinterpret_cast<double2*>(&dbuf[cur][gid][2 * tig]) = make_double2(acc[t][0], acc[t][1]);
+      }
+    }
+    __syncthreads();
+  }
+  if (la) return;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const size_t o = (size_t)r * kTB + 8 * t + 2 * tig;
+    *reinterpret_cast<double2*>(tile + o) = make_double2(acc[t][0], acc[t][1]);
+    *reinterpret_cast<double2*>(P + o) = make_double2(-acc[t][0], -acc[t][1]);
+  }
+}
+
 // ------------------------------------------------------------------ assemble / fix up / extract (as tcfactor.cu, in fp64)
 __global__ void __launch_bounds__(256) d_assemble_kernel(GjArgs<double> a, double* __restrict__ Mout, int nb) {
   const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
@@ -498,7 +670,9 @@ static cudaError_t d_sweep(int B, const DArgs& base, bool ldl, cudaStream_t st, 
   const int nb = a.nb;
   for (int k = 0; k < nb; ++k) {
     a.k = k;
-    d_pivot_kernel<<<B, 512, 0, st>>>(a);
+    static const bool piv_v1 = [] { const char* e = getenv("LQPB_D_PIVOT"); return e && e[0] == '1'; }();
+    if (piv_v1) d_pivot_kernel<<<B, 512, 0, st>>>(a);            // developer switch: rank-1 register sweep (A/B)
+    else d_pivot8_kernel<<<B, kDP8Threads, 0, st>>>(a);
     ++*launches;
     const int span = ldl ? nb - 1 - k : nb - 1;
     if (span > 0) {

@@ -106,6 +106,13 @@ iterate_row_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* n
   for (size_t t = tid; t < (size_t)nprob * geo.prob_elems; t += kRowThreads) base[t] = T(0);
   if (tid < 8) s_flags[tid >> 2][tid & 3] = 0;
   __syncthreads();
+  // cluster mode: a CTA's shared memory may only be written by its peers (DSMEM stores at the stop checks) once it has
+  // started executing -- one cluster barrier up front establishes that (compute-sanitizer racecheck: "block that might not
+  // have entered yet" without it)
+  if (geo.cluster && gridDim.x > 1) {
+    row_cluster_arrive();
+    row_cluster_wait();
+  }
   if constexpr (!FUSED) {
     const int ntv = P::nt(n), ntiles = P::ntiles(n);
     const size_t per = (size_t)ntiles * P::TILE;

@@ -1,5 +1,5 @@
 """One forward + backward per kernel family, small enough to run under compute-sanitizer (tools/gpu_sanitize.sh):
-    python tools/sanitize_cases.py rows|packed|stream|fused|adapt|unroll|f64"""
+    python tools/sanitize_cases.py rows|packed|stream|fused|adapt|unroll|f64|f64blk"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,7 +16,8 @@ cfg = {"rows": (64, 6, torch.float32, {}),            # Gauss-Jordan factorisati
        "fused": (320, 3, torch.float32, {}),           # tcgen05 block sweep as ONE persistent warp-specialised kernel (tcfused.cu)
        "adapt": (60, 4, torch.float64, {"rho": 100.0}),  # adaptive-rho refactorisation (host relaunch)
        "unroll": (64, 3, torch.float64, {"unroll": True}),
-       "f64": (150, 3, torch.float64, {})}[case]
+       "f64": (100, 3, torch.float64, {}),               # Gauss-Jordan factorisation in fp64
+       "f64blk": (200, 3, torch.float64, {})}[case]      # blocked sweep with DMMA tile products (f64block.cu)
 n, B, dt, kw = cfg
 data = [t.to(dev).requires_grad_(True) for t in create_qp_data(n, B, 2 * n, seed=0, requires_grad=False, dtype=dt)[:6]]
 x = SolveBoxQP(control=box_qp_control(eps_rel=1e-5, eps_abs=1e-5, **kw)).forward(*data)

@@ -28,8 +28,12 @@ LQPB_TC_FUSED=0 timeout 900 ncu --set full --clock-control none --import-source 
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_tile32.log 2>&1
 LQPB_TC_FUSED=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'tc_pivot8' -s 12 -c 1 -o gpurun_out/tc_pivot_f32 -f \
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_pivot32.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gj_inverse_kernel' -s 6 -c 1 -o gpurun_out/gj_f64 -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'d_tile_kernel|d_pivot8_kernel' -s 9 -c 3 -o gpurun_out/f64_block -f \
+  python bench.py --steps 1 --warmup 3 --dtype f64 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_f64blk.log 2>&1
+LQPB_FACTOR=gj timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gj_inverse_kernel' -s 6 -c 1 -o gpurun_out/gj_f64 -f \
   python bench.py --steps 1 --warmup 3 --dtype f64 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_gj64.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_f64.csv \
+  python bench.py --dtype f64 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_launch64.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'iterate_kernel' -s 3 -c 1 -o gpurun_out/iterate_f32_dz1000 -f \
   python bench.py --dz 1000 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-extras > gpurun_out/ncu_iter1000.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'iterate_row_kernel' -s 3 -c 1 -o gpurun_out/iterate_row_f32_dz100 -f \

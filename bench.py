@@ -607,6 +607,7 @@ def iterate_roofline(n, B, s, it, it_ms, peaks, hbm_peak, dtype_name):
     bound = "l2" if resident else "hbm"
     l2_peak = peaks.get("l2_read_gbs") if peaks else None
     peak = (l2_peak if resident else hbm_peak) or hbm_peak
+    no_l2_peak = resident and not l2_peak        # --no-extras: the L2 ceiling was not measured in this run
     sec = it_ms * 1e-3
     achieved = alg_launch / sec / 1e9
     moved = moved_launch / sec / 1e9
@@ -623,8 +624,10 @@ def iterate_roofline(n, B, s, it, it_ms, peaks, hbm_peak, dtype_name):
                 "peak": None, "unit": "GB/s", "frac": None, "traffic": None, "bytes_per_launch": alg_launch,
                 "ms_per_launch": it_ms, "admm_passes": passes, "checks": checks,
                 "us_per_admm_iteration": it_ms * 1e3 / passes, "note": note}
-    out = {"kernel": "iterate_kernel", "regime": REGIMES.get(regime), "bound": bound, "achieved": achieved, "peak": peak, "unit": "GB/s",
-           "frac": achieved / peak, "achieved_moved": moved, "frac_moved": moved / peak,
+    out = {"kernel": "iterate_kernel", "regime": REGIMES.get(regime), "bound": bound, "achieved": achieved,
+           "peak": None if no_l2_peak else peak, "unit": "GB/s",
+           "frac": None if no_l2_peak else achieved / peak, "achieved_moved": moved,
+           "frac_moved": None if no_l2_peak else moved / peak,
            "peak_source": ("measured in this run (lqpb_dev_stream_read on an L2-resident buffer)" if resident and l2_peak
                            else "MEASURED_PEAKS.json hbm_gbs" if hbm_peak_measured() else "fallback 6650 GB/s"),
            "frac_vs_hbm_copy_peak": achieved / hbm_peak, "hbm_peak": hbm_peak,

@@ -807,3 +807,16 @@ def test_fused_block_sweep_equals_per_phase_kernels():
                            text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         assert "bit-identical" in r.stdout and '"finite": true' in r.stdout, r.stdout[-2000:]
+
+
+def test_blocked_sweeps_beyond_the_baseline_shapes():
+    """Shapes the golden / baseline sets do not reach, against the CPU oracle (tools/big_shape_check.py): 6 and 8 block rows
+    of the fp64 DMMA sweep (dz = 700 / 1000: transposed PANEL jobs at every level) and 20 equality rows inside the blocked
+    sweeps (the "hard" generator at n = 400), fp64 at 1e-8 / 1e-7."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "big_shape_check.py")], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "ALL OK" in r.stdout and "FAIL" not in r.stdout.replace("FAILURES", ""), r.stdout[-2000:]

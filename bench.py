@@ -748,31 +748,40 @@ def run_e2e(cx, a, host_sets, dtype, K, W):
     pin_sets = [[t.pin_memory() for t in d] for d in host_sets]
     g_host = torch.ones(B, n, 1, dtype=dtype).pin_memory()
 
-    def step_host(k):
+    def step_host(k, announce):
         # leaves as experiments/utils.py:41-50 creates them: Q and p require grad, A, b, lb, ub do not
         ins = [t.detach().requires_grad_(j < 2) for j, t in enumerate(pin_sets[k % len(pin_sets)])]
         x = QP.forward(*ins)
+        if announce:
+            # a data loader that knows its next batch: the upload of step k + 1 (copy stream, H2D) runs while step k's
+            # backward computes and streams dQ down (D2H) -- PCIe is full duplex.  Every step's H2D and D2H are inside
+            # the timed region either way.
+            QP.prefetch(*pin_sets[(k + 1) % len(pin_sets)])
         x.backward(g_host)
         return x, ins
-    # warm-up until torch's caching pinned-host allocator holds every staging block a step needs
-    # (a fresh cudaHostAlloc of a 128 MB gradient block costs tens of ms and is not steady state)
-    for k in range(max(W, 5)):
-        x, ins = step_host(k)
-    cx.sync_all()
+
+    def timed(announce):
+        # warm-up until torch's caching pinned-host allocator holds every staging block a step needs
+        # (a fresh cudaHostAlloc of a 128 MB gradient block costs tens of ms and is not steady state)
+        for k in range(max(W, 5)):
+            x, ins = step_host(k, announce)
+        cx.sync_all()
+        # timed on the device like `value`: events on the compute stream bracket the Ke steps (every step ends with the
+        # copy stream joined back into it and the host buffers valid), max over ranks below
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        h0.record()
+        for k in range(Ke):
+            x, ins = step_host(max(W, 5) + k, announce)
+        h1.record()
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        if world > 1:
+            cx.dist.barrier()
+        return cx.max_over_ranks(h0.elapsed_time(h1) * 1e-3), wall, x, ins
     Ke = max(3, min(K, 20))
-    # timed on the device like `value`: events on the compute stream bracket the Ke steps (every step ends with the
-    # copy stream joined back into it and the host buffers valid), max over ranks below
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    h0.record()
-    for k in range(Ke):
-        x, ins = step_host(5 + k)
-    h1.record()
-    torch.cuda.synchronize(dev)
-    wall = time.perf_counter() - t0
-    if world > 1:
-        cx.dist.barrier()
-    dt = cx.max_over_ranks(h0.elapsed_time(h1) * 1e-3)
+    dt_serial, _, x, ins = timed(False)
+    dt, wall, x, ins = timed(True)
     h2d = sum(t.numel() for t in pin_sets[0]) * s + g_host.numel() * s
     grads = [t.grad for t in ins if t.grad is not None]
     d2h = (x.numel() + sum(t.numel() for t in grads)) * s
@@ -801,16 +810,46 @@ def run_e2e(cx, a, host_sets, dtype, K, W):
     if world > 1:
         cx.dist.barrier()
     ct = cx.max_over_ranks(c0.elapsed_time(c1) * 1e-3)
-    log(f"e2e done: {dt / Ke * 1e3:.3f} ms per step (copy ceiling {ct / Ke * 1e3:.3f} ms)")
+    # ... and the full-duplex ceiling: uploads on one stream, downloads on another
+    up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def copy_duplex(k):
+        with torch.cuda.stream(up):
+            for d, h in zip(dev_in, pin_sets[k % len(pin_sets)]):
+                d.copy_(h, non_blocking=True)
+            dev_g.copy_(g_host, non_blocking=True)
+        with torch.cuda.stream(down):
+            for h, d in zip(host_out, dev_out):
+                h.copy_(d, non_blocking=True)
+    cx.sync_all()
+    t1 = time.perf_counter()
+    for k in range(Ke):
+        copy_duplex(k)
+    torch.cuda.synchronize(dev)
+    cd = time.perf_counter() - t1
+    if world > 1:
+        cx.dist.barrier()
+    cd = cx.max_over_ranks(cd)
+    log(f"e2e done: {dt / Ke * 1e3:.3f} ms per step with the next batch announced, {dt_serial / Ke * 1e3:.3f} ms without "
+        f"(copy ceilings: {ct / Ke * 1e3:.3f} ms serial, {cd / Ke * 1e3:.3f} ms duplex)")
     return {"value": B * world * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": Ke, "ms_per_step": dt / Ke * 1e3, "host_wall_ms_per_step": wall / Ke * 1e3,
             "copy_ceiling": {"ms_per_step": ct / Ke * 1e3, "value": B * world * Ke / ct, "unit": UNIT,
                              "gbs_per_gpu": (h2d + d2h) / (ct / Ke) / 1e9,
                              "how": "the step's H2D + D2H copies alone (same pinned buffers, same stream order, no "
                                     "kernels), max over ranks"},
-            "frac_of_copy_ceiling": (ct / Ke) / (dt / Ke),
+            "copy_ceiling_duplex": {"ms_per_step": cd / Ke * 1e3, "value": B * world * Ke / cd, "unit": UNIT,
+                                    "how": "the same copies with uploads and downloads on two streams (PCIe is full "
+                                           "duplex); host wall clock around Ke steps, max over ranks"},
+            "frac_of_copy_ceiling": (cd / Ke) / (dt / Ke),
+            "without_prefetch": {"value": B * world * Ke / dt_serial, "unit": UNIT, "ms_per_step": dt_serial / Ke * 1e3,
+                                 "frac_of_serial_copy_ceiling": (ct / Ke) / (dt_serial / Ke),
+                                 "how": "the same loop without SolveBoxQP.prefetch: upload, solve, backward and download "
+                                        "of a step strictly one after the other"},
             "how": "SolveBoxQP.forward + x.backward on pinned CPU tensors (Q, p require grad as in "
-                   "experiments/utils.py:41-50; x, dQ, dp come back to the host); copies in the timed region"}
+                   "experiments/utils.py:41-50; x, dQ, dp come back to the host), the next step's inputs announced with "
+                   "SolveBoxQP.prefetch between forward and backward (their upload overlaps this step's gradient "
+                   "download); every step's H2D and D2H copies are inside the timed region"}
 
 
 def run_configs(cx, a, peaks, hbm_peak):

@@ -568,7 +568,9 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
   if (host) {
     CK(pipe_init(), "copy stream");
     cs = g_pipe.cs;
-    CK(cudaMemcpyAsync((void*)dl_dz, host->dl_dz, (size_t)B * n * sizeof(T), cudaMemcpyHostToDevice, st), "H2D dl_dz");
+    // cudaMemcpyDefault: the "host" dl_dz may already be a device copy (a caller that uploaded it itself so that its own
+    // H2D traffic -- e.g. the prefetch of the next batch -- is ordered behind it); the copy engine serves H2D in order
+    CK(cudaMemcpyAsync((void*)dl_dz, host->dl_dz, (size_t)B * n * sizeof(T), cudaMemcpyDefault, st), "H2D dl_dz");
   }
   for (int c = 0; c < C; ++c) {
     const int b0 = chunk_lo(B, C, c), bc = chunk_lo(B, C, c + 1) - b0;

@@ -49,6 +49,12 @@ class SolveBoxQP(nn.Module):
             return torch_solve_box_qp(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub, control=self.control)
         return SolveBoxQPLayer.apply(Q, p, A, b, lb, ub, self.control)
 
+    @staticmethod
+    def prefetch(Q, p, A, b, lb, ub):
+        """Addition to the reference's API (see :func:`prefetch_inputs`): start uploading the NEXT batch of host tensors
+        while the GPU and the PCIe downlink are busy with the current one."""
+        return prefetch_inputs(Q, p, A, b, lb, ub)
+
 
 class SolveBoxQPLayer(torch.autograd.Function):
     """ADMM forward solve + implicit (fixed-point) backward (reference :21-67)."""
@@ -218,6 +224,81 @@ def _cuda_device(ref):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_PREFETCH = {}            # inputs on their way to the device: key = identity of the caller's host tensors
+_PREFETCH_STREAM = {}     # one copy stream per device
+
+
+def _prefetch_key(tensors):
+    return tuple(None if t is None else (t.data_ptr(), tuple(t.shape), t.dtype, t._version) for t in tensors)
+
+
+def prefetch_inputs(Q, p, A, b, lb, ub):
+    """Announce a batch of host tensors that a LATER ``SolveBoxQP.forward`` / ``torch_solve_box_qp`` call will be given
+    (the same tensor objects, unmodified in between), so that its host -> device copy can overlap the work in flight.
+    The reference's callers hold CPU tensors, so a training step moves ``Q`` up and ``dQ`` down over PCIe; the link is
+    full duplex, and a data loader that announces its next batch between ``forward`` and ``backward`` lets the upload of
+    step k + 1 run on a copy stream while step k's backward computes and streams its gradients down.
+
+    The copies are STARTED by the next backward of a host caller, right after it has submitted its own ``dl_dz`` upload
+    (the H2D copy engine serves its queue in order: a 128 MB prefetch submitted first would hold the backward up for the
+    whole transfer -- measured), or by the forward that consumes the announcement if no backward came in between.  That
+    forward finds the device copies by the identity of the host tensors (data pointer, shape, dtype, version counter),
+    waits for the copy's event on its own stream and takes the device-pointer path; a call on tensors that were never
+    announced, or were modified since, uploads as before.  Pinned host memory is what makes the copy asynchronous.
+    Returns True when the batch was registered (CPU tensors and a CUDA device), False otherwise."""
+    ts = (Q, p, A, b, lb, ub)
+    if not _all_on_host(ts) or not torch.cuda.is_available():
+        return False
+    for k, t in zip(("Q", "p", "A", "b", "lb", "ub"), ts):
+        if t is not None and t.dtype != p.dtype:
+            raise TypeError(f"all tensors must share one dtype, got {p.dtype} and {t.dtype} ({k})")
+    key = _prefetch_key(ts)
+    if key in _PREFETCH:
+        return True
+    while len(_PREFETCH) >= 4:                       # announcements that were never used must not pile up
+        _PREFETCH.pop(next(iter(_PREFETCH)))
+    _PREFETCH[key] = dict(dev=_cuda_device(p), tensors=None, event=None, hold=ts)   # `hold` keeps the host buffers alive
+    return True
+
+
+def _launch_prefetches():
+    """Start the copies of every announced batch that has not been started yet (copy stream, one event per batch)."""
+    for pf in _PREFETCH.values():
+        if pf["event"] is not None:
+            continue
+        dev, ts = pf["dev"], pf["hold"]
+        with _on_device(dev):
+            st = _PREFETCH_STREAM.get(dev)
+            if st is None:
+                st = _PREFETCH_STREAM[dev] = torch.cuda.Stream(device=dev)
+            cur = torch.cuda.current_stream(dev)
+            names = ("Q", "p", "A", "b", "lb", "ub")
+            dt = ts[1].dtype
+            dv = {k: (None if t is None else torch.empty(t.shape, dtype=dt, device=dev)) for k, t in zip(names, ts)}
+            st.wait_stream(cur)                      # the buffers were allocated in the current stream's order
+            with torch.cuda.stream(st):
+                for k, t in zip(names, ts):
+                    if t is not None:
+                        dv[k].copy_(_host_view(t), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+        pf["tensors"], pf["event"] = dv, ev
+
+
+def _take_prefetched(tensors):
+    """The device copies announced for exactly these host tensors, ordered into the current stream; None otherwise."""
+    if not _PREFETCH:
+        return None
+    key = _prefetch_key(tensors)
+    if key not in _PREFETCH:
+        return None
+    if _PREFETCH[key]["event"] is None:
+        _launch_prefetches()                         # no backward came in between: the copy starts now
+    pf = _PREFETCH.pop(key)
+    torch.cuda.current_stream(pf["dev"]).wait_event(pf["event"])
+    return pf["tensors"]
+
+
 def _stage(tensors):
     """Move a dict of (optional) tensors to one CUDA device, contiguous, same dtype."""
     ref = next(t for t in tensors.values() if t is not None)
@@ -385,7 +466,13 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
     prepared = False
     deferred = False
     tape_info = None
-    if host_mode:
+    pre_dv = _take_prefetched((Q, p, A, b, lb, ub)) if host_mode else None
+    if pre_dv is not None:
+        # the batch was announced (prefetch_inputs): its device copies are on their way / there; from here on this is the
+        # device-pointer path, only the results travel back to the caller's host tensors
+        host_mode = False
+        dv = pre_dv
+    elif host_mode:
         # CPU tensors in (the reference's callers): lqpb_forward_host_* uploads Q in chunks on a copy stream and
         # overlaps the per-problem setup with the transfer; the device copies it fills are kept for the backward
         hv = {k: _host_view(t) for k, t in dict(Q=Q, p=p, A=A, b=b, lb=lb, ub=ub).items()}
@@ -415,7 +502,7 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
         info = _abi.Info()
         stream = _raw_stream(dev)
         flag = C.c_int32(0)
-        # the tensor-core sizes (fp32, n + m > 128) queue the backward's factorisation behind the solve (prep); the
+        # the blocked-sweep sizes (n + m > 128, fp32 and fp64) queue the backward's factorisation behind the solve (prep); the
         # others can take the asynchronous forward
         rho_vec = None
         user_rho_t = control.get('rho', None)
@@ -427,7 +514,7 @@ def _solve_device(Q, p, A, b, lb, ub, control, host_keys=None, prep=None, tape_c
             prep = None                # (the per-problem rho travels through lqpb_forward_warm_* only)
             rho_vec = user_rho_t.detach().to(device=dev, dtype=dt).reshape(B).contiguous()
         use_async = (allow_async and not host_mode and tape_cap is None and z0 is None and u0 is None and not cfg.verbose
-                     and rho_vec is None and not (dt == torch.float32 and n + m > 128))
+                     and rho_vec is None and not (n + m > 128))
         if host_mode:
             hx = torch.empty((B, n, 1), dtype=dt, pin_memory=True)
             rc = getattr(L, f"lqpb_forward_host_{sfx}")(
@@ -1082,11 +1169,18 @@ def _grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, kkt, any_bounds,
         dbuf = [None if s is None else torch.empty(s, dtype=dt, device=dev) for s in shapes]
         hbuf = [None if s is None else torch.empty(s, dtype=dt, pin_memory=True) for s in shapes]
         g_dev = torch.empty((B, n, 1), dtype=dt, device=dev)
+        g_src = g
+        if _PREFETCH:
+            # a batch is announced: dl_dz goes up FIRST (the H2D engine serves its queue in order), then the announced
+            # copies start, and the C call below is handed the device copy of dl_dz
+            g_src = torch.empty((B, n, 1), dtype=dt, device=dev)
+            g_src.copy_(g.reshape(B, n, 1), non_blocking=True)
+            _launch_prefetches()
         ws_bytes = _ws_bytes("backward", sfx, B, n, m)
         ws = prepared_ws if prepared_ws is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         stream = _raw_stream(dev)
         rc = getattr(L, f"lqpb_backward_host_{sfx}")(
-            B, n, m, 1 if kkt else 0, _abi.ptr(g), _abi.ptr(g_dev), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams),
+            B, n, m, 1 if kkt else 0, _abi.ptr(g_src), _abi.ptr(g_dev), _abi.ptr(x), _abi.ptr(u), _abi.ptr(lams),
             _abi.ptr(nus), _abi.ptr(Q), _abi.ptr(A), _abi.ptr(lb), _abi.ptr(ub), _abi.ptr(rho_dev), rho_scalar,
             *[_abi.ptr(t) for t in dbuf], *[_abi.ptr(t) for t in hbuf], None, _abi.ptr(ws), ws_bytes,
             C.c_void_p(stream), 0, 1 if prepared_ws is not None else 0)

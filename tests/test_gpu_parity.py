@@ -820,3 +820,37 @@ def test_blocked_sweeps_beyond_the_baseline_shapes():
                        timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "ALL OK" in r.stdout and "FAIL" not in r.stdout.replace("FAILURES", ""), r.stdout[-2000:]
+
+
+def test_prefetched_inputs_equal_the_host_path(dev):
+    """SolveBoxQP.prefetch (upload of an announced batch on a copy stream) must not change a single bit: the later forward
+    finds the device copies by the identity of the host tensors and takes the device-pointer path; a batch modified after
+    the announcement is uploaded again."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP, prefetch_inputs, _PREFETCH
+    n, B = 300, 8
+    raw = [t.pin_memory() for t in orc.make_exp1_data(n, B, seed=5, dtype=torch.float32)]
+    g = torch.randn(B, n, 1, generator=torch.Generator().manual_seed(1)).pin_memory()
+
+    def run(announce):
+        ins = [t.detach().requires_grad_(j < 2) for j, t in enumerate(raw)]
+        if announce:
+            assert prefetch_inputs(*raw)
+        x = SolveBoxQP(control=box_qp_control(eps_rel=1e-5, eps_abs=1e-5)).forward(*ins)
+        x.backward(g)
+        return x.detach().clone(), ins[0].grad.clone(), ins[1].grad.clone()
+    base = run(False)
+    pre = run(True)
+    assert not _PREFETCH, "the announced batch was not consumed"
+    for a_, b_ in zip(base, pre):
+        assert a_.device.type == "cpu" and torch.equal(a_, b_)
+    # stale announcement: the version counter of Q moves, the copy must not be used
+    assert prefetch_inputs(*raw)
+    raw[1].mul_(1.5)
+    moved = run(False)
+    fresh = [t.clone().pin_memory() for t in raw]
+    ins = [t.detach().requires_grad_(j < 2) for j, t in enumerate(fresh)]
+    x = SolveBoxQP(control=box_qp_control(eps_rel=1e-5, eps_abs=1e-5)).forward(*ins)
+    assert torch.equal(moved[0], x.detach())
+    assert not torch.equal(moved[0], base[0])
+    _PREFETCH.clear()

@@ -6,20 +6,22 @@
 // :252-254 and the LU inside torch.linalg.solve, :393), but scheduled differently: round 1 ran pivot -> PANEL -> TRAIL as
 // 3 launches per block step and batch slice (48 launches per training step), every launch paying its own pipeline fill,
 // the pivot launches leaving 84 of 148 SMs idle and the slices competing for SMs.  Here CTA b owns problem b (b + grid,
-// ...) for all nb block steps: no grid-wide dependency is left, so there is ONE launch per factorisation and the
-// problem's tiles stay in the L2 slice traffic of one SM.
+// ...) for all nb block steps: no grid-wide dependency is left, so there is ONE launch per factorisation and a tile
+// product reads operands its own SM wrote moments before (L2 hits).  Measurements, and the shapes for which the
+// per-phase kernels stay the better form, are in DESIGN.md 5a; the dispatch is tc_sweep (tcfactor.cu).
 //
 // Inside the CTA (17 warps) a block step is
 //   pivot   all 17 warps: pivot8_body (tcmma.cuh) inverts M_kk on the FP32 pipe
 //   PANEL   W_i = M_ik P_k     } warp-specialised pipeline over the step's tile jobs:
 //   TRAIL   M_ij -= W_i V_j^T  }
-//     warps  8-15  staging : operand slabs (32 K-columns of X and Y) global -> registers (two slabs in flight per thread)
+//     warps  8-15  staging : operand slabs (32 K-columns of X and Y) global -> registers (one slab in flight per thread,
+//                            every register refilled with the next slab's data as soon as it has been stored)
 //                            -> hi / lo split -> K-major SWIZZLE_128B shared-memory stage (2 stages of 64 KB); PANEL
 //                            also writes the raw copy V_i
 //     warp   16    MMA     : one thread issues the 12 tcgen05.mma of a slab when its stage is full, tcgen05.commit frees
 //                            the stage; two accumulator sets in TMEM (2 x 256 columns: hi*hi | cross terms)
-//     warps  0-7   epilogue: TMEM -> registers -> swizzled shared tile -> coalesced global stores; TRAIL holds the C tile
-//                            of its NEXT job in registers (fetched while the current job's MMAs run)
+//     warps  0-7   epilogue: TMEM -> registers -> swizzled shared tile -> coalesced global stores; TRAIL fetches the first
+//                            half of its C tile into registers while the job's MMAs run, the second while it stores the first
 //   so the split of job j + 1, the MMAs of job j and the write-back of job j - 1 overlap.  Stage hand-over is by
 //   mbarriers (full / empty per stage, accfull / accempty per accumulator set); phases are separated by __syncthreads,
 //   which is also what orders a phase's global writes before the next phase's reads (same CTA; operands are read with

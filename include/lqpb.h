@@ -241,7 +241,12 @@ int lqpb_backward_finish_f64(int B, int n, int m, int kkt, const double* dl_dz, 
  * copy stream have drained (the host buffers are valid on return).  forward_host can prepare the backward like
  * lqpb_forward_prep_* (bwd_workspace may be NULL: no preparation; *prepared tells whether it happened), and
  * backward_host with prepared != 0 then runs only the substitution and the gradient assembly per chunk on that
- * workspace, so the first dQ rows start their trip to the host without waiting for a factorisation. */
+ * workspace, so the first dQ rows start their trip to the host without waiting for a factorisation.
+ * Overlapping the NEXT batch's upload with this batch's gradient download (PCIe is full duplex): h_dl_dz may also be a
+ * DEVICE pointer (it is copied with cudaMemcpyDefault).  The H2D copy engine serves its queue in submission order, so a
+ * caller that wants the overlap uploads dl_dz itself, THEN enqueues the next batch's cudaMemcpyAsync(s) on a stream of
+ * its own, THEN calls backward_host with the device copy of dl_dz, and gives the next lqpb_forward_prep_* the device
+ * buffers once its copy event has completed (lqp_py_b200.solve_box_qp_admm_torch.prefetch_inputs does exactly this). */
 int lqpb_forward_host_f32(const lqpb_config* cfg, int B, int n, int m, const float* hQ, const float* hp,
                           const float* hA, const float* hb, const float* hlb, const float* hub, float* Q,
                           float* p, float* A, float* b, float* lb, float* ub, float* x, float* z, float* u,

@@ -832,8 +832,14 @@ def run_e2e(cx, a, host_sets, dtype, K, W):
     cd = cx.max_over_ranks(cd)
     log(f"e2e done: {dt / Ke * 1e3:.3f} ms per step with the next batch announced, {dt_serial / Ke * 1e3:.3f} ms without "
         f"(copy ceilings: {ct / Ke * 1e3:.3f} ms serial, {cd / Ke * 1e3:.3f} ms duplex)")
-    return {"value": B * world * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": Ke, "ms_per_step": dt / Ke * 1e3, "host_wall_ms_per_step": wall / Ke * 1e3,
+    # the headline is the loop a user would run: with the next batch announced where that pays (it does until the host
+    # memory system is the limit -- at 8 ranks per host both forms sit on the same ceiling), else without; both are reported
+    announced = dt <= dt_serial
+    best = dt if announced else dt_serial
+    return {"value": B * world * Ke / best, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": Ke, "ms_per_step": best / Ke * 1e3, "host_wall_ms_per_step": wall / Ke * 1e3,
+            "mode": "next batch announced (SolveBoxQP.prefetch)" if announced else "unannounced",
+            "with_prefetch": {"value": B * world * Ke / dt, "unit": UNIT, "ms_per_step": dt / Ke * 1e3},
             "copy_ceiling": {"ms_per_step": ct / Ke * 1e3, "value": B * world * Ke / ct, "unit": UNIT,
                              "gbs_per_gpu": (h2d + d2h) / (ct / Ke) / 1e9,
                              "how": "the step's H2D + D2H copies alone (same pinned buffers, same stream order, no "
@@ -841,15 +847,16 @@ def run_e2e(cx, a, host_sets, dtype, K, W):
             "copy_ceiling_duplex": {"ms_per_step": cd / Ke * 1e3, "value": B * world * Ke / cd, "unit": UNIT,
                                     "how": "the same copies with uploads and downloads on two streams (PCIe is full "
                                            "duplex); host wall clock around Ke steps, max over ranks"},
-            "frac_of_copy_ceiling": (cd / Ke) / (dt / Ke),
+            "frac_of_copy_ceiling": (cd / Ke) / (best / Ke),
             "without_prefetch": {"value": B * world * Ke / dt_serial, "unit": UNIT, "ms_per_step": dt_serial / Ke * 1e3,
                                  "frac_of_serial_copy_ceiling": (ct / Ke) / (dt_serial / Ke),
                                  "how": "the same loop without SolveBoxQP.prefetch: upload, solve, backward and download "
                                         "of a step strictly one after the other"},
             "how": "SolveBoxQP.forward + x.backward on pinned CPU tensors (Q, p require grad as in "
-                   "experiments/utils.py:41-50; x, dQ, dp come back to the host), the next step's inputs announced with "
-                   "SolveBoxQP.prefetch between forward and backward (their upload overlaps this step's gradient "
-                   "download); every step's H2D and D2H copies are inside the timed region"}
+                   "experiments/utils.py:41-50; x, dQ, dp come back to the host); measured twice -- with the next step's "
+                   "inputs announced through SolveBoxQP.prefetch between forward and backward (their upload overlaps this "
+                   "step's gradient download) and without -- `value` is the faster of the two (`mode`); every step's H2D "
+                   "and D2H copies are inside the timed region either way"}
 
 
 def run_configs(cx, a, peaks, hbm_peak):

@@ -55,6 +55,17 @@ class SolveBoxQP(nn.Module):
         while the GPU and the PCIe downlink are busy with the current one."""
         return prefetch_inputs(Q, p, A, b, lb, ub)
 
+    def solve_ahead(self, Q, p, A, b, lb, ub, requires_grad=True):
+        """Addition to the reference's API: announce a batch like :meth:`prefetch` AND let the layer solve it with this
+        module's control as soon as its upload has landed (a worker thread and a second stream: the solve of step k + 1
+        runs while step k's gradients still travel to the host).  The later ``forward`` on the same, unmodified tensors
+        with an unchanged control returns the finished solution; anything else falls back to the prefetched / plain
+        path.  ``requires_grad``: also queue the dl_dz-independent part of the backward (as ``forward`` does for leaves
+        that require grad)."""
+        if self.control.get('unroll', False):
+            return prefetch_inputs(Q, p, A, b, lb, ub)
+        return prefetch_inputs(Q, p, A, b, lb, ub, control=self.control, requires_grad=requires_grad)
+
 
 class SolveBoxQPLayer(torch.autograd.Function):
     """ADMM forward solve + implicit (fixed-point) backward (reference :21-67)."""
@@ -66,7 +77,10 @@ class SolveBoxQPLayer(torch.autograd.Function):
         # whatever preceded this call: the backward then starts launching as soon as autograd reaches it
         ctx.pre = None
         prep = None
-        if not p.is_cuda and any(ctx.needs_input_grad[:6]) and _all_on_host((Q, p, A, b, lb, ub)) and torch.cuda.is_available():
+        ahead = _take_solved_ahead((Q, p, A, b, lb, ub), control, any(ctx.needs_input_grad[:6])) if _PREFETCH else None
+        if ahead is not None:
+            sol, ctx.pre = ahead
+        elif not p.is_cuda and any(ctx.needs_input_grad[:6]) and _all_on_host((Q, p, A, b, lb, ub)) and torch.cuda.is_available():
             # host callers: only the workspace is needed here (their gradient buffers are pinned host memory)
             L = _abi.lib()
             dev = _cuda_device(p)
@@ -79,7 +93,8 @@ class SolveBoxQPLayer(torch.autograd.Function):
             # system) is queued right behind the solve by the same C call (lqpb_forward_prep_*): the GPU works through
             # it while Python travels from here to .backward()
             prep = dict(ws=ctx.pre["ws"], kkt=control.get('backward', 'fixed_point') == 'kkt')
-        sol = _solve_device(Q, p, A, b, lb, ub, control, host_keys=("x",), prep=prep, allow_async=True)
+        if ahead is None:
+            sol = _solve_device(Q, p, A, b, lb, ub, control, host_keys=("x",), prep=prep, allow_async=True)
         ctx.prepared = bool(sol.get("_prepared", False))
         # reference :33-38 -- with no finite bound the caller's dict is switched to rho = 0
         if not (sol["_any_lb"] or sol["_any_ub"]):
@@ -232,7 +247,7 @@ def _prefetch_key(tensors):
     return tuple(None if t is None else (t.data_ptr(), tuple(t.shape), t.dtype, t._version) for t in tensors)
 
 
-def prefetch_inputs(Q, p, A, b, lb, ub):
+def prefetch_inputs(Q, p, A, b, lb, ub, control=None, requires_grad=True):
     """Announce a batch of host tensors that a LATER ``SolveBoxQP.forward`` / ``torch_solve_box_qp`` call will be given
     (the same tensor objects, unmodified in between), so that its host -> device copy can overlap the work in flight.
     The reference's callers hold CPU tensors, so a training step moves ``Q`` up and ``dQ`` down over PCIe; the link is
@@ -245,7 +260,15 @@ def prefetch_inputs(Q, p, A, b, lb, ub):
     forward finds the device copies by the identity of the host tensors (data pointer, shape, dtype, version counter),
     waits for the copy's event on its own stream and takes the device-pointer path; a call on tensors that were never
     announced, or were modified since, uploads as before.  Pinned host memory is what makes the copy asynchronous.
-    Returns True when the batch was registered (CPU tensors and a CUDA device), False otherwise."""
+    Returns True when the batch was registered (CPU tensors and a CUDA device), False otherwise.
+
+    With ``control`` (``SolveBoxQP.solve_ahead``) the batch is also SOLVED ahead of the call that asks for it: a worker
+    thread runs the forward (and, with ``requires_grad``, the dl_dz-independent part of the backward) on a second
+    stream behind the copy's event, so the kernels of step k + 1 run while step k's gradients are still on their way to
+    the host.  Announced two batches ahead, the H2D engine, the GPU and the D2H engine each work on a different step
+    and the loop runs at the pace of the slowest of the three.  The consuming forward checks the
+    identity of the tensors, the control dict (compared by value with a snapshot taken here) and whether gradients
+    are wanted; on any mismatch the solution is dropped and the call proceeds as if only the upload had been announced."""
     ts = (Q, p, A, b, lb, ub)
     if not _all_on_host(ts) or not torch.cuda.is_available():
         return False
@@ -257,7 +280,10 @@ def prefetch_inputs(Q, p, A, b, lb, ub):
         return True
     while len(_PREFETCH) >= 4:                       # announcements that were never used must not pile up
         _PREFETCH.pop(next(iter(_PREFETCH)))
-    _PREFETCH[key] = dict(dev=_cuda_device(p), tensors=None, event=None, hold=ts)   # `hold` keeps the host buffers alive
+    pf = _PREFETCH[key] = dict(dev=_cuda_device(p), tensors=None, event=None, hold=ts)   # `hold` keeps the host buffers alive
+    if control is not None and not any(torch.is_tensor(v) for v in control.values()):
+        pf["control"] = dict(control)                # snapshot: the consuming forward compares it with its own dict
+        pf["requires_grad"] = bool(requires_grad)
     return True
 
 
@@ -283,6 +309,65 @@ def _launch_prefetches():
                 ev = torch.cuda.Event()
                 ev.record(st)
         pf["tensors"], pf["event"] = dv, ev
+        if "control" in pf:
+            pf["future"] = _ahead_pool().submit(_solve_ahead, pf)
+
+
+_AHEAD_POOL = []
+_AHEAD_STREAM = {}
+
+
+def _ahead_pool():
+    if not _AHEAD_POOL:
+        from concurrent.futures import ThreadPoolExecutor
+        _AHEAD_POOL.append(ThreadPoolExecutor(max_workers=1, thread_name_prefix="lqpb-solve-ahead"))
+    return _AHEAD_POOL[0]
+
+
+def _solve_ahead(pf):
+    """Worker thread: the forward solve of an announced batch (what SolveBoxQPLayer.forward does for a host caller whose
+    tensors were prefetched) on the solve-ahead stream of the device, behind the event of the batch's upload."""
+    dev, dv, control = pf["dev"], pf["tensors"], pf["control"]
+    with torch.cuda.device(dev):
+        st = _AHEAD_STREAM.get(dev)
+        if st is None:
+            st = _AHEAD_STREAM[dev] = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            st.wait_event(pf["event"])
+            pre = prep = None
+            if pf["requires_grad"]:
+                pd = dv["p"]
+                nb_ws = _ws_bytes("backward", _abi.suffix(pd.dtype), dv["Q"].shape[0], pd.shape[1], get_ncon(dv["A"], dim=1))
+                pre = dict(ws=torch.empty(nb_ws, dtype=torch.uint8, device=dev), key=None)
+                prep = dict(ws=pre["ws"], kkt=control.get('backward', 'fixed_point') == 'kkt')
+            sol = _solve_device(dv["Q"], dv["p"], dv["A"], dv["b"], dv["lb"], dv["ub"], control, host_keys=(), prep=prep)
+            sol["x"] = _to_device_of(sol["_x_dev"], torch.device("cpu"))     # pinned, synchronised
+    return sol, pre
+
+
+def _take_solved_ahead(tensors, control, wants_grad):
+    """The finished forward of a batch announced through ``SolveBoxQP.solve_ahead`` -- ``(sol, pre)`` as
+    ``SolveBoxQPLayer.forward`` would have produced them -- or None (never announced, tensors modified since, another
+    control, gradients wanted but not prepared)."""
+    key = _prefetch_key(tensors)
+    pf = _PREFETCH.get(key)
+    if pf is None or "control" not in pf:
+        return None
+    if pf["event"] is None:
+        _launch_prefetches()                         # no backward came in between: copy and solve start now
+    sol, pre = pf.pop("future").result()             # (a failed solve raises here, in the caller's thread)
+    same = (not any(torch.is_tensor(v) for v in control.values())) and dict(control) == pf.pop("control")
+    if not same or (wants_grad and pre is None):
+        return None                                  # the entry stays: its device copies serve the prefetched path
+    _PREFETCH.pop(key)
+    # the solve's tensors were allocated in the solve-ahead stream's pool and are used on the caller's stream from here on
+    cur = torch.cuda.current_stream(pf["dev"])
+    held = [v for v in sol.values() if torch.is_tensor(v) and v.is_cuda] + [v for v in sol["_dev"].values() if v is not None]
+    if pre is not None:
+        held.append(pre["ws"])
+    for t in held:
+        t.record_stream(cur)
+    return sol, pre
 
 
 def _take_prefetched(tensors):
@@ -295,6 +380,9 @@ def _take_prefetched(tensors):
     if _PREFETCH[key]["event"] is None:
         _launch_prefetches()                         # no backward came in between: the copy starts now
     pf = _PREFETCH.pop(key)
+    fut = pf.pop("future", None)
+    if fut is not None:                              # a solve-ahead nobody took (e.g. torch_solve_box_qp called directly)
+        fut.result()
     torch.cuda.current_stream(pf["dev"]).wait_event(pf["event"])
     return pf["tensors"]
 

@@ -854,3 +854,66 @@ def test_prefetched_inputs_equal_the_host_path(dev):
     assert torch.equal(moved[0], x.detach())
     assert not torch.equal(moved[0], base[0])
     _PREFETCH.clear()
+
+
+def test_solve_ahead_equals_the_host_path(dev):
+    """SolveBoxQP.solve_ahead (upload + forward of announced batches on a worker thread and a second stream, two batches
+    in flight) must not change a single bit of x, dQ, dp; a control changed after the announcement, or a batch modified
+    since, must drop the speculated solution."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import SolveBoxQP, _PREFETCH
+    n, B = 300, 8
+    sets = [[t.pin_memory() for t in orc.make_exp1_data(n, B, seed=5 + k, dtype=torch.float32)] for k in range(4)]
+    g = torch.randn(B, n, 1, generator=torch.Generator().manual_seed(1)).pin_memory()
+    ctl = lambda **kw: box_qp_control(eps_rel=1e-5, eps_abs=1e-5, **kw)
+
+    def step(QP, raw):
+        ins = [t.detach().requires_grad_(j < 2) for j, t in enumerate(raw)]
+        x = QP.forward(*ins)
+        return x, ins
+
+    def finish(x, ins):
+        x.backward(g)
+        return x.detach().clone(), ins[0].grad.clone(), ins[1].grad.clone()
+    base = [finish(*step(SolveBoxQP(control=ctl()), raw)) for raw in sets]
+    for backward in ("fixed_point", "kkt"):
+        QP = SolveBoxQP(control=ctl(backward=backward))
+        ref = base if backward == "fixed_point" else [finish(*step(SolveBoxQP(control=ctl(backward="kkt")), raw)) for raw in sets]
+        # the loop of bench.py's e2e leg: two batches announced ahead, uploads / solves started by the backward
+        assert QP.solve_ahead(*sets[0]) and QP.solve_ahead(*sets[1])
+        out = []
+        for k in range(len(sets)):
+            x, ins = step(QP, sets[k])
+            if k + 2 < len(sets):
+                assert QP.solve_ahead(*sets[k + 2])
+            out.append(finish(x, ins))
+        assert not _PREFETCH, "an announced batch was not consumed"
+        for r_, o_ in zip(ref, out):
+            for a_, b_ in zip(r_, o_):
+                assert a_.device.type == "cpu" and torch.equal(a_, b_)
+    # another control at the consuming call: the speculated solution must not be used
+    QP = SolveBoxQP(control=ctl())
+    assert QP.solve_ahead(*sets[0])
+    QP.control['eps_abs'] = 1e-3
+    QP.control['eps_rel'] = 1e-3
+    x, ins = step(QP, sets[0])
+    loose = finish(x, ins)
+    want = finish(*step(SolveBoxQP(control=box_qp_control(eps_rel=1e-3, eps_abs=1e-3)), sets[0]))
+    assert torch.equal(loose[0], want[0]) and not torch.equal(loose[0], base[0][0])
+    assert not _PREFETCH
+    # a batch modified after the announcement is solved afresh
+    QP = SolveBoxQP(control=ctl())
+    assert QP.solve_ahead(*sets[1])
+    sets[1][1].mul_(1.5)
+    moved = finish(*step(QP, sets[1]))
+    fresh = [t.clone().pin_memory() for t in sets[1]]
+    want = finish(*step(SolveBoxQP(control=ctl()), fresh))
+    assert torch.equal(moved[0], want[0]) and not torch.equal(moved[0], base[1][0])
+    _PREFETCH.clear()
+    # no gradient wanted: nothing of the backward is prepared, the forward result is the same
+    QP = SolveBoxQP(control=ctl())
+    assert QP.solve_ahead(*sets[2], requires_grad=False)
+    with torch.no_grad():
+        x = QP.forward(*sets[2])
+    assert torch.equal(x, base[2][0])
+    assert not _PREFETCH

@@ -246,7 +246,8 @@ int lqpb_backward_finish_f64(int B, int n, int m, int kkt, const double* dl_dz, 
  * DEVICE pointer (it is copied with cudaMemcpyDefault).  The H2D copy engine serves its queue in submission order, so a
  * caller that wants the overlap uploads dl_dz itself, THEN enqueues the next batch's cudaMemcpyAsync(s) on a stream of
  * its own, THEN calls backward_host with the device copy of dl_dz, and gives the next lqpb_forward_prep_* the device
- * buffers once its copy event has completed (lqp_py_b200.solve_box_qp_admm_torch.prefetch_inputs does exactly this). */
+ * buffers once its copy event has completed (lqp_py_b200.solve_box_qp_admm_torch.prefetch_inputs does exactly this).
+ * h_dl_dz == dl_dz means "dl_dz is already in place" (no copy at all: e.g. brought up with lqpb_copy_mapped). */
 int lqpb_forward_host_f32(const lqpb_config* cfg, int B, int n, int m, const float* hQ, const float* hp,
                           const float* hA, const float* hb, const float* hlb, const float* hub, float* Q,
                           float* p, float* A, float* b, float* lb, float* ub, float* x, float* z, float* u,
@@ -410,6 +411,16 @@ int lqpb_dev_tc_inverse_f32(int B, int N, const float* A, float* Ainv, void* wor
  * buffer smaller than the L2 (and on one far larger) to measure the read-bandwidth ceilings the iteration kernel's
  * roofline is quoted against.  sink: 4 bytes of device memory (never written for real data). */
 int lqpb_dev_stream_read(const void* buf, size_t bytes, int reps, void* sink, void* stream);
+
+/* ---- small transfers beside the copy engines ----------------------------------------------------
+ * Copies `bytes` (a multiple of 4; both pointers 4-byte aligned) between a device buffer and PAGE-LOCKED host memory
+ * (cudaMallocHost / cudaHostAlloc / torch pin_memory: mapped into the device's address space under unified addressing)
+ * with a kernel on `stream` -- SM loads / stores over PCIe -- instead of a copy engine.  A copy engine finishes the
+ * transfer it has started before it serves the next one, so a caller that keeps both engines busy with 128 MB batches
+ * (next batch up, last gradients down: SolveBoxQP.solve_ahead) moves dl_dz, x and the control block this way; the
+ * library itself reads the control block at the end of every forward segment like this.  The host side of the data is
+ * valid once `stream` has reached the point after the call (event / stream synchronisation), as with cudaMemcpyAsync. */
+int lqpb_copy_mapped(void* dst, const void* src, size_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

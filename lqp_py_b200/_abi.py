@@ -35,6 +35,7 @@ EXPORTS = (
     "lqpb_lu_factor_f32", "lqpb_lu_factor_f64", "lqpb_lu_solve_f32", "lqpb_lu_solve_f64",
     "lqpb_outer_f32", "lqpb_outer_f64",
     "lqpb_dev_tc_inverse_work_bytes", "lqpb_dev_tc_inverse_f32", "lqpb_dev_stream_read",
+    "lqpb_copy_mapped",
 )
 
 
@@ -166,6 +167,7 @@ def lib():
     L.lqpb_dev_tc_inverse_work_bytes.argtypes, L.lqpb_dev_tc_inverse_work_bytes.restype = [i32, i32], sz
     L.lqpb_dev_tc_inverse_f32.argtypes, L.lqpb_dev_tc_inverse_f32.restype = [i32, i32, vp, vp, vp, vp], i32
     L.lqpb_dev_stream_read.argtypes, L.lqpb_dev_stream_read.restype = [vp, sz, i32, vp, vp], i32
+    L.lqpb_copy_mapped.argtypes, L.lqpb_copy_mapped.restype = [vp, vp, sz, vp], i32
     if L.lqpb_abi_version() != 1:
         raise ImportError("lqpb ABI version mismatch: rebuild with `python -m lqp_py_b200.build --force`")
     _lib = L

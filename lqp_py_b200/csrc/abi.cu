@@ -15,6 +15,7 @@ cudaError_t launch_lu_solve(int B, int N, int nrhs, const T* LU, const int32_t* 
                             cudaStream_t st);
 template <typename T>
 cudaError_t launch_outer(int B, int N, int M, const T* a, const T* b, T* C, cudaStream_t st);
+cudaError_t launch_mapped_copy(void* dst, const void* src, size_t bytes, cudaStream_t st);   // hostio.cu
 }  // namespace lqpb
 
 using namespace lqpb;
@@ -473,7 +474,10 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
     CK(launch_finalize<T>(w, x, z, u, lams, rho_out, st), "finalize");
     if (prof) cudaEventRecord(g_prof.ev[3], st);
     g_prof.launches += 2;
-    CK(cudaMemcpyAsync(hc, w.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st), "copy ctrl");
+    // (the control block travels as SM stores into the page-locked buffer, not through the D2H copy engine: that engine
+    // may be in the middle of another call's 128 MB of gradients -- solve-ahead, DESIGN.md 4a -- and would hold the
+    // end of this solve up until it is through)
+    CK(launch_mapped_copy(hc, w.ctrl, sizeof(Ctrl), st), "copy ctrl");
     if (host && host->x)     // wasted (and overwritten later) only in the rare segment that ends in a refactorisation
       CK(cudaMemcpyAsync(host->x, x, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToHost, st), "D2H x");
     if (prep) {
@@ -570,7 +574,8 @@ int backward_impl(int B, int n, int m, const T* dl_dz, const T* x, const T* u, c
     cs = g_pipe.cs;
     // cudaMemcpyDefault: the "host" dl_dz may already be a device copy (a caller that uploaded it itself so that its own
     // H2D traffic -- e.g. the prefetch of the next batch -- is ordered behind it); the copy engine serves H2D in order
-    CK(cudaMemcpyAsync((void*)dl_dz, host->dl_dz, (size_t)B * n * sizeof(T), cudaMemcpyDefault, st), "H2D dl_dz");
+    if (host->dl_dz != dl_dz)
+      CK(cudaMemcpyAsync((void*)dl_dz, host->dl_dz, (size_t)B * n * sizeof(T), cudaMemcpyDefault, st), "H2D dl_dz");
   }
   for (int c = 0; c < C; ++c) {
     const int b0 = chunk_lo(B, C, c), bc = chunk_lo(B, C, c + 1) - b0;

@@ -341,7 +341,14 @@ def _solve_ahead(pf):
                 pre = dict(ws=torch.empty(nb_ws, dtype=torch.uint8, device=dev), key=None)
                 prep = dict(ws=pre["ws"], kkt=control.get('backward', 'fixed_point') == 'kkt')
             sol = _solve_device(dv["Q"], dv["p"], dv["A"], dv["b"], dv["lb"], dv["ub"], control, host_keys=(), prep=prep)
-            sol["x"] = _to_device_of(sol["_x_dev"], torch.device("cpu"))     # pinned, synchronised
+            # x goes to the host as SM stores into page-locked memory (lqpb_copy_mapped), not through the D2H copy engine:
+            # that engine is in the middle of the previous batch's gradients and would hold this solve up to their end
+            xd = sol["_x_dev"]
+            hx = torch.empty(xd.shape, dtype=xd.dtype, pin_memory=True)
+            _abi.check(_abi.lib().lqpb_copy_mapped(_abi.ptr(hx), _abi.ptr(xd), xd.numel() * xd.element_size(),
+                                                   C.c_void_p(_raw_stream(dev))), "lqpb_copy_mapped")
+            st.synchronize()
+            sol["x"] = hx
     return sol, pre
 
 
@@ -1260,9 +1267,18 @@ def _grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, kkt, any_bounds,
         g_src = g
         if _PREFETCH:
             # a batch is announced: dl_dz goes up FIRST (the H2D engine serves its queue in order), then the announced
-            # copies start, and the C call below is handed the device copy of dl_dz
-            g_src = torch.empty((B, n, 1), dtype=dt, device=dev)
-            g_src.copy_(g.reshape(B, n, 1), non_blocking=True)
+            # copies start, and the C call below is handed the device copy of dl_dz.  With batches solved ahead the H2D
+            # engine may still be busy with the batch announced a step ago: dl_dz is then read by a kernel straight from
+            # page-locked memory (lqpb_copy_mapped) and never meets the engine's queue
+            if any("control" in pf for pf in _PREFETCH.values()):
+                gp = g if g.is_pinned() else torch.empty(g.shape, dtype=dt, pin_memory=True).copy_(g)
+                _abi.check(L.lqpb_copy_mapped(_abi.ptr(g_dev), _abi.ptr(gp), gp.numel() * gp.element_size(),
+                                              C.c_void_p(_raw_stream(dev))), "lqpb_copy_mapped")
+                g_src = g_dev                        # "already in place"
+                keep_alive = gp
+            else:
+                g_src = torch.empty((B, n, 1), dtype=dt, device=dev)
+                g_src.copy_(g.reshape(B, n, 1), non_blocking=True)
             _launch_prefetches()
         ws_bytes = _ws_bytes("backward", sfx, B, n, m)
         ws = prepared_ws if prepared_ws is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

@@ -478,6 +478,7 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
     // may be in the middle of another call's 128 MB of gradients -- solve-ahead, DESIGN.md 4a -- and would hold the
     // end of this solve up until it is through)
     CK(launch_mapped_copy(hc, w.ctrl, sizeof(Ctrl), st), "copy ctrl");
+    g_prof.launches += 1;
     if (host && host->x)     // wasted (and overwritten later) only in the rare segment that ends in a refactorisation
       CK(cudaMemcpyAsync(host->x, x, (size_t)B * n * sizeof(T), cudaMemcpyDeviceToHost, st), "D2H x");
     if (prep) {

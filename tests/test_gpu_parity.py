@@ -917,3 +917,23 @@ def test_solve_ahead_equals_the_host_path(dev):
         x = QP.forward(*sets[2])
     assert torch.equal(x, base[2][0])
     assert not _PREFETCH
+    # the other factorisation paths: fp64 blocked sweep (n + m > 128) and the small-problem path (no prepared backward)
+    for n2, dt in ((200, torch.float64), (40, torch.float64), (40, torch.float32)):
+        sets2 = [[t.pin_memory() for t in orc.make_exp1_data(n2, B, seed=11 + k, dtype=dt)] for k in range(3)]
+        g2 = torch.randn(B, n2, 1, generator=torch.Generator().manual_seed(2), dtype=dt).pin_memory()
+
+        def run2(QP, raw, ahead):
+            ins = [t.detach().requires_grad_(j < 2) for j, t in enumerate(raw)]
+            x = QP.forward(*ins)
+            if ahead is not None:
+                assert QP.solve_ahead(*ahead)
+            x.backward(g2)
+            return x.detach().clone(), ins[0].grad.clone(), ins[1].grad.clone()
+        ref2 = [run2(SolveBoxQP(control=ctl()), raw, None) for raw in sets2]
+        QP = SolveBoxQP(control=ctl())
+        assert QP.solve_ahead(*sets2[0]) and QP.solve_ahead(*sets2[1])
+        out2 = [run2(QP, sets2[k], sets2[k + 2] if k + 2 < len(sets2) else None) for k in range(len(sets2))]
+        assert not _PREFETCH
+        for r_, o_ in zip(ref2, out2):
+            for a_, b_ in zip(r_, o_):
+                assert torch.equal(a_, b_), (n2, dt)

@@ -937,3 +937,37 @@ def test_solve_ahead_equals_the_host_path(dev):
         for r_, o_ in zip(ref2, out2):
             for a_, b_ in zip(r_, o_):
                 assert torch.equal(a_, b_), (n2, dt)
+
+
+def test_pageable_inputs_are_staged_bit_identically(dev):
+    """Ordinary (pageable) CPU tensors -- what the reference's callers hold -- are uploaded through page-locked staging
+    memory (caller's thread for a plain call, worker thread for announced batches); x, dQ, dp must equal the page-locked
+    run bit for bit in the plain, prefetched and solved-ahead forms."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200 import solve_box_qp_admm_torch as M
+    n, B = 300, 16
+    raw = [orc.make_exp1_data(n, B, seed=21 + k, dtype=torch.float32) for k in range(3)]
+    assert M._needs_staging(raw[0][0]) and not M._needs_staging(raw[0][0].pin_memory())
+    g = torch.randn(B, n, 1, generator=torch.Generator().manual_seed(3))
+    ctl = lambda: box_qp_control(eps_rel=1e-5, eps_abs=1e-5)
+
+    def run(QP, ts, announce=None):
+        ins = [t.detach().requires_grad_(j < 2) for j, t in enumerate(ts)]
+        x = QP.forward(*ins)
+        if announce is not None:
+            announce()
+        x.backward(g)
+        return x.detach().clone(), ins[0].grad.clone(), ins[1].grad.clone()
+    want = [run(M.SolveBoxQP(control=ctl()), [t.pin_memory() for t in ts]) for ts in raw]
+    plain = [run(M.SolveBoxQP(control=ctl()), ts) for ts in raw]
+    QP = M.SolveBoxQP(control=ctl())
+    pre = [run(QP, raw[k], (lambda k=k: QP.prefetch(*raw[k + 1])) if k + 1 < len(raw) else None) for k in range(len(raw))]
+    assert not M._PREFETCH
+    QP = M.SolveBoxQP(control=ctl())
+    assert QP.solve_ahead(*raw[0]) and QP.solve_ahead(*raw[1])
+    ahead = [run(QP, raw[k], (lambda k=k: QP.solve_ahead(*raw[k + 2])) if k + 2 < len(raw) else None) for k in range(len(raw))]
+    assert not M._PREFETCH
+    for got in (plain, pre, ahead):
+        for w_, g_ in zip(want, got):
+            for a_, b_ in zip(w_, g_):
+                assert a_.device.type == "cpu" and torch.equal(a_, b_)

@@ -565,7 +565,8 @@ def source_digest():
     return h.hexdigest()[:16]
 
 
-REGIMES = {0: "stream", 1: "packed-resident", 2: "dense-rows", 3: "fused dense-rows (one-launch forward)"}
+REGIMES = {0: "stream", 1: "packed-resident", 2: "dense-rows", 3: "fused dense-rows (one-launch forward)",
+           4: "stream, every problem split over a cluster of 2 / 4 CTAs (small batches)"}
 
 
 def iterate_regime(n, B, dtype_name):
@@ -624,7 +625,8 @@ def iterate_roofline(n, B, s, it, it_ms, peaks, hbm_peak, dtype_name):
                 "peak": None, "unit": "GB/s", "frac": None, "traffic": None, "bytes_per_launch": alg_launch,
                 "ms_per_launch": it_ms, "admm_passes": passes, "checks": checks,
                 "us_per_admm_iteration": it_ms * 1e3 / passes, "note": note}
-    out = {"kernel": "iterate_kernel", "regime": REGIMES.get(regime), "bound": bound, "achieved": achieved,
+    out = {"kernel": "iterate_split_kernel" if regime == 4 else "iterate_kernel", "regime": REGIMES.get(regime),
+           "bound": bound, "achieved": achieved,
            "peak": None if no_l2_peak else peak, "unit": "GB/s",
            "frac": None if no_l2_peak else achieved / peak, "achieved_moved": moved,
            "frac_moved": None if no_l2_peak else moved / peak,

@@ -153,7 +153,8 @@ int lqpb_forward_collect(const void* pinned_ctrl, const lqpb_config* cfg, lqpb_i
 /* Which iteration kernel a forward solve of this shape takes on the current device (SURVEY App. C regimes; needs a CUDA
  * device): the x-update operator streamed from L2 / HBM every iteration, held in shared memory as packed tiles, held in
  * shared memory as dense matrices, or the latter inside the one-launch forward.  -1: no sm_100 device. */
-enum { LQPB_REGIME_STREAM = 0, LQPB_REGIME_PACKED_RESIDENT = 1, LQPB_REGIME_ROWS = 2, LQPB_REGIME_FUSED_ROWS = 3 };
+enum { LQPB_REGIME_STREAM = 0, LQPB_REGIME_PACKED_RESIDENT = 1, LQPB_REGIME_ROWS = 2, LQPB_REGIME_FUSED_ROWS = 3,
+       LQPB_REGIME_STREAM_SPLIT = 4 /* streamed, every problem split over a cluster of 2 or 4 CTAs (small batches) */ };
 int lqpb_iterate_regime_f32(const lqpb_config* cfg, int B, int n, int m);
 int lqpb_iterate_regime_f64(const lqpb_config* cfg, int B, int n, int m);
 int lqpb_solution_status_f32(const lqpb_config* cfg, int B, int n, int m, void* workspace, size_t workspace_bytes,

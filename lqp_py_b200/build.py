@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "_lqpb.so")
 STAMP = os.path.join(PKG, "_lqpb.stamp")
-SOURCES = ["abi.cu", "scale.cu", "factor.cu", "tcfactor.cu", "tcfused.cu", "f64block.cu", "iterate.cu", "iterate_res.cu", "iterate_row.cu", "unroll.cu", "backward.cu", "lu.cu", "devtools.cu", "hostio.cu"]
+SOURCES = ["abi.cu", "scale.cu", "factor.cu", "tcfactor.cu", "tcfused.cu", "f64block.cu", "iterate.cu", "iterate_split.cu", "iterate_res.cu", "iterate_row.cu", "unroll.cu", "backward.cu", "lu.cu", "devtools.cu", "hostio.cu"]
 HEADERS = ["common.cuh", "layout.cuh", "itergeom.cuh", "tcmma.cuh", os.path.join("..", "..", "include", "lqpb.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-warn-spills"]

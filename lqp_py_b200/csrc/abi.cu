@@ -16,6 +16,8 @@ cudaError_t launch_lu_solve(int B, int N, int nrhs, const T* LU, const int32_t* 
 template <typename T>
 cudaError_t launch_outer(int B, int N, int M, const T* a, const T* b, T* C, cudaStream_t st);
 cudaError_t launch_mapped_copy(void* dst, const void* src, size_t bytes, cudaStream_t st);   // hostio.cu
+template <typename T>
+int iterate_split_size(const FwdWs<T>& w);                                                    // iterate_split.cu
 }  // namespace lqpb
 
 using namespace lqpb;
@@ -846,6 +848,7 @@ size_t lqpb_ctrl_bytes(void) { return sizeof(Ctrl); }
     if (cfg->keep_operators == 0 && forward_fused_applies<T>(*cfg, w)) return LQPB_REGIME_FUSED_ROWS;      \
     if (iterate_rows_applies<T>(*cfg, w)) return LQPB_REGIME_ROWS;                                         \
     if (iterate_resident_applies<T>(*cfg, w)) return LQPB_REGIME_PACKED_RESIDENT;                          \
+    if (iterate_split_size<T>(w) > 0) return LQPB_REGIME_STREAM_SPLIT;                                     \
     return LQPB_REGIME_STREAM;                                                                             \
   }
 REGIME_ENTRY(f32, float)

@@ -479,6 +479,10 @@ bool plan_resident(const FwdWs<T>& w, const lqpb_config& cfg, int max_smem, int 
 }
 
 template <typename T>
+cudaError_t launch_iterate_split(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
+                                 int* launches, cudaStream_t st, bool* taken);      // iterate_split.cu
+
+template <typename T>
 cudaError_t launch_iterate_resident(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
                                     int* launches, cudaStream_t st, bool* taken) {
   *taken = false;
@@ -493,7 +497,8 @@ cudaError_t launch_iterate_resident(const lqpb_config& cfg, const FwdWs<T>& w, i
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   ResGeom geo{};
   size_t smem = 0;
-  if (!plan_resident(w, cfg, max_smem - 2048, sms, &geo, &smem)) return cudaSuccess;
+  if (!plan_resident(w, cfg, max_smem - 2048, sms, &geo, &smem))      // streamed regime: small batches split every
+    return launch_iterate_split<T>(cfg, w, i0, skip_rho_check, nus_out, launches, st, taken);   // problem over a cluster
   e = cudaMemsetAsync(&w.ctrl->barrier, 0, sizeof(unsigned), st);
   if (e != cudaSuccess) return e;
   void* kern = (void*)iterate_res_kernel<T>;

@@ -1,0 +1,510 @@
+// K3, streamed regime, SMALL BATCHES: the ADMM iteration kernel of iterate.cu with every problem split over a thread-block
+// cluster of CS = 2 or 4 CTAs.
+//
+// Why: one CTA per problem (iterate.cu) is bound by what ONE SM can pull and apply -- the loop takes 0.526 ms for 32
+// problems and 0.549 ms for 128 at dz = 500 -- so a batch of 32 (the mini-batch of the reference's Experiment 2,
+// experiments/experiment_2.py:52-99) leaves 116 of 148 SMs idle for the whole solve.  Here the tile sequence of a matrix
+// is cut into CS x nwarps runs instead of nwarps: CTA `crank` of the cluster streams and applies its share through the
+// same per-warp bulk-TMA rings, reduces its warps' partial sums in a fixed order into a shared-memory vector, and after ONE
+// hardware cluster barrier per pass every CTA adds the CS shares (its own and its peers' through distributed shared
+// memory, in rank order) -- so all CTAs of a cluster hold bit-identical x~, z, u and next right-hand side and run the O(n)
+// vector phase redundantly; z and u live in shared memory for the whole solve and only the rank-0 CTA writes the problem's
+// state, stop-check record and flags to global memory.  Same loop, decisions and global stop semantics as iterate.cu
+// (reference lqp_py/solve_box_qp_admm_torch.py:235-313, :327); the rounding differs from the unsplit kernel only through
+// the grouping of the partial sums.  Chosen by launch_iterate_split when B x 4 CTAs are co-resident as clusters (cooperative
+// cluster launch: the grid barrier of the stop checks needs all of them), i.e. B <= 37 on a B200; LQPB_ITER_SPLIT=0
+// switches it off, =2 / =4 force a cluster size (B x 2 <= #SMs).
+#include <cstring>
+#include "itergeom.cuh"
+
+namespace lqpb {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// hardware barrier over all threads of the cluster (release / acquire: shared-memory writes before it are visible to the
+// peers' distributed-shared-memory reads after it)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_cluster(const float* local, int rank) {
+  uint32_t ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_cluster(const double* local, int rank) {
+  uint32_t ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kIterMaxThreads, 1)
+iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, IterGeom geo, int CS) {
+  constexpr bool TAPE = false;
+  Tape<T> tape{};
+  using P = Pack<T>;
+  constexpr int TC = P::TC, TILE = P::TILE;
+  using V4 = typename Vec<T>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int n = w.n, m = w.m, ld = w.ld, np = geo.np;
+  const int nthreads = blockDim.x, nwarps = geo.nwarps, depth = geo.depth;
+  const int ntv = geo.nt, ntiles = geo.ntiles;
+  T* ring = reinterpret_cast<T*>(smem_raw);                 // [nwarps][depth][TILE]
+  T* xpart = ring + (size_t)nwarps * depth * TILE;          // [nwarps][np] per-warp partial sums of K v
+  T* v = xpart + (size_t)nwarps * np;                       // [np] rhs of the x-update (zero padded)
+  T* xs = v + np;                                           // [np] x~ of this iteration (zero padded)
+  T* Ds = xs + np;                                          // [np] D
+  T* tdot = Ds + np;                                        // [max(m,1)] K21 rhs
+  T* red = tdot + (m > 0 ? round_up(m, 4) : 4);             // [6][16] reduction scratch
+  T* xloc = red + 6 * 16 + 4;                               // [2][np] this CTA's share of K v / Q~ x~ (double-buffered: peers read it)
+  T* zs = xloc + 2 * np;                                    // [np] z (every CTA of the cluster keeps the whole state)
+  T* us = zs + np;                                          // [np] u
+  uint64_t* full = reinterpret_cast<uint64_t*>(us + np);    // [nwarps][depth]
+  __shared__ int s_dec[4];
+  const int crank = (int)cluster_ctarank();                 // which share of the problem's tiles this CTA streams
+  const int prob = (int)blockIdx.x / CS;                    // the ONE problem of this cluster
+  const bool lead = crank == 0;                             // the CTA that writes the problem's state and flags
+  int xbuf = 0;
+
+  const int tid = threadIdx.x;
+  const int wid = tid >> 5, lane = tid & 31;
+  constexpr int nprob = 1;
+  Ctrl* ctrl = w.ctrl;
+
+  if (tid == 0) {
+    for (int s = 0; s < nwarps * depth; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  for (int e = tid; e < nwarps * np; e += nthreads) xpart[e] = T(0);
+  for (int e = tid; e < np; e += nthreads) {
+    v[e] = T(0); xs[e] = T(0); Ds[e] = T(1);
+    xloc[e] = T(0); xloc[np + e] = T(0);
+    const bool in = e < n;
+    zs[e] = in ? w.z[(size_t)prob * ld + e] : T(0);
+    us[e] = in ? w.u[(size_t)prob * ld + e] : T(0);
+  }
+  __syncthreads();
+  // a CTA's shared memory may only be read by its peers once it has started executing and initialised it
+  cluster_sync_all();
+
+  const bool any_lb = ctrl->any_lb != 0, any_ub = ctrl->any_ub != 0;
+  int last_wants = ctrl->last_wants, last_rout = ctrl->last_ratio_out;
+  const int check = cfg.check_solved;
+  const T eps_abs = (T)cfg.eps_abs, eps_rel = (T)cfg.eps_rel, zc = (T)cfg.zero_clamp;
+  const T thr = (T)cfg.adaptive_rho_threshold, ar_tol = (T)cfg.adaptive_rho_tol, ar_tol_inv = (T)(1.0 / cfg.adaptive_rho_tol);
+
+  // ---- this warp's run of tiles (the same for every matrix) and the tile it starts with
+  const int gwid = crank * nwarps + wid, gwarps = CS * nwarps;
+  const int run_lo = (int)((long long)gwid * ntiles / gwarps);
+  const int run_len = (int)((long long)(gwid + 1) * ntiles / gwarps) - run_lo;
+  int Jc_first = 0, I_first = 0;
+  {
+    int rem = run_lo;
+    while (Jc_first < geo.nbc && rem >= ntv - Jc_first / P::R) { rem -= ntv - Jc_first / P::R; ++Jc_first; }
+    I_first = Jc_first / P::R + rem;
+  }
+  T* const ring_w = ring + (size_t)wid * depth * TILE;
+  uint64_t* const full_w = full + wid * depth;
+  T* const xp = xpart + (size_t)wid * np;
+
+  // ---- the warp's tile stream: position of the next tile to fetch (p_*) and ring bookkeeping.  The stream
+  //      is  for i: for problem k: K11 run, then (check iterations) Q~ run;  it is fetched `depth` tiles ahead.
+  int p_i = i0, p_k = 0, p_pass = 0, p_r = 0, p_slot = 0;
+  int c_slot = 0;
+  uint32_t c_phase = 0;
+  int in_flight = 0;
+  uint64_t pol_keep = 0, pol_stream = 0;
+  if (lane == 0) { pol_keep = l2_policy_evict_last(); pol_stream = l2_policy_evict_first(); }
+  auto issue_next = [&]() {
+    if (run_len == 0 || p_i >= cfg.max_iters) return;
+    if (lane == 0) {
+      const int b = prob;
+      const T* src = (p_pass == 0 ? w.Kp : w.Qp) + ((size_t)b * ntiles + run_lo + p_r) * TILE;
+      mbar_arrive_expect_tx(&full_w[p_slot], (uint32_t)(TILE * sizeof(T)));
+      tma_load_1d_hint(ring_w + (size_t)p_slot * TILE, src, (uint32_t)(TILE * sizeof(T)), &full_w[p_slot],
+                       p_pass == 0 ? pol_keep : pol_stream);
+    }
+    ++in_flight;
+    if (++p_slot == depth) p_slot = 0;
+    if (++p_r == run_len) {
+      p_r = 0;
+      if (++p_pass == ((p_i % check) == 0 ? 2 : 1)) {
+        p_pass = 0;
+        if (++p_k == nprob) { p_k = 0; ++p_i; }
+      }
+    }
+  };
+  for (int d = 0; d < depth; ++d) issue_next();
+
+  // ---- one symmetric pass over the warp's run:  xp += (this warp's share of)  S vec,  S = K11 or Q~
+  auto sym_pass = [&](const T* vec) {
+    if (run_len == 0) return;
+    int Jc = Jc_first, I = I_first;
+    SymAcc<T> sa;
+    auto flush_cols = [&]() {
+      const T tot = sa.reduce(lane);
+      __syncwarp();
+      if (lane < TC) xp[Jc * TC + lane] += tot;
+      __syncwarp();
+    };
+    sa.load_vJ(vec + Jc * TC);
+    auto load_vJ = [&]() { sa.load_vJ(vec + Jc * TC); };
+    bool dirty = false;
+    for (int r = 0; r < run_len; ++r) {
+      mbar_wait(&full_w[c_slot], c_phase);
+      const T* tp = ring_w + (size_t)c_slot * TILE;
+      V4 kv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) kv[k] = *reinterpret_cast<const V4*>(tp + P::in_tile(lane, k));
+      const T vI = vec[I * kPackRows + lane];
+      xp[I * kPackRows + lane] += sa.apply(kv, vI);
+      __syncwarp();                       // every lane has consumed the slot: it can be re-armed
+      if (++c_slot == depth) { c_slot = 0; c_phase ^= 1u; }
+      --in_flight;
+      issue_next();
+      dirty = true;
+      if (++I == ntv) {
+        flush_cols();
+        dirty = false;
+        ++Jc;
+        I = Jc / P::R;
+        if (r + 1 < run_len) load_vJ();
+      }
+    }
+    if (dirty) flush_cols();
+  };
+
+  bool have_v = false;      // v already holds the rhs of this iteration (single-problem CTAs)
+  int i = i0;
+  int status = 0;
+  unsigned barrier_epoch = 0;
+
+  while (true) {
+    // ---------------- adaptive rho (:237-256): decided from the previous check, applied before iteration i
+    if (cfg.adaptive_rho && i > 0 && i < cfg.adaptive_rho_max_iter && (i % cfg.adaptive_rho_iter) == 0 &&
+        !(i == i0 && skip_rho_check)) {
+      if (last_wants && last_rout) {
+        for (int k = tid; k < nprob; k += nthreads) {
+          const int b = prob;
+          if (lead && w.wants[b]) {
+            T r = w.rho[b] * w.ratio[b];
+            r = t_min(t_max(r, (T)cfg.rho_min), (T)cfg.rho_max);
+            w.rho[b] = r;
+          }
+        }
+        status = 3;
+        break;
+      }
+    }
+    const bool is_check = (i % check) == 0;
+    const bool is_last = i == cfg.max_iters - 1;
+    const bool maybe_final = TAPE || is_check || is_last;
+
+    int cta_notopt = 0, cta_wants = 0, cta_rout = 0, cta_bad = 0;
+    for (int k = 0; k < nprob; ++k) {
+      const int b = prob;
+      const size_t vo = (size_t)b * ld;
+      const T rho = w.rho[b];
+      if (!have_v) {
+        for (int e = tid; e < n; e += nthreads) v[e] = -w.pt[vo + e] + rho * (zs[e] - us[e]);
+        __syncthreads();
+      }
+      // ---- x~ = K11 v (+ c below): symmetric sweep over the packed tiles
+      sym_pass(v);
+      __syncthreads();
+      // this CTA's share of K11 v in a fixed order, published to the cluster
+      for (int e = tid; e < np; e += nthreads) {
+        T a = T(0);
+        for (int ww = 0; ww < nwarps; ++ww) {
+          a += xpart[(size_t)ww * np + e];
+          xpart[(size_t)ww * np + e] = T(0);
+        }
+        xloc[xbuf * np + e] = a;
+      }
+      cluster_sync_all();
+      // ---- K21 rhs for nu (:327), from the rhs of THIS solve (before v is overwritten)
+      if (maybe_final && m > 0) {
+        const T* Gt = w.Gt + (size_t)b * m * ld;
+        for (int l = wid; l < m; l += nwarps) {
+          T d = T(0);
+          for (int e = lane; e < n; e += 32) d += Gt[(size_t)l * ld + e] * v[e];
+          d = warp_sum(d);
+          if (lane == 0) tdot[l] = d;
+        }
+        __syncthreads();
+      }
+      // ---- element-wise ADMM update (:271-282) and the rhs of the next iteration (:259-262)
+      T mx_p = T(0), mx_d = T(0), mx_x = T(0), mx_z = T(0), mx_y = T(0);
+      for (int e = tid; e < n; e += nthreads) {
+        T x = T(0);
+        for (int r = 0; r < CS; ++r) x += ld_cluster(xloc + xbuf * np + e, r);     // shares in rank order: every CTA gets the same x
+        x += w.c[vo + e];
+        const T z_prev = zs[e], u_prev = us[e];
+        T zn = x + u_prev;
+        if (any_lb) zn = t_max(zn, w.lbt[vo + e]);
+        if (any_ub) zn = t_min(zn, w.ubt[vo + e]);
+        const T r = x - zn;
+        const T sres = rho * (zn - z_prev);
+        const T un = u_prev + r;
+        zs[e] = zn;
+        us[e] = un;
+        if (lead) {
+          w.z[vo + e] = zn;
+          w.u[vo + e] = un;
+        }
+        v[e] = -w.pt[vo + e] + rho * (zn - un);
+        if (maybe_final) {
+          xs[e] = x;
+          if (lead) w.xs[vo + e] = x;
+        }
+        if (TAPE) {
+          const size_t to = ((size_t)b * tape.n_iter + i) * n + e;
+          tape.x[to] = x;
+          tape.z[to] = zn;
+          tape.u[to] = un;
+        }
+        if (is_check) {
+          if (!(t_abs(x) < t_inf<T>())) cta_bad = 1;       // NaN / inf iterate: numerical breakdown
+          const T d = w.D[vo + e];
+          Ds[e] = d;
+          mx_p = t_max(mx_p, t_abs(d * r));
+          mx_d = t_max(mx_d, t_abs(d * sres));
+          mx_x = t_max(mx_x, t_abs(d * x));
+          mx_z = t_max(mx_z, t_abs(d * zn));
+          mx_y = t_max(mx_y, t_abs(rho * d * un));
+        }
+      }
+      have_v = (nprob == 1);
+      xbuf ^= 1;
+      __syncthreads();
+      if (lead && maybe_final && m > 0 && tid < m) {     // nu = K21 rhs + K22 b~, unscaled by E (:327)
+        const T* K22 = w.Sinv + (size_t)b * m * m;
+        T a = tdot[tid];
+        for (int l = 0; l < m; ++l) a += K22[tid * m + l] * w.bt[(size_t)b * m + l];
+        if (!TAPE || nus_out) nus_out[(size_t)b * m + tid] = a * w.E[(size_t)b * m + tid];
+        if (TAPE) tape.nu[((size_t)b * tape.n_iter + i) * m + tid] = a;
+      }
+      if (is_check) {
+        // ---- ||Q~ x~ / D||_inf (:299): the same symmetric sweep over the packed Q~ tiles
+        sym_pass(xs);
+        __syncthreads();
+        for (int e = tid; e < np; e += nthreads) {
+          T a = T(0);
+          for (int ww = 0; ww < nwarps; ++ww) {
+            a += xpart[(size_t)ww * np + e];
+            xpart[(size_t)ww * np + e] = T(0);
+          }
+          xloc[xbuf * np + e] = a;
+        }
+        cluster_sync_all();
+        T mx_q = T(0);
+        for (int e = tid; e < n; e += nthreads) {
+          T y = T(0);
+          for (int r = 0; r < CS; ++r) y += ld_cluster(xloc + xbuf * np + e, r);
+          mx_q = t_max(mx_q, t_abs(y / Ds[e]));
+        }
+        xbuf ^= 1;
+        // ---- block reduction of the six maxima
+        mx_p = warp_max(mx_p); mx_d = warp_max(mx_d); mx_x = warp_max(mx_x);
+        mx_z = warp_max(mx_z); mx_y = warp_max(mx_y); mx_q = warp_max(mx_q);
+        if (lane == 0) {
+          red[0 * 16 + wid] = mx_p; red[1 * 16 + wid] = mx_d; red[2 * 16 + wid] = mx_x;
+          red[3 * 16 + wid] = mx_z; red[4 * 16 + wid] = mx_y; red[5 * 16 + wid] = mx_q;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          T mm[6];
+          for (int a = 0; a < 6; ++a) {
+            T r = red[a * 16];
+            for (int ww = 1; ww < nwarps; ++ww) r = t_max(r, red[a * 16 + ww]);
+            mm[a] = r;
+          }
+          const T primal = mm[0], dual = mm[1];
+          const T tol_p_rel = t_max(t_max(mm[2], mm[3]), zc);                      // :301
+          const T tol_p = eps_abs + eps_rel * tol_p_rel;                           // :302
+          const T tol_d_rel = t_max(t_max(t_max(mm[4], mm[5]), w.pnorm[b]), zc);   // :303
+          const T tol_d = eps_abs + eps_rel * tol_d_rel;                           // :304
+          const bool optimal = (primal < tol_p) && (dual < tol_d);                // :307-309
+          const bool wants = (primal > t_max(tol_p, thr)) || (dual > t_max(tol_d, thr));   // :310-311
+          const T num = t_max(primal / tol_p_rel, zc), den = t_max(dual / tol_d_rel, zc);  // :239-242
+          const T ratio = t_sqrt(num / den);                                       // :243
+          if (lead) {
+            w.chk[4 * b + 0] = primal; w.chk[4 * b + 1] = dual;
+            w.chk[4 * b + 2] = tol_p_rel; w.chk[4 * b + 3] = tol_d_rel;
+            w.wants[b] = wants ? 1 : 0;
+            w.ratio[b] = ratio;
+            cta_notopt += optimal ? 0 : 1;
+            cta_wants |= wants ? 1 : 0;
+            cta_rout |= (ratio > ar_tol || ratio < ar_tol_inv) ? 1 : 0;            // :244-245
+          }
+          if (lead && cfg.verbose) {
+            const int ci = i / check;
+            if (ci < LQPB_LOG_CAP) {
+              atomic_max_nonneg(&ctrl->log_primal[ci], (double)primal);
+              atomic_max_nonneg(&ctrl->log_dual[ci], (double)dual);
+              ctrl->log_iter[ci] = i;
+            }
+          }
+        }
+        __syncthreads();   // red[] reusable
+      }
+    }
+    // ---- publish this CTA's flags and make the decision global (:312 torch.all)
+    if (is_check) {
+      cta_bad = __syncthreads_or(cta_bad) && lead;
+      if (tid == 0) {
+        int* slot = ctrl->slot[(i / check) & 3];
+        if (cta_notopt) atomicAdd(&slot[0], cta_notopt);
+        if (cta_wants) atomicOr(&slot[1], 1);
+        if (cta_rout) atomicOr(&slot[2], 1);
+        if (cta_bad) atomicOr(&slot[3], 1);
+        __threadfence();
+        atomicAdd(&ctrl->barrier, 1u);
+        const unsigned target = (barrier_epoch + 1) * gridDim.x;
+        while (ld_acquire_u32(&ctrl->barrier) < target) {
+        }
+        __threadfence();
+        s_dec[0] = *(volatile int*)&slot[0];
+        s_dec[1] = *(volatile int*)&slot[1];
+        s_dec[2] = *(volatile int*)&slot[2];
+        s_dec[3] = *(volatile int*)&slot[3];
+        if (blockIdx.x == 0) {
+          int* nxt = ctrl->slot[((i / check) + 2) & 3];
+          nxt[0] = 0; nxt[1] = 0; nxt[2] = 0; nxt[3] = 0;
+          ctrl->last_wants = s_dec[1];
+          ctrl->last_ratio_out = s_dec[2];
+          if (cfg.verbose) ctrl->n_log = min(i / check + 1, LQPB_LOG_CAP);
+          __threadfence();
+        }
+      }
+      ++barrier_epoch;
+      __syncthreads();
+      const int notopt = s_dec[0];
+      last_wants = s_dec[1];
+      last_rout = s_dec[2];
+      const int broken = s_dec[3];
+      __syncthreads();
+      if (broken) { status = 4; break; }           // LQPB_STATUS_BREAKDOWN: some iterate is NaN / inf
+      if (notopt == 0) { status = 1; break; }
+    }
+    if (is_last) { status = 2; break; }
+    ++i;
+  }
+  // ---- drain the tiles that were fetched ahead (a CTA must not exit with bulk copies in flight)
+  while (in_flight > 0) {
+    mbar_wait(&full_w[c_slot], c_phase);
+    if (++c_slot == depth) { c_slot = 0; c_phase ^= 1u; }
+    --in_flight;
+  }
+  // no CTA may exit while a peer can still read its shared memory
+  cluster_sync_all();
+  if (blockIdx.x == 0 && tid == 0) {
+    ctrl->status = status;
+    if (status == 3) ctrl->next_i = i;
+    else ctrl->iter = i;
+  }
+}
+
+
+// Largest cluster size (4, then 2) for which B clusters of the kernel are co-resident; 0 = do not split.
+template <typename T>
+cudaError_t launch_iterate_split(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
+                                 int* launches, cudaStream_t st, bool* taken) {
+  *taken = false;
+  int want = 0;
+  {
+    const char* e = getenv("LQPB_ITER_SPLIT");     // developer switch: 0 = never, 2 / 4 = only that cluster size
+    if (e && *e) want = atoi(e);
+    if (e && *e && want == 0) return cudaSuccess;
+  }
+  int dev = 0, max_smem = 0, sms = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (w.B * 2 > sms) return cudaSuccess;
+  if (!want && w.B * 4 > sms) return cudaSuccess;
+  using P = Pack<T>;
+  const size_t extra = (size_t)4 * kPackRows * P::nt(w.n) * sizeof(T);        // xloc[2], z, u
+  size_t smem = 0;
+  IterGeom geo{};
+  if (!make_geom(w, max_smem - 1024 - (int)extra, &geo, &smem)) return cudaSuccess;
+  smem += extra;
+  e = cudaFuncSetAttribute(iterate_split_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  lqpb_config c = cfg;
+  FwdWs<T> ww = w;
+  for (int CS = 4; CS >= 2; CS /= 2) {
+    // default: clusters of 4 only (B <= 37 on 148 SMs).  Measured at dz = 500: B = 32 x 4 CTAs 0.524 -> 0.345 ms per solve,
+    // B = 64 x 2 CTAs 0.531 -> 0.446 ms -- too little to give up that a 64-problem shard reproduces the bits of the
+    // 128-problem batch it was cut from (tests/test_gpu_parity.py::test_full_size_properties); LQPB_ITER_SPLIT=2 forces it
+    if (want ? want != CS : CS != 4) continue;
+    if (w.B * CS > sms || geo.ntiles < 2 * CS * geo.nwarps / 4) continue;     // (a warp should own a tile or more on average)
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(w.B * CS);
+    lc.blockDim = dim3(geo.nwarps * 32);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeCooperative;
+    at[1].val.cooperative = 1;
+    lc.attrs = at;
+    lc.numAttrs = 2;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, iterate_split_kernel<T>, &lc) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    if (nclusters < w.B) continue;
+    e = cudaMemsetAsync(&w.ctrl->barrier, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    e = cudaLaunchKernelEx(&lc, iterate_split_kernel<T>, c, ww, i0, skip_rho_check, nus_out, geo, CS);
+    if (e != cudaSuccess) {          // (e.g. a driver that refuses cooperative cluster launches: the unsplit kernel takes over)
+      cudaGetLastError();
+      return cudaSuccess;
+    }
+    if (launches) ++*launches;
+    *taken = true;
+    return cudaSuccess;
+  }
+  return cudaSuccess;
+}
+
+template <typename T>
+int iterate_split_size(const FwdWs<T>& w) {
+  const char* e = getenv("LQPB_ITER_SPLIT");
+  int want = (e && *e) ? atoi(e) : -1;
+  if (want == 0) return 0;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ntiles = Pack<T>::ntiles(w.n);
+  for (int CS = 4; CS >= 2; CS /= 2) {
+    if (want > 0 ? want != CS : CS != 4) continue;
+    if (w.B * CS <= sms && ntiles >= 2 * CS * kIterMaxWarps / 4) return CS;
+  }
+  return 0;
+}
+template int iterate_split_size<float>(const FwdWs<float>&);
+template int iterate_split_size<double>(const FwdWs<double>&);
+
+#define INST(T)                                                                                                       \
+  template cudaError_t launch_iterate_split<T>(const lqpb_config&, const FwdWs<T>&, int, int, T*, int*, cudaStream_t, \
+                                               bool*);
+INST(float)
+INST(double)
+#undef INST
+
+}  // namespace lqpb

@@ -5,9 +5,9 @@
 // problems and 0.549 ms for 128 at dz = 500 -- so a batch of 32 (the mini-batch of the reference's Experiment 2,
 // experiments/experiment_2.py:52-99) leaves 116 of 148 SMs idle for the whole solve.  Here the tile sequence of a matrix
 // is cut into CS x nwarps runs instead of nwarps: CTA `crank` of the cluster streams and applies its share through the
-// same per-warp bulk-TMA rings, reduces its warps' partial sums in a fixed order into a shared-memory vector, and after ONE
-// hardware cluster barrier per pass every CTA adds the CS shares (its own and its peers' through distributed shared
-// memory, in rank order) -- so all CTAs of a cluster hold bit-identical x~, z, u and next right-hand side and run the O(n)
+// same per-warp bulk-TMA rings, reduces its warps' partial sums in a fixed order and stores the result into its slot of
+// EVERY CTA of the cluster (distributed-shared-memory stores: nobody waits for them), and after ONE hardware cluster
+// barrier per pass every CTA adds the CS shares from its own shared memory, in rank order -- so all CTAs of a cluster hold bit-identical x~, z, u and next right-hand side and run the O(n)
 // vector phase redundantly; z and u live in shared memory for the whole solve and only the rank-0 CTA writes the problem's
 // state, stop-check record and flags to global memory.  Same loop, decisions and global stop semantics as iterate.cu
 // (reference lqp_py/solve_box_qp_admm_torch.py:235-313, :327); the rounding differs from the unsplit kernel only through
@@ -30,19 +30,15 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float ld_cluster(const float* local, int rank) {
+__device__ __forceinline__ void st_cluster(float* local, int rank, float v) {
   uint32_t ra;
-  float v;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-  return v;
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
 }
-__device__ __forceinline__ double ld_cluster(const double* local, int rank) {
+__device__ __forceinline__ void st_cluster(double* local, int rank, double v) {
   uint32_t ra;
-  double v;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local)), "r"(rank));
-  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
-  return v;
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
 }
 
 template <typename T>
@@ -64,8 +60,9 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
   T* Ds = xs + np;                                          // [np] D
   T* tdot = Ds + np;                                        // [max(m,1)] K21 rhs
   T* red = tdot + (m > 0 ? round_up(m, 4) : 4);             // [6][16] reduction scratch
-  T* xloc = red + 6 * 16 + 4;                               // [2][np] this CTA's share of K v / Q~ x~ (double-buffered: peers read it)
-  T* zs = xloc + 2 * np;                                    // [np] z (every CTA of the cluster keeps the whole state)
+  T* xloc = red + 6 * 16 + 4;                               // [2][CS][np] the CS shares of K v / Q~ x~: slot [buf][r] is WRITTEN by CTA r
+                                                            // of the cluster (DSMEM stores), double-buffered over passes
+  T* zs = xloc + 2 * CS * np;                               // [np] z (every CTA of the cluster keeps the whole state)
   T* us = zs + np;                                          // [np] u
   uint64_t* full = reinterpret_cast<uint64_t*>(us + np);    // [nwarps][depth]
   __shared__ int s_dec[4];
@@ -86,7 +83,7 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
   for (int e = tid; e < nwarps * np; e += nthreads) xpart[e] = T(0);
   for (int e = tid; e < np; e += nthreads) {
     v[e] = T(0); xs[e] = T(0); Ds[e] = T(1);
-    xloc[e] = T(0); xloc[np + e] = T(0);
+    for (int q = 0; q < 2 * CS; ++q) xloc[q * np + e] = T(0);
     const bool in = e < n;
     zs[e] = in ? w.z[(size_t)prob * ld + e] : T(0);
     us[e] = in ? w.u[(size_t)prob * ld + e] : T(0);
@@ -227,7 +224,8 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
           a += xpart[(size_t)ww * np + e];
           xpart[(size_t)ww * np + e] = T(0);
         }
-        xloc[xbuf * np + e] = a;
+        T* slot = xloc + (size_t)(xbuf * CS + crank) * np + e;
+        for (int r = 0; r < CS; ++r) st_cluster(slot, r, a);       // fire-and-forget stores into every CTA's copy
       }
       cluster_sync_all();
       // ---- K21 rhs for nu (:327), from the rhs of THIS solve (before v is overwritten)
@@ -245,7 +243,7 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
       T mx_p = T(0), mx_d = T(0), mx_x = T(0), mx_z = T(0), mx_y = T(0);
       for (int e = tid; e < n; e += nthreads) {
         T x = T(0);
-        for (int r = 0; r < CS; ++r) x += ld_cluster(xloc + xbuf * np + e, r);     // shares in rank order: every CTA gets the same x
+        for (int r = 0; r < CS; ++r) x += xloc[(size_t)(xbuf * CS + r) * np + e];  // shares in rank order: every CTA gets the same x
         x += w.c[vo + e];
         const T z_prev = zs[e], u_prev = us[e];
         T zn = x + u_prev;
@@ -302,13 +300,14 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
             a += xpart[(size_t)ww * np + e];
             xpart[(size_t)ww * np + e] = T(0);
           }
-          xloc[xbuf * np + e] = a;
+          T* slot = xloc + (size_t)(xbuf * CS + crank) * np + e;
+          for (int r = 0; r < CS; ++r) st_cluster(slot, r, a);
         }
         cluster_sync_all();
         T mx_q = T(0);
         for (int e = tid; e < n; e += nthreads) {
           T y = T(0);
-          for (int r = 0; r < CS; ++r) y += ld_cluster(xloc + xbuf * np + e, r);
+          for (int r = 0; r < CS; ++r) y += xloc[(size_t)(xbuf * CS + r) * np + e];
           mx_q = t_max(mx_q, t_abs(y / Ds[e]));
         }
         xbuf ^= 1;
@@ -433,7 +432,7 @@ cudaError_t launch_iterate_split(const lqpb_config& cfg, const FwdWs<T>& w, int 
   if (w.B * 2 > sms) return cudaSuccess;
   if (!want && w.B * 4 > sms) return cudaSuccess;
   using P = Pack<T>;
-  const size_t extra = (size_t)4 * kPackRows * P::nt(w.n) * sizeof(T);        // xloc[2], z, u
+  const size_t extra = (size_t)(2 * 4 + 2) * kPackRows * P::nt(w.n) * sizeof(T);        // xloc[2][<= 4], z, u
   size_t smem = 0;
   IterGeom geo{};
   if (!make_geom(w, max_smem - 1024 - (int)extra, &geo, &smem)) return cudaSuccess;

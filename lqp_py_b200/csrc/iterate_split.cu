@@ -413,6 +413,19 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
 }
 
 
+// Nsight Compute (2025.2) cannot launch a cooperative launch that also has a cluster dimension: the kernel shows up with a
+// (0, 0, 0) grid, "LaunchFailed", and under application replay runs without its cluster (illegal address at the first DSMEM
+// store).  A process started by ncu (its directories are on LD_LIBRARY_PATH / CUDA_INJECTION64_PATH, its process-tracking
+// variables are set) therefore keeps the one-CTA-per-problem kernel unless LQPB_ITER_SPLIT asks for the split explicitly.
+static bool under_nsight_compute() {
+  const char* vars[] = {"CUDA_INJECTION64_PATH", "LD_LIBRARY_PATH"};
+  for (const char* v : vars) {
+    const char* e = getenv(v);
+    if (e && strstr(e, "nsight-compute")) return true;
+  }
+  return getenv("NVIDIA-PROCESS-TRACKING-CONFIGURATION") != nullptr;
+}
+
 // Largest cluster size (4, then 2) for which B clusters of the kernel are co-resident; 0 = do not split.
 template <typename T>
 cudaError_t launch_iterate_split(const lqpb_config& cfg, const FwdWs<T>& w, int i0, int skip_rho_check, T* nus_out,
@@ -423,6 +436,7 @@ cudaError_t launch_iterate_split(const lqpb_config& cfg, const FwdWs<T>& w, int 
     const char* e = getenv("LQPB_ITER_SPLIT");     // developer switch: 0 = never, 2 / 4 = only that cluster size
     if (e && *e) want = atoi(e);
     if (e && *e && want == 0) return cudaSuccess;
+    if (!want && under_nsight_compute()) return cudaSuccess;
   }
   int dev = 0, max_smem = 0, sms = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -485,7 +499,7 @@ template <typename T>
 int iterate_split_size(const FwdWs<T>& w) {
   const char* e = getenv("LQPB_ITER_SPLIT");
   int want = (e && *e) ? atoi(e) : -1;
-  if (want == 0) return 0;
+  if (want == 0 || (want < 0 && under_nsight_compute())) return 0;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

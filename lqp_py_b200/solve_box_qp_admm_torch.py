@@ -302,24 +302,56 @@ def _copy_stream(dev):
     return st
 
 
+_STAGE_POOL = {}
+
+
+def _stage_pool():
+    """Threads for the pageable -> page-locked staging copies, or None when torch's own intra-op pool is wide enough.
+    Under torchrun every rank runs with OMP_NUM_THREADS=1: torch's host copy is then single-threaded (128 MB: 13 ms, slower
+    than the driver's own pageable path), so the copy is cut over a few Python threads instead (ctypes ``memmove``, no GIL) --
+    the usable CPUs divided by the ranks on this host, at most 8."""
+    if torch.get_num_threads() >= 4:
+        return None, 1
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = os.cpu_count() or 1
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    k = max(1, min(8, cpus // ranks))
+    if k < 2:
+        return None, 1
+    if k not in _STAGE_POOL:
+        from concurrent.futures import ThreadPoolExecutor
+        _STAGE_POOL[k] = ThreadPoolExecutor(max_workers=k, thread_name_prefix="lqpb-stage")
+    return _STAGE_POOL[k], k
+
+
 def _copy_up(dst, src, st):
-    """``dst`` (device) <- ``src`` (host) on stream ``st``.  The reference's callers hold ordinary (pageable) CPU tensors;
-    cudaMemcpyAsync moves those through the driver's own bounce buffer at ~11 GB/s (128 MB of Q: 11.2 ms against 2.4 ms
-    from page-locked memory).  Large pageable sources therefore go through page-locked staging memory here, chunk by
-    chunk: torch's multi-threaded host copy fills chunk c + 1 (~49 GB/s) while the copy engine moves chunk c."""
+    """``dst`` (device) <- ``src`` (host, contiguous) on stream ``st``.  The reference's callers hold ordinary (pageable) CPU
+    tensors; cudaMemcpyAsync moves those through the driver's own bounce buffer at ~11 GB/s (128 MB of Q: 11.2 ms against
+    2.4 ms from page-locked memory).  Large pageable sources therefore go through page-locked staging memory here, chunk
+    by chunk: a multi-threaded host copy fills chunk c + 1 (~49 GB/s with 16 threads) while the copy engine moves chunk c."""
     if not _needs_staging(src):
         with torch.cuda.stream(st):
             dst.copy_(src, non_blocking=True)
         return
-    rows_total = src.shape[0]
-    per_row = max(1, src[0].numel() * src.element_size())
-    rows = max(1, _STAGE_CHUNK_BYTES // per_row)
-    pin = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)     # (torch's caching host allocator keeps the block
-    for r0 in range(0, rows_total, rows):                              # alive until the copies that read it are through)
-        r1 = min(rows_total, r0 + rows)
-        pin[r0:r1].copy_(src[r0:r1])
+    flat_src, flat_dst = src.reshape(-1), dst.view(-1)
+    total = flat_src.numel()
+    chunk = max(1, _STAGE_CHUNK_BYTES // src.element_size())
+    pin = torch.empty(total, dtype=src.dtype, pin_memory=True)         # (torch's caching host allocator keeps the block
+    pool, k = _stage_pool()                                            # alive until the copies that read it are through)
+    for a in range(0, total, chunk):
+        b = min(total, a + chunk)
+        if pool is None:
+            pin[a:b].copy_(flat_src[a:b])
+        else:
+            es, sp, dp = src.element_size(), flat_src.data_ptr(), pin.data_ptr()
+            step = -(-(b - a) // k)
+            futs = [pool.submit(C.memmove, dp + c * es, sp + c * es, (min(b, c + step) - c) * es) for c in range(a, b, step)]
+            for fu in futs:                          # (ctypes calls run without the GIL)
+                fu.result()
         with torch.cuda.stream(st):
-            dst[r0:r1].copy_(pin[r0:r1], non_blocking=True)
+            flat_dst[a:b].copy_(pin[a:b], non_blocking=True)
 
 
 def _launch_prefetches():

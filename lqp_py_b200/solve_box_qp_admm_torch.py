@@ -1369,8 +1369,7 @@ def _grad_host(dl_dz, x, u, lams, nus, Q, A, lb, ub, rho, need, kkt, any_bounds,
                 gp = g if g.is_pinned() else torch.empty(g.shape, dtype=dt, pin_memory=True).copy_(g)
                 _abi.check(L.lqpb_copy_mapped(_abi.ptr(g_dev), _abi.ptr(gp), gp.numel() * gp.element_size(),
                                               C.c_void_p(_raw_stream(dev))), "lqpb_copy_mapped")
-                g_src = g_dev                        # "already in place"
-                keep_alive = gp
+                g_src = g_dev                        # "already in place" (gp stays referenced until the call below has synchronised)
             else:
                 g_src = torch.empty((B, n, 1), dtype=dt, device=dev)
                 g_src.copy_(g.reshape(B, n, 1), non_blocking=True)

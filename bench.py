@@ -171,7 +171,9 @@ class ClockSampler:
 
 
 def log(msg):
-    """progress marker on stderr (stdout carries only the JSON line)"""
+    """progress marker on stderr (stdout carries only the JSON line); rank 0 only under torchrun"""
+    if int(os.environ.get("RANK", "0") or 0) != 0:
+        return
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 

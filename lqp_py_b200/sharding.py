@@ -102,8 +102,9 @@ def train_learn_p(qp_layer, Q, p_true, A, b, lb, ub, feats, n_epochs=100, n_mini
         loss = torch.zeros((), dtype=Q.dtype, device=device)
         if hi > lo:
             p_hat = model(feats[idx]).unsqueeze(2)
-            z = qp_layer(Q[idx], p_hat, A[idx], b[idx], lb[idx], ub[idx])
-            loss = qp_cost(z, Q[idx], p_true[idx])
+            Qi = Q[idx]                                # one gather of the mini-batch's matrices (32 MB at dz = 500) for both uses
+            z = qp_layer(Qi, p_hat, A[idx], b[idx], lb[idx], ub[idx])
+            loss = qp_cost(z, Qi, p_true[idx])
             loss.backward()
         allreduce_grads(model.parameters())
         opt.step()

@@ -78,7 +78,7 @@ lu_factor_kernel(int N, const T* __restrict__ A, T* LUall, int32_t* __restrict__
 constexpr int kSolveThreads = 256;
 
 template <typename T>
-__global__ void __launch_bounds__(kSolveThreads)
+__global__ void __launch_bounds__(kSolveThreads, 2)
 lu_solve_kernel(int N, int nrhs, const T* __restrict__ LUall, const int32_t* __restrict__ pivall,
                 const T* __restrict__ rhs, T* __restrict__ xout, int negate) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

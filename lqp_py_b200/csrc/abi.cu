@@ -423,6 +423,7 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
     }
     CK(cudaStreamWaitEvent(st, g_pipe.vec, 0), "vec wait");
     CK(launch_bound_flags<T>(w, lb, ub, st), "bound_flags");
+    g_prof.launches += 1;
     if (prof) cudaEventRecord(g_prof.ev[1], st);
     if (prof) cudaEventRecord(g_prof.fac0[0], st);
     for (int c = 0; c < C; ++c) {
@@ -432,7 +433,7 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
       CK(launch_scale<T>(*cfg, wc, Q + (size_t)b0 * n * n, p + (size_t)b0 * n, off(A, (size_t)b0 * m * n),
                          off(b, (size_t)b0 * m), lb + (size_t)b0 * n, ub + (size_t)b0 * n, st), "scale");
       CK(launch_select_rho<T>(*cfg, wc, st), "select_rho");
-      g_prof.launches += 4 + (cfg->scale ? 1 : 0);
+      g_prof.launches += 3 + (cfg->scale ? 1 : 0);      // (colmax), scale_vec, scale_pack, select_rho: kernels only
       rc = factor_forward<T>(wc, true, st);
       if (rc) return rc;
     }
@@ -442,7 +443,7 @@ int forward_impl(const lqpb_config* cfg, int B, int n, int m, const T* Q, const 
   } else {
     CK(launch_scale<T>(*cfg, w, Q, p, A, b, lb, ub, st), "scale");
     CK(launch_select_rho<T>(*cfg, w, st), "select_rho");
-    g_prof.launches += 4 + (cfg->scale ? 1 : 0);
+    g_prof.launches += 3 + (cfg->scale ? 1 : 0);        // (colmax), scale_vec, scale_pack, select_rho: kernels only
     if (prof) cudaEventRecord(g_prof.ev[1], st);
   }
 

@@ -971,3 +971,28 @@ def test_pageable_inputs_are_staged_bit_identically(dev):
         for w_, g_ in zip(want, got):
             for a_, b_ in zip(w_, g_):
                 assert a_.device.type == "cpu" and torch.equal(a_, b_)
+
+
+@pytest.mark.parametrize("split", ["0", None])
+def test_adaptive_rho_refactorisation_in_the_streamed_regimes(dev, split, monkeypatch):
+    """A badly chosen rho (100, as in the golden case adapt_rho100 at n = 60) at a STREAMED size: the iteration kernel exits
+    with a refactorisation request, the host refactors and relaunches it mid-solve (i0 > 0) -- through the one-CTA-per-problem
+    kernel (LQPB_ITER_SPLIT=0) and through the cluster-split kernel a small batch takes by default.  fp64 against the oracle:
+    same number of factorisations, iteration count within 2, x / duals / rho at 1e-8 (1e-7 where rho amplifies round-off)."""
+    from lqp_py_b200.control import box_qp_control
+    from lqp_py_b200.solve_box_qp_admm_torch import _solve_device
+    if split is None:
+        monkeypatch.delenv("LQPB_ITER_SPLIT", raising=False)
+    else:
+        monkeypatch.setenv("LQPB_ITER_SPLIT", split)
+    n, B = 320, 3
+    data = orc.make_exp1_data(n, B, seed=31, dtype=torch.float64)
+    control = box_qp_control(eps_abs=1e-8, eps_rel=1e-8, rho=100.0, adaptive_rho_iter=40)
+    ref = orc.solve(*data, dict(control))
+    sol = _solve_device(*[t.to(dev) for t in data], dict(control))      # (torch_solve_box_qp's dict + n_factor)
+    assert sol["n_factor"] == ref["factorisations"] >= 2, "the case must refactorise at least once"
+    assert abs(sol["iter"] - ref["iter"]) <= 2
+    assert torch.is_tensor(sol["rho"]) and rel_err(sol["rho"].cpu().numpy(), ref["rho"].numpy()) <= 1e-8
+    for k, t in (("x", 1e-8), ("z", 1e-8), ("lams", 1e-7), ("nus", 1e-7), ("u", 1e-7)):
+        e = rel_err(sol[k].cpu().numpy(), ref[k].numpy())
+        assert e <= t, f"{k}: {e:.2e} > {t:.1e}"

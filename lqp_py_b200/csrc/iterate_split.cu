@@ -44,8 +44,6 @@ __device__ __forceinline__ void st_cluster(double* local, int rank, double v) {
 template <typename T>
 __global__ void __launch_bounds__(kIterMaxThreads, 1)
 iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T* nus_out, IterGeom geo, int CS) {
-  constexpr bool TAPE = false;
-  Tape<T> tape{};
   using P = Pack<T>;
   constexpr int TC = P::TC, TILE = P::TILE;
   using V4 = typename Vec<T>::type;
@@ -203,7 +201,7 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
     }
     const bool is_check = (i % check) == 0;
     const bool is_last = i == cfg.max_iters - 1;
-    const bool maybe_final = TAPE || is_check || is_last;
+    const bool maybe_final = is_check || is_last;
 
     int cta_notopt = 0, cta_wants = 0, cta_rout = 0, cta_bad = 0;
     for (int k = 0; k < nprob; ++k) {
@@ -263,12 +261,6 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
           xs[e] = x;
           if (lead) w.xs[vo + e] = x;
         }
-        if (TAPE) {
-          const size_t to = ((size_t)b * tape.n_iter + i) * n + e;
-          tape.x[to] = x;
-          tape.z[to] = zn;
-          tape.u[to] = un;
-        }
         if (is_check) {
           if (!(t_abs(x) < t_inf<T>())) cta_bad = 1;       // NaN / inf iterate: numerical breakdown
           const T d = w.D[vo + e];
@@ -287,8 +279,7 @@ iterate_split_kernel(lqpb_config cfg, FwdWs<T> w, int i0, int skip_rho_check, T*
         const T* K22 = w.Sinv + (size_t)b * m * m;
         T a = tdot[tid];
         for (int l = 0; l < m; ++l) a += K22[tid * m + l] * w.bt[(size_t)b * m + l];
-        if (!TAPE || nus_out) nus_out[(size_t)b * m + tid] = a * w.E[(size_t)b * m + tid];
-        if (TAPE) tape.nu[((size_t)b * tape.n_iter + i) * m + tid] = a;
+        nus_out[(size_t)b * m + tid] = a * w.E[(size_t)b * m + tid];
       }
       if (is_check) {
         // ---- ||Q~ x~ / D||_inf (:299): the same symmetric sweep over the packed Q~ tiles
